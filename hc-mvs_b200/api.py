@@ -1,0 +1,274 @@
+"""ctypes binding of the C ABI in include/hcmvs_b200.h (libhcmvs_b200.so, CUDA sm_100a).
+
+No fallback: loading fails loudly when the CUDA library is missing, and ``Context`` raises when
+``hcmvs_create`` cannot find a CUDA device.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhcmvs_b200.so")
+
+EXPORTS = [
+    "hcmvs_default_params", "hcmvs_last_error", "hcmvs_create", "hcmvs_destroy", "hcmvs_set_params", "hcmvs_sync",
+    "hcmvs_set_view", "hcmvs_set_neighbors", "hcmvs_init_depthmap", "hcmvs_set_depthmap", "hcmvs_get_depthmap",
+    "hcmvs_set_prior", "hcmvs_get_gradient_map", "hcmvs_score_depthmap", "hcmvs_estimate_depthmap", "hcmvs_end_depthmap", "hcmvs_score_hypotheses",
+    "hcmvs_filter_depthmap", "hcmvs_commit_filtered", "hcmvs_set_fuse_priority", "hcmvs_fuse_depthmaps",
+    "hcmvs_free_pointcloud", "hcmvs_get_depthmap_device", "hcmvs_set_depth_range", "hcmvs_alloc_depthmap",
+    "hcmvs_get_timers", "hcmvs_reset_timers", "hcmvs_stream",
+]
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("nNumViews", C.c_uint32), ("nMaxViews", C.c_uint32), ("nMinViews", C.c_uint32), ("nMinViewsTrustPoint", C.c_uint32),
+        ("nMinViewsFuse", C.c_uint32), ("nMinViewsFilter", C.c_uint32), ("nMinViewsFilterAdjust", C.c_uint32),
+        ("bFilterAdjust", C.c_int32),
+        ("fNCCThresholdKeep", C.c_float),
+        ("nEstimationIters", C.c_uint32), ("nEstimationIters_external", C.c_uint32), ("nRandomIters", C.c_uint32),
+        ("fRandomDepthRatio", C.c_float), ("fRandomAngle1Range", C.c_float), ("fRandomAngle2Range", C.c_float),
+        ("fRandomSmoothDepth", C.c_float), ("fRandomSmoothNormal", C.c_float), ("fRandomSmoothBonus", C.c_float),
+        ("fDescriptorMinMagnitudeThreshold", C.c_float),
+        ("fDepthDiffThreshold", C.c_float), ("fNormalDiffThreshold", C.c_float), ("depthweight", C.c_float), ("normalweight", C.c_float),
+        ("adapthalfwin", C.c_int32), ("propagatehalfwin", C.c_int32), ("propagatestep", C.c_int32), ("photo2geo", C.c_int32),
+        ("photometric_flow", C.c_float), ("para_prior", C.c_float), ("fsigmaPrior", C.c_float),
+        ("rb_far_reach", C.c_int32), ("sampler", C.c_int32),
+    ]
+
+
+class PointCloudC(C.Structure):
+    _fields_ = [
+        ("n_points", C.c_uint64), ("points", C.POINTER(C.c_float)), ("normals", C.POINTER(C.c_float)),
+        ("colors", C.POINTER(C.c_uint8)), ("view_offsets", C.POINTER(C.c_uint32)), ("views", C.POINTER(C.c_uint32)),
+        ("weights", C.POINTER(C.c_float)),
+    ]
+
+
+class Timers(C.Structure):
+    _fields_ = [
+        ("ms_score", C.c_double), ("ms_sweeps", C.c_double), ("ms_end", C.c_double), ("ms_prep", C.c_double),
+        ("ms_filter", C.c_double), ("ms_fuse", C.c_double),
+        ("n_hypotheses", C.c_uint64), ("n_pixel_iters", C.c_uint64), ("n_view_scores", C.c_uint64),
+        ("n_launches", C.c_uint32), ("n_fuse_rounds", C.c_uint64),
+    ]
+
+
+class HcmvsError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libhcmvs_b200.so (raises ImportError if it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing — build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
+                          "hcmvs_b200 has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, u32, i32, f32 = C.c_void_p, C.c_uint32, C.c_int, C.c_float
+    L.hcmvs_last_error.restype = C.c_char_p
+    L.hcmvs_create.restype = vp
+    L.hcmvs_create.argtypes = [i32, C.POINTER(Params)]
+    L.hcmvs_destroy.argtypes = [vp]
+    L.hcmvs_default_params.argtypes = [C.POINTER(Params)]
+    L.hcmvs_set_params.argtypes = [vp, C.POINTER(Params)]
+    L.hcmvs_sync.argtypes = [vp]
+    L.hcmvs_set_view.argtypes = [vp, u32, i32, i32, vp, vp, vp, vp, vp]
+    L.hcmvs_set_neighbors.argtypes = [vp, u32, vp, vp, i32, i32]
+    L.hcmvs_init_depthmap.argtypes = [vp, u32, vp, vp, f32, f32]
+    L.hcmvs_set_depthmap.argtypes = [vp, u32, vp, vp, vp, f32, f32]
+    L.hcmvs_get_depthmap.argtypes = [vp, u32, vp, vp, vp, C.POINTER(f32), C.POINTER(f32)]
+    L.hcmvs_set_prior.argtypes = [vp, u32, vp]
+    L.hcmvs_get_gradient_map.argtypes = [vp, u32, vp]
+    L.hcmvs_score_depthmap.argtypes = [vp, u32, i32, C.c_uint64]
+    L.hcmvs_estimate_depthmap.argtypes = [vp, u32, i32, C.c_uint64]
+    L.hcmvs_end_depthmap.argtypes = [vp, u32]
+    L.hcmvs_score_hypotheses.argtypes = [vp, u32, vp, vp, i32, vp]
+    L.hcmvs_filter_depthmap.argtypes = [vp, u32, vp, i32, i32, vp, vp]
+    L.hcmvs_commit_filtered.argtypes = [vp]
+    L.hcmvs_set_fuse_priority.argtypes = [vp, u32, f32]
+    L.hcmvs_fuse_depthmaps.argtypes = [vp, i32, i32, C.POINTER(PointCloudC)]
+    L.hcmvs_free_pointcloud.argtypes = [C.POINTER(PointCloudC)]
+    L.hcmvs_get_depthmap_device.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(vp), C.POINTER(f32), C.POINTER(f32)]
+    L.hcmvs_set_depth_range.argtypes = [vp, u32, f32, f32]
+    L.hcmvs_alloc_depthmap.argtypes = [vp, u32]
+    L.hcmvs_get_timers.argtypes = [vp, C.POINTER(Timers)]
+    L.hcmvs_reset_timers.argtypes = [vp]
+    L.hcmvs_stream.restype = vp
+    L.hcmvs_stream.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def default_params(**over):
+    p = Params()
+    load().hcmvs_default_params(C.byref(p))
+    for k, v in over.items():
+        if not hasattr(p, k):
+            raise KeyError(k)
+        setattr(p, k, v)
+    return p
+
+
+def _p(a):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One device context == the reference's ``DepthMapsData`` object (libs/MVS/SceneDensify.h:49-88)."""
+
+    def __init__(self, device=0, params=None, **over):
+        self.L = load()
+        self.params = params if params is not None else default_params(**over)
+        self.h = self.L.hcmvs_create(int(device), C.byref(self.params))
+        if not self.h:
+            raise HcmvsError(self.L.hcmvs_last_error().decode())
+        self.sizes = {}
+
+    def _ck(self, r):
+        if r != 0:
+            raise HcmvsError(f"[{r}] " + self.L.hcmvs_last_error().decode())
+
+    def set_params(self, **over):
+        for k, v in over.items():
+            if not hasattr(self.params, k):
+                raise KeyError(k)
+            setattr(self.params, k, v)
+        self._ck(self.L.hcmvs_set_params(self.h, C.byref(self.params)))
+
+    def set_view(self, view, K, R, Cc, gray, bgr=None):
+        gray = np.ascontiguousarray(gray, np.float32)
+        h, w = gray.shape
+        if bgr is not None:
+            bgr = np.ascontiguousarray(bgr, np.uint8)
+        K = np.ascontiguousarray(K, np.float64).reshape(9); R = np.ascontiguousarray(R, np.float64).reshape(9); Cc = np.ascontiguousarray(Cc, np.float64).reshape(3)
+        self._ck(self.L.hcmvs_set_view(self.h, view, w, h, _p(K), _p(R), _p(Cc), _p(gray), _p(bgr)))
+        self.sizes[view] = (h, w)
+
+    def set_neighbors(self, ref, ids, n_match, scores=None):
+        ids = np.ascontiguousarray(ids, np.uint32)
+        sc = np.ascontiguousarray(scores, np.float32) if scores is not None else None
+        self._ck(self.L.hcmvs_set_neighbors(self.h, ref, _p(ids), _p(sc), int(n_match), len(ids)))
+
+    def init_depthmap(self, ref, depth0, normal0, dmin, dmax):
+        depth0 = np.ascontiguousarray(depth0, np.float32)
+        normal0 = np.ascontiguousarray(normal0, np.float32) if normal0 is not None else None
+        self._ck(self.L.hcmvs_init_depthmap(self.h, ref, _p(depth0), _p(normal0), dmin, dmax))
+
+    def set_depthmap(self, view, depth, normal, conf, dmin, dmax):
+        depth = np.ascontiguousarray(depth, np.float32)
+        normal = np.ascontiguousarray(normal, np.float32) if normal is not None else None
+        conf = np.ascontiguousarray(conf, np.float32) if conf is not None else None
+        self._ck(self.L.hcmvs_set_depthmap(self.h, view, _p(depth), _p(normal), _p(conf), dmin, dmax))
+
+    def get_depthmap(self, view):
+        h, w = self.sizes[view]
+        d = np.zeros((h, w), np.float32); n = np.zeros((h, w, 3), np.float32); c = np.zeros((h, w), np.float32)
+        a = C.c_float(); b = C.c_float()
+        self._ck(self.L.hcmvs_get_depthmap(self.h, view, _p(d), _p(n), _p(c), C.byref(a), C.byref(b)))
+        return d, n, c, a.value, b.value
+
+    def gradient_map(self, view):
+        h, w = self.sizes[view]
+        g = np.zeros((h, w), np.uint8)
+        self._ck(self.L.hcmvs_get_gradient_map(self.h, view, _p(g)))
+        return g
+
+    def set_prior(self, ref, prior):
+        prior = np.ascontiguousarray(prior, np.float32) if prior is not None else None
+        self._ck(self.L.hcmvs_set_prior(self.h, ref, _p(prior)))
+
+    def score_depthmap(self, ref, it_external=0, seed=1):
+        self._ck(self.L.hcmvs_score_depthmap(self.h, ref, it_external, seed))
+
+    def estimate_depthmap(self, ref, it_external=0, seed=1):
+        self._ck(self.L.hcmvs_estimate_depthmap(self.h, ref, it_external, seed))
+
+    def end_depthmap(self, ref):
+        self._ck(self.L.hcmvs_end_depthmap(self.h, ref))
+
+    def score_hypotheses(self, ref, depth, normal, smooth_mode=0):
+        h, w = self.sizes[ref]
+        depth = np.ascontiguousarray(depth, np.float32); normal = np.ascontiguousarray(normal, np.float32)
+        out = np.zeros((h, w), np.float32)
+        self._ck(self.L.hcmvs_score_hypotheses(self.h, ref, _p(depth), _p(normal), smooth_mode, _p(out)))
+        return out
+
+    def filter_depthmap(self, ref, nb_idx, adjust=True, download=True):
+        h, w = self.sizes[ref]
+        nb = np.ascontiguousarray(nb_idx, np.uint32)
+        d = np.zeros((h, w), np.float32) if download else None
+        c = np.zeros((h, w), np.float32) if download else None
+        self._ck(self.L.hcmvs_filter_depthmap(self.h, ref, _p(nb), len(nb), int(adjust), _p(d), _p(c)))
+        return d, c
+
+    def commit_filtered(self):
+        self._ck(self.L.hcmvs_commit_filtered(self.h))
+
+    def set_fuse_priority(self, view, score):
+        self._ck(self.L.hcmvs_set_fuse_priority(self.h, view, float(score)))
+
+    def fuse_depthmaps(self, color=True, normal=True):
+        pc = PointCloudC()
+        self._ck(self.L.hcmvs_fuse_depthmaps(self.h, int(color), int(normal), C.byref(pc)))
+        n = int(pc.n_points)
+        out = dict(xyz=np.zeros((0, 3), np.float32), normals=None, colors=None, n_views=np.zeros(0, np.int32),
+                   views=np.zeros(0, np.uint32), weights=np.zeros(0, np.float32))
+        if n:
+            out["xyz"] = np.ctypeslib.as_array(pc.points, (n, 3)).copy()
+            off = np.ctypeslib.as_array(pc.view_offsets, (n + 1,)).copy()
+            m = int(off[-1])
+            out["n_views"] = np.diff(off.astype(np.int64)).astype(np.int32)
+            out["views"] = np.ctypeslib.as_array(pc.views, (m,)).copy()
+            out["weights"] = np.ctypeslib.as_array(pc.weights, (m,)).copy()
+            if pc.normals:
+                out["normals"] = np.ctypeslib.as_array(pc.normals, (n, 3)).copy()
+            if pc.colors:
+                out["colors"] = np.ctypeslib.as_array(pc.colors, (n, 3)).copy()
+        self.L.hcmvs_free_pointcloud(C.byref(pc))
+        return out
+
+    def depthmap_device(self, view):
+        dn = C.c_void_p(); cf = C.c_void_p(); a = C.c_float(); b = C.c_float()
+        self._ck(self.L.hcmvs_get_depthmap_device(self.h, view, C.byref(dn), C.byref(cf), C.byref(a), C.byref(b)))
+        return dn.value, cf.value, a.value, b.value
+
+    def set_depth_range(self, view, dmin, dmax):
+        self._ck(self.L.hcmvs_set_depth_range(self.h, view, dmin, dmax))
+
+    def alloc_depthmap(self, view):
+        self._ck(self.L.hcmvs_alloc_depthmap(self.h, view))
+
+    def sync(self):
+        self._ck(self.L.hcmvs_sync(self.h))
+
+    def timers(self):
+        t = Timers()
+        self._ck(self.L.hcmvs_get_timers(self.h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in Timers._fields_}
+
+    def reset_timers(self):
+        self._ck(self.L.hcmvs_reset_timers(self.h))
+
+    def stream(self):
+        return self.L.hcmvs_stream(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.hcmvs_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,467 @@
+// C ABI implementation (include/hcmvs_b200.h): context, device-resident scene, stage orchestration.
+// Host-side mirror of DepthMapsData's state (libs/MVS/SceneDensify.h:49-88): `views` plays the role of
+// arrDepthData (+ scene.images cameras); every compute step is a CUDA kernel — there is no CPU path.
+#include "hcmvs_device.cuh"
+#include "hcmvs_internal.h"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <cstdarg>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+static thread_local std::string g_lastError;
+void hcmvs_set_error(const char* fmt, ...) {
+	char buf[1024]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+	g_lastError = buf;
+}
+extern "C" const char* hcmvs_last_error(void) { return g_lastError.c_str(); }
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { hcmvs_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return HCMVS_ERR_CUDA; } } while (0)
+
+extern "C" void hcmvs_default_params(hcmvs_params* p) {
+	// OPTDENSE defaults, libs/MVS/DepthMap.cpp:69-143 (CLI defaults where the CLI overrides them)
+	std::memset(p, 0, sizeof(*p));
+	p->nNumViews = 5; p->nMaxViews = 12; p->nMinViews = 2; p->nMinViewsTrustPoint = 2;
+	p->nMinViewsFuse = 2; p->nMinViewsFilter = 2; p->nMinViewsFilterAdjust = 1; p->bFilterAdjust = 1;
+	p->fNCCThresholdKeep = 0.55f;
+	p->nEstimationIters = 3; p->nEstimationIters_external = 1; p->nRandomIters = 6;
+	p->fRandomDepthRatio = 0.003f; p->fRandomAngle1Range = 16.f; p->fRandomAngle2Range = 10.f;
+	p->fRandomSmoothDepth = 0.02f; p->fRandomSmoothNormal = 13.f; p->fRandomSmoothBonus = 0.93f;
+	p->fDescriptorMinMagnitudeThreshold = 0.01f;
+	p->fDepthDiffThreshold = 0.01f; p->fNormalDiffThreshold = 25.f; p->depthweight = 1.f; p->normalweight = 1.f;
+	p->adapthalfwin = 5; p->propagatehalfwin = 1; p->propagatestep = 4; p->photo2geo = 2;
+	p->photometric_flow = 0.f; p->para_prior = 0.3f; p->fsigmaPrior = 0.2f;
+	p->rb_far_reach = 11; p->sampler = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ context
+static int CheckParams(const hcmvs_params& p) {
+	if (p.adapthalfwin < 1 || p.adapthalfwin > 7) { hcmvs_set_error("adapthalfwin must be in [1,7] (reference nTexels = 64, DepthMap.h:358)"); return HCMVS_ERR_ARG; }
+	if (p.nRandomIters > 64 || p.nEstimationIters > 60) { hcmvs_set_error("iteration counts out of range"); return HCMVS_ERR_ARG; }
+	if (p.rb_far_reach < 1) { hcmvs_set_error("rb_far_reach must be >= 1"); return HCMVS_ERR_ARG; }
+	if (!(p.fNCCThresholdKeep > 0.f)) { hcmvs_set_error("fNCCThresholdKeep must be > 0"); return HCMVS_ERR_ARG; }
+	return HCMVS_OK;
+}
+
+extern "C" hcmvs_ctx* hcmvs_create(int device, const hcmvs_params* p) {
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n <= 0) { hcmvs_set_error("no CUDA device: %s (hcmvs_b200 has no CPU path)", cudaGetErrorString(e)); return nullptr; }
+	if (device < 0 || device >= n) { hcmvs_set_error("device %d out of range (%d devices)", device, n); return nullptr; }
+	hcmvs_params P; if (p) P = *p; else hcmvs_default_params(&P);
+	if (CheckParams(P) != HCMVS_OK) return nullptr;
+	if (cudaSetDevice(device) != cudaSuccess) { hcmvs_set_error("cudaSetDevice failed"); return nullptr; }
+	hcmvs_ctx* ctx = new hcmvs_ctx();
+	ctx->device = device; ctx->P = P;
+	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaMalloc(&ctx->counters_d, 8*sizeof(unsigned long long)) != cudaSuccess ||
+	    cudaMemset(ctx->counters_d, 0, 8*sizeof(unsigned long long)) != cudaSuccess) {
+		hcmvs_set_error("context allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+		delete ctx; return nullptr;
+	}
+	return ctx;
+}
+
+static void FreeView(View& v) {
+	if (v.tex) cudaDestroyTextureObject(v.tex);
+	if (v.arr) cudaFreeArray(v.arr);
+	cudaFree(v.img_d); cudaFree(v.bgr_d); cudaFree(v.gra_d); cudaFree(v.dn_d); cudaFree(v.conf_d); cudaFree(v.prior_d); cudaFree(v.fdepth_d); cudaFree(v.fconf_d); cudaFree(v.claim_d);
+	v = View();
+}
+
+extern "C" void hcmvs_destroy(hcmvs_ctx* ctx) {
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	for (View& v: ctx->views) FreeView(v);
+	for (auto& te: ctx->timed) { cudaEventDestroy(te.a); cudaEventDestroy(te.b); }
+	for (cudaEvent_t ev: ctx->eventPool) cudaEventDestroy(ev);
+	cudaFree(ctx->scratch_d); cudaFree(ctx->counters_d);
+	hcmvs_fuse_release(ctx);
+	cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+extern "C" int hcmvs_set_params(hcmvs_ctx* ctx, const hcmvs_params* p) {
+	if (!ctx || !p) { hcmvs_set_error("null argument"); return HCMVS_ERR_ARG; }
+	const int r = CheckParams(*p); if (r != HCMVS_OK) return r;
+	ctx->P = *p; return HCMVS_OK;
+}
+extern "C" int hcmvs_sync(hcmvs_ctx* ctx) { if (!ctx) return HCMVS_ERR_ARG; cudaSetDevice(ctx->device); CK(cudaStreamSynchronize(ctx->stream)); return HCMVS_OK; }
+extern "C" void* hcmvs_stream(hcmvs_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int hcmvs_scratch(hcmvs_ctx* ctx, size_t bytes, void** out) {
+	if (ctx->scratchBytes < bytes) {
+		CK(cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->scratch_d); ctx->scratch_d = nullptr; ctx->scratchBytes = 0;
+		CK(cudaMalloc(&ctx->scratch_d, bytes));
+		ctx->scratchBytes = bytes;
+	}
+	*out = ctx->scratch_d; return HCMVS_OK;
+}
+
+// ---- stage timing with CUDA events on the context stream
+static cudaEvent_t GetEvent(hcmvs_ctx* ctx) {
+	if (!ctx->eventPool.empty()) { cudaEvent_t e = ctx->eventPool.back(); ctx->eventPool.pop_back(); return e; }
+	cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void hcmvs_time_begin(hcmvs_ctx* ctx, int stage) {
+	TimedSpan ts; ts.stage = stage; ts.a = GetEvent(ctx); ts.b = GetEvent(ctx);
+	cudaEventRecord(ts.a, ctx->stream);
+	ctx->timed.push_back(ts);
+}
+void hcmvs_time_end(hcmvs_ctx* ctx) { cudaEventRecord(ctx->timed.back().b, ctx->stream); }
+
+static void DrainTimers(hcmvs_ctx* ctx) {
+	cudaStreamSynchronize(ctx->stream);
+	for (TimedSpan& ts: ctx->timed) {
+		float ms = 0.f; cudaEventElapsedTime(&ms, ts.a, ts.b);
+		ctx->stageMs[ts.stage] += ms;
+		ctx->eventPool.push_back(ts.a); ctx->eventPool.push_back(ts.b);
+	}
+	ctx->timed.clear();
+}
+extern "C" int hcmvs_get_timers(hcmvs_ctx* ctx, hcmvs_timers* t) {
+	if (!ctx || !t) return HCMVS_ERR_ARG;
+	cudaSetDevice(ctx->device);
+	DrainTimers(ctx);
+	unsigned long long c[8];
+	CK(cudaMemcpy(c, ctx->counters_d, sizeof(c), cudaMemcpyDeviceToHost));
+	t->ms_score = ctx->stageMs[ST_SCORE]; t->ms_sweeps = ctx->stageMs[ST_SWEEPS]; t->ms_end = ctx->stageMs[ST_END];
+	t->ms_prep = ctx->stageMs[ST_PREP]; t->ms_filter = ctx->stageMs[ST_FILTER]; t->ms_fuse = ctx->stageMs[ST_FUSE];
+	t->n_hypotheses = c[0]; t->n_view_scores = c[1]; t->n_pixel_iters = c[2];
+	t->n_launches = ctx->nLaunches; t->n_fuse_rounds = ctx->fuseRounds;
+	return HCMVS_OK;
+}
+extern "C" int hcmvs_reset_timers(hcmvs_ctx* ctx) {
+	if (!ctx) return HCMVS_ERR_ARG;
+	cudaSetDevice(ctx->device);
+	DrainTimers(ctx);
+	for (double& m: ctx->stageMs) m = 0;
+	ctx->nLaunches = 0;
+	CK(cudaMemset(ctx->counters_d, 0, 8*sizeof(unsigned long long)));
+	return HCMVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ small f64 maths
+// cv::Matx semantics (plain triple loop, left-to-right accumulation), as the reference's Camera / ViewData use.
+static void Mul33(const double* A, const double* B, double* C) {
+	for (int i=0; i<3; ++i) for (int j=0; j<3; ++j) { double s = A[i*3]*B[j]; s += A[i*3+1]*B[3+j]; s += A[i*3+2]*B[6+j]; C[i*3+j] = s; }
+}
+static void Mul33Bt(const double* A, const double* B, double* C) {
+	for (int i=0; i<3; ++i) for (int j=0; j<3; ++j) { double s = A[i*3]*B[j*3]; s += A[i*3+1]*B[j*3+1]; s += A[i*3+2]*B[j*3+2]; C[i*3+j] = s; }
+}
+static void Mul3v(const double* A, const double* v, double* o) {
+	for (int i=0; i<3; ++i) { double s = A[i*3]*v[0]; s += A[i*3+1]*v[1]; s += A[i*3+2]*v[2]; o[i] = s; }
+}
+static void Inv33(const double* a, double* b) { // cv::Matx33 inverse: adjugate over determinant
+	double d = a[0]*(a[4]*a[8]-a[5]*a[7]) - a[1]*(a[3]*a[8]-a[5]*a[6]) + a[2]*(a[3]*a[7]-a[4]*a[6]);
+	d = 1./d;
+	b[0] = (a[4]*a[8]-a[5]*a[7])*d; b[1] = (a[2]*a[7]-a[1]*a[8])*d; b[2] = (a[1]*a[5]-a[2]*a[4])*d;
+	b[3] = (a[5]*a[6]-a[3]*a[8])*d; b[4] = (a[0]*a[8]-a[2]*a[6])*d; b[5] = (a[2]*a[3]-a[0]*a[5])*d;
+	b[6] = (a[3]*a[7]-a[4]*a[6])*d; b[7] = (a[1]*a[6]-a[0]*a[7])*d; b[8] = (a[0]*a[4]-a[1]*a[3])*d;
+}
+static void ComposeP(const double* K, const double* R, const double* C, double* P) { // Camera.cpp:174-181
+	double M[9]; Mul33(K, R, M);
+	const double nC[3] = {-C[0], -C[1], -C[2]}; double t[3]; Mul3v(M, nC, t);
+	for (int i=0; i<3; ++i) { P[i*4] = M[i*3]; P[i*4+1] = M[i*3+1]; P[i*4+2] = M[i*3+2]; P[i*4+3] = t[i]; }
+}
+
+// ------------------------------------------------------------------------------------------------ scene upload
+static View* GetView(hcmvs_ctx* ctx, uint32_t view, bool mustExist) {
+	if (!ctx) { hcmvs_set_error("null context"); return nullptr; }
+	if (view >= ctx->views.size()) {
+		if (mustExist) { hcmvs_set_error("view %u not set", view); return nullptr; }
+		if (view > (1u<<20)) { hcmvs_set_error("view id %u too large", view); return nullptr; }
+		ctx->views.resize(view+1);
+	}
+	View* v = &ctx->views[view];
+	if (mustExist && !v->set) { hcmvs_set_error("view %u not set", view); return nullptr; }
+	return v;
+}
+
+extern "C" int hcmvs_set_view(hcmvs_ctx* ctx, uint32_t view, int W, int H, const double K[9], const double R[9], const double C[3],
+	const float* gray, const uint8_t* bgr)
+{
+	if (!ctx || !K || !R || !C || !gray) { hcmvs_set_error("null argument"); return HCMVS_ERR_ARG; }
+	if (W < 2*HCMVS_HW+2 || H < 2*HCMVS_HW+2 || W > 65535 || H > 65535) { hcmvs_set_error("image size %dx%d unsupported", W, H); return HCMVS_ERR_ARG; }
+	if (K[1] != 0.0 || K[3] != 0.0 || K[6] != 0.0 || K[7] != 0.0) { hcmvs_set_error("K must be upper triangular with zero skew"); return HCMVS_ERR_UNSUPPORTED; }
+	cudaSetDevice(ctx->device);
+	View* v = GetView(ctx, view, false); if (!v) return HCMVS_ERR_ARG;
+	if (v->set) { CK(cudaStreamSynchronize(ctx->stream)); FreeView(*v); }
+	v->w = W; v->h = H;
+	std::memcpy(v->K, K, 72); std::memcpy(v->R, R, 72); std::memcpy(v->C, C, 24);
+	ComposeP(K, R, C, v->P);
+	const size_t n = (size_t)W*H;
+	cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
+	CK(cudaMallocArray(&v->arr, &desc, W, H, cudaArrayTextureGather));
+	CK(cudaMemcpy2DToArrayAsync(v->arr, 0, 0, gray, (size_t)W*4, (size_t)W*4, H, cudaMemcpyHostToDevice, ctx->stream));
+	cudaResourceDesc rd; std::memset(&rd, 0, sizeof(rd)); rd.resType = cudaResourceTypeArray; rd.res.array.array = v->arr;
+	cudaTextureDesc td; std::memset(&td, 0, sizeof(td));
+	td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp; td.filterMode = cudaFilterModePoint;
+	td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+	CK(cudaCreateTextureObject(&v->tex, &rd, &td, nullptr));
+	CK(cudaMalloc(&v->img_d, n*4));
+	CK(cudaMemcpyAsync(v->img_d, gray, n*4, cudaMemcpyHostToDevice, ctx->stream));
+	if (bgr) {
+		CK(cudaMalloc(&v->bgr_d, n*3));
+		CK(cudaMemcpyAsync(v->bgr_d, bgr, n*3, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	CK(cudaStreamSynchronize(ctx->stream)); // host buffers may be released by the caller
+	v->set = true;
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_set_neighbors(hcmvs_ctx* ctx, uint32_t ref, const uint32_t* ids, const float* scores, int n_match, int n_all) {
+	View* v = GetView(ctx, ref, true); if (!v) return HCMVS_ERR_ARG;
+	if (!ids || n_all < 0 || n_match < 0 || n_match > n_all || n_match > HCMVS_MAX_MATCH_VIEWS || n_all > HCMVS_MAX_FUSE_VIEWS) {
+		hcmvs_set_error("bad neighbour list (n_match %d <= %d, n_all %d <= %d)", n_match, HCMVS_MAX_MATCH_VIEWS, n_all, HCMVS_MAX_FUSE_VIEWS); return HCMVS_ERR_ARG;
+	}
+	for (int i=0; i<n_all; ++i) if (ids[i] == ref) { hcmvs_set_error("view %u lists itself as neighbour", ref); return HCMVS_ERR_ARG; }
+	v->nbIds.assign(ids, ids+n_all);
+	v->nbScores.assign(n_all, 0.f);
+	if (scores) v->nbScores.assign(scores, scores+n_all);
+	v->nMatch = n_match;
+	return HCMVS_OK;
+}
+
+static int AllocMaps(hcmvs_ctx* ctx, View* v) {
+	const size_t n = (size_t)v->w*v->h;
+	if (!v->dn_d) { CK(cudaMalloc(&v->dn_d, n*sizeof(float4))); CK(cudaMemsetAsync(v->dn_d, 0, n*sizeof(float4), ctx->stream)); }
+	if (!v->conf_d) { CK(cudaMalloc(&v->conf_d, n*4)); CK(cudaMemsetAsync(v->conf_d, 0, n*4, ctx->stream)); }
+	return HCMVS_OK;
+}
+
+static int UploadMaps(hcmvs_ctx* ctx, View* v, const float* depth, const float* normal, const float* conf) {
+	const size_t n = (size_t)v->w*v->h;
+	int r = AllocMaps(ctx, v); if (r) return r;
+	float* tmp; r = hcmvs_scratch(ctx, n*16, (void**)&tmp); if (r) return r;
+	CK(cudaMemcpyAsync(tmp, depth, n*4, cudaMemcpyHostToDevice, ctx->stream));
+	if (normal) CK(cudaMemcpyAsync(tmp+n, normal, n*12, cudaMemcpyHostToDevice, ctx->stream));
+	CK(hcmvs_launch_pack(tmp, normal ? tmp+n : nullptr, v->dn_d, n, ctx->stream)); ++ctx->nLaunches;
+	if (conf) CK(cudaMemcpyAsync(v->conf_d, conf, n*4, cudaMemcpyHostToDevice, ctx->stream));
+	else CK(cudaMemsetAsync(v->conf_d, 0, n*4, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_init_depthmap(hcmvs_ctx* ctx, uint32_t ref, const float* depth0, const float* normal0, float dMin, float dMax) {
+	View* v = GetView(ctx, ref, true); if (!v) return HCMVS_ERR_ARG;
+	if (!depth0 || !(dMin > 0.f) || !(dMin < dMax)) { hcmvs_set_error("bad depth range [%g,%g)", dMin, dMax); return HCMVS_ERR_ARG; }
+	cudaSetDevice(ctx->device);
+	const size_t n = (size_t)v->w*v->h;
+	hcmvs_time_begin(ctx, ST_PREP);
+	int r = UploadMaps(ctx, v, depth0, normal0, nullptr); if (r) return r;
+	v->dMin = dMin; v->dMax = dMax; v->hasMaps = true;
+	// InitGraMap, SceneDensify.cpp:815-819
+	if (!v->gra_d) CK(cudaMalloc(&v->gra_d, n));
+	if (v->bgr_d) { CK(hcmvs_launch_gramap(v->bgr_d, v->gra_d, v->w, v->h, ctx->stream)); ++ctx->nLaunches; }
+	else CK(cudaMemsetAsync(v->gra_d, 0, n, ctx->stream));
+	hcmvs_time_end(ctx);
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_set_depthmap(hcmvs_ctx* ctx, uint32_t view, const float* depth, const float* normal, const float* conf, float dMin, float dMax) {
+	View* v = GetView(ctx, view, true); if (!v) return HCMVS_ERR_ARG;
+	if (!depth) { hcmvs_set_error("null depth"); return HCMVS_ERR_ARG; }
+	cudaSetDevice(ctx->device);
+	int r = UploadMaps(ctx, v, depth, normal, conf); if (r) return r;
+	v->dMin = dMin; v->dMax = dMax; v->hasMaps = true;
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_alloc_depthmap(hcmvs_ctx* ctx, uint32_t view) {
+	View* v = GetView(ctx, view, true); if (!v) return HCMVS_ERR_ARG;
+	cudaSetDevice(ctx->device);
+	int r = AllocMaps(ctx, v); if (r) return r;
+	v->hasMaps = true;
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_get_depthmap(hcmvs_ctx* ctx, uint32_t view, float* depth, float* normal, float* conf, float* dMin, float* dMax) {
+	View* v = GetView(ctx, view, true); if (!v) return HCMVS_ERR_ARG;
+	if (!v->hasMaps) { hcmvs_set_error("view %u has no depth map", view); return HCMVS_ERR_STATE; }
+	cudaSetDevice(ctx->device);
+	const size_t n = (size_t)v->w*v->h;
+	float* tmp; int r = hcmvs_scratch(ctx, n*16, (void**)&tmp); if (r) return r;
+	if (depth || normal) {
+		CK(hcmvs_launch_unpack(v->dn_d, tmp, tmp+n, n, ctx->stream)); ++ctx->nLaunches;
+		if (depth) CK(cudaMemcpyAsync(depth, tmp, n*4, cudaMemcpyDeviceToHost, ctx->stream));
+		if (normal) CK(cudaMemcpyAsync(normal, tmp+n, n*12, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	if (conf) CK(cudaMemcpyAsync(conf, v->conf_d, n*4, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	if (dMin) *dMin = v->dMin;
+	if (dMax) *dMax = v->dMax;
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_get_depthmap_device(hcmvs_ctx* ctx, uint32_t view, void** dn_d, void** conf_d, float* dMin, float* dMax) {
+	View* v = GetView(ctx, view, true); if (!v) return HCMVS_ERR_ARG;
+	if (!v->hasMaps) { hcmvs_set_error("view %u has no depth map", view); return HCMVS_ERR_STATE; }
+	if (dn_d) *dn_d = v->dn_d;
+	if (conf_d) *conf_d = v->conf_d;
+	if (dMin) *dMin = v->dMin;
+	if (dMax) *dMax = v->dMax;
+	return HCMVS_OK;
+}
+extern "C" int hcmvs_set_depth_range(hcmvs_ctx* ctx, uint32_t view, float dMin, float dMax) {
+	View* v = GetView(ctx, view, true); if (!v) return HCMVS_ERR_ARG;
+	v->dMin = dMin; v->dMax = dMax; return HCMVS_OK;
+}
+
+extern "C" int hcmvs_get_gradient_map(hcmvs_ctx* ctx, uint32_t view, uint8_t* gra) {
+	View* v = GetView(ctx, view, true); if (!v) return HCMVS_ERR_ARG;
+	if (!gra || !v->gra_d) { hcmvs_set_error("view %u has no gradient map", view); return HCMVS_ERR_STATE; }
+	cudaSetDevice(ctx->device);
+	CK(cudaMemcpyAsync(gra, v->gra_d, (size_t)v->w*v->h, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_set_prior(hcmvs_ctx* ctx, uint32_t ref, const float* prior) {
+	View* v = GetView(ctx, ref, true); if (!v) return HCMVS_ERR_ARG;
+	cudaSetDevice(ctx->device);
+	const size_t n = (size_t)v->w*v->h;
+	if (!prior) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(v->prior_d); v->prior_d = nullptr; return HCMVS_OK; }
+	if (!v->prior_d) CK(cudaMalloc(&v->prior_d, n*4));
+	CK(cudaMemcpyAsync(v->prior_d, prior, n*4, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return HCMVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ estimation
+static int BuildRefConst(hcmvs_ctx* ctx, View* v, uint32_t ref, int it_external, uint64_t seed, RefConst& rc) {
+	const hcmvs_params& P = ctx->P;
+	if (v->nMatch < 1) { hcmvs_set_error("view %u has no matching neighbours (call hcmvs_set_neighbors)", ref); return HCMVS_ERR_STATE; }
+	std::memset(&rc, 0, sizeof(rc));
+	rc.w = v->w; rc.h = v->h;
+	rc.fx = v->K[0]; rc.fy = v->K[4]; rc.cx = v->K[2]; rc.cy = v->K[5];
+	Inv33(v->K, rc.Hr);
+	rc.img0 = v->img_d; rc.pitch0 = v->w; rc.gra = v->gra_d; rc.prior = v->prior_d;
+	rc.dn = v->dn_d; rc.conf = v->conf_d;
+	rc.nViews = v->nMatch;
+	for (int i=0; i<v->nMatch; ++i) {
+		View* nb = GetView(ctx, v->nbIds[i], true);
+		if (!nb) { hcmvs_set_error("neighbour view %u of %u not set", v->nbIds[i], ref); return HCMVS_ERR_STATE; }
+		NbViewConst& c = rc.nb[i];
+		// DepthEstimator::ViewData, DepthMap.h:430-433: Hl = K1 R1 R0^T, Hm = K1 R1 (C0-C1)
+		double KR[9]; Mul33(nb->K, nb->R, KR);
+		Mul33Bt(KR, v->R, c.Hl);
+		const double dC[3] = {v->C[0]-nb->C[0], v->C[1]-nb->C[1], v->C[2]-nb->C[2]};
+		Mul3v(KR, dC, c.Hm);
+		c.tex = nb->tex; c.img = nb->img_d; c.pitch = nb->w; c.w = nb->w; c.h = nb->h;
+	}
+	// DepthEstimator constants, DepthMap.cpp:413-433
+	const float FPI = (float)3.14159265358979323846;
+	auto FD2R = [FPI](float d) { return d*(FPI/180.f); };
+	rc.dMin = v->dMin; rc.dMax = v->dMax; rc.dMinSqr = std::sqrt(v->dMin); rc.dMaxSqr = std::sqrt(v->dMax);
+	rc.keep = P.fNCCThresholdKeep;
+	rc.thConfSmall = P.fNCCThresholdKeep*0.2f; rc.thConfBig = P.fNCCThresholdKeep*0.4f;
+	rc.thConfRand = P.fNCCThresholdKeep*0.9f; rc.thRobust = P.fNCCThresholdKeep*1.2f;
+	rc.smoothBonusDepth = 1.f-P.fRandomSmoothBonus; rc.smoothBonusNormal = (1.f-P.fRandomSmoothBonus)*0.96f;
+	rc.smoothSigmaDepth = -1.f/(2.f*(P.fRandomSmoothDepth*P.fRandomSmoothDepth));
+	{ const float r = FD2R(P.fRandomSmoothNormal); rc.smoothSigmaNormal = -1.f/(2.f*(r*r)); }
+	rc.angle1Range = FD2R(P.fRandomAngle1Range); rc.angle2Range = FD2R(P.fRandomAngle2Range);
+	rc.depthRatio = P.fRandomDepthRatio;
+	rc.nRandomIters = (int)P.nRandomIters; rc.adapthalfwin = P.adapthalfwin; rc.farReach = P.rb_far_reach;
+	rc.it_external = it_external; rc.photo2geo = P.photo2geo;
+	rc.photometric_flow = P.photometric_flow; rc.para_prior = P.para_prior; rc.sigmaPrior = P.fsigmaPrior;
+	rc.key0 = (uint32_t)seed; rc.key1 = (uint32_t)(seed>>32)^(ref*0x9E3779B9u);
+	rc.pass = 0;
+	rc.counters = ctx->counters_d;
+	return HCMVS_OK;
+}
+
+static int RequireMaps(View* v, uint32_t ref) {
+	if (!v->hasMaps || !v->dn_d) { hcmvs_set_error("view %u has no depth map (call hcmvs_init_depthmap)", ref); return HCMVS_ERR_STATE; }
+	if (!(v->dMin > 0.f && v->dMin < v->dMax)) { hcmvs_set_error("view %u has no valid depth range", ref); return HCMVS_ERR_STATE; }
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_score_depthmap(hcmvs_ctx* ctx, uint32_t ref, int it_external, uint64_t seed) {
+	View* v = GetView(ctx, ref, true); if (!v) return HCMVS_ERR_ARG;
+	int r = RequireMaps(v, ref); if (r) return r;
+	cudaSetDevice(ctx->device);
+	RefConst rc; r = BuildRefConst(ctx, v, ref, it_external, seed, rc); if (r) return r;
+	hcmvs_time_begin(ctx, ST_SCORE);
+	CK(hcmvs_launch_score_init(rc, ctx->P.sampler == 0, ctx->stream)); ++ctx->nLaunches;
+	hcmvs_time_end(ctx);
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_end_depthmap(hcmvs_ctx* ctx, uint32_t ref) {
+	View* v = GetView(ctx, ref, true); if (!v) return HCMVS_ERR_ARG;
+	int r = RequireMaps(v, ref); if (r) return r;
+	cudaSetDevice(ctx->device);
+	hcmvs_time_begin(ctx, ST_END);
+	CK(hcmvs_launch_end(v->dn_d, v->conf_d, (size_t)v->w*v->h, ctx->P.fNCCThresholdKeep, ctx->stream)); ++ctx->nLaunches;
+	hcmvs_time_end(ctx);
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_estimate_depthmap(hcmvs_ctx* ctx, uint32_t ref, int it_external, uint64_t seed) {
+	View* v = GetView(ctx, ref, true); if (!v) return HCMVS_ERR_ARG;
+	int r = RequireMaps(v, ref); if (r) return r;
+	if (it_external != 0) { hcmvs_set_error("it_external >= 1 (adaptive '+' propagation, priors) is not built yet"); return HCMVS_ERR_UNSUPPORTED; }
+	cudaSetDevice(ctx->device);
+	const hcmvs_params& P = ctx->P;
+	const size_t n = (size_t)v->w*v->h;
+	RefConst rc; r = BuildRefConst(ctx, v, ref, it_external, seed, rc); if (r) return r;
+	const bool tex = P.sampler == 0;
+	// cv::medianBlur(depthMap, depthMap, 3), SceneDensify.cpp:859
+	hcmvs_time_begin(ctx, ST_PREP);
+	float4* tmp; r = hcmvs_scratch(ctx, n*sizeof(float4), (void**)&tmp); if (r) return r;
+	CK(hcmvs_launch_median3(v->dn_d, tmp, v->w, v->h, ctx->stream)); ++ctx->nLaunches;
+	CK(cudaMemcpyAsync(v->dn_d, tmp, n*sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+	hcmvs_time_end(ctx);
+	// PASS A, SceneDensify.cpp:915-934
+	hcmvs_time_begin(ctx, ST_SCORE);
+	CK(hcmvs_launch_score_init(rc, tex, ctx->stream)); ++ctx->nLaunches;
+	hcmvs_time_end(ctx);
+	// PASS B, SceneDensify.cpp:949-981 — each iteration = red half-sweep + black half-sweep
+	hcmvs_time_begin(ctx, ST_SWEEPS);
+	for (unsigned iter=0; iter<P.nEstimationIters; ++iter) {
+		rc.pass = 1u+iter+(uint32_t)it_external*64u;
+		for (int colour=0; colour<2; ++colour) { CK(hcmvs_launch_sweep(rc, colour, tex, ctx->stream)); ++ctx->nLaunches; }
+	}
+	hcmvs_time_end(ctx);
+	// PASS C, SceneDensify.cpp:1035-1056
+	if (it_external == (int)P.nEstimationIters_external-1) {
+		hcmvs_time_begin(ctx, ST_END);
+		CK(hcmvs_launch_end(v->dn_d, v->conf_d, n, P.fNCCThresholdKeep, ctx->stream)); ++ctx->nLaunches;
+		hcmvs_time_end(ctx);
+	}
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_score_hypotheses(hcmvs_ctx* ctx, uint32_t ref, const float* depth, const float* normal, int smooth_mode, float* score_out) {
+	View* v = GetView(ctx, ref, true); if (!v) return HCMVS_ERR_ARG;
+	if (!depth || !normal || !score_out) { hcmvs_set_error("null argument"); return HCMVS_ERR_ARG; }
+	cudaSetDevice(ctx->device);
+	const size_t n = (size_t)v->w*v->h;
+	// hypotheses do not need the view's own maps, only its depth range is irrelevant here
+	const bool hadRange = v->dMin > 0.f && v->dMin < v->dMax;
+	if (!hadRange) { v->dMin = 1e-6f; v->dMax = 3e38f; }
+	RefConst rc; int r = BuildRefConst(ctx, v, ref, 0, 0, rc);
+	if (!hadRange) { v->dMin = 0.f; v->dMax = 0.f; }
+	if (r) return r;
+	if (!v->gra_d) {
+		CK(cudaMalloc(&v->gra_d, n));
+		if (v->bgr_d) { CK(hcmvs_launch_gramap(v->bgr_d, v->gra_d, v->w, v->h, ctx->stream)); ++ctx->nLaunches; }
+		else CK(cudaMemsetAsync(v->gra_d, 0, n, ctx->stream));
+		rc.gra = v->gra_d;
+	}
+	char* buf; r = hcmvs_scratch(ctx, n*(16+16+4), (void**)&buf); if (r) return r;
+	float* stage = (float*)buf; float4* hyp = (float4*)(buf+n*16); float* out = (float*)(buf+n*32);
+	CK(cudaMemcpyAsync(stage, depth, n*4, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(stage+n, normal, n*12, cudaMemcpyHostToDevice, ctx->stream));
+	CK(hcmvs_launch_pack(stage, stage+n, hyp, n, ctx->stream)); ++ctx->nLaunches;
+	rc.counters = nullptr;
+	CK(hcmvs_launch_score_hyp(rc, hyp, smooth_mode, out, ctx->P.sampler == 0, ctx->stream)); ++ctx->nLaunches;
+	CK(cudaMemcpyAsync(score_out, out, n*4, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return HCMVS_OK;
+}

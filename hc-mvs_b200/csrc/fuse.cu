@@ -1,0 +1,449 @@
+// DepthMapsData::FuseDepthMaps (libs/MVS/SceneDensify.cpp:3265-3495) on the GPU, with the CPU's exact
+// sequential semantics.
+//
+// The reference fuses greedily: views in connection order, pixels in raster order; a seed pixel probes one
+// pixel in each neighbour view, claims the agreeing ones, and — if it survives nMinViewsFuse — zeroes the
+// depths it occludes. Later seeds see those claims / zeroed depths, so the result is order dependent.
+// That order is kept here by "deterministic reservations": views are still processed one after another, but
+// inside a view every undecided seed reserves (atomicMin of its raster index) each neighbour pixel it would
+// touch; a seed that holds all its reservations precedes every undecided seed it conflicts with, so it can
+// run its CPU action immediately. Seeds with disjoint footprints commit in the same round; the lowest
+// undecided seed always commits, so the loop terminates, and the outcome is bit-identical to the raster
+// scan. One cooperative launch per view (grid.sync between the reserve and commit phases), then a
+// raster-ordered scan/compaction writes the points in the CPU's order.
+#include "hcmvs_internal.h"
+#include "camera.cuh"
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
+#include <vector>
+#include <algorithm>
+#include <cstring>
+#include <cstdlib>
+
+namespace cg = cooperative_groups;
+
+namespace hcmvs {
+
+#define CLAIM_FREE 0xFFFFFFFFu
+#define CLAIM_TAKEN 0xFFFFFFFEu
+
+struct FuseView {
+	float4* dn; const float* conf; const uint8_t* bgr; uint32_t* claim;
+	int w, h; int hasMaps;
+	CamConst cam;
+};
+
+struct FuseArgs {
+	FuseView* views;
+	int ref;
+	int nNb; int nb[HCMVS_MAX_FUSE_VIEWS];
+	unsigned nMinViewsFuse;
+	float depthTh, normalError;
+	uint8_t* state;   // per ref pixel: 0 not a seed / removed, 1 undecided, 2 emitted
+	uint32_t* mask;   // merged neighbours (bit k = nb[k]) of emitted seeds
+	int* counters;    // [0] undecided seeds, [1] rounds, [2] seeds
+};
+
+struct Probe { int q; float z; };
+
+// project the seed's 3-D point into neighbour view B (SceneDensify.cpp:3386-3394)
+__device__ __forceinline__ Probe probe_view(const FuseView& B, const float3 point) {
+	Probe pr; pr.q = -1; pr.z = 0.f;
+	const float3 pt = cam_ProjectP3f(B.cam, point);
+	if (pt.z <= 0.f) return pr;
+	const int xB = round2int(__fdiv_rn(pt.x, pt.z)), yB = round2int(__fdiv_rn(pt.y, pt.z));
+	if (xB < 0 || yB < 0 || xB >= B.w || yB >= B.h) return pr;
+	pr.q = yB*B.w+xB; pr.z = pt.z;
+	return pr;
+}
+__device__ __forceinline__ float3 seed_point(const FuseView& R, int x, int y, float depth) {
+	const D3 P = cam_I2W(R.cam, (double)x, (double)y, (double)depth);
+	return make_float3((float)P.x, (float)P.y, (float)P.z);
+}
+__device__ __forceinline__ float conf2weight(float conf, float depth) { // Conf2Weight, SceneDensify.cpp:154-156
+	return __fdiv_rn(1.f, __fmul_rn(__fmul_rn(fmaxf(__fsub_rn(1.f, conf), 0.03f), depth), depth));
+}
+__device__ __forceinline__ float dot3f(const float3 a, const float3 b) { return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z)); }
+
+__global__ void __launch_bounds__(256) k_fuse_view(const FuseArgs a) {
+	cg::grid_group grid = cg::this_grid();
+	const FuseView& R = a.views[a.ref];
+	const int nPix = R.w*R.h;
+	const int tid = blockIdx.x*blockDim.x+threadIdx.x, nThreads = gridDim.x*blockDim.x;
+	// ---- phase 0: find the seeds (valid depth, not yet claimed), SceneDensify.cpp:3347-3354
+	int mySeeds = 0;
+	for (int p=tid; p<nPix; p+=nThreads) {
+		const bool seed = R.dn[p].w != 0.f && R.claim[p] != CLAIM_TAKEN;
+		a.state[p] = seed ? 1 : 0;
+		mySeeds += seed;
+	}
+	mySeeds = cg::reduce(cg::tiled_partition<32>(cg::this_thread_block()), mySeeds, cg::plus<int>());
+	if ((threadIdx.x&31) == 0 && mySeeds) { atomicAdd(&a.counters[0], mySeeds); atomicAdd(&a.counters[2], mySeeds); }
+	grid.sync();
+	int undecided = *(volatile int*)&a.counters[0];
+	int round = 0;
+	while (undecided > 0) {
+		// ---- phase 1: reserve every live neighbour pixel this seed would touch
+		for (int p=tid; p<nPix; p+=nThreads) {
+			if (a.state[p] != 1) continue;
+			const int x = p%R.w, y = p/R.w;
+			const float3 point = seed_point(R, x, y, R.dn[p].w);
+			for (int k=0; k<a.nNb; ++k) {
+				const FuseView& B = a.views[a.nb[k]];
+				if (!B.hasMaps) continue;
+				const Probe pr = probe_view(B, point);
+				if (pr.q < 0) continue;
+				if (B.dn[pr.q].w == 0.f) continue;
+				if (B.claim[pr.q] == CLAIM_TAKEN) continue;
+				atomicMin(&B.claim[pr.q], (uint32_t)p);
+			}
+		}
+		grid.sync();
+		// ---- phase 2: seeds holding all their reservations run the reference's per-pixel action
+		int nDone = 0;
+		for (int p=tid; p<nPix; p+=nThreads) {
+			if (a.state[p] != 1) continue;
+			const int x = p%R.w, y = p/R.w;
+			const float4 e = R.dn[p];
+			const float3 point = seed_point(R, x, y, e.w);
+			const float3 normal = cam_NormalC2W(R.cam, make_float3(e.x, e.y, e.z));
+			int qs[HCMVS_MAX_FUSE_VIEWS];
+			uint32_t live = 0, merged = 0, inval = 0;
+			unsigned nViews = 1;
+			bool ready = true;
+			for (int k=0; k<a.nNb && ready; ++k) {
+				qs[k] = -1;
+				const FuseView& B = a.views[a.nb[k]];
+				if (!B.hasMaps) continue;
+				const Probe pr = probe_view(B, point);
+				if (pr.q < 0) continue;
+				const float4 eB = B.dn[pr.q];
+				const float depthB = eB.w;
+				if (depthB == 0.f) continue;
+				const uint32_t c = *(volatile uint32_t*)&B.claim[pr.q];
+				if (c == CLAIM_TAKEN) continue;
+				if (c != (uint32_t)p) { ready = false; break; }
+				qs[k] = pr.q; live |= 1u<<k;
+				if (depth_similar(pr.z, depthB, a.depthTh)) { // SceneDensify.cpp:3400-3423
+					const float3 normalB = cam_NormalC2W(B.cam, make_float3(eB.x, eB.y, eB.z));
+					if (dot3f(normal, normalB) > a.normalError) { merged |= 1u<<k; ++nViews; continue; }
+				}
+				if (pr.z < depthB) inval |= 1u<<k; // :3424-3427
+			}
+			if (!ready) continue;
+			const bool emit = nViews >= a.nMinViewsFuse; // :3429
+			for (int k=0; k<a.nNb; ++k) {
+				if (!(live & (1u<<k))) continue;
+				const FuseView& B = a.views[a.nb[k]];
+				if (emit && (merged & (1u<<k))) B.claim[qs[k]] = CLAIM_TAKEN;
+				else {
+					if (emit && (inval & (1u<<k))) B.dn[qs[k]].w = 0.f; // invalidate occluded depths, :3447-3449
+					B.claim[qs[k]] = CLAIM_FREE;
+				}
+			}
+			if (emit) { R.claim[p] = CLAIM_TAKEN; a.mask[p] = merged; a.state[p] = 2; }
+			else a.state[p] = 0;
+			++nDone;
+		}
+		nDone = cg::reduce(cg::tiled_partition<32>(cg::this_thread_block()), nDone, cg::plus<int>());
+		if ((threadIdx.x&31) == 0 && nDone) atomicSub(&a.counters[0], nDone);
+		grid.sync();
+		undecided = *(volatile int*)&a.counters[0];
+		++round;
+	}
+	if (tid == 0) a.counters[1] = round;
+}
+
+// ------------------------------------------------------------------ raster-ordered compaction of the emitted seeds
+#define FUSE_CHUNK 1024 // pixels per block
+__global__ void __launch_bounds__(256) k_fuse_count(const uint8_t* __restrict__ state, const uint32_t* __restrict__ mask, int nPix, uint2* __restrict__ blockSums) {
+	__shared__ unsigned sP[8], sV[8];
+	unsigned nP = 0, nV = 0;
+	const int base = blockIdx.x*FUSE_CHUNK;
+	for (int i=threadIdx.x; i<FUSE_CHUNK; i+=256) {
+		const int p = base+i;
+		if (p < nPix && state[p] == 2) { ++nP; nV += 1+__popc(mask[p]); }
+	}
+	for (int s=16; s>0; s>>=1) { nP += __shfl_xor_sync(0xffffffffu, nP, s); nV += __shfl_xor_sync(0xffffffffu, nV, s); }
+	if ((threadIdx.x&31) == 0) { sP[threadIdx.x>>5] = nP; sV[threadIdx.x>>5] = nV; }
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned a = 0, b = 0;
+		for (int i=0; i<8; ++i) { a += sP[i]; b += sV[i]; }
+		blockSums[blockIdx.x] = make_uint2(a, b);
+	}
+}
+// single-block exclusive scan of the per-chunk sums; totals go to blockSums[nBlocks]
+__global__ void __launch_bounds__(1024) k_fuse_scan(uint2* __restrict__ blockSums, int nBlocks) {
+	__shared__ unsigned sP[1024], sV[1024];
+	__shared__ unsigned carryP, carryV;
+	if (threadIdx.x == 0) { carryP = 0; carryV = 0; }
+	__syncthreads();
+	for (int base=0; base<nBlocks; base+=1024) {
+		const int i = base+threadIdx.x;
+		const uint2 v = i < nBlocks ? blockSums[i] : make_uint2(0, 0);
+		sP[threadIdx.x] = v.x; sV[threadIdx.x] = v.y;
+		__syncthreads();
+		for (int off=1; off<1024; off<<=1) {
+			unsigned tp = 0, tv = 0;
+			if (threadIdx.x >= off) { tp = sP[threadIdx.x-off]; tv = sV[threadIdx.x-off]; }
+			__syncthreads();
+			sP[threadIdx.x] += tp; sV[threadIdx.x] += tv;
+			__syncthreads();
+		}
+		if (i < nBlocks) blockSums[i] = make_uint2(carryP+sP[threadIdx.x]-v.x, carryV+sV[threadIdx.x]-v.y);
+		__syncthreads();
+		if (threadIdx.x == 1023) { carryP += sP[1023]; carryV += sV[1023]; }
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) blockSums[nBlocks] = make_uint2(carryP, carryV);
+}
+
+struct FuseOut {
+	float* points; float* normals; uint8_t* colors; uint32_t* viewOffsets; uint32_t* views; float* weights;
+	unsigned long long basePoint, baseView;
+	int estimateColor, estimateNormal;
+};
+
+__global__ void __launch_bounds__(256) k_fuse_emit(const FuseArgs a, const uint2* __restrict__ blockSums, const FuseOut out) {
+	// each thread owns 4 consecutive pixels of the chunk so that the output keeps raster order
+	__shared__ unsigned sP[256], sV[256];
+	const FuseView& R = a.views[a.ref];
+	const int nPix = R.w*R.h;
+	const int p0 = blockIdx.x*FUSE_CHUNK+threadIdx.x*4;
+	unsigned nP = 0, nV = 0;
+	for (int i=0; i<4; ++i) { const int p = p0+i; if (p < nPix && a.state[p] == 2) { ++nP; nV += 1+__popc(a.mask[p]); } }
+	sP[threadIdx.x] = nP; sV[threadIdx.x] = nV;
+	__syncthreads();
+	for (int off=1; off<256; off<<=1) {
+		unsigned tp = 0, tv = 0;
+		if (threadIdx.x >= off) { tp = sP[threadIdx.x-off]; tv = sV[threadIdx.x-off]; }
+		__syncthreads();
+		sP[threadIdx.x] += tp; sV[threadIdx.x] += tv;
+		__syncthreads();
+	}
+	const uint2 bs = blockSums[blockIdx.x];
+	unsigned long long ip = out.basePoint+bs.x+(sP[threadIdx.x]-nP);
+	unsigned long long iv = out.baseView+bs.y+(sV[threadIdx.x]-nV);
+	for (int i=0; i<4; ++i) {
+		const int p = p0+i;
+		if (p >= nPix || a.state[p] != 2) continue;
+		const int x = p%R.w, y = p/R.w;
+		const float4 e = R.dn[p];
+		const float depth = e.w;
+		const float3 point = seed_point(R, x, y, depth);
+		const float3 normal = cam_NormalC2W(R.cam, make_float3(e.x, e.y, e.z));
+		const uint32_t merged = a.mask[p];
+		// SceneDensify.cpp:3359-3379
+		uint32_t vid[HCMVS_MAX_FUSE_VIEWS+1]; float vw[HCMVS_MAX_FUSE_VIEWS+1]; int nv = 1;
+		vid[0] = (uint32_t)a.ref; vw[0] = conf2weight(R.conf[p], depth);
+		double confidence = (double)vw[0];
+		double X0 = (double)(float)dmul((double)point.x, confidence), X1 = (double)(float)dmul((double)point.y, confidence), X2 = (double)(float)dmul((double)point.z, confidence);
+		float C[3] = {0.f, 0.f, 0.f};
+		if (R.bgr) for (int c=0; c<3; ++c) C[c] = (float)dmul(confidence, (double)(float)R.bgr[(size_t)p*3+c]);
+		float3 N = make_float3((float)dmul((double)normal.x, confidence), (float)dmul((double)normal.y, confidence), (float)dmul((double)normal.z, confidence));
+		for (int k=0; k<a.nNb; ++k) {
+			if (!(merged & (1u<<k))) continue;
+			const FuseView& B = a.views[a.nb[k]];
+			const Probe pr = probe_view(B, point);
+			const int xB = pr.q%B.w, yB = pr.q/B.w;
+			const float4 eB = B.dn[pr.q];
+			const float depthB = eB.w;
+			const float confidenceB = conf2weight(B.conf[pr.q], depthB);
+			// InsertSort by view id, :3407-3409
+			int pos = nv;
+			while (pos > 0 && vid[pos-1] > (uint32_t)a.nb[k]) { vid[pos] = vid[pos-1]; vw[pos] = vw[pos-1]; --pos; }
+			vid[pos] = (uint32_t)a.nb[k]; vw[pos] = confidenceB; ++nv;
+			const D3 XB = cam_I2W(B.cam, (double)xB, (double)yB, (double)depthB);
+			X0 = dadd(X0, dmul(XB.x, (double)confidenceB)); X1 = dadd(X1, dmul(XB.y, (double)confidenceB)); X2 = dadd(X2, dmul(XB.z, (double)confidenceB));
+			if (out.estimateColor && B.bgr) for (int c=0; c<3; ++c) C[c] = __fadd_rn(C[c], __fmul_rn((float)B.bgr[(size_t)pr.q*3+c], confidenceB));
+			if (out.estimateNormal) {
+				const float3 normalB = cam_NormalC2W(B.cam, make_float3(eB.x, eB.y, eB.z));
+				N.x = __fadd_rn(N.x, __fmul_rn(normalB.x, confidenceB)); N.y = __fadd_rn(N.y, __fmul_rn(normalB.y, confidenceB)); N.z = __fadd_rn(N.z, __fmul_rn(normalB.z, confidenceB));
+			}
+			confidence = dadd(confidence, (double)confidenceB);
+		}
+		const double nrm = 1.0/confidence; // :3441-3446
+		out.points[ip*3+0] = (float)dmul(X0, nrm); out.points[ip*3+1] = (float)dmul(X1, nrm); out.points[ip*3+2] = (float)dmul(X2, nrm);
+		const float fn = (float)nrm;
+		if (out.estimateColor) for (int c=0; c<3; ++c) out.colors[ip*3+c] = (uint8_t)min(max(round2int(__fmul_rn(C[c], fn)), 0), 255);
+		if (out.estimateNormal) {
+			const float3 nvv = make_float3(__fmul_rn(N.x, fn), __fmul_rn(N.y, fn), __fmul_rn(N.z, fn));
+			const float inv = __fdiv_rn(1.f, __fsqrt_rn(dot3f(nvv, nvv)));
+			out.normals[ip*3+0] = __fmul_rn(nvv.x, inv); out.normals[ip*3+1] = __fmul_rn(nvv.y, inv); out.normals[ip*3+2] = __fmul_rn(nvv.z, inv);
+		}
+		out.viewOffsets[ip] = (uint32_t)iv;
+		for (int j=0; j<nv; ++j) { out.views[iv+j] = vid[j]; out.weights[iv+j] = vw[j]; }
+		++ip; iv += nv;
+	}
+}
+
+__global__ void k_fill_u32(uint32_t* p, uint32_t v, size_t n) { const size_t i = (size_t)blockIdx.x*blockDim.x+threadIdx.x; if (i < n) p[i] = v; }
+
+} // namespace hcmvs
+using namespace hcmvs;
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { hcmvs_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return HCMVS_ERR_CUDA; } } while (0)
+
+struct FuseState {
+	FuseView* views_d = nullptr; size_t nViews = 0;
+	uint8_t* state_d = nullptr; uint32_t* mask_d = nullptr; size_t pixCap = 0;
+	uint2* blockSums_d = nullptr; size_t blockCap = 0;
+	int* counters_d = nullptr;
+	// growing output
+	float* points = nullptr; float* normals = nullptr; uint8_t* colors = nullptr; uint32_t* viewOffsets = nullptr; size_t capPoints = 0;
+	uint32_t* oviews = nullptr; float* weights = nullptr; size_t capViews = 0;
+	int coopBlocks = 0;
+};
+
+void hcmvs_fuse_release(hcmvs_ctx* ctx) {
+	FuseState* f = ctx->fuse; if (!f) return;
+	cudaFree(f->views_d); cudaFree(f->state_d); cudaFree(f->mask_d); cudaFree(f->blockSums_d); cudaFree(f->counters_d);
+	cudaFree(f->points); cudaFree(f->normals); cudaFree(f->colors); cudaFree(f->viewOffsets); cudaFree(f->oviews); cudaFree(f->weights);
+	delete f; ctx->fuse = nullptr;
+}
+
+template<typename T>
+static int Grow(hcmvs_ctx* ctx, T*& ptr, size_t used, size_t newCap, size_t elemsPer) {
+	T* np = nullptr;
+	CK(cudaMalloc(&np, newCap*elemsPer*sizeof(T)));
+	if (ptr && used) CK(cudaMemcpyAsync(np, ptr, used*elemsPer*sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	cudaFree(ptr); ptr = np;
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_set_fuse_priority(hcmvs_ctx* ctx, uint32_t view, float score) {
+	if (!ctx || view >= ctx->views.size() || !ctx->views[view].set) { hcmvs_set_error("view %u not set", view); return HCMVS_ERR_ARG; }
+	ctx->views[view].fusePriority = score; ctx->views[view].hasFusePriority = true;
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int estimate_normal, hcmvs_pointcloud* out) {
+	if (!ctx || !out) { hcmvs_set_error("null argument"); return HCMVS_ERR_ARG; }
+	memset(out, 0, sizeof(*out));
+	cudaSetDevice(ctx->device);
+	const hcmvs_params& P = ctx->P;
+	const size_t V = ctx->views.size();
+	if (!ctx->fuse) ctx->fuse = new FuseState();
+	FuseState* f = ctx->fuse;
+	// connections: valid views sorted by the size of their scored-neighbour list, SceneDensify.cpp:3286-3303 (ties by index)
+	struct Conn { uint32_t idx; float score; };
+	std::vector<Conn> conns;
+	size_t maxPix = 0; bool anyColor = false;
+	std::vector<FuseView> hv(V);
+	for (size_t i=0; i<V; ++i) {
+		View& v = ctx->views[i];
+		FuseView& fv = hv[i]; memset(&fv, 0, sizeof(fv));
+		if (!v.set || !v.hasMaps) continue;
+		const size_t n = (size_t)v.w*v.h;
+		if (!v.claim_d) CK(cudaMalloc(&v.claim_d, n*4));
+		k_fill_u32<<<(unsigned)((n+255)/256), 256, 0, ctx->stream>>>(v.claim_d, CLAIM_FREE, n); ++ctx->nLaunches;
+		fv.dn = v.dn_d; fv.conf = v.conf_d; fv.bgr = v.bgr_d; fv.claim = v.claim_d; fv.w = v.w; fv.h = v.h; fv.hasMaps = 1;
+		hcmvs_fill_cam(v, fv.cam);
+		if (v.bgr_d) anyColor = true;
+		if (!v.nbIds.empty()) { conns.push_back(Conn{(uint32_t)i, v.hasFusePriority ? v.fusePriority : (float)v.nbIds.size()}); maxPix = std::max(maxPix, n); }
+	}
+	if (conns.empty()) { hcmvs_set_error("no view with depth map and neighbours to fuse"); return HCMVS_ERR_STATE; }
+	std::stable_sort(conns.begin(), conns.end(), [](const Conn& a, const Conn& b) { return a.score > b.score; });
+	if (estimate_color && !anyColor) estimate_color = 0;
+	if (f->nViews < V) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(f->views_d); CK(cudaMalloc(&f->views_d, V*sizeof(FuseView))); f->nViews = V; }
+	CK(cudaMemcpyAsync(f->views_d, hv.data(), V*sizeof(FuseView), cudaMemcpyHostToDevice, ctx->stream));
+	if (f->pixCap < maxPix) {
+		CK(cudaStreamSynchronize(ctx->stream));
+		cudaFree(f->state_d); cudaFree(f->mask_d);
+		CK(cudaMalloc(&f->state_d, maxPix)); CK(cudaMalloc(&f->mask_d, maxPix*4)); f->pixCap = maxPix;
+	}
+	const size_t maxBlocks = (maxPix+FUSE_CHUNK-1)/FUSE_CHUNK;
+	if (f->blockCap < maxBlocks+1) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(f->blockSums_d); CK(cudaMalloc(&f->blockSums_d, (maxBlocks+1)*sizeof(uint2))); f->blockCap = maxBlocks+1; }
+	if (!f->counters_d) CK(cudaMalloc(&f->counters_d, 4*sizeof(int)));
+	if (!f->coopBlocks) {
+		int dev = ctx->device, coop = 0, sms = 0, perSm = 0;
+		cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+		if (!coop) { hcmvs_set_error("device lacks cooperative launch"); return HCMVS_ERR_UNSUPPORTED; }
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_fuse_view, 256, 0));
+		if (perSm < 1) { hcmvs_set_error("fuse kernel does not fit"); return HCMVS_ERR_CUDA; }
+		f->coopBlocks = sms*std::min(perSm, 4);
+	}
+	const unsigned nMinViewsFuse = std::min<unsigned>(P.nMinViewsFuse, (unsigned)std::count_if(ctx->views.begin(), ctx->views.end(), [](const View& v) { return v.set; }));
+	const float FPI = (float)3.14159265358979323846;
+	const float normalError = std::cos((P.fNormalDiffThreshold*P.normalweight)*(FPI/180.f));
+	size_t nPoints = 0, nViewRefs = 0;
+	hcmvs_time_begin(ctx, ST_FUSE);
+	uint64_t totalRounds = 0;
+	for (const Conn& conn: conns) {
+		View& v = ctx->views[conn.idx];
+		FuseArgs a; memset(&a, 0, sizeof(a));
+		a.views = f->views_d; a.ref = (int)conn.idx;
+		a.nNb = 0;
+		for (uint32_t id: v.nbIds) { if (id < V) a.nb[a.nNb++] = (int)id; }
+		a.nMinViewsFuse = nMinViewsFuse;
+		a.depthTh = P.fDepthDiffThreshold*P.depthweight; a.normalError = normalError;
+		a.state = f->state_d; a.mask = f->mask_d; a.counters = f->counters_d;
+		const int nPix = v.w*v.h;
+		CK(cudaMemsetAsync(f->counters_d, 0, 4*sizeof(int), ctx->stream));
+		void* args[] = {(void*)&a};
+		CK(cudaLaunchCooperativeKernel((void*)k_fuse_view, dim3(f->coopBlocks), dim3(256), args, 0, ctx->stream)); ++ctx->nLaunches;
+		const int nBlocks = (nPix+FUSE_CHUNK-1)/FUSE_CHUNK;
+		k_fuse_count<<<nBlocks, 256, 0, ctx->stream>>>(f->state_d, f->mask_d, nPix, f->blockSums_d); ++ctx->nLaunches;
+		k_fuse_scan<<<1, 1024, 0, ctx->stream>>>(f->blockSums_d, nBlocks); ++ctx->nLaunches;
+		uint2 tot; int cnt[4];
+		CK(cudaMemcpyAsync(&tot, f->blockSums_d+nBlocks, sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaMemcpyAsync(cnt, f->counters_d, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		totalRounds += (uint64_t)cnt[1];
+		if (tot.x == 0) continue;
+		if (nPoints+tot.x > f->capPoints) {
+			const size_t nc = std::max<size_t>((nPoints+tot.x)*2, (size_t)1<<20);
+			int r;
+			if ((r = Grow(ctx, f->points, nPoints, nc, 3))) return r;
+			if ((r = Grow(ctx, f->normals, nPoints, nc, 3))) return r;
+			if ((r = Grow(ctx, f->colors, nPoints, nc, 3))) return r;
+			if ((r = Grow(ctx, f->viewOffsets, nPoints, nc+1, 1))) return r;
+			f->capPoints = nc;
+		}
+		if (nViewRefs+tot.y > f->capViews) {
+			const size_t nc = std::max<size_t>((nViewRefs+tot.y)*2, (size_t)1<<21);
+			int r;
+			if ((r = Grow(ctx, f->oviews, nViewRefs, nc, 1))) return r;
+			if ((r = Grow(ctx, f->weights, nViewRefs, nc, 1))) return r;
+			f->capViews = nc;
+		}
+		FuseOut fo; fo.points = f->points; fo.normals = f->normals; fo.colors = f->colors; fo.viewOffsets = f->viewOffsets; fo.views = f->oviews; fo.weights = f->weights;
+		fo.basePoint = nPoints; fo.baseView = nViewRefs; fo.estimateColor = estimate_color; fo.estimateNormal = estimate_normal;
+		k_fuse_emit<<<nBlocks, 256, 0, ctx->stream>>>(a, f->blockSums_d, fo); ++ctx->nLaunches;
+		CK(cudaGetLastError());
+		nPoints += tot.x; nViewRefs += tot.y;
+	}
+	hcmvs_time_end(ctx);
+	ctx->fuseRounds = totalRounds;
+	// hand the cloud to the host
+	out->n_points = nPoints;
+	if (nPoints) {
+		out->points = (float*)malloc(nPoints*12);
+		out->view_offsets = (uint32_t*)malloc((nPoints+1)*4);
+		out->views = (uint32_t*)malloc(nViewRefs*4);
+		out->weights = (float*)malloc(nViewRefs*4);
+		if (estimate_normal) out->normals = (float*)malloc(nPoints*12);
+		if (estimate_color) out->colors = (uint8_t*)malloc(nPoints*3);
+		if (!out->points || !out->view_offsets || !out->views || !out->weights || (estimate_normal && !out->normals) || (estimate_color && !out->colors)) {
+			hcmvs_free_pointcloud(out); hcmvs_set_error("out of host memory"); return HCMVS_ERR_ARG;
+		}
+		CK(cudaMemcpyAsync(out->points, f->points, nPoints*12, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaMemcpyAsync(out->view_offsets, f->viewOffsets, nPoints*4, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaMemcpyAsync(out->views, f->oviews, nViewRefs*4, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaMemcpyAsync(out->weights, f->weights, nViewRefs*4, cudaMemcpyDeviceToHost, ctx->stream));
+		if (estimate_normal) CK(cudaMemcpyAsync(out->normals, f->normals, nPoints*12, cudaMemcpyDeviceToHost, ctx->stream));
+		if (estimate_color) CK(cudaMemcpyAsync(out->colors, f->colors, nPoints*3, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		out->view_offsets[nPoints] = (uint32_t)nViewRefs;
+	} else CK(cudaStreamSynchronize(ctx->stream));
+	return HCMVS_OK;
+}
+
+extern "C" void hcmvs_free_pointcloud(hcmvs_pointcloud* pc) {
+	if (!pc) return;
+	free(pc->points); free(pc->normals); free(pc->colors); free(pc->view_offsets); free(pc->views); free(pc->weights);
+	memset(pc, 0, sizeof(*pc));
+}

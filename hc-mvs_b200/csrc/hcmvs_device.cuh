@@ -1,0 +1,45 @@
+// Shared device-side types for the hcmvs_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "hcmvs_b200.h"
+
+#define HCMVS_HW 7                      // DepthEstimator::nSizeHalfWindow (libs/MVS/DepthMap.h:354)
+#define HCMVS_MAXV HCMVS_MAX_MATCH_VIEWS
+#define HCMVS_NT 128                    // threads per CTA of the scoring kernels
+
+// per matching-neighbour constants (DepthEstimator::ViewData, DepthMap.h:412-444)
+struct NbViewConst {
+	double Hl[9];                // K1 R1 R0^T
+	double Hm[3];                // K1 R1 (C0-C1)
+	cudaTextureObject_t tex;     // point-sampled f32 gather texture of the neighbour gray image
+	const float* img;            // the same image, linear (global-load sampler)
+	int pitch;                   // elements per row of img
+	int w, h;
+};
+
+// everything one reference view's scoring kernels need; passed by value as a __grid_constant__
+struct RefConst {
+	int w, h;
+	double fx, fy, cx, cy;       // K0
+	double Hr[9];                // K0^-1
+	const float* img0; int pitch0;
+	const uint8_t* gra;          // gradient map (u8) or nullptr
+	const float* prior;          // depthMapPrior or nullptr
+	float4* dn;                  // (nx,ny,nz,depth) per pixel
+	float* conf;
+	int nViews;
+	NbViewConst nb[HCMVS_MAXV];
+	float dMin, dMax, dMinSqr, dMaxSqr;
+	float keep, thRobust, thConfSmall, thConfBig, thConfRand;
+	float smoothBonusDepth, smoothBonusNormal, smoothSigmaDepth, smoothSigmaNormal;
+	float angle1Range, angle2Range, depthRatio;
+	int nRandomIters, adapthalfwin, farReach, it_external, photo2geo;
+	float photometric_flow, para_prior, sigmaPrior;
+	uint32_t key0, key1, pass;
+	unsigned long long* counters; // [0] hypotheses, [1] view scores, [2] pixel-iterations
+};
+
+struct CamConst { // f64 camera for the filter / fuse kernels (libs/MVS/Camera.h)
+	double K[9], R[9], C[3], P[12];
+};

@@ -1,0 +1,61 @@
+// Internal host-side state of libhcmvs_b200.so (not part of the ABI).
+#pragma once
+#include "hcmvs_device.cuh"
+#include <vector>
+
+enum { ST_SCORE = 0, ST_SWEEPS, ST_END, ST_PREP, ST_FILTER, ST_FUSE, ST_COUNT };
+
+struct View { // one scene image + its DepthData (libs/MVS/DepthMap.h:214-347)
+	bool set = false, hasMaps = false;
+	int w = 0, h = 0;
+	double K[9], R[9], C[3], P[12];
+	cudaArray_t arr = nullptr; cudaTextureObject_t tex = 0; // gray image, gather texture
+	float* img_d = nullptr;       // gray image, linear
+	uint8_t* bgr_d = nullptr;     // colour image (fusion colours, gradient map)
+	uint8_t* gra_d = nullptr;     // DepthData::graMap
+	float4* dn_d = nullptr;       // (normal.xyz, depth)
+	float* conf_d = nullptr;
+	float* prior_d = nullptr;     // DepthData::depthMapPrior
+	float* fdepth_d = nullptr; float* fconf_d = nullptr; bool hasFiltered = false; // pending FilterDepthMap output
+	uint32_t* claim_d = nullptr;  // FuseDepthMaps' arrDepthIdx (claim / reservation word per pixel)
+	float dMin = 0.f, dMax = 0.f;
+	std::vector<uint32_t> nbIds;  // DepthData::neighbors (sorted by score)
+	std::vector<float> nbScores;
+	int nMatch = 0;               // first nMatch ids = DepthData::images[1..]
+	float fusePriority = 0.f; bool hasFusePriority = false; // #scored neighbours (FuseDepthMaps connection score)
+};
+
+struct TimedSpan { int stage; cudaEvent_t a, b; };
+
+struct FuseState; // fuse.cu
+
+struct hcmvs_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	hcmvs_params P;
+	std::vector<View> views;
+	void* scratch_d = nullptr; size_t scratchBytes = 0;
+	unsigned long long* counters_d = nullptr;
+	std::vector<TimedSpan> timed; std::vector<cudaEvent_t> eventPool;
+	double stageMs[ST_COUNT] = {0, 0, 0, 0, 0, 0};
+	uint32_t nLaunches = 0;
+	uint64_t fuseRounds = 0;
+	FuseState* fuse = nullptr;
+};
+
+void hcmvs_set_error(const char* fmt, ...);
+int  hcmvs_scratch(hcmvs_ctx* ctx, size_t bytes, void** out);
+void hcmvs_time_begin(hcmvs_ctx* ctx, int stage);
+void hcmvs_time_end(hcmvs_ctx* ctx);
+void hcmvs_fuse_release(hcmvs_ctx* ctx);
+void hcmvs_fill_cam(const View& v, CamConst& c);
+
+// patchmatch.cu
+cudaError_t hcmvs_launch_score_init(const RefConst& rc, bool tex, cudaStream_t st);
+cudaError_t hcmvs_launch_score_hyp(const RefConst& rc, const float4* hyp, int smoothMode, float* out, bool tex, cudaStream_t st);
+cudaError_t hcmvs_launch_sweep(const RefConst& rc, int colour, bool tex, cudaStream_t st);
+cudaError_t hcmvs_launch_end(float4* dn, float* conf, size_t n, float keep, cudaStream_t st);
+cudaError_t hcmvs_launch_median3(const float4* in, float4* out, int w, int h, cudaStream_t st);
+cudaError_t hcmvs_launch_gramap(const uint8_t* bgr, uint8_t* gra, int w, int h, cudaStream_t st);
+cudaError_t hcmvs_launch_pack(const float* depth, const float* normal, float4* dn, size_t n, cudaStream_t st);
+cudaError_t hcmvs_launch_unpack(const float4* dn, float* depth, float* normal, size_t n, cudaStream_t st);

@@ -1,0 +1,140 @@
+/* hcmvs_b200 — C ABI of the B200-native HC-MVS dense-reconstruction hot path.
+ *
+ * Drop-in boundary for the reference's de-facto operator surface, `class DepthMapsData`
+ * (libs/MVS/SceneDensify.h:49-88) and its three thread procs (SceneDensify.h:73-75); the reference has no
+ * FFI of its own. Every entry point below names the reference interface it replaces.
+ *
+ * Conventions: plain pointers and sizes only; all pointers are HOST memory unless suffixed `_d`; row-major
+ * images; status `int` (0 ok, <0 error, text via hcmvs_last_error()) mirroring the reference's bool returns;
+ * no exceptions cross the boundary. One context drives ONE CUDA device (one process per GPU); calls on a
+ * context are thread-compatible (one thread at a time — the reference serialises EstimateDepthMap with a
+ * Semaphore(1), SceneDensify.cpp:3503,3895). There is no CPU fallback: creation fails without a CUDA device.
+ */
+#ifndef HCMVS_B200_H_
+#define HCMVS_B200_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HCMVS_OK 0
+#define HCMVS_ERR_ARG (-1)
+#define HCMVS_ERR_CUDA (-2)
+#define HCMVS_ERR_STATE (-3)
+#define HCMVS_ERR_UNSUPPORTED (-4)
+#define HCMVS_MAX_MATCH_VIEWS 16   /* matching neighbours per reference view (reference runs use 5..10) */
+#define HCMVS_MAX_FUSE_VIEWS 32    /* neighbours probed during fusion (OPTDENSE::nMaxViews = 12) */
+
+/* The OPTDENSE fields the hot path reads (libs/MVS/DepthMap.cpp:69-143). */
+typedef struct hcmvs_params {
+	uint32_t nNumViews, nMaxViews, nMinViews, nMinViewsTrustPoint;
+	uint32_t nMinViewsFuse, nMinViewsFilter, nMinViewsFilterAdjust;
+	int32_t  bFilterAdjust;
+	float fNCCThresholdKeep;
+	uint32_t nEstimationIters, nEstimationIters_external, nRandomIters;
+	float fRandomDepthRatio, fRandomAngle1Range, fRandomAngle2Range;
+	float fRandomSmoothDepth, fRandomSmoothNormal, fRandomSmoothBonus;
+	float fDescriptorMinMagnitudeThreshold;
+	float fDepthDiffThreshold, fNormalDiffThreshold, depthweight, normalweight;
+	int32_t adapthalfwin, propagatehalfwin, propagatestep, photo2geo;
+	float photometric_flow, para_prior, fsigmaPrior;
+	/* B200 reformulation knobs (no reference counterpart) */
+	int32_t rb_far_reach;   /* red-black propagation: per direction the best-confidence pixel among odd offsets 1..rb_far_reach */
+	int32_t sampler;        /* 0 = texture gather path (default), 1 = global-memory loads */
+} hcmvs_params;
+
+typedef struct hcmvs_ctx hcmvs_ctx;
+
+/* Fused point cloud (libs/MVS/PointCloud.h:49-109). Arrays are owned by the library; free with hcmvs_free_pointcloud. */
+typedef struct hcmvs_pointcloud {
+	uint64_t n_points;
+	float*   points;      /* n*3 */
+	float*   normals;     /* n*3 or NULL */
+	uint8_t* colors;      /* n*3 in the image's channel order, or NULL */
+	uint32_t* view_offsets; /* n+1: CSR offsets into views/weights */
+	uint32_t* views;      /* sorted view ids per point (PointCloud::pointViews) */
+	float*   weights;     /* PointCloud::pointWeights */
+} hcmvs_pointcloud;
+
+/* Per-stage device times (CUDA events on the context's stream) and work counters since the last reset. */
+typedef struct hcmvs_timers {
+	double ms_score, ms_sweeps, ms_end, ms_prep, ms_filter, ms_fuse;
+	uint64_t n_hypotheses;     /* ScorePixel evaluations inside the sweeps */
+	uint64_t n_pixel_iters;    /* pixels processed x PatchMatch iterations inside the sweeps */
+	uint64_t n_view_scores;    /* ScorePixelImage evaluations inside the sweeps */
+	uint32_t n_launches;       /* kernels launched */
+	uint64_t n_fuse_rounds;    /* reserve/commit rounds of the last hcmvs_fuse_depthmaps */
+} hcmvs_timers;
+
+void hcmvs_default_params(hcmvs_params* p);              /* OPTDENSE defaults, DepthMap.cpp:69-143 */
+const char* hcmvs_last_error(void);
+
+/* DepthMapsData::DepthMapsData(Scene&) — SceneDensify.cpp:158-166 */
+hcmvs_ctx* hcmvs_create(int device, const hcmvs_params* p);
+void hcmvs_destroy(hcmvs_ctx* ctx);
+int  hcmvs_set_params(hcmvs_ctx* ctx, const hcmvs_params* p);
+int  hcmvs_sync(hcmvs_ctx* ctx);
+
+/* Scene image + camera upload: what DepthMapsData::InitViews prepares per view (SceneDensify.cpp:336-397):
+ * gray = Image::toGray(BGR2GRAY, normalised) in [0,1] (Common/Types.inl:2352-2402); bgr may be NULL
+ * (then the gradient map is zero and fused colours are omitted). K must have zero skew. */
+int hcmvs_set_view(hcmvs_ctx* ctx, uint32_t view, int W, int H, const double K[9], const double R[9], const double C[3],
+                   const float* gray, const uint8_t* bgr);
+/* Result of DepthMapsData::SelectViews (SceneDensify.cpp:307-327): ids[0..n_all) sorted by score; the first
+ * n_match are the matching views InitViews keeps (SceneDensify.cpp:361-376); all n_all are probed by fusion. */
+int hcmvs_set_neighbors(hcmvs_ctx* ctx, uint32_t ref, const uint32_t* ids, const float* scores, int n_match, int n_all);
+/* it_external==0 initialisation of EstimateDepthMap (SceneDensify.cpp:772-819): caller-provided rough depth
+ * (0 = unknown), optional normals, depth range; builds the gradient map (InitGraMap, :581-595) on device. */
+int hcmvs_init_depthmap(hcmvs_ctx* ctx, uint32_t ref, const float* depth0, const float* normal0, float dMin, float dMax);
+/* Load finished maps (DepthData::Load / IncRef, DepthMap.cpp:231-302) — used before filter/fuse-only runs. */
+int hcmvs_set_depthmap(hcmvs_ctx* ctx, uint32_t view, const float* depth, const float* normal, const float* conf, float dMin, float dMax);
+int hcmvs_get_depthmap(hcmvs_ctx* ctx, uint32_t view, float* depth, float* normal, float* conf, float* dMin, float* dMax);
+/* DepthData::graMap (u8, H*W) built by hcmvs_init_depthmap (InitGraMap, SceneDensify.cpp:581-595). */
+int hcmvs_get_gradient_map(hcmvs_ctx* ctx, uint32_t view, uint8_t* gra);
+/* Optional plane prior (DepthData::depthMapPrior, DepthMap.cpp:941-955); NULL clears it. */
+int hcmvs_set_prior(hcmvs_ctx* ctx, uint32_t ref, const float* prior);
+
+/* DepthMapsData::ScoreDepthMapTmp (PASS A) — SceneDensify.cpp:649-675 */
+int hcmvs_score_depthmap(hcmvs_ctx* ctx, uint32_t ref, int it_external, uint64_t seed);
+/* DepthMapsData::EstimateDepthMap — SceneDensify.cpp:758-1072: median blur, PASS A, nEstimationIters red-black
+ * sweeps (EstimateDepthMapTmp / DepthEstimator::ProcessPixel, DepthMap.cpp:1050-1501) and, on the last outer
+ * iteration, EndDepthMapTmp (SceneDensify.cpp:688-744). */
+int hcmvs_estimate_depthmap(hcmvs_ctx* ctx, uint32_t ref, int it_external, uint64_t seed);
+/* DepthMapsData::EndDepthMapTmp (PASS C) alone — SceneDensify.cpp:688-744 */
+int hcmvs_end_depthmap(hcmvs_ctx* ctx, uint32_t ref);
+/* Parity hook: DepthEstimator::ScorePixel (DepthMap.cpp:987-1046) for caller-fixed per-pixel hypotheses.
+ * smooth_mode 0: no smoothness neighbours (PASS A semantics); 1: the 4-neighbourhood of the given maps. */
+int hcmvs_score_hypotheses(hcmvs_ctx* ctx, uint32_t ref, const float* depth, const float* normal, int smooth_mode, float* score_out);
+
+/* DepthMapsData::FilterDepthMap — SceneDensify.cpp:3006-3259. nb_idx index DepthData::neighbors of `ref`.
+ * Outputs (either may be NULL) are the filtered depth / confidence maps the reference writes to
+ * depthNNNN.filtered.dmap/.cmap; they also stay pending on the device until hcmvs_commit_filtered. */
+int hcmvs_filter_depthmap(hcmvs_ctx* ctx, uint32_t ref, const uint32_t* nb_idx, int n, int bAdjust,
+                          float* out_depth, float* out_conf);
+/* Replace every filtered view's depth/confidence by its pending filtered maps — the second phase of
+ * Scene::DenseReconstructionFilter (SceneDensify.cpp:4146-4178: all views are filtered from the
+ * un-filtered maps first, then the .filtered files replace the originals). */
+int hcmvs_commit_filtered(hcmvs_ctx* ctx);
+/* FuseDepthMaps processes views in decreasing order of scene.images[i].neighbors.GetSize() — the UN-filtered
+ * scored-neighbour count of Scene::SelectNeighborViews (SceneDensify.cpp:3286-3303). Defaults to n_all. */
+int hcmvs_set_fuse_priority(hcmvs_ctx* ctx, uint32_t view, float score);
+/* DepthMapsData::FuseDepthMaps — SceneDensify.cpp:3265-3495 */
+int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int estimate_normal, hcmvs_pointcloud* out);
+void hcmvs_free_pointcloud(hcmvs_pointcloud* pc);
+
+/* Device pointers of a view's maps for GPU<->GPU exchange by the host plumbing (NCCL / P2P):
+ * dn_d = float4 (nx,ny,nz,depth) per pixel, conf_d = float per pixel. */
+int hcmvs_get_depthmap_device(hcmvs_ctx* ctx, uint32_t view, void** dn_d, void** conf_d, float* dMin, float* dMax);
+int hcmvs_set_depth_range(hcmvs_ctx* ctx, uint32_t view, float dMin, float dMax);
+/* Allocate (zeroed) device maps for a view without uploading — receive buffers for the exchange. */
+int hcmvs_alloc_depthmap(hcmvs_ctx* ctx, uint32_t view);
+
+int hcmvs_get_timers(hcmvs_ctx* ctx, hcmvs_timers* t);
+int hcmvs_reset_timers(hcmvs_ctx* ctx);
+/* CUDA stream the context launches on (cudaStream_t as void*), for event timing by the caller. */
+void* hcmvs_stream(hcmvs_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -411,7 +411,7 @@ bool DepthEstimator::FillPixelPatch() {
 			const float I = img.at(x0x+j, x0y+i);
 			const float wColor = SQUARE(I-colCenter)*sigmaColor;
 			const float wSpatial = float(SQUARE(j)+SQUARE(i))*sigmaSpatial;
-			const float wgt = std::exp(wColor+wSpatial);
+			const float wgt = (float)std::exp((double)(wColor+wSpatial)); // q10: correctly rounded DENSE_EXP
 			tempWeights[n] = I; weights[n] = wgt;
 			nsq += I*wgt;
 			sumWeights += wgt;

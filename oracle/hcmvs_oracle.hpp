@@ -25,6 +25,11 @@
 //     ProcessPixel score with whatever plane the last InitPlane left (DepthMap.cpp:1450-1453 never
 //     calls InitPlane). Serial mode reproduces that; red-black mode defines the stale plane as the
 //     plane of the pixel's current estimate (see EstimateRedBlack).
+// q10 GetWeight's DENSE_EXP is libm expf (DepthMap.h:68-70,546), whose last bit is platform dependent (glibc's
+//     expf differs from the correctly rounded value for 6e-4 of arguments, and its x86 FMA/non-FMA ifunc variants
+//     differ from each other). Because normSq1 = sumSq - sum^2/sumW cancels catastrophically on low-texture
+//     patches, a 1-ulp weight change moves the NCC by up to 5e-4 there. The oracle pins the weight to the
+//     correctly rounded value (float)exp((double)x), which every conforming libm is within 1 ulp of.
 //  q8 FilterDepthMap's strict branch indexes the projected maps one pixel outside the image at the
 //     border (SceneDensify.cpp:3216-3219); out-of-image reads are defined as depth 0 here.
 #pragma once
