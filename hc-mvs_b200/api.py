@@ -17,7 +17,7 @@ EXPORTS = [
     "hcmvs_set_prior", "hcmvs_get_gradient_map", "hcmvs_score_depthmap", "hcmvs_estimate_depthmap", "hcmvs_end_depthmap", "hcmvs_score_hypotheses",
     "hcmvs_filter_depthmap", "hcmvs_commit_filtered", "hcmvs_set_fuse_priority", "hcmvs_fuse_depthmaps",
     "hcmvs_free_pointcloud", "hcmvs_get_depthmap_device", "hcmvs_set_depth_range", "hcmvs_alloc_depthmap",
-    "hcmvs_get_timers", "hcmvs_reset_timers", "hcmvs_stream",
+    "hcmvs_export_maps_d", "hcmvs_import_maps_d", "hcmvs_get_timers", "hcmvs_reset_timers", "hcmvs_stream",
 ]
 
 
@@ -50,7 +50,7 @@ class Timers(C.Structure):
     _fields_ = [
         ("ms_score", C.c_double), ("ms_sweeps", C.c_double), ("ms_end", C.c_double), ("ms_prep", C.c_double),
         ("ms_filter", C.c_double), ("ms_fuse", C.c_double),
-        ("n_hypotheses", C.c_uint64), ("n_pixel_iters", C.c_uint64), ("n_view_scores", C.c_uint64),
+        ("n_hypotheses", C.c_uint64), ("n_pixel_iters", C.c_uint64), ("n_view_scores", C.c_uint64), ("n_smooth_terms", C.c_uint64),
         ("n_launches", C.c_uint32), ("n_fuse_rounds", C.c_uint64),
     ]
 
@@ -98,6 +98,8 @@ def load():
     L.hcmvs_get_depthmap_device.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(vp), C.POINTER(f32), C.POINTER(f32)]
     L.hcmvs_set_depth_range.argtypes = [vp, u32, f32, f32]
     L.hcmvs_alloc_depthmap.argtypes = [vp, u32]
+    L.hcmvs_export_maps_d.argtypes = [vp, u32, vp, vp]
+    L.hcmvs_import_maps_d.argtypes = [vp, u32, vp, vp, f32, f32]
     L.hcmvs_get_timers.argtypes = [vp, C.POINTER(Timers)]
     L.hcmvs_reset_timers.argtypes = [vp]
     L.hcmvs_stream.restype = vp
@@ -244,6 +246,12 @@ class Context:
 
     def set_depth_range(self, view, dmin, dmax):
         self._ck(self.L.hcmvs_set_depth_range(self.h, view, dmin, dmax))
+
+    def export_maps_d(self, view, dn_ptr, conf_ptr):
+        self._ck(self.L.hcmvs_export_maps_d(self.h, view, dn_ptr, conf_ptr))
+
+    def import_maps_d(self, view, dn_ptr, conf_ptr, dmin, dmax):
+        self._ck(self.L.hcmvs_import_maps_d(self.h, view, dn_ptr, conf_ptr, dmin, dmax))
 
     def alloc_depthmap(self, view):
         self._ck(self.L.hcmvs_alloc_depthmap(self.h, view))

@@ -131,7 +131,7 @@ extern "C" int hcmvs_get_timers(hcmvs_ctx* ctx, hcmvs_timers* t) {
 	CK(cudaMemcpy(c, ctx->counters_d, sizeof(c), cudaMemcpyDeviceToHost));
 	t->ms_score = ctx->stageMs[ST_SCORE]; t->ms_sweeps = ctx->stageMs[ST_SWEEPS]; t->ms_end = ctx->stageMs[ST_END];
 	t->ms_prep = ctx->stageMs[ST_PREP]; t->ms_filter = ctx->stageMs[ST_FILTER]; t->ms_fuse = ctx->stageMs[ST_FUSE];
-	t->n_hypotheses = c[0]; t->n_view_scores = c[1]; t->n_pixel_iters = c[2];
+	t->n_hypotheses = c[0]; t->n_view_scores = c[1]; t->n_pixel_iters = c[2]; t->n_smooth_terms = c[3];
 	t->n_launches = ctx->nLaunches; t->n_fuse_rounds = ctx->fuseRounds;
 	return HCMVS_OK;
 }
@@ -305,6 +305,25 @@ extern "C" int hcmvs_get_depthmap_device(hcmvs_ctx* ctx, uint32_t view, void** d
 	if (conf_d) *conf_d = v->conf_d;
 	if (dMin) *dMin = v->dMin;
 	if (dMax) *dMax = v->dMax;
+	return HCMVS_OK;
+}
+extern "C" int hcmvs_export_maps_d(hcmvs_ctx* ctx, uint32_t view, void* dn_d, void* conf_d) {
+	View* v = GetView(ctx, view, true); if (!v) return HCMVS_ERR_ARG;
+	if (!v->hasMaps) { hcmvs_set_error("view %u has no depth map", view); return HCMVS_ERR_STATE; }
+	cudaSetDevice(ctx->device);
+	const size_t n = (size_t)v->w*v->h;
+	if (dn_d) CK(cudaMemcpyAsync(dn_d, v->dn_d, n*sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+	if (conf_d) CK(cudaMemcpyAsync(conf_d, v->conf_d, n*4, cudaMemcpyDeviceToDevice, ctx->stream));
+	return HCMVS_OK;
+}
+extern "C" int hcmvs_import_maps_d(hcmvs_ctx* ctx, uint32_t view, const void* dn_d, const void* conf_d, float dMin, float dMax) {
+	View* v = GetView(ctx, view, true); if (!v) return HCMVS_ERR_ARG;
+	cudaSetDevice(ctx->device);
+	int r = AllocMaps(ctx, v); if (r) return r;
+	const size_t n = (size_t)v->w*v->h;
+	if (dn_d) CK(cudaMemcpyAsync(v->dn_d, dn_d, n*sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+	if (conf_d) CK(cudaMemcpyAsync(v->conf_d, conf_d, n*4, cudaMemcpyDeviceToDevice, ctx->stream));
+	v->dMin = dMin; v->dMax = dMax; v->hasMaps = true;
 	return HCMVS_OK;
 }
 extern "C" int hcmvs_set_depth_range(hcmvs_ctx* ctx, uint32_t view, float dMin, float dMax) {

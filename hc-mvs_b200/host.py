@@ -1,0 +1,168 @@
+"""ctypes binding of the host-side mirror of MVS::Scene / MVS::DepthMapsData (include/hcmvs_host.h).
+
+``HostScene.dense_reconstruction`` is the public end-to-end call: Scene::DenseReconstruction
+(libs/MVS/SceneDensify.cpp:3532-3574) driven through the C ABI with host buffers.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import api
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        api.load()  # libhcmvs_host.so links the CUDA library
+        path = os.path.join(_HERE, "libhcmvs_host.so")
+        if not os.path.exists(path):
+            raise ImportError(f"{path} missing: run __graft_entry__.build()")
+        L = C.CDLL(path)
+        vp, i32 = C.c_void_p, C.c_int
+        L.hcmvs_host_scene_create.restype = vp
+        L.hcmvs_host_scene_destroy.argtypes = [vp]
+        L.hcmvs_host_last_error.restype = C.c_char_p
+        L.hcmvs_host_last_error.argtypes = [vp]
+        L.hcmvs_host_add_image.argtypes = [vp, i32, i32, vp, vp, vp, vp, C.c_char_p]
+        L.hcmvs_host_set_sparse.argtypes = [vp, i32, vp, vp, vp]
+        L.hcmvs_host_select_views.argtypes = [vp, C.POINTER(api.Params), i32]
+        L.hcmvs_host_get_neighbors.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, i32]
+        L.hcmvs_host_get_gray.argtypes = [vp, i32, vp]
+        L.hcmvs_host_init_depth.argtypes = [vp, i32, vp, vp]
+        L.hcmvs_host_dense_reconstruction.argtypes = [vp, vp, C.POINTER(api.Params), C.c_uint64, i32, C.c_char_p, vp]
+        L.hcmvs_host_cloud_size.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.hcmvs_host_cloud_get.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.hcmvs_host_cloud_save_ply.argtypes = [vp, C.c_char_p]
+        L.hcmvs_host_write_dmap.argtypes = [C.c_char_p, C.c_char_p, vp, i32, i32, i32, vp, vp, vp, C.c_float, C.c_float, i32, i32, vp, vp, vp]
+        L.hcmvs_host_read_dmap_header.argtypes = [C.c_char_p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+        L.hcmvs_host_read_dmap.argtypes = [C.c_char_p, vp, vp, vp, vp, vp, vp, vp, vp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class HostScene:
+    def __init__(self):
+        self.L = lib()
+        self.h = self.L.hcmvs_host_scene_create()
+        self.sizes = []
+
+    @classmethod
+    def from_synth(cls, syn, images=None):
+        s = cls()
+        for i in range(syn.n_views):
+            bgr = images[i] if images is not None else syn.render(i, want_depth=False, want_normal=False)[0]
+            s.add_image(syn.K[i], syn.R[i], syn.Cc[i], bgr, name=f"{i:05d}.png")
+        s.set_sparse(syn.sparse_xyz, syn.sparse_off, syn.sparse_views)
+        return s
+
+    def add_image(self, K, R, Cc, bgr, name=""):
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        h, w = bgr.shape[:2]
+        K = np.ascontiguousarray(K, np.float64); R = np.ascontiguousarray(R, np.float64); Cc = np.ascontiguousarray(Cc, np.float64)
+        i = self.L.hcmvs_host_add_image(self.h, w, h, _p(K), _p(R), _p(Cc), _p(bgr), name.encode())
+        if i < 0:
+            raise RuntimeError("hcmvs_host_add_image failed")
+        self.sizes.append((h, w))
+        return i
+
+    def set_sparse(self, xyz, off, views):
+        xyz = np.ascontiguousarray(xyz, np.float32); off = np.ascontiguousarray(off, np.int32); views = np.ascontiguousarray(views, np.uint32)
+        self.L.hcmvs_host_set_sparse(self.h, len(xyz), _p(xyz), _p(off), _p(views))
+
+    def select_views(self, params, idx):
+        return self.L.hcmvs_host_select_views(self.h, C.byref(params), idx)
+
+    def neighbors(self, idx, which=1, cap=64):
+        ids = np.zeros(cap, np.uint32); pts = np.zeros(cap, np.uint32)
+        sc = np.zeros(cap, np.float32); an = np.zeros(cap, np.float32); ar = np.zeros(cap, np.float32); s = np.zeros(cap, np.float32)
+        n = min(max(self.L.hcmvs_host_get_neighbors(self.h, idx, which, _p(ids), _p(pts), _p(sc), _p(an), _p(ar), _p(s), cap), 0), cap)
+        return dict(ids=ids[:n], points=pts[:n], scale=sc[:n], angle=an[:n], area=ar[:n], score=s[:n])
+
+    def init_depth(self, idx):
+        """Sparse-point initial depth map of a selected view -> (depth, dMin, dMax)."""
+        h, w = self.sizes[idx]
+        d = np.zeros((h, w), np.float32); mm = np.zeros(2, np.float32)
+        if self.L.hcmvs_host_init_depth(self.h, idx, _p(d), _p(mm)) != 0:
+            raise RuntimeError("view not selected")
+        return d, float(mm[0]), float(mm[1])
+
+    def gray(self, idx):
+        h, w = self.sizes[idx]
+        g = np.zeros((h, w), np.float32)
+        self.L.hcmvs_host_get_gray(self.h, idx, _p(g))
+        return g
+
+    def dense_reconstruction(self, ctx, seed=1, run_filter=True, dmap_dir=None):
+        """Scene::DenseReconstruction: select views, upload, estimate all depth maps, (filter,) fuse. Returns stats."""
+        st = np.zeros(8)
+        r = self.L.hcmvs_host_dense_reconstruction(self.h, ctx.h, C.byref(ctx.params), seed, int(run_filter),
+                                                   dmap_dir.encode() if dmap_dir else None, _p(st))
+        if r != 0:
+            raise RuntimeError(self.L.hcmvs_host_last_error(self.h).decode())
+        for i, sz in enumerate(self.sizes):
+            ctx.sizes.setdefault(i, sz)
+        return dict(sec_select=st[0], sec_upload=st[1], sec_estimate=st[2], sec_filter=st[3], sec_fuse=st[4],
+                    h2d_bytes=int(st[5]), d2h_bytes=int(st[6]), n_points=int(st[7]))
+
+    def cloud(self):
+        n = C.c_uint64(); m = C.c_uint64()
+        self.L.hcmvs_host_cloud_size(self.h, C.byref(n), C.byref(m))
+        n, m = n.value, m.value
+        xyz = np.zeros((n, 3), np.float32); nrm = np.zeros((n, 3), np.float32); col = np.zeros((n, 3), np.uint8)
+        off = np.zeros(n + 1, np.uint32); views = np.zeros(m, np.uint32); wts = np.zeros(m, np.float32)
+        if n:
+            self.L.hcmvs_host_cloud_get(self.h, _p(xyz), _p(nrm), _p(col), _p(off), _p(views), _p(wts))
+        return dict(xyz=xyz, normals=nrm, colors=col, n_views=np.diff(off.astype(np.int64)).astype(np.int32), views=views, weights=wts)
+
+    def save_ply(self, path):
+        if self.L.hcmvs_host_cloud_save_ply(self.h, path.encode()) != 0:
+            raise RuntimeError("PointCloud::Save failed")
+
+    def close(self):
+        if self.h:
+            self.L.hcmvs_host_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def write_dmap(path, image_name, ids, image_size, K, R, Cc, dmin, dmax, depth, normal=None, conf=None):
+    """MVS::ExportDepthDataRaw (libs/MVS/DepthMap.cpp:2781-2846)."""
+    depth = np.ascontiguousarray(depth, np.float32); h, w = depth.shape
+    normal = np.ascontiguousarray(normal, np.float32) if normal is not None else None
+    conf = np.ascontiguousarray(conf, np.float32) if conf is not None else None
+    ids = np.ascontiguousarray(ids, np.uint32)
+    K = np.ascontiguousarray(K, np.float64); R = np.ascontiguousarray(R, np.float64); Cc = np.ascontiguousarray(Cc, np.float64)
+    r = lib().hcmvs_host_write_dmap(path.encode(), image_name.encode(), _p(ids), len(ids), image_size[0], image_size[1],
+                                    _p(K), _p(R), _p(Cc), dmin, dmax, w, h, _p(depth), _p(normal), _p(conf))
+    if r != 0:
+        raise IOError(path)
+
+
+def read_dmap(path):
+    """MVS::ImportDepthDataRaw (libs/MVS/DepthMap.cpp:2848-2925)."""
+    L = lib()
+    w = C.c_int(); h = C.c_int(); n = C.c_int(); hn = C.c_int(); hc = C.c_int()
+    if L.hcmvs_host_read_dmap_header(path.encode(), C.byref(w), C.byref(h), C.byref(n), C.byref(hn), C.byref(hc)) != 0:
+        raise IOError(path)
+    ids = np.zeros(n.value, np.uint32); K = np.zeros(9); R = np.zeros(9); Cc = np.zeros(3); mm = np.zeros(2, np.float32)
+    depth = np.zeros((h.value, w.value), np.float32)
+    normal = np.zeros((h.value, w.value, 3), np.float32) if hn.value else None
+    conf = np.zeros((h.value, w.value), np.float32) if hc.value else None
+    L.hcmvs_host_read_dmap(path.encode(), _p(ids), _p(K), _p(R), _p(Cc), _p(mm), _p(depth), _p(normal), _p(conf))
+    return dict(ids=ids, K=K, R=R, C=Cc, dmin=float(mm[0]), dmax=float(mm[1]), depth=depth, normal=normal, conf=conf)

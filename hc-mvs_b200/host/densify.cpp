@@ -1,0 +1,413 @@
+// Host-side mirror of DepthMapsData / Scene::DenseReconstruction over the C ABI — see densify.h.
+#include "densify.h"
+#include <algorithm>
+#include <chrono>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace hcmvs_host {
+
+static double Now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static const float kPi = (float)3.14159265358979323846;
+static inline float Deg2Rad(float d) { return d*(kPi/180.f); } // FD2R, Common/Types.h:566
+
+// ------------------------------------------------------------------------------------------------ camera
+// cv::Matx products: plain loops, left-to-right accumulation (libs/MVS/Camera.cpp:174-181)
+void Camera::ComposeP() {
+	double M[9];
+	for (int r=0; r<3; ++r) for (int c=0; c<3; ++c) {
+		double acc = K[r*3]*R[c];
+		acc += K[r*3+1]*R[3+c];
+		acc += K[r*3+2]*R[6+c];
+		M[r*3+c] = acc;
+	}
+	for (int r=0; r<3; ++r) {
+		double acc = M[r*3]*(-C[0]);
+		acc += M[r*3+1]*(-C[1]);
+		acc += M[r*3+2]*(-C[2]);
+		P[r*4] = M[r*3]; P[r*4+1] = M[r*3+1]; P[r*4+2] = M[r*3+2]; P[r*4+3] = acc;
+	}
+}
+// Camera::PointDepth, Camera.cpp:112-115
+static inline double PointDepth(const Camera& cam, const float* X) { return cam.P[8]*X[0] + cam.P[9]*X[1] + cam.P[10]*X[2] + cam.P[11]; }
+// Camera::ProjectPointP<float>, Camera.h:273-285
+static inline void ProjectPointP(const Camera& cam, const float* X, float& u, float& v) {
+	const double* p = cam.P;
+	const float qx = (float)(p[0]*X[0] + p[1]*X[1] + p[2]*X[2] + p[3]);
+	const float qy = (float)(p[4]*X[0] + p[5]*X[1] + p[6]*X[2] + p[7]);
+	const float qz = (float)(p[8]*X[0] + p[9]*X[1] + p[10]*X[2] + p[11]);
+	const float invZ = qz == 0.f ? FLT_MAX : 1.f/qz; // INVERT, Common/Types.h:1216-1219
+	u = qx*invZ; v = qy*invZ;
+}
+
+void ToGray(const uint8_t* bgr, int w, int h, float* gray) {
+	// Image::toGray(COLOR_BGR2GRAY, bNormalize), Common/Types.inl:2352-2402 with NormRGB_t (:1588-1592)
+	const float inv255 = 1.f/255.f;
+	for (size_t i=0, n=(size_t)w*h; i<n; ++i)
+		gray[i] = 0.114f*(float(bgr[i*3])*inv255) + 0.587f*(float(bgr[i*3+1])*inv255) + 0.299f*(float(bgr[i*3+2])*inv255);
+}
+
+// ------------------------------------------------------------------------------------------------ view selection
+static inline float CosAngle(const float* a, const float* b) { // ComputeAngle<float,float>, Common/Util.inl:416-420
+	const float c = (a[0]*b[0]+a[1]*b[1]+a[2]*b[2])/std::sqrt((a[0]*a[0]+a[1]*a[1]+a[2]*a[2])*(b[0]*b[0]+b[1]*b[1]+b[2]*b[2]));
+	return std::min(std::max(c, -1.f), 1.f);
+}
+static inline bool Contains(const std::vector<uint32_t>& sortedViews, uint32_t id) { return std::binary_search(sortedViews.begin(), sortedViews.end(), id); }
+
+bool Scene::SelectNeighborViews(uint32_t ID, std::vector<uint32_t>& points, unsigned nMinViews, unsigned nMinPointViews, float fOptimAngle) {
+	// Scene.cpp:545-662, "Multi-View Stereo for Community Photo Collections" style view scoring
+	Image& ref = images[ID];
+	ref.neighbors.clear();
+	struct Acc { float score = 0, scale = 0, angle = 0; uint32_t n = 0; };
+	std::vector<Acc> acc(images.size());
+	nMinPointViews = std::min(nMinPointViews, nCalibratedImages());
+	unsigned nSeen = 0;
+	ref.avgDepth = 0;
+	for (size_t ip=0; ip<pointcloud.size(); ++ip) {
+		const std::vector<uint32_t>& pv = pointcloud.views[ip];
+		if (!Contains(pv, ID)) continue;
+		const float* X = &pointcloud.xyz[ip*3];
+		if (pv.size() >= nMinPointViews) points.push_back((uint32_t)ip);
+		ref.avgDepth += (float)PointDepth(ref.camera, X);
+		++nSeen;
+		const float toRef[3] = {(float)(ref.camera.C[0]-(double)X[0]), (float)(ref.camera.C[1]-(double)X[1]), (float)(ref.camera.C[2]-(double)X[2])};
+		const float fpRef = (float)(ref.camera.K[0]/PointDepth(ref.camera, X)); // Footprint, Scene.cpp:531-539
+		for (uint32_t other: pv) {
+			if (other == ID) continue;
+			const Image& o = images[other];
+			const float toOther[3] = {(float)(o.camera.C[0]-(double)X[0]), (float)(o.camera.C[1]-(double)X[1]), (float)(o.camera.C[2]-(double)X[2])};
+			const float ang = std::acos(CosAngle(toRef, toOther));
+			const float wAngle = std::min(std::pow(ang/fOptimAngle, 1.5f), 1.f);
+			const float fpOther = (float)(o.camera.K[0]/PointDepth(o.camera, X));
+			const float ratio = fpRef/fpOther;
+			float wScale;
+			if (ratio > 1.6f) { const float q = 1.6f/ratio; wScale = q*q; }
+			else if (ratio >= 1.f) wScale = 1.f;
+			else wScale = ratio*ratio;
+			Acc& a = acc[other];
+			a.score += wAngle*wScale; a.scale += ratio; a.angle += ang; ++a.n;
+		}
+	}
+	ref.avgDepth /= nSeen;
+	std::vector<float> projA;
+	for (uint32_t IDB=0; IDB<images.size(); ++IDB) {
+		const Acc& a = acc[IDB];
+		if (a.n < 3) continue;
+		const Image& B = images[IDB];
+		const float wA = (float)ref.width, hA = (float)ref.height, wB = (float)B.width, hB = (float)B.height;
+		projA.clear();
+		for (uint32_t ip: points) {
+			if (!Contains(pointcloud.views[ip], IDB)) continue;
+			const float* X = &pointcloud.xyz[(size_t)ip*3];
+			float ua, va, ub, vb;
+			ProjectPointP(ref.camera, X, ua, va);
+			ProjectPointP(B.camera, X, ub, vb);
+			if (ua >= 0 && va >= 0 && ua < wA && va < hA && ub >= 0 && vb >= 0 && ub < wB && vb < hB) { projA.push_back(ua); projA.push_back(va); }
+		}
+		if (projA.empty()) continue;
+		// ComputeCoveredArea<float,2,16,false>, Common/Util.inl:711-730
+		bool cell[16][16] = {};
+		for (size_t k=0; k<projA.size(); k+=2) {
+			const float gx = (projA[k]/wA+0.f)*16.f, gy = (projA[k+1]/hA+0.f)*16.f;
+			cell[(int)std::floor(gx)][(int)std::floor(gy)] = true;
+		}
+		unsigned covered = 0;
+		for (auto& row: cell) for (bool c: row) covered += c ? 1u : 0u;
+		const float area = float(covered)/256;
+		ViewScore vs;
+		vs.ID = IDB; vs.points = a.n; vs.scale = a.scale/a.n; vs.angle = a.angle/a.n; vs.area = area; vs.score = a.score*area;
+		ref.neighbors.push_back(vs);
+	}
+	std::stable_sort(ref.neighbors.begin(), ref.neighbors.end(), [](const ViewScore& l, const ViewScore& r) { return l.score > r.score; });
+	return points.size() > 3 && ref.neighbors.size() >= std::min(nMinViews, nCalibratedImages()-1);
+}
+
+bool Scene::FilterNeighborViews(std::vector<ViewScore>& nb, float fMinArea, float fMinScale, float fMaxScale, float fMinAngle, float fMaxAngle, unsigned nMaxViews) {
+	// Scene.cpp:665-678
+	std::vector<ViewScore> kept;
+	for (const ViewScore& v: nb) {
+		const bool scaleOk = fMinScale <= v.scale && v.scale < fMaxScale, angleOk = fMinAngle <= v.angle && v.angle < fMaxAngle;
+		if (v.area >= fMinArea && scaleOk && angleOk) kept.push_back(v);
+	}
+	if (kept.size() > nMaxViews) kept.resize(nMaxViews);
+	nb.swap(kept);
+	return !nb.empty();
+}
+
+// ------------------------------------------------------------------------------------------------ DepthMapsData
+DepthMapsData::DepthMapsData(Scene& s, hcmvs_ctx* c, const hcmvs_params& p, const ViewSelectionParams& vs)
+	: arrDepthData(s.images.size()), scene(s), ctx(c), P(p), VS(vs) {}
+
+bool DepthMapsData::Fail(const char* what) {
+	lastError = std::string(what)+": "+hcmvs_last_error();
+	return false;
+}
+
+bool DepthMapsData::SelectViews(uint32_t idxImage) {
+	// SceneDensify.cpp:307-327
+	DepthData& dd = arrDepthData[idxImage];
+	dd.points.clear(); dd.neighbors.clear(); dd.valid = false;
+	if (!scene.SelectNeighborViews(idxImage, dd.points, P.nMinViews, P.nMinViewsTrustPoint > 1 ? P.nMinViewsTrustPoint : 2, Deg2Rad(VS.fOptimAngle)))
+		return false;
+	dd.neighbors = scene.images[idxImage].neighbors;
+	if (!Scene::FilterNeighborViews(dd.neighbors, VS.fMinArea, 0.2f, 3.2f, Deg2Rad(VS.fMinAngle), Deg2Rad(VS.fMaxAngle), P.nMaxViews))
+		return false;
+	dd.valid = true;
+	return true;
+}
+
+bool DepthMapsData::UploadView(uint32_t idxImage) {
+	DepthData& dd = arrDepthData[idxImage];
+	if (dd.uploaded) return true;
+	Image& im = scene.images[idxImage];
+	if (im.gray.empty()) {
+		if (im.bgr.empty()) { lastError = "image has neither gray nor colour pixels"; return false; }
+		im.gray.resize((size_t)im.width*im.height);
+		ToGray(im.bgr.data(), im.width, im.height, im.gray.data());
+	}
+	if (hcmvs_set_view(ctx, idxImage, im.width, im.height, im.camera.K, im.camera.R, im.camera.C, im.gray.data(), im.bgr.empty() ? nullptr : im.bgr.data()) != HCMVS_OK)
+		return Fail("hcmvs_set_view");
+	dd.uploaded = true;
+	return true;
+}
+
+bool DepthMapsData::InitViews(uint32_t idxImage, uint32_t numNeighbors) {
+	// SceneDensify.cpp:336-397 (idxNeighbor == NO_ID branch). Neighbour rescaling for |scale-1| >= 0.15
+	// (DepthMap.h:232-238) is not built: such neighbours are rejected with an error instead of silently mis-scored.
+	DepthData& dd = arrDepthData[idxImage];
+	if (dd.neighbors.empty()) { lastError = "InitViews before SelectViews"; return false; }
+	dd.images.assign(1, idxImage);
+	const float fMinScore = std::max(dd.neighbors.front().score*(VS.fViewMinScoreRatio*0.1f), VS.fViewMinScore);
+	for (const ViewScore& nb: dd.neighbors) {
+		if ((numNeighbors && dd.images.size() > numNeighbors) || nb.score < fMinScore) break;
+		if (std::abs(nb.scale-1.f) >= 0.15f) { lastError = "neighbour needs rescaling (|scale-1| >= 0.15): not supported"; dd.images.clear(); return false; }
+		dd.images.push_back(nb.ID);
+	}
+	if (dd.images.size() < 2) { dd.images.clear(); return false; }
+	if (dd.images.size()-1 > HCMVS_MAX_MATCH_VIEWS) dd.images.resize(HCMVS_MAX_MATCH_VIEWS+1);
+	for (uint32_t id: dd.images) if (!UploadView(id)) return false;
+	std::vector<uint32_t> ids; std::vector<float> scores;
+	for (const ViewScore& nb: dd.neighbors) { ids.push_back(nb.ID); scores.push_back(nb.score); }
+	// matching views are the first entries of the (sorted) neighbour list
+	if (hcmvs_set_neighbors(ctx, idxImage, ids.data(), scores.data(), (int)dd.images.size()-1, (int)ids.size()) != HCMVS_OK) return Fail("hcmvs_set_neighbors");
+	if (hcmvs_set_fuse_priority(ctx, idxImage, (float)scene.images[idxImage].neighbors.size()) != HCMVS_OK) return Fail("hcmvs_set_fuse_priority");
+	return true;
+}
+
+void SparseInitDepth(const Scene& scene, uint32_t idxImage, const std::vector<uint32_t>& points, std::vector<float>& depth, float& dMin, float& dMax) {
+	// it_external == 0 block of EstimateDepthMap, nMinViewsTrustPoint < 2 branch (SceneDensify.cpp:783-808): splat the
+	// sparse points into 5x5 windows and derive the depth range. (The CGAL Delaunay initialisation of
+	// InitDepthMap, DepthMap.cpp:1879-1936, is out of scope — SURVEY §8a P8.)
+	const Image& im = scene.images[idxImage];
+	const Camera& cam = im.camera;
+	const int w = im.width, h = im.height;
+	depth.assign((size_t)w*h, 0.f);
+	dMin = FLT_MAX; dMax = 0;
+	for (uint32_t ip: points) {
+		const float* X = &scene.pointcloud.xyz[(size_t)ip*3];
+		const double d0 = (double)X[0]-cam.C[0], d1 = (double)X[1]-cam.C[1], d2 = (double)X[2]-cam.C[2];
+		double c[3];
+		for (int r=0; r<3; ++r) { double a = cam.R[r*3]*d0; a += cam.R[r*3+1]*d1; a += cam.R[r*3+2]*d2; c[r] = a; } // TransformPointW2C
+		const double u = cam.K[2]+cam.K[0]*(c[0]/c[2]), v = cam.K[5]+cam.K[4]*(c[1]/c[2]); // TransformPointC2I
+		const int x = (int)std::floor(u+.5), y = (int)std::floor(v+.5); // ROUND2INT
+		const float d = (float)c[2];
+		const int sx = std::max(x-2, 0), sy = std::max(y-2, 0), ex = std::min(x+2, w-1), ey = std::min(y+2, h-1);
+		for (int yy=sy; yy<=ey; ++yy) for (int xx=sx; xx<=ex; ++xx) depth[(size_t)yy*w+xx] = d;
+		dMin = std::min(dMin, d); dMax = std::max(dMax, d);
+	}
+	dMin *= 0.9f; dMax *= 1.1f;
+}
+
+bool DepthMapsData::InitDepthMap(uint32_t idxImage) {
+	DepthData& dd = arrDepthData[idxImage];
+	std::vector<float> depth;
+	SparseInitDepth(scene, idxImage, dd.points, depth, dd.dMin, dd.dMax);
+	if (hcmvs_init_depthmap(ctx, idxImage, depth.data(), nullptr, dd.dMin, dd.dMax) != HCMVS_OK) return Fail("hcmvs_init_depthmap");
+	return true;
+}
+
+bool DepthMapsData::EstimateDepthMap(int it_external, uint32_t idxImage, uint64_t seed) {
+	if (it_external == 0 && !InitDepthMap(idxImage)) return false;
+	if (hcmvs_estimate_depthmap(ctx, idxImage, it_external, seed) != HCMVS_OK) return Fail("hcmvs_estimate_depthmap");
+	return true;
+}
+
+bool DepthMapsData::FilterDepthMap(uint32_t idxImage, const std::vector<uint32_t>& idxNeighbors, bool bAdjust) {
+	if (hcmvs_filter_depthmap(ctx, idxImage, idxNeighbors.data(), (int)idxNeighbors.size(), bAdjust ? 1 : 0, nullptr, nullptr) != HCMVS_OK) return Fail("hcmvs_filter_depthmap");
+	return true;
+}
+
+bool DepthMapsData::FuseDepthMaps(PointCloud& pc, bool bEstimateColor, bool bEstimateNormal) {
+	hcmvs_pointcloud out;
+	if (hcmvs_fuse_depthmaps(ctx, bEstimateColor, bEstimateNormal, &out) != HCMVS_OK) return Fail("hcmvs_fuse_depthmaps");
+	const size_t n = (size_t)out.n_points;
+	pc = PointCloud();
+	if (n) {
+		pc.points.assign(out.points, out.points+n*3);
+		pc.viewOffsets.assign(out.view_offsets, out.view_offsets+n+1);
+		const size_t m = out.view_offsets[n];
+		pc.views.assign(out.views, out.views+m);
+		pc.weights.assign(out.weights, out.weights+m);
+		if (out.normals) pc.normals.assign(out.normals, out.normals+n*3);
+		if (out.colors) pc.colors.assign(out.colors, out.colors+n*3);
+	}
+	hcmvs_free_pointcloud(&out);
+	return true;
+}
+
+bool DepthMapsData::SaveDepthMapRaw(uint32_t idxImage, const std::string& fileName) {
+	const Image& im = scene.images[idxImage];
+	const size_t n = (size_t)im.width*im.height;
+	std::vector<float> d(n), nrm(n*3), c(n); float dMin, dMax;
+	if (hcmvs_get_depthmap(ctx, idxImage, d.data(), nrm.data(), c.data(), &dMin, &dMax) != HCMVS_OK) return Fail("hcmvs_get_depthmap");
+	return ExportDepthDataRaw(fileName, im.name, arrDepthData[idxImage].images, im.width, im.height, im.camera.K, im.camera.R, im.camera.C,
+		dMin, dMax, im.width, im.height, d.data(), nrm.data(), c.data());
+}
+
+// ------------------------------------------------------------------------------------------------ file formats
+#pragma pack(push, 1)
+struct HeaderDepthDataRaw { // libs/MVS/Interface.h:634-652 (28 bytes)
+	uint16_t name; uint8_t type, padding; uint32_t imageWidth, imageHeight, depthWidth, depthHeight; float dMin, dMax;
+};
+#pragma pack(pop)
+static_assert(sizeof(HeaderDepthDataRaw) == 28, "HeaderDepthDataRaw layout");
+
+bool ExportDepthDataRaw(const std::string& fileName, const std::string& imageFileName, const std::vector<uint32_t>& IDs, int imageW, int imageH,
+	const double K[9], const double R[9], const double C[3], float dMin, float dMax, int w, int h,
+	const float* depth, const float* normal, const float* conf)
+{
+	// ExportDepthDataRaw, libs/MVS/DepthMap.cpp:2781-2846
+	FILE* f = fopen(fileName.c_str(), "wb");
+	if (!f) return false;
+	HeaderDepthDataRaw hd;
+	hd.name = 0x5244; // "DR" little endian
+	hd.type = 1 | (normal ? 2 : 0) | (conf ? 4 : 0); hd.padding = 0;
+	hd.imageWidth = (uint32_t)imageW; hd.imageHeight = (uint32_t)imageH; hd.depthWidth = (uint32_t)w; hd.depthHeight = (uint32_t)h;
+	hd.dMin = dMin; hd.dMax = dMax;
+	fwrite(&hd, sizeof(hd), 1, f);
+	const uint16_t nName = (uint16_t)imageFileName.size();
+	fwrite(&nName, 2, 1, f); fwrite(imageFileName.data(), 1, nName, f);
+	const uint32_t nIDs = (uint32_t)IDs.size();
+	fwrite(&nIDs, 4, 1, f); fwrite(IDs.data(), 4, nIDs, f);
+	fwrite(K, 8, 9, f); fwrite(R, 8, 9, f); fwrite(C, 8, 3, f);
+	const size_t n = (size_t)w*h;
+	fwrite(depth, 4, n, f);
+	if (normal) fwrite(normal, 12, n, f);
+	if (conf) fwrite(conf, 4, n, f);
+	const bool ok = ferror(f) == 0;
+	fclose(f);
+	return ok;
+}
+
+bool ImportDepthDataRaw(const std::string& fileName, std::string& imageFileName, std::vector<uint32_t>& IDs, int& imageW, int& imageH,
+	double K[9], double R[9], double C[3], float& dMin, float& dMax, int& w, int& h,
+	std::vector<float>& depth, std::vector<float>& normal, std::vector<float>& conf)
+{
+	// ImportDepthDataRaw, libs/MVS/DepthMap.cpp:2848-2925
+	FILE* f = fopen(fileName.c_str(), "rb");
+	if (!f) return false;
+	HeaderDepthDataRaw hd;
+	if (fread(&hd, sizeof(hd), 1, f) != 1 || hd.name != 0x5244 || (hd.type & 1) == 0 || hd.depthWidth == 0 || hd.depthHeight == 0 ||
+	    hd.imageWidth < hd.depthWidth || hd.imageHeight < hd.depthHeight) { fclose(f); return false; }
+	uint16_t nName = 0; bool ok = fread(&nName, 2, 1, f) == 1;
+	imageFileName.resize(nName); if (nName) ok = ok && fread(&imageFileName[0], 1, nName, f) == nName;
+	uint32_t nIDs = 0; ok = ok && fread(&nIDs, 4, 1, f) == 1;
+	if (!ok || nIDs > (1u<<20)) { fclose(f); return false; }
+	IDs.resize(nIDs); if (nIDs) ok = ok && fread(IDs.data(), 4, nIDs, f) == nIDs;
+	ok = ok && fread(K, 8, 9, f) == 9 && fread(R, 8, 9, f) == 9 && fread(C, 8, 3, f) == 3;
+	dMin = hd.dMin; dMax = hd.dMax; imageW = (int)hd.imageWidth; imageH = (int)hd.imageHeight; w = (int)hd.depthWidth; h = (int)hd.depthHeight;
+	const size_t n = (size_t)w*h;
+	depth.resize(n); ok = ok && fread(depth.data(), 4, n, f) == n;
+	normal.clear(); conf.clear();
+	if (hd.type & 2) { normal.resize(n*3); ok = ok && fread(normal.data(), 12, n, f) == n; }
+	if (hd.type & 4) { conf.resize(n); ok = ok && fread(conf.data(), 4, n, f) == n; }
+	fclose(f);
+	return ok;
+}
+
+bool PointCloud::Save(const std::string& fileName) const {
+	// PointCloud::Save, libs/MVS/PointCloud.cpp:188-242 with BasicPLY::vert_props (:105-131); header text as
+	// PLY::header_complete writes it (libs/IO/PLY.cpp:269-338, new-style type names)
+	const size_t n = size();
+	if (!n) return false;
+	FILE* f = fopen(fileName.c_str(), "wb");
+	if (!f) return false;
+	const bool hasN = !normals.empty();
+	fprintf(f, "ply\nformat binary_little_endian 1.0\nelement vertex %d\n", (int)n);
+	fprintf(f, "property float32 x\nproperty float32 y\nproperty float32 z\nproperty uint8 red\nproperty uint8 green\nproperty uint8 blue\n");
+	if (hasN) fprintf(f, "property float32 nx\nproperty float32 ny\nproperty float32 nz\n");
+	fprintf(f, "end_header\n");
+	std::vector<uint8_t> rec(hasN ? 27 : 15);
+	for (size_t i=0; i<n; ++i) {
+		memcpy(&rec[0], &points[i*3], 12);
+		if (!colors.empty()) { rec[12] = colors[i*3+2]; rec[13] = colors[i*3+1]; rec[14] = colors[i*3]; } // stored b,g,r
+		else rec[12] = rec[13] = rec[14] = 255; // Color::WHITE
+		if (hasN) memcpy(&rec[15], &normals[i*3], 12);
+		fwrite(rec.data(), 1, rec.size(), f);
+	}
+	const bool ok = ferror(f) == 0;
+	fclose(f);
+	return ok;
+}
+
+// ------------------------------------------------------------------------------------------------ driver
+bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, const ViewSelectionParams& VS, uint64_t seed, bool runFilter,
+	const std::string& dmapDir, DenseReconstructionStats* stats, std::string* err)
+{
+	// Scene::DenseReconstruction -> ComputeDepthMaps (SceneDensify.cpp:3532-3730) -> FuseDepthMaps (:3544)
+	DenseReconstructionStats st;
+	DepthMapsData data(scene, ctx, P, VS);
+	auto fail = [&](const std::string& m) { if (err) *err = m; return false; };
+	double t0 = Now();
+	const uint32_t nImages = (uint32_t)scene.images.size();
+	for (Image& im: scene.images) im.camera.ComposeP();
+	std::vector<uint32_t> valid;
+	for (uint32_t i=0; i<nImages; ++i) if (data.SelectViews(i)) valid.push_back(i); // :3652-3667
+	if (valid.empty()) return fail("no image has enough neighbour views");
+	double t1 = Now(); st.secSelect = t1-t0;
+	for (uint32_t i: valid) {
+		if (!data.InitViews(i, P.nNumViews)) { if (!data.lastError.empty()) return fail(data.lastError); data.arrDepthData[i].valid = false; }
+	}
+	for (uint32_t i=0; i<nImages; ++i) {
+		const Image& im = scene.images[i];
+		if (data.arrDepthData[i].uploaded) st.h2dBytes += (uint64_t)im.width*im.height*(4+(im.bgr.empty() ? 0 : 3));
+	}
+	double t2 = Now(); st.secUpload = t2-t1;
+	for (unsigned it=0; it<P.nEstimationIters_external; ++it) // :3684
+		for (uint32_t i: valid) {
+			if (!data.arrDepthData[i].valid) continue;
+			if (!data.EstimateDepthMap((int)it, i, seed)) return fail(data.lastError);
+			if (it == 0) st.h2dBytes += (uint64_t)scene.images[i].width*scene.images[i].height*4;
+		}
+	if (hcmvs_sync(ctx) != HCMVS_OK) return fail(hcmvs_last_error());
+	double t3 = Now(); st.secEstimate = t3-t2;
+	if (!dmapDir.empty())
+		for (uint32_t i: valid) if (data.arrDepthData[i].valid) {
+			char name[64]; snprintf(name, sizeof(name), "/depth%04u.dmap", i);
+			if (!data.SaveDepthMapRaw(i, dmapDir+name)) return fail("cannot write "+dmapDir+name);
+			st.d2hBytes += (uint64_t)scene.images[i].width*scene.images[i].height*20;
+		}
+	if (runFilter) {
+		// Scene::DenseReconstructionFilter, SceneDensify.cpp:4093-4185: neighbours = those with a depth map, at most 8
+		for (uint32_t i: valid) {
+			const DepthData& dd = data.arrDepthData[i];
+			if (!dd.valid) continue;
+			std::vector<uint32_t> idxNb;
+			for (uint32_t k=0; k<dd.neighbors.size() && idxNb.size() < 8; ++k) if (data.arrDepthData[dd.neighbors[k].ID].valid) idxNb.push_back(k);
+			if (idxNb.size() < std::min(P.nMinViewsFilter, scene.nCalibratedImages()-1)) continue;
+			if (!data.FilterDepthMap(i, idxNb, P.bFilterAdjust != 0)) return fail(data.lastError);
+		}
+		if (hcmvs_commit_filtered(ctx) != HCMVS_OK) return fail(hcmvs_last_error());
+		if (hcmvs_sync(ctx) != HCMVS_OK) return fail(hcmvs_last_error());
+	}
+	double t4 = Now(); st.secFilter = t4-t3;
+	if (!data.FuseDepthMaps(scene.densecloud, true, true)) return fail(data.lastError);
+	st.d2hBytes += (uint64_t)scene.densecloud.size()*(12+12+3+4)+(uint64_t)scene.densecloud.views.size()*8;
+	st.secFuse = Now()-t4;
+	if (stats) *stats = st;
+	return true;
+}
+
+} // namespace hcmvs_host

@@ -1,0 +1,112 @@
+// Host-side mirror of the reference's operator surface over the C ABI (include/hcmvs_b200.h).
+//
+//   reference                                               here
+//   MVS::Scene (libs/MVS/Scene.h:52-116)                    hcmvs_host::Scene
+//   MVS::DepthMapsData (libs/MVS/SceneDensify.h:49-88)      hcmvs_host::DepthMapsData  (same method names)
+//   Scene::DenseReconstruction (SceneDensify.cpp:3532-3574) hcmvs_host::DenseReconstruction
+//
+// Everything numeric on the hot path runs in libhcmvs_b200.so (CUDA); this layer keeps what the
+// reference keeps on the host: scene bookkeeping, neighbour-view selection (Scene::SelectNeighborViews,
+// Scene.cpp:545-662 — host code in the reference too, bit-exact parity required), image preparation,
+// the sparse-point depth initialisation, and the .dmap / .ply writers.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "hcmvs_b200.h"
+
+namespace hcmvs_host {
+
+struct Camera {
+	double K[9], R[9], C[3], P[12]; // P = K R [I|-C], libs/MVS/Camera.h:46-54
+	void ComposeP();
+};
+
+struct ViewScore { // MVS::ViewScore = TIndexScore<ViewInfo,float>, libs/MVS/Image.h:52-71
+	uint32_t ID, points;
+	float scale, angle, area, score;
+};
+
+struct Image {
+	int width = 0, height = 0;
+	Camera camera;
+	std::string name;
+	std::vector<uint8_t> bgr;    // height*width*3 (may be empty)
+	std::vector<float> gray;     // Image::toGray(BGR2GRAY, normalised), Common/Types.inl:2352-2402
+	std::vector<ViewScore> neighbors; // all scored neighbours, best first (Image::neighbors)
+	float avgDepth = 0;
+};
+
+struct SparsePoints { // the part of MVS::PointCloud the densifier reads
+	std::vector<float> xyz;                      // 3 per point
+	std::vector<std::vector<uint32_t>> views;    // sorted view ids per point
+	size_t size() const { return views.size(); }
+};
+
+struct PointCloud { // fused output, libs/MVS/PointCloud.h:49-109
+	std::vector<float> points, normals, weights;
+	std::vector<uint8_t> colors;
+	std::vector<uint32_t> viewOffsets, views;
+	size_t size() const { return points.size()/3; }
+	bool Save(const std::string& fileName) const; // PointCloud::Save, PointCloud.cpp:188-242 (binary little-endian PLY)
+};
+
+struct Scene {
+	std::vector<Image> images;
+	SparsePoints pointcloud;
+	PointCloud densecloud;
+	unsigned nCalibratedImages() const { return (unsigned)images.size(); }
+	// Scene::SelectNeighborViews / FilterNeighborViews, libs/MVS/Scene.cpp:545-678
+	bool SelectNeighborViews(uint32_t ID, std::vector<uint32_t>& points, unsigned nMinViews, unsigned nMinPointViews, float fOptimAngle);
+	static bool FilterNeighborViews(std::vector<ViewScore>& neighbors, float fMinArea, float fMinScale, float fMaxScale, float fMinAngle, float fMaxAngle, unsigned nMaxViews);
+};
+
+struct DepthData { // host part of MVS::DepthData, libs/MVS/DepthMap.h:214-347
+	std::vector<uint32_t> images;     // [0] = reference, [1..] = matching views
+	std::vector<ViewScore> neighbors; // filtered, <= nMaxViews
+	std::vector<uint32_t> points;
+	float dMin = 0, dMax = 0;
+	bool valid = false, uploaded = false;
+};
+
+struct ViewSelectionParams { // OPTDENSE fields SelectViews reads, DepthMap.cpp:69-143
+	float fViewMinScore = 0.f, fViewMinScoreRatio = 0.3f;
+	float fMinArea = 0.01f, fMinAngle = 3.f, fOptimAngle = 10.f, fMaxAngle = 65.f;
+};
+
+void ToGray(const uint8_t* bgr, int w, int h, float* gray);
+// sparse-point initialisation of a depth map (SceneDensify.cpp:783-808)
+void SparseInitDepth(const Scene& scene, uint32_t idxImage, const std::vector<uint32_t>& points, std::vector<float>& depth, float& dMin, float& dMax);
+
+class DepthMapsData {
+public:
+	DepthMapsData(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& params, const ViewSelectionParams& vs = ViewSelectionParams());
+	bool SelectViews(uint32_t idxImage);                                   // SceneDensify.cpp:307-327
+	bool InitViews(uint32_t idxImage, uint32_t numNeighbors);              // SceneDensify.cpp:336-397
+	bool InitDepthMap(uint32_t idxImage);                                  // SceneDensify.cpp:772-808 (sparse-point splat branch)
+	bool EstimateDepthMap(int it_external, uint32_t idxImage, uint64_t seed); // SceneDensify.cpp:758-1072
+	bool FilterDepthMap(uint32_t idxImage, const std::vector<uint32_t>& idxNeighbors, bool bAdjust); // SceneDensify.cpp:3006-3259
+	bool FuseDepthMaps(PointCloud& pointcloud, bool bEstimateColor, bool bEstimateNormal);           // SceneDensify.cpp:3265-3495
+	// raw "DR" depth-data file, ExportDepthDataRaw, DepthMap.cpp:2781-2846
+	bool SaveDepthMapRaw(uint32_t idxImage, const std::string& fileName);
+	bool UploadView(uint32_t idxImage);
+	std::vector<DepthData> arrDepthData;
+	std::string lastError;
+private:
+	Scene& scene; hcmvs_ctx* ctx; hcmvs_params P; ViewSelectionParams VS;
+	bool Fail(const char* what);
+};
+
+struct DenseReconstructionStats { double secSelect = 0, secUpload = 0, secEstimate = 0, secFilter = 0, secFuse = 0; uint64_t h2dBytes = 0, d2hBytes = 0; };
+// Scene::DenseReconstruction, SceneDensify.cpp:3532-3574 (+ the optional filter stage, :3722-3760)
+bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, const ViewSelectionParams& VS, uint64_t seed, bool runFilter,
+	const std::string& dmapDir, DenseReconstructionStats* stats, std::string* err);
+
+bool ExportDepthDataRaw(const std::string& fileName, const std::string& imageFileName, const std::vector<uint32_t>& IDs, int imageW, int imageH,
+	const double K[9], const double R[9], const double C[3], float dMin, float dMax, int w, int h,
+	const float* depth, const float* normal, const float* conf);
+bool ImportDepthDataRaw(const std::string& fileName, std::string& imageFileName, std::vector<uint32_t>& IDs, int& imageW, int& imageH,
+	double K[9], double R[9], double C[3], float& dMin, float& dMax, int& w, int& h,
+	std::vector<float>& depth, std::vector<float>& normal, std::vector<float>& conf);
+
+} // namespace hcmvs_host

@@ -1,0 +1,137 @@
+// C handle API over densify.h — see include/hcmvs_host.h.
+#include "hcmvs_host.h"
+#include "densify.h"
+#include <cstring>
+#include <algorithm>
+
+using namespace hcmvs_host;
+
+struct hcmvs_host_scene {
+	Scene scene;
+	std::vector<DepthData> dd;
+	std::string err;
+};
+
+extern "C" {
+
+hcmvs_host_scene* hcmvs_host_scene_create(void) { return new hcmvs_host_scene(); }
+void hcmvs_host_scene_destroy(hcmvs_host_scene* s) { delete s; }
+const char* hcmvs_host_last_error(hcmvs_host_scene* s) { return s ? s->err.c_str() : "null scene"; }
+
+int hcmvs_host_add_image(hcmvs_host_scene* s, int w, int h, const double K[9], const double R[9], const double C[3], const uint8_t* bgr, const char* name) {
+	if (!s || !K || !R || !C || !bgr || w <= 0 || h <= 0) return -1;
+	Image im; im.width = w; im.height = h;
+	memcpy(im.camera.K, K, 72); memcpy(im.camera.R, R, 72); memcpy(im.camera.C, C, 24);
+	im.camera.ComposeP();
+	im.bgr.assign(bgr, bgr+(size_t)w*h*3);
+	im.gray.resize((size_t)w*h);
+	ToGray(bgr, w, h, im.gray.data());
+	if (name) im.name = name;
+	s->scene.images.push_back(std::move(im));
+	return (int)s->scene.images.size()-1;
+}
+
+int hcmvs_host_set_sparse(hcmvs_host_scene* s, int n, const float* xyz, const int32_t* offsets, const uint32_t* view_ids) {
+	if (!s || n < 0) return -1;
+	SparsePoints& pc = s->scene.pointcloud;
+	pc.xyz.assign(xyz, xyz+(size_t)n*3);
+	pc.views.resize(n);
+	for (int i=0; i<n; ++i) { pc.views[i].assign(view_ids+offsets[i], view_ids+offsets[i+1]); std::sort(pc.views[i].begin(), pc.views[i].end()); }
+	return 0;
+}
+
+int hcmvs_host_select_views(hcmvs_host_scene* s, const hcmvs_params* p, int idx) {
+	if (!s || !p || idx < 0 || idx >= (int)s->scene.images.size()) return -1;
+	DepthMapsData data(s->scene, nullptr, *p);
+	if (!data.SelectViews((uint32_t)idx)) return -1;
+	if (s->dd.size() != s->scene.images.size()) s->dd.resize(s->scene.images.size());
+	s->dd[idx] = data.arrDepthData[idx];
+	return (int)s->dd[idx].neighbors.size();
+}
+
+int hcmvs_host_get_neighbors(hcmvs_host_scene* s, int idx, int which, uint32_t* ids, uint32_t* points, float* scale, float* angle, float* area, float* score, int cap) {
+	if (!s || idx < 0 || idx >= (int)s->scene.images.size()) return -1;
+	static const std::vector<ViewScore> empty;
+	const std::vector<ViewScore>& v = which == 0 ? s->scene.images[idx].neighbors : (idx < (int)s->dd.size() ? s->dd[idx].neighbors : empty);
+	for (int i=0; i<std::min((int)v.size(), cap); ++i) {
+		if (ids) ids[i] = v[i].ID;
+		if (points) points[i] = v[i].points;
+		if (scale) scale[i] = v[i].scale;
+		if (angle) angle[i] = v[i].angle;
+		if (area) area[i] = v[i].area;
+		if (score) score[i] = v[i].score;
+	}
+	return (int)v.size();
+}
+
+int hcmvs_host_init_depth(hcmvs_host_scene* s, int idx, float* depth, float* dminmax) {
+	if (!s || idx < 0 || idx >= (int)s->dd.size() || !s->dd[idx].valid) return -1;
+	std::vector<float> d; float a, b;
+	SparseInitDepth(s->scene, (uint32_t)idx, s->dd[idx].points, d, a, b);
+	memcpy(depth, d.data(), d.size()*4);
+	dminmax[0] = a; dminmax[1] = b;
+	return 0;
+}
+
+int hcmvs_host_get_gray(hcmvs_host_scene* s, int idx, float* gray) {
+	if (!s || idx < 0 || idx >= (int)s->scene.images.size()) return -1;
+	const Image& im = s->scene.images[idx];
+	memcpy(gray, im.gray.data(), im.gray.size()*4);
+	return 0;
+}
+
+int hcmvs_host_dense_reconstruction(hcmvs_host_scene* s, hcmvs_ctx* ctx, const hcmvs_params* p, uint64_t seed, int run_filter, const char* dmap_dir, double* stats) {
+	if (!s || !ctx || !p) return -1;
+	DenseReconstructionStats st;
+	for (Image& im: s->scene.images) im.neighbors.clear();
+	if (!DenseReconstruction(s->scene, ctx, *p, ViewSelectionParams(), seed, run_filter != 0, dmap_dir ? dmap_dir : "", &st, &s->err)) return -2;
+	if (stats) {
+		stats[0] = st.secSelect; stats[1] = st.secUpload; stats[2] = st.secEstimate; stats[3] = st.secFilter; stats[4] = st.secFuse;
+		stats[5] = (double)st.h2dBytes; stats[6] = (double)st.d2hBytes; stats[7] = (double)s->scene.densecloud.size();
+	}
+	return 0;
+}
+
+int hcmvs_host_cloud_size(hcmvs_host_scene* s, uint64_t* n_points, uint64_t* n_view_refs) {
+	if (!s) return -1;
+	if (n_points) *n_points = s->scene.densecloud.size();
+	if (n_view_refs) *n_view_refs = s->scene.densecloud.views.size();
+	return 0;
+}
+int hcmvs_host_cloud_get(hcmvs_host_scene* s, float* xyz, float* normals, uint8_t* colors, uint32_t* view_offsets, uint32_t* views, float* weights) {
+	if (!s) return -1;
+	const PointCloud& pc = s->scene.densecloud;
+	if (xyz) memcpy(xyz, pc.points.data(), pc.points.size()*4);
+	if (normals && !pc.normals.empty()) memcpy(normals, pc.normals.data(), pc.normals.size()*4);
+	if (colors && !pc.colors.empty()) memcpy(colors, pc.colors.data(), pc.colors.size());
+	if (view_offsets) memcpy(view_offsets, pc.viewOffsets.data(), pc.viewOffsets.size()*4);
+	if (views) memcpy(views, pc.views.data(), pc.views.size()*4);
+	if (weights) memcpy(weights, pc.weights.data(), pc.weights.size()*4);
+	return 0;
+}
+int hcmvs_host_cloud_save_ply(hcmvs_host_scene* s, const char* file) { return (s && file && s->scene.densecloud.Save(file)) ? 0 : -1; }
+
+int hcmvs_host_write_dmap(const char* file, const char* image_name, const uint32_t* ids, int n_ids, int image_w, int image_h,
+	const double K[9], const double R[9], const double C[3], float dmin, float dmax, int w, int h, const float* depth, const float* normal, const float* conf)
+{
+	std::vector<uint32_t> IDs(ids, ids+n_ids);
+	return ExportDepthDataRaw(file, image_name ? image_name : "", IDs, image_w, image_h, K, R, C, dmin, dmax, w, h, depth, normal, conf) ? 0 : -1;
+}
+int hcmvs_host_read_dmap_header(const char* file, int* w, int* h, int* n_ids, int* has_normal, int* has_conf) {
+	std::string name; std::vector<uint32_t> IDs; int iw, ih, ww, hh; double K[9], R[9], C[3]; float a, b; std::vector<float> d, n, c;
+	if (!ImportDepthDataRaw(file, name, IDs, iw, ih, K, R, C, a, b, ww, hh, d, n, c)) return -1;
+	*w = ww; *h = hh; *n_ids = (int)IDs.size(); *has_normal = !n.empty(); *has_conf = !c.empty();
+	return 0;
+}
+int hcmvs_host_read_dmap(const char* file, uint32_t* ids, double K[9], double R[9], double C[3], float* dminmax, float* depth, float* normal, float* conf) {
+	std::string name; std::vector<uint32_t> IDs; int iw, ih, ww, hh; float a, b; std::vector<float> d, n, c;
+	if (!ImportDepthDataRaw(file, name, IDs, iw, ih, K, R, C, a, b, ww, hh, d, n, c)) return -1;
+	if (ids) memcpy(ids, IDs.data(), IDs.size()*4);
+	if (dminmax) { dminmax[0] = a; dminmax[1] = b; }
+	if (depth) memcpy(depth, d.data(), d.size()*4);
+	if (normal && !n.empty()) memcpy(normal, n.data(), n.size()*4);
+	if (conf && !c.empty()) memcpy(conf, c.data(), c.size()*4);
+	return 0;
+}
+
+} // extern "C"

@@ -62,6 +62,7 @@ typedef struct hcmvs_timers {
 	uint64_t n_hypotheses;     /* ScorePixel evaluations inside the sweeps */
 	uint64_t n_pixel_iters;    /* pixels processed x PatchMatch iterations inside the sweeps */
 	uint64_t n_view_scores;    /* ScorePixelImage evaluations inside the sweeps */
+	uint64_t n_smooth_terms;   /* smoothness-neighbour terms evaluated inside the sweeps (sum over hypotheses) */
 	uint32_t n_launches;       /* kernels launched */
 	uint64_t n_fuse_rounds;    /* reserve/commit rounds of the last hcmvs_fuse_depthmaps */
 } hcmvs_timers;
@@ -126,6 +127,10 @@ void hcmvs_free_pointcloud(hcmvs_pointcloud* pc);
  * dn_d = float4 (nx,ny,nz,depth) per pixel, conf_d = float per pixel. */
 int hcmvs_get_depthmap_device(hcmvs_ctx* ctx, uint32_t view, void** dn_d, void** conf_d, float* dMin, float* dMax);
 int hcmvs_set_depth_range(hcmvs_ctx* ctx, uint32_t view, float dMin, float dMax);
+/* Device-to-device copies of a view's maps out of / into caller-owned device buffers (e.g. NCCL send/receive
+ * slots): dn_d holds H*W float4 (nx,ny,nz,depth), conf_d holds H*W float. Enqueued on the context stream. */
+int hcmvs_export_maps_d(hcmvs_ctx* ctx, uint32_t view, void* dn_d, void* conf_d);
+int hcmvs_import_maps_d(hcmvs_ctx* ctx, uint32_t view, const void* dn_d, const void* conf_d, float dMin, float dMax);
 /* Allocate (zeroed) device maps for a view without uploading — receive buffers for the exchange. */
 int hcmvs_alloc_depthmap(hcmvs_ctx* ctx, uint32_t view);
 

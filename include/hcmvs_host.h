@@ -1,0 +1,44 @@
+/* C handle API over the host-side mirror (hc-mvs_b200/host/densify.h) — what a Python / C caller drives.
+ * The C++ classes in densify.h are the drop-in for C++ callers (same method names as MVS::DepthMapsData). */
+#ifndef HCMVS_HOST_H_
+#define HCMVS_HOST_H_
+#include <stdint.h>
+#include "hcmvs_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hcmvs_host_scene hcmvs_host_scene;
+
+hcmvs_host_scene* hcmvs_host_scene_create(void);
+void hcmvs_host_scene_destroy(hcmvs_host_scene* s);
+const char* hcmvs_host_last_error(hcmvs_host_scene* s);
+/* MVS::Image + camera (libs/MVS/Image.h, Camera.h). bgr: H*W*3 u8. Returns the image index. */
+int hcmvs_host_add_image(hcmvs_host_scene* s, int w, int h, const double K[9], const double R[9], const double C[3], const uint8_t* bgr, const char* name);
+/* Sparse MVS::PointCloud (points + per-point view lists, CSR). */
+int hcmvs_host_set_sparse(hcmvs_host_scene* s, int n, const float* xyz, const int32_t* offsets, const uint32_t* view_ids);
+/* DepthMapsData::SelectViews for one image (host only, needs no device). Returns #filtered neighbours or -1. */
+int hcmvs_host_select_views(hcmvs_host_scene* s, const hcmvs_params* p, int idx);
+/* which: 0 = Image::neighbors (all scored), 1 = DepthData::neighbors (filtered). Returns the list length. */
+int hcmvs_host_get_neighbors(hcmvs_host_scene* s, int idx, int which, uint32_t* ids, uint32_t* points, float* scale, float* angle, float* area, float* score, int cap);
+/* sparse-point initial depth map + depth range of a selected view (SceneDensify.cpp:783-808) */
+int hcmvs_host_init_depth(hcmvs_host_scene* s, int idx, float* depth, float* dminmax);
+int hcmvs_host_get_gray(hcmvs_host_scene* s, int idx, float* gray);
+/* Scene::DenseReconstruction (SceneDensify.cpp:3532-3574) through the C ABI with HOST buffers.
+ * stats[8] = sec select, upload, estimate, filter, fuse, h2d bytes, d2h bytes, #points. dmap_dir may be NULL. */
+int hcmvs_host_dense_reconstruction(hcmvs_host_scene* s, hcmvs_ctx* ctx, const hcmvs_params* p, uint64_t seed, int run_filter, const char* dmap_dir, double* stats);
+/* fused cloud access */
+int hcmvs_host_cloud_size(hcmvs_host_scene* s, uint64_t* n_points, uint64_t* n_view_refs);
+int hcmvs_host_cloud_get(hcmvs_host_scene* s, float* xyz, float* normals, uint8_t* colors, uint32_t* view_offsets, uint32_t* views, float* weights);
+int hcmvs_host_cloud_save_ply(hcmvs_host_scene* s, const char* file);
+/* raw "DR" depth-data files (MVS::ExportDepthDataRaw / ImportDepthDataRaw, DepthMap.cpp:2781-2925) */
+int hcmvs_host_write_dmap(const char* file, const char* image_name, const uint32_t* ids, int n_ids, int image_w, int image_h,
+                          const double K[9], const double R[9], const double C[3], float dmin, float dmax, int w, int h,
+                          const float* depth, const float* normal, const float* conf);
+int hcmvs_host_read_dmap_header(const char* file, int* w, int* h, int* n_ids, int* has_normal, int* has_conf);
+int hcmvs_host_read_dmap(const char* file, uint32_t* ids, double K[9], double R[9], double C[3], float* dminmax, float* depth, float* normal, float* conf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
