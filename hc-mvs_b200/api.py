@@ -34,7 +34,7 @@ class Params(C.Structure):
         ("fDepthDiffThreshold", C.c_float), ("fNormalDiffThreshold", C.c_float), ("depthweight", C.c_float), ("normalweight", C.c_float),
         ("adapthalfwin", C.c_int32), ("propagatehalfwin", C.c_int32), ("propagatestep", C.c_int32), ("photo2geo", C.c_int32),
         ("photometric_flow", C.c_float), ("para_prior", C.c_float), ("fsigmaPrior", C.c_float),
-        ("rb_far_reach", C.c_int32), ("sampler", C.c_int32),
+        ("rb_far_reach", C.c_int32), ("rb_prop_dirs", C.c_int32), ("sampler", C.c_int32),
     ]
 
 

@@ -33,7 +33,7 @@ extern "C" void hcmvs_default_params(hcmvs_params* p) {
 	p->fDepthDiffThreshold = 0.01f; p->fNormalDiffThreshold = 25.f; p->depthweight = 1.f; p->normalweight = 1.f;
 	p->adapthalfwin = 5; p->propagatehalfwin = 1; p->propagatestep = 4; p->photo2geo = 2;
 	p->photometric_flow = 0.f; p->para_prior = 0.3f; p->fsigmaPrior = 0.2f;
-	p->rb_far_reach = 11; p->sampler = 0;
+	p->rb_far_reach = 11; p->rb_prop_dirs = 2; p->sampler = 0;
 }
 
 // ------------------------------------------------------------------------------------------------ context
@@ -41,6 +41,7 @@ static int CheckParams(const hcmvs_params& p) {
 	if (p.adapthalfwin < 1 || p.adapthalfwin > 7) { hcmvs_set_error("adapthalfwin must be in [1,7] (reference nTexels = 64, DepthMap.h:358)"); return HCMVS_ERR_ARG; }
 	if (p.nRandomIters > 64 || p.nEstimationIters > 60) { hcmvs_set_error("iteration counts out of range"); return HCMVS_ERR_ARG; }
 	if (p.rb_far_reach < 1) { hcmvs_set_error("rb_far_reach must be >= 1"); return HCMVS_ERR_ARG; }
+	if (p.rb_prop_dirs != 2 && p.rb_prop_dirs != 4) { hcmvs_set_error("rb_prop_dirs must be 2 or 4"); return HCMVS_ERR_ARG; }
 	if (!(p.fNCCThresholdKeep > 0.f)) { hcmvs_set_error("fNCCThresholdKeep must be > 0"); return HCMVS_ERR_ARG; }
 	return HCMVS_OK;
 }
@@ -385,7 +386,7 @@ static int BuildRefConst(hcmvs_ctx* ctx, View* v, uint32_t ref, int it_external,
 	{ const float r = FD2R(P.fRandomSmoothNormal); rc.smoothSigmaNormal = -1.f/(2.f*(r*r)); }
 	rc.angle1Range = FD2R(P.fRandomAngle1Range); rc.angle2Range = FD2R(P.fRandomAngle2Range);
 	rc.depthRatio = P.fRandomDepthRatio;
-	rc.nRandomIters = (int)P.nRandomIters; rc.adapthalfwin = P.adapthalfwin; rc.farReach = P.rb_far_reach;
+	rc.nRandomIters = (int)P.nRandomIters; rc.adapthalfwin = P.adapthalfwin; rc.farReach = P.rb_far_reach; rc.propDirs = P.rb_prop_dirs;
 	rc.it_external = it_external; rc.photo2geo = P.photo2geo;
 	rc.photometric_flow = P.photometric_flow; rc.para_prior = P.para_prior; rc.sigmaPrior = P.fsigmaPrior;
 	rc.key0 = (uint32_t)seed; rc.key1 = (uint32_t)(seed>>32)^(ref*0x9E3779B9u);

@@ -7,6 +7,12 @@
 #define HCMVS_HW 7                      // DepthEstimator::nSizeHalfWindow (libs/MVS/DepthMap.h:354)
 #define HCMVS_MAXV HCMVS_MAX_MATCH_VIEWS
 #define HCMVS_NT 128                    // threads per CTA of the scoring kernels
+#ifndef HCMVS_MINB
+#define HCMVS_MINB 3
+#endif
+#ifndef HCMVS_EARLY_REJECT
+#define HCMVS_EARLY_REJECT 0
+#endif
 
 // per matching-neighbour constants (DepthEstimator::ViewData, DepthMap.h:412-444)
 struct NbViewConst {
@@ -34,7 +40,7 @@ struct RefConst {
 	float keep, thRobust, thConfSmall, thConfBig, thConfRand;
 	float smoothBonusDepth, smoothBonusNormal, smoothSigmaDepth, smoothSigmaNormal;
 	float angle1Range, angle2Range, depthRatio;
-	int nRandomIters, adapthalfwin, farReach, it_external, photo2geo;
+	int nRandomIters, adapthalfwin, farReach, propDirs, it_external, photo2geo;
 	float photometric_flow, para_prior, sigmaPrior;
 	uint32_t key0, key1, pass;
 	unsigned long long* counters; // [0] hypotheses, [1] view scores, [2] pixel-iterations

@@ -40,6 +40,7 @@ typedef struct hcmvs_params {
 	float photometric_flow, para_prior, fsigmaPrior;
 	/* B200 reformulation knobs (no reference counterpart) */
 	int32_t rb_far_reach;   /* red-black propagation: per direction the best-confidence pixel among odd offsets 1..rb_far_reach */
+	int32_t rb_prop_dirs;   /* 2 (default): one source per image axis = the reference's 2 propagation hypotheses per pixel-iteration; 4: one per direction */
 	int32_t sampler;        /* 0 = texture gather path (default), 1 = global-memory loads */
 } hcmvs_params;
 

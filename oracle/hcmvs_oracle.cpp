@@ -899,6 +899,7 @@ static void RBProcessPixel(DepthEstimator& est, int px, int py, const uint32_t k
 	// propagation: one source per direction
 	static const int DX[4] = {-1, 0, 1, 0}, DY[4] = {0, -1, 0, 1};
 	const int reach = cfg.useFar ? cfg.farReach : 1;
+	int srcX[4], srcY[4]; float srcC[4];
 	for (int dirn=0; dirn<4; ++dirn) {
 		int bx = -1, by = -1; float bconf = P.fNCCThresholdKeep;
 		for (int k=1; k<=reach; k+=2) {
@@ -908,6 +909,18 @@ static void RBProcessPixel(DepthEstimator& est, int px, int py, const uint32_t k
 			const float c = confMap0.at(nx, ny);
 			if (c < bconf) { bconf = c; bx = nx; by = ny; }
 		}
+		srcX[dirn] = bx; srcY[dirn] = by; srcC[dirn] = bconf;
+	}
+	if (cfg.nDirs == 2) {
+		// one source per axis: the better of the two opposite directions (ties: left / up)
+		for (int a=0; a<2; ++a) {
+			const int d0 = a, d1 = a+2;
+			if (srcX[d1] >= 0 && (srcX[d0] < 0 || srcC[d1] < srcC[d0])) { srcX[d0] = srcX[d1]; srcY[d0] = srcY[d1]; srcC[d0] = srcC[d1]; }
+			srcX[d1] = -1;
+		}
+	}
+	for (int dirn=0; dirn<4; ++dirn) {
+		const int bx = srcX[dirn], by = srcY[dirn];
 		if (bx < 0) continue;
 		Depth nd = depthMap0.at(bx, by); Vec3f nn = normalMap0[(size_t)by*w+bx];
 		nd = est.InterpolatePixel(bx, by, nd, nn);

@@ -1,0 +1,88 @@
+"""GPU parity of FilterDepthMap and FuseDepthMaps against the CPU oracle: integer / index work is bit-exact,
+and because the GPU fusion reproduces the CPU's sequential claim order the whole cloud must be identical."""
+import numpy as np
+import pytest
+
+import common
+
+pytestmark = pytest.mark.gpu
+
+
+def noisy_maps(gt, seed, outliers=0.02, sigma=0.002):
+    """C5-style maps: GT depth * (1 + N(0, sigma)), a few outliers, rotated normals, conf ~ U(0.5, 1)."""
+    rng = np.random.default_rng(seed)
+    d, n = gt
+    h, w = d.shape
+    valid = d > 0
+    depth = (d * (1 + sigma * rng.standard_normal((h, w)))).astype(np.float32)
+    out = rng.uniform(size=(h, w)) < outliers
+    depth[out] = rng.uniform(d[valid].min() * 0.8, d[valid].max() * 1.2, int(out.sum())).astype(np.float32)
+    depth[rng.uniform(size=(h, w)) < 0.05] = 0          # holes
+    depth[~valid] = 0
+    nn = n.astype(np.float64) + 0.05 * rng.standard_normal((h, w, 3))
+    nn /= np.maximum(np.linalg.norm(nn, axis=2, keepdims=True), 1e-9)
+    conf = rng.uniform(0.5, 1.0, (h, w)).astype(np.float32)
+    conf[depth == 0] = 0
+    return depth, nn.astype(np.float32), conf
+
+
+@pytest.fixture(scope="module")
+def loaded():
+    syn, osc, gt, imgs, ok = common.make_scene(2, 0.2, 12)
+    ctx = common.make_context(syn, osc, imgs, ok)
+    maps = [noisy_maps(gt[i], 100 + i) for i in range(syn.n_views)]
+    yield syn, osc, ctx, maps, ok
+    ctx.close()
+
+
+def load_maps(syn, osc, ctx, maps):
+    for i in range(syn.n_views):
+        d, n, c = maps[i]
+        lo, hi = float(d[d > 0].min() * 0.5), float(d.max() * 2.0)
+        osc.set_depthmap(i, d, n, c, lo, hi)
+        ctx.set_depthmap(i, d, n, c, lo, hi)
+
+
+@pytest.mark.parametrize("adjust", [True, False])
+def test_filter_depthmap_bit_exact(loaded, adjust):
+    syn, osc, ctx, maps, ok = loaded
+    load_maps(syn, osc, ctx, maps)
+    for ref in (0, 5):
+        nb = list(range(min(8, len(osc.neighbors(ref, 1)["ids"]))))
+        want = osc.filter(ref, nb, adjust)
+        got = ctx.filter_depthmap(ref, nb, adjust)
+        assert want is not None
+        assert np.array_equal(want[0] == 0, got[0] == 0), "kept/discarded pixel sets differ"
+        assert np.array_equal(want[0], got[0]), np.abs(want[0] - got[0]).max()
+        assert np.array_equal(want[1], got[1]), np.abs(want[1] - got[1]).max()
+        assert (want[0] > 0).sum() > 1000  # the case is not vacuous
+
+
+def test_fuse_depthmaps_identical_cloud(loaded):
+    syn, osc, ctx, maps, ok = loaded
+    load_maps(syn, osc, ctx, maps)
+    want = osc.fuse(True, True)
+    got = ctx.fuse_depthmaps(True, True)
+    assert len(want["xyz"]) > 10000
+    assert len(want["xyz"]) == len(got["xyz"]), (len(want["xyz"]), len(got["xyz"]))
+    assert np.array_equal(want["n_views"], got["n_views"])
+    assert np.array_equal(want["views"], got["views"])          # claim bookkeeping: exact
+    assert np.array_equal(want["xyz"], got["xyz"])               # f64 accumulation, un-fused: exact
+    assert np.array_equal(want["weights"], got["weights"])
+    assert np.array_equal(want["colors"], got["colors"])
+    assert np.array_equal(want["normals"], got["normals"])
+    # fusion zeroes occluded depths in place (SceneDensify.cpp:3447-3449): the maps must end up identical too
+    for i in range(syn.n_views):
+        assert np.array_equal(osc.get_depthmap(i)[0], ctx.get_depthmap(i)[0]), f"view {i}"
+    print(f"\nfused {len(got['xyz'])} points in {ctx.timers()['n_fuse_rounds']} reserve/commit rounds")
+
+
+def test_fuse_is_idempotent_on_reloaded_maps(loaded):
+    """Size-independent property: re-loading the same maps and fusing again gives the same cloud (no state leaks)."""
+    syn, osc, ctx, maps, ok = loaded
+    load_maps(syn, osc, ctx, maps)
+    a = ctx.fuse_depthmaps(True, True)
+    load_maps(syn, osc, ctx, maps)
+    b = ctx.fuse_depthmaps(True, True)
+    for k in ("xyz", "views", "weights", "colors", "normals"):
+        assert np.array_equal(a[k], b[k])
