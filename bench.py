@@ -264,7 +264,7 @@ def run_b200(args):
         exchange()
         n = 0
         if rank == 0:
-            n = len(ctx.fuse_depthmaps(True, True)["xyz"])
+            n = ctx.fuse_depthmaps_device(True, True)[0]  # the fused cloud stays in HBM; e2e below downloads it
         ctx.sync()
         return n
 
@@ -339,6 +339,7 @@ def run_b200(args):
             ctx2.close()
         e2e = {"value": pix_iters_step / float(np.mean(ts)) / 1e6, "unit": "Mpix*iter/s", "h2d_bytes_per_step": st["h2d_bytes"],
                "d2h_bytes_per_step": st["d2h_bytes"], "seconds_per_scene": float(np.mean(ts)), "points": st["n_points"],
+               "seconds": {k: round(float(st[k]), 4) for k in ("sec_select", "sec_upload", "sec_estimate", "sec_filter", "sec_fuse")},
                "api": "hcmvs_host.DenseReconstruction (select views, upload, estimate, filter, fuse, download cloud)"}
     elif world > 1:
         e2e = {"value": None, "unit": "Mpix*iter/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "note": "measured at N=1 only"}

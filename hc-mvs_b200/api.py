@@ -16,7 +16,7 @@ EXPORTS = [
     "hcmvs_set_view", "hcmvs_set_neighbors", "hcmvs_init_depthmap", "hcmvs_set_depthmap", "hcmvs_get_depthmap",
     "hcmvs_set_prior", "hcmvs_get_gradient_map", "hcmvs_score_depthmap", "hcmvs_estimate_depthmap", "hcmvs_end_depthmap", "hcmvs_score_hypotheses",
     "hcmvs_filter_depthmap", "hcmvs_commit_filtered", "hcmvs_set_fuse_priority", "hcmvs_fuse_depthmaps",
-    "hcmvs_free_pointcloud", "hcmvs_get_depthmap_device", "hcmvs_set_depth_range", "hcmvs_alloc_depthmap",
+    "hcmvs_free_pointcloud", "hcmvs_get_fused_device", "hcmvs_get_depthmap_device", "hcmvs_set_depth_range", "hcmvs_alloc_depthmap",
     "hcmvs_export_maps_d", "hcmvs_import_maps_d", "hcmvs_get_timers", "hcmvs_reset_timers", "hcmvs_stream",
 ]
 
@@ -95,6 +95,7 @@ def load():
     L.hcmvs_set_fuse_priority.argtypes = [vp, u32, f32]
     L.hcmvs_fuse_depthmaps.argtypes = [vp, i32, i32, C.POINTER(PointCloudC)]
     L.hcmvs_free_pointcloud.argtypes = [C.POINTER(PointCloudC)]
+    L.hcmvs_get_fused_device.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)] + [C.POINTER(vp)] * 6
     L.hcmvs_get_depthmap_device.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(vp), C.POINTER(f32), C.POINTER(f32)]
     L.hcmvs_set_depth_range.argtypes = [vp, u32, f32, f32]
     L.hcmvs_alloc_depthmap.argtypes = [vp, u32]
@@ -218,6 +219,13 @@ class Context:
 
     def set_fuse_priority(self, view, score):
         self._ck(self.L.hcmvs_set_fuse_priority(self.h, view, float(score)))
+
+    def fuse_depthmaps_device(self, color=True, normal=True):
+        """FuseDepthMaps leaving the cloud in HBM; returns (n_points, n_view_refs)."""
+        self._ck(self.L.hcmvs_fuse_depthmaps(self.h, int(color), int(normal), None))
+        n = C.c_uint64(); m = C.c_uint64()
+        self._ck(self.L.hcmvs_get_fused_device(self.h, C.byref(n), C.byref(m), None, None, None, None, None, None))
+        return int(n.value), int(m.value)
 
     def fuse_depthmaps(self, color=True, normal=True):
         pc = PointCloudC()

@@ -46,7 +46,8 @@ typedef struct hcmvs_params {
 
 typedef struct hcmvs_ctx hcmvs_ctx;
 
-/* Fused point cloud (libs/MVS/PointCloud.h:49-109). Arrays are owned by the library; free with hcmvs_free_pointcloud. */
+/* Fused point cloud (libs/MVS/PointCloud.h:49-109). The arrays live in pinned host memory owned by the context: they stay
+ * valid until the next hcmvs_fuse_depthmaps / hcmvs_destroy on that context; hcmvs_free_pointcloud only clears the struct. */
 typedef struct hcmvs_pointcloud {
 	uint64_t n_points;
 	float*   points;      /* n*3 */
@@ -123,6 +124,10 @@ int hcmvs_set_fuse_priority(hcmvs_ctx* ctx, uint32_t view, float score);
 /* DepthMapsData::FuseDepthMaps — SceneDensify.cpp:3265-3495 */
 int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int estimate_normal, hcmvs_pointcloud* out);
 void hcmvs_free_pointcloud(hcmvs_pointcloud* pc);
+/* hcmvs_fuse_depthmaps with out == NULL leaves the cloud on the device; this returns its device arrays
+ * (points/normals float[3n], colors u8[3n], view_offsets u32[n+1], views u32[m], weights float[m]). */
+int hcmvs_get_fused_device(hcmvs_ctx* ctx, uint64_t* n_points, uint64_t* n_view_refs, void** points_d, void** normals_d, void** colors_d,
+                           void** view_offsets_d, void** views_d, void** weights_d);
 
 /* Device pointers of a view's maps for GPU<->GPU exchange by the host plumbing (NCCL / P2P):
  * dn_d = float4 (nx,ny,nz,depth) per pixel, conf_d = float per pixel. */
