@@ -215,35 +215,29 @@ def run_b200(args):
     # initial depth maps (sparse splat, SceneDensify.cpp:783-808) computed once on the host
     init = {i: hs.init_depth(i) for i in valid}
     # views are dealt round-robin in fusion (connection) order — SURVEY §8(e)
-    order = sorted(valid, key=lambda i: (-nall[i], i))
-    mine = [v for k, v in enumerate(order) if k % world == rank]
+    from hcmvs_b200 import shard
+    plan = shard.make_plan(valid, nall, world)
+    order, mine = plan.order, plan.views_of(rank)
     inner = (W - 14) * (H - 14)
     pix_iters_step = inner * int(P.nEstimationIters) * len(valid)
 
     # exchange buffers (one slot per view, replicated on every rank)
     if world > 1:
-        slots = (len(order) + world - 1) // world
-        send_dn = torch.zeros((slots, H, W, 4), dtype=torch.float32, device=dev)
-        send_cf = torch.zeros((slots, H, W), dtype=torch.float32, device=dev)
-        recv_dn = torch.zeros((world, slots, H, W, 4), dtype=torch.float32, device=dev)
-        recv_cf = torch.zeros((world, slots, H, W), dtype=torch.float32, device=dev)
+        send_dn = torch.zeros((plan.slots, H, W, 4), dtype=torch.float32, device=dev)
+        send_cf = torch.zeros((plan.slots, H, W), dtype=torch.float32, device=dev)
+        recv_dn = torch.zeros((world, plan.slots, H, W, 4), dtype=torch.float32, device=dev)
+        recv_cf = torch.zeros((world, plan.slots, H, W), dtype=torch.float32, device=dev)
     lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
 
     def exchange():
         """All-gather every rank's (normal, depth) and confidence maps over NCCL; import the others' maps."""
         if world == 1:
             return
-        for k, v in enumerate(mine):
-            ctx.export_maps_d(v, send_dn[k].data_ptr(), send_cf[k].data_ptr())
-        ctx.sync()
-        dist.all_gather_into_tensor(recv_dn.view(-1), send_dn.view(-1))
-        dist.all_gather_into_tensor(recv_cf.view(-1), send_cf.view(-1))
-        torch.cuda.synchronize()
-        for k, v in enumerate(order):
-            r, s = k % world, k // world
-            if r != rank:
-                ctx.import_maps_d(v, recv_dn[r, s].data_ptr(), recv_cf[r, s].data_ptr(), init[v][1], init[v][2])
-        ctx.sync()
+        shard.exchange_maps(
+            plan, rank, send_dn, send_cf, recv_dn, recv_cf,
+            export_fn=lambda v, s: ctx.export_maps_d(v, send_dn[s].data_ptr(), send_cf[s].data_ptr()),
+            import_fn=lambda v, r, s: ctx.import_maps_d(v, recv_dn[r, s].data_ptr(), recv_cf[r, s].data_ptr(), init[v][1], init[v][2]),
+            sync_fn=ctx.sync, dist=dist, post_sync=torch.cuda.synchronize)
 
     def upload_initial():
         # H2D of the rough depth maps: done before the clock starts (`value` = inputs resident in HBM)

@@ -1,0 +1,53 @@
+"""View sharding and map exchange plan for N ranks (one process per GPU).
+
+The scene shards by reference view: every rank holds all images and cameras, estimates the
+depth maps of its own views, and the ranks all-gather the (normal, depth) / confidence maps so that
+filtering and fusion see every neighbour. Views are dealt round-robin in FuseDepthMaps' connection order
+(decreasing scored-neighbour count, ties by index — SceneDensify.cpp:3286-3303) which balances the load
+and keeps neighbouring views on different ranks.
+"""
+from dataclasses import dataclass
+from typing import Dict, List
+
+
+@dataclass
+class ShardPlan:
+    order: List[int]          # views in connection order
+    world: int
+    slots: int                # exchange slots per rank
+
+    def owner(self, k: int) -> int:
+        return k % self.world
+
+    def slot(self, k: int) -> int:
+        return k // self.world
+
+    def views_of(self, rank: int) -> List[int]:
+        return [v for k, v in enumerate(self.order) if k % self.world == rank]
+
+    def location(self) -> Dict[int, tuple]:
+        """view -> (rank, slot) of its maps in the gathered buffer."""
+        return {v: (k % self.world, k // self.world) for k, v in enumerate(self.order)}
+
+
+def make_plan(valid_views, n_scored_neighbors, world):
+    order = sorted(valid_views, key=lambda i: (-n_scored_neighbors[i], i))
+    slots = (len(order) + world - 1) // world if order else 0
+    return ShardPlan(order=order, world=world, slots=slots)
+
+
+def exchange_maps(plan, rank, send_dn, send_cf, recv_dn, recv_cf, export_fn, import_fn, sync_fn, dist, post_sync=None):
+    """All-gather the ranks' maps. export_fn(view, slot) fills the send buffers, import_fn(view, rank, slot)
+    consumes a received slot; `dist` is torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
+    mine = plan.views_of(rank)
+    for s, v in enumerate(mine):
+        export_fn(v, s)
+    sync_fn()
+    dist.all_gather_into_tensor(recv_dn.view(-1), send_dn.view(-1))
+    dist.all_gather_into_tensor(recv_cf.view(-1), send_cf.view(-1))
+    if post_sync:
+        post_sync()
+    for v, (r, s) in plan.location().items():
+        if r != rank:
+            import_fn(v, r, s)
+    sync_fn()

@@ -128,11 +128,11 @@ static inline int Reflect101(int p, int len) { // cv::BORDER_REFLECT_101
 }
 void InitGraMap(const uint8_t* bgr, int w, int h, Image8U& gra) {
 	// SceneDensify.cpp:581-595: cvtColor(BGR2GRAY) u8 -> Sobel 3x3 CV_16S (x and y) -> convertScaleAbs -> addWeighted(.5,.5)
-	// third-party arithmetic (OpenCV 4.x, not vendored): gray = (B*1868 + G*9617 + R*4899 + 8192) >> 14;
+	// third-party arithmetic (OpenCV 4.x, not vendored): gray = (B*3735 + G*19235 + R*9798 + 16384) >> 15 (the 15-bit BT.601 constants of OpenCV >= 3.4, checked against cv2 4.13);
 	// Sobel border = BORDER_REFLECT_101; convertScaleAbs = saturate_u8(|v|); addWeighted = saturate_u8(round-half-even(a*.5+b*.5)).
 	std::vector<uint8_t> g((size_t)w*h);
 	for (size_t i=0, n=(size_t)w*h; i<n; ++i)
-		g[i] = (uint8_t)((bgr[i*3+0]*1868 + bgr[i*3+1]*9617 + bgr[i*3+2]*4899 + 8192) >> 14);
+		g[i] = (uint8_t)((bgr[i*3+0]*3735 + bgr[i*3+1]*19235 + bgr[i*3+2]*9798 + 16384) >> 15);
 	gra.w = w; gra.h = h; gra.d.resize((size_t)w*h);
 	for (int y=0; y<h; ++y) {
 		const int ym = Reflect101(y-1, h), yp = Reflect101(y+1, h);

@@ -1,0 +1,66 @@
+"""world_size-2 gloo test of the multi-rank host plumbing (the N>1 path of bench.py): view sharding + map all-gather.
+The CUDA library is replaced here by per-rank numpy 'maps' — the collective, the slot layout and the import/export
+order are exactly those the GPU run uses (hcmvs_b200.shard.exchange_maps)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _expected(view, h, w):
+    rng = np.random.default_rng(1000 + view)
+    return rng.standard_normal((h, w, 4)).astype(np.float32), rng.uniform(0, 1, (h, w)).astype(np.float32)
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    from hcmvs_b200 import shard
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    h, w = 6, 9
+    valid = list(range(11)); nall = {v: 12 - (v % 4) for v in valid}
+    plan = shard.make_plan(valid, nall, world)
+    have = {v: _expected(v, h, w) for v in plan.views_of(rank)}      # this rank "estimated" only its own views
+    send_dn = torch.zeros((plan.slots, h, w, 4)); send_cf = torch.zeros((plan.slots, h, w))
+    recv_dn = torch.zeros((world, plan.slots, h, w, 4)); recv_cf = torch.zeros((world, plan.slots, h, w))
+
+    def export_fn(v, s):
+        send_dn[s] = torch.from_numpy(have[v][0]); send_cf[s] = torch.from_numpy(have[v][1])
+
+    def import_fn(v, r, s):
+        have[v] = (recv_dn[r, s].numpy().copy(), recv_cf[r, s].numpy().copy())
+
+    shard.exchange_maps(plan, rank, send_dn, send_cf, recv_dn, recv_cf, export_fn, import_fn, lambda: None, dist)
+    ok = sorted(have) == valid and all(np.array_equal(have[v][0], _expected(v, h, w)[0]) and np.array_equal(have[v][1], _expected(v, h, w)[1]) for v in valid)
+    # max-over-ranks timing reduction used by bench.py
+    t = torch.tensor([float(rank + 1)])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    q.put((rank, ok, float(t.item())))
+    dist.destroy_process_group()
+
+
+def test_two_rank_map_exchange_gloo():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(r[0] for r in res) == [0, 1]
+    assert all(r[1] for r in res), "a rank did not end up with every view's maps"
+    assert all(r[2] == 2.0 for r in res)

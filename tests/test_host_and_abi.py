@@ -1,0 +1,113 @@
+"""CPU tests of the host-side mirror (view selection, image prep, file formats) and of the C-ABI surface."""
+import ctypes as C
+import os
+import re
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import common
+import oracle_lib as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(hcmvs_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_every_declared_symbol_is_exported(built):
+    """The shared libraries load without a GPU and export every entry point include/*.h declares."""
+    from hcmvs_b200 import api, host, synth
+    L = api.load()
+    for name in _declared("hcmvs_b200.h"):
+        assert hasattr(L, name), f"libhcmvs_b200.so lacks {name}"
+    assert set(api.EXPORTS) <= set(_declared("hcmvs_b200.h"))
+    H = host.lib()
+    for name in _declared("hcmvs_host.h"):
+        assert hasattr(H, name), f"libhcmvs_host.so lacks {name}"
+    S = synth.lib()
+    for name in _declared("hcmvs_synth.h"):
+        assert hasattr(S, name), f"libhcmvs_host.so lacks {name}"
+    # only sm_100a code is embedded (no multi-arch fatbin, no PTX fallback for other GPUs)
+    out = subprocess.run(["cuobjdump", "-lelf", api.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback_and_error_convention(built):
+    """Without a CUDA device creation fails with a message (bool-return convention -> status codes); defaults mirror OPTDENSE."""
+    import torch
+    from hcmvs_b200 import api
+    p = api.default_params()
+    assert (p.nNumViews, p.nMaxViews, p.nMinViewsFuse, p.nRandomIters) == (5, 12, 2, 6)
+    assert abs(p.fNCCThresholdKeep - 0.55) < 1e-7 and abs(p.fRandomDepthRatio - 0.003) < 1e-9 and p.adapthalfwin == 5
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the negative path is covered on the CPU box")
+    with pytest.raises(api.HcmvsError, match="no CUDA device"):
+        api.Context(0)
+    L = api.load()
+    assert L.hcmvs_sync(None) < 0 and L.hcmvs_set_neighbors(None, 0, None, None, 0, 0) < 0
+
+
+def test_host_view_selection_and_image_prep_bit_exact(built):
+    """Scene::SelectNeighborViews / FilterNeighborViews (Scene.cpp:545-678) in the product host code == oracle, bit for bit."""
+    from hcmvs_b200 import api, host
+    for cfg, scale, nv in ((1, 0.25, 0), (2, 0.125, 0), (4, 0.125, 30)):
+        syn, osc, gt, imgs, ok = common.make_scene(cfg, scale, nv)
+        hs = host.HostScene.from_synth(syn, imgs)
+        P = api.default_params(nMinViewsTrustPoint=1)
+        for i in range(syn.n_views):
+            r = hs.select_views(P, i)
+            assert (r > 0) == ok[i]
+            for which in (0, 1):
+                a, b = hs.neighbors(i, which), osc.neighbors(i, which)
+                for k in a:
+                    assert np.array_equal(a[k], b[k]), (cfg, i, which, k)
+            assert np.array_equal(hs.gray(i), osc.gray(i))
+            if ok[i]:
+                osc.init_depth_sparse(i)
+                d0, _, _, lo, hi = osc.get_depthmap(i)
+                d1, lo1, hi1 = hs.init_depth(i)
+                assert np.array_equal(d0, d1) and lo == lo1 and hi == hi1
+
+
+def test_dmap_roundtrip_and_layout(built, tmp_path):
+    """Raw 'DR' depth-data file (Interface.h:634-652, DepthMap.cpp:2781-2925): 28-byte header, name, ids, K R C, maps."""
+    from hcmvs_b200 import host
+    rng = np.random.default_rng(0)
+    h, w = 13, 17
+    d = rng.uniform(1, 5, (h, w)).astype(np.float32); n = rng.standard_normal((h, w, 3)).astype(np.float32); c = rng.uniform(0, 1, (h, w)).astype(np.float32)
+    K = np.array([100, 0, 8, 0, 100, 6, 0, 0, 1.0]); R = np.eye(3).ravel(); Cc = np.array([1.0, 2, 3])
+    path = str(tmp_path / "depth0007.dmap")
+    host.write_dmap(path, "00007.png", [7, 3, 9], (w, h), K, R, Cc, 0.5, 9.5, d, n, c)
+    raw = open(path, "rb").read()
+    name, typ, pad, iw, ih, dw, dh, dmin, dmax = struct.unpack("<HBBIIIIff", raw[:28])
+    assert (name, typ, iw, ih, dw, dh) == (0x5244, 7, w, h, w, h) and raw[:2] == b"DR" and (dmin, dmax) == (0.5, 9.5)
+    assert struct.unpack("<H", raw[28:30])[0] == 9 and raw[30:39] == b"00007.png"
+    assert struct.unpack("<I3I", raw[39:55]) == (3, 7, 3, 9)
+    assert len(raw) == 55 + 21 * 8 + h * w * 4 * 5
+    back = host.read_dmap(path)
+    assert np.array_equal(back["depth"], d) and np.array_equal(back["normal"], n) and np.array_equal(back["conf"], c)
+    assert list(back["ids"]) == [7, 3, 9] and np.array_equal(back["K"], K) and back["dmin"] == 0.5
+    host.write_dmap(path, "x", [1], (w, h), K, R, Cc, 1, 2, d)                 # depth only
+    back = host.read_dmap(path)
+    assert back["normal"] is None and back["conf"] is None
+
+
+def test_shard_plan_covers_every_view_once():
+    from hcmvs_b200 import shard
+    valid = [0, 1, 2, 4, 5, 7, 8, 9, 11]
+    nall = {v: (v * 7) % 5 + 3 for v in valid}
+    for world in (1, 2, 4, 8):
+        plan = shard.make_plan(valid, nall, world)
+        owned = [v for r in range(world) for v in plan.views_of(r)]
+        assert sorted(owned) == valid
+        assert max(len(plan.views_of(r)) for r in range(world)) - min(len(plan.views_of(r)) for r in range(world)) <= 1
+        assert [nall[v] for v in plan.order] == sorted((nall[v] for v in valid), reverse=True)
+        loc = plan.location()
+        assert len({loc[v] for v in valid}) == len(valid) and all(s < plan.slots for _, s in loc.values())
