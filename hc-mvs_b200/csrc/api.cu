@@ -387,7 +387,7 @@ static int BuildRefConst(hcmvs_ctx* ctx, View* v, uint32_t ref, int it_external,
 	rc.angle1Range = FD2R(P.fRandomAngle1Range); rc.angle2Range = FD2R(P.fRandomAngle2Range);
 	rc.depthRatio = P.fRandomDepthRatio;
 	rc.nRandomIters = (int)P.nRandomIters; rc.adapthalfwin = P.adapthalfwin; rc.farReach = P.rb_far_reach; rc.propDirs = P.rb_prop_dirs;
-	rc.it_external = it_external; rc.photo2geo = P.photo2geo;
+	rc.it_external = it_external; rc.photo2geo = P.photo2geo; rc.propagatehalfwin = P.propagatehalfwin; rc.propagatestep = P.propagatestep;
 	rc.photometric_flow = P.photometric_flow; rc.para_prior = P.para_prior; rc.sigmaPrior = P.fsigmaPrior;
 	rc.key0 = (uint32_t)seed; rc.key1 = (uint32_t)(seed>>32)^(ref*0x9E3779B9u);
 	rc.pass = 0;
@@ -425,7 +425,16 @@ extern "C" int hcmvs_end_depthmap(hcmvs_ctx* ctx, uint32_t ref) {
 extern "C" int hcmvs_estimate_depthmap(hcmvs_ctx* ctx, uint32_t ref, int it_external, uint64_t seed) {
 	View* v = GetView(ctx, ref, true); if (!v) return HCMVS_ERR_ARG;
 	int r = RequireMaps(v, ref); if (r) return r;
-	if (it_external != 0) { hcmvs_set_error("it_external >= 1 (adaptive '+' propagation, priors) is not built yet"); return HCMVS_ERR_UNSUPPORTED; }
+	if (it_external < 0) { hcmvs_set_error("negative outer iteration"); return HCMVS_ERR_ARG; }
+	if (it_external >= 1) {
+		// the fork's "+"-shaped candidate set (DepthMap.cpp:1064-1274) must stay on the opposite checkerboard colour
+		// (odd offsets 1, 1+step, ...) and fit the 8 candidate slots of the kernel
+		const hcmvs_params& Q = ctx->P;
+		const int phwMax = std::max(Q.propagatehalfwin, 5);
+		if (Q.propagatestep < 1 || Q.propagatehalfwin < 1) { hcmvs_set_error("propagatehalfwin / propagatestep must be >= 1"); return HCMVS_ERR_ARG; }
+		if ((Q.propagatestep & 1) && phwMax > 1) { hcmvs_set_error("odd propagatestep puts candidates on the pixel's own checkerboard colour: unsupported"); return HCMVS_ERR_UNSUPPORTED; }
+		if (1+2*Q.propagatestep <= phwMax) { hcmvs_set_error("more than 2 candidate rings (propagatehalfwin %d, step %d): unsupported", Q.propagatehalfwin, Q.propagatestep); return HCMVS_ERR_UNSUPPORTED; }
+	}
 	cudaSetDevice(ctx->device);
 	const hcmvs_params& P = ctx->P;
 	const size_t n = (size_t)v->w*v->h;

@@ -40,7 +40,7 @@ struct RefConst {
 	float keep, thRobust, thConfSmall, thConfBig, thConfRand;
 	float smoothBonusDepth, smoothBonusNormal, smoothSigmaDepth, smoothSigmaNormal;
 	float angle1Range, angle2Range, depthRatio;
-	int nRandomIters, adapthalfwin, farReach, propDirs, it_external, photo2geo;
+	int nRandomIters, adapthalfwin, farReach, propDirs, it_external, photo2geo, propagatehalfwin, propagatestep;
 	float photometric_flow, para_prior, sigmaPrior;
 	uint32_t key0, key1, pass;
 	unsigned long long* counters; // [0] hypotheses, [1] view scores, [2] pixel-iterations

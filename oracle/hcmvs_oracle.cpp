@@ -888,14 +888,27 @@ static void RBProcessPixel(DepthEstimator& est, int px, int py, const uint32_t k
 			est.neighborsClose.push_back(NeighborEstimate{nd, normalMap0[(size_t)ny*w+nx], Vec3f{(float)Xd.x, (float)Xd.y, (float)Xd.z}});
 		}
 	};
+	struct Src { int x, y; };
+	std::vector<Src> sources;
+	if (est.nIteration_external >= 1) {
+		// DepthMap.cpp:1064-1274: the fork's "+"-shaped candidate set; every candidate with depth > 0 is both a
+		// propagation source and a smoothness neighbour. Offsets 1, 1+step, .. must be odd for the checkerboard
+		// (the shipped runs use step 4: offsets 1 and 5).
+		const float tx = dd.graMap.d.empty() ? 0.f : (float)dd.graMap.at(x0, y0);
+		const int step = P.propagatestep;
+		const int phw = (tx > 150) ? 5 : P.propagatehalfwin;
+		std::vector<Src> cand;
+		if (x0 > phw && y0 > phw && x0 < w-phw && y0 < h-phw) {
+			for (int i=1; i<=phw; i+=step) { cand.push_back({x0, y0-i}); cand.push_back({x0, y0+i}); cand.push_back({x0-i, y0}); cand.push_back({x0+i, y0}); }
+		} else if (x0 > hw && y0 > hw && x0 < w-hw && y0 < h-hw) {
+			cand = {{x0, y0-1}, {x0, y0+1}, {x0-1, y0}, {x0+1, y0}};
+		}
+		for (const Src& c: cand) if (depthMap0.at(c.x, c.y) > 0) { addClose(c.x, c.y); sources.push_back(c); }
+	} else {
 	if (x0 > hw) addClose(x0-1, y0);
 	if (y0 > hw) addClose(x0, y0-1);
 	if (x0 < w-hw) addClose(x0+1, y0);
 	if (y0 < h-hw) addClose(x0, y0+1);
-	float& conf = confMap0.d[(size_t)y0*w+x0];
-	Depth& depth = depthMap0.d[(size_t)y0*w+x0];
-	Vec3f& normal = normalMap0[(size_t)y0*w+x0];
-	const Vec3f viewDir{(float)est.X0.x, (float)est.X0.y, (float)est.X0.z};
 	// propagation: one source per direction
 	static const int DX[4] = {-1, 0, 1, 0}, DY[4] = {0, -1, 0, 1};
 	const int reach = cfg.useFar ? cfg.farReach : 1;
@@ -919,9 +932,15 @@ static void RBProcessPixel(DepthEstimator& est, int px, int py, const uint32_t k
 			srcX[d1] = -1;
 		}
 	}
-	for (int dirn=0; dirn<4; ++dirn) {
-		const int bx = srcX[dirn], by = srcY[dirn];
-		if (bx < 0) continue;
+	for (int dirn=0; dirn<4; ++dirn) if (srcX[dirn] >= 0) sources.push_back({srcX[dirn], srcY[dirn]});
+	}
+	float& conf = confMap0.d[(size_t)y0*w+x0];
+	Depth& depth = depthMap0.d[(size_t)y0*w+x0];
+	Vec3f& normal = normalMap0[(size_t)y0*w+x0];
+	const Vec3f viewDir{(float)est.X0.x, (float)est.X0.y, (float)est.X0.z};
+	for (const Src& sc: sources) {
+		const int bx = sc.x, by = sc.y;
+		if (confMap0.at(bx, by) >= P.fNCCThresholdKeep) continue; // DepthMap.cpp:1412
 		Depth nd = depthMap0.at(bx, by); Vec3f nn = normalMap0[(size_t)by*w+bx];
 		nd = est.InterpolatePixel(bx, by, nd, nn);
 		est.CorrectNormal(nn);

@@ -131,3 +131,35 @@ def test_end_depthmap_exact(scene, ctx):
     od, on, oc, _, _ = osc.get_depthmap(ref)
     gd, gn, gc, _, _ = ctx.get_depthmap(ref)
     assert np.array_equal(od, gd) and np.array_equal(on, gn) and np.array_equal(oc, gc)
+
+
+def test_outer_iteration_plus_pattern_matches_oracle(scene, ctx):
+    """it_external >= 1: the fork's '+'-shaped candidate set (DepthMap.cpp:1064-1274, offsets 1 and 5 with the authors'
+    propagatehalfwin 5 / step 4) — GPU vs the CPU red-black restatement, two outer iterations."""
+    syn, osc, gt, imgs, ok = scene
+    ref = 6
+    over = dict(nEstimationIters=2, nEstimationIters_external=2, propagatehalfwin=5, propagatestep=4)
+    osc.set_params(**over); ctx.set_params(**over)
+    osc.init_depth_sparse(ref)
+    d0, n0, c0, dmin, dmax = osc.get_depthmap(ref)
+    ctx.init_depthmap(ref, d0, None, dmin, dmax)
+    ctx.reset_timers()
+    for it in range(2):
+        ctx.estimate_depthmap(ref, it, seed=21)
+        osc.estimate(ref, it_external=it, seed=21, threads=8, mode=2, far_reach=11)
+    gd, gn, gc, _, _ = ctx.get_depthmap(ref)
+    od, on, oc, _, _ = osc.get_depthmap(ref)
+    t = ctx.timers()
+    back = dict(nEstimationIters=3, nEstimationIters_external=1, propagatehalfwin=1, propagatestep=4)
+    osc.set_params(**back); ctx.set_params(**back)
+    a = common.agreement(od, gd)
+    hyp = t["n_hypotheses"] / max(t["n_pixel_iters"], 1)
+    print(f"\nouter-iteration run: GPU vs oracle-redblack {a:.4f}, hyp/pixel-iter {hyp:.2f}, within 1% of GT {common.agreement(gt[ref][0], gd, mask=gd > 0):.4f}")
+    assert np.array_equal(od == 0, gd == 0) or a > 0.995
+    assert a >= 0.995
+    assert 8.0 < hyp <= 14.0      # 2 (first outer iteration) / up to 8 (second) propagation + 6 refinement hypotheses
+    # unsupported candidate geometry is refused, not silently mis-handled
+    ctx.set_params(propagatestep=3, propagatehalfwin=5)
+    with pytest.raises(Exception, match="checkerboard"):
+        ctx.estimate_depthmap(ref, 1, seed=1)
+    ctx.set_params(**back)
