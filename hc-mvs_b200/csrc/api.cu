@@ -57,6 +57,7 @@ extern "C" hcmvs_ctx* hcmvs_create(int device, const hcmvs_params* p) {
 	hcmvs_ctx* ctx = new hcmvs_ctx();
 	ctx->device = device; ctx->P = P;
 	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) != cudaSuccess ||
 	    cudaMalloc(&ctx->counters_d, 8*sizeof(unsigned long long)) != cudaSuccess ||
 	    cudaMemset(ctx->counters_d, 0, 8*sizeof(unsigned long long)) != cudaSuccess) {
 		hcmvs_set_error("context allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -68,6 +69,7 @@ extern "C" hcmvs_ctx* hcmvs_create(int device, const hcmvs_params* p) {
 static void FreeView(View& v) {
 	if (v.tex) cudaDestroyTextureObject(v.tex);
 	if (v.arr) cudaFreeArray(v.arr);
+	if (v.ready) cudaEventDestroy(v.ready);
 	cudaFree(v.img_d); cudaFree(v.bgr_d); cudaFree(v.gra_d); cudaFree(v.dn_d); cudaFree(v.conf_d); cudaFree(v.prior_d); cudaFree(v.fdepth_d); cudaFree(v.fconf_d); cudaFree(v.claim_d);
 	v = View();
 }
@@ -79,7 +81,8 @@ extern "C" void hcmvs_destroy(hcmvs_ctx* ctx) {
 	for (View& v: ctx->views) FreeView(v);
 	for (auto& te: ctx->timed) { cudaEventDestroy(te.a); cudaEventDestroy(te.b); }
 	for (cudaEvent_t ev: ctx->eventPool) cudaEventDestroy(ev);
-	cudaFree(ctx->scratch_d); cudaFree(ctx->counters_d);
+	cudaFree(ctx->scratch_d); cudaFree(ctx->counters_d); cudaFree(ctx->upload_d);
+	if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
 	hcmvs_fuse_release(ctx);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -191,25 +194,32 @@ extern "C" int hcmvs_set_view(hcmvs_ctx* ctx, uint32_t view, int W, int H, const
 	if (K[1] != 0.0 || K[3] != 0.0 || K[6] != 0.0 || K[7] != 0.0) { hcmvs_set_error("K must be upper triangular with zero skew"); return HCMVS_ERR_UNSUPPORTED; }
 	cudaSetDevice(ctx->device);
 	View* v = GetView(ctx, view, false); if (!v) return HCMVS_ERR_ARG;
-	if (v->set) { CK(cudaStreamSynchronize(ctx->stream)); FreeView(*v); }
+	const bool reuse = v->set && v->w == W && v->h == H && (v->bgr_d != nullptr) == (bgr != nullptr);
+	if (v->set) {
+		// the image may still be read by queued kernels
+		CK(cudaStreamSynchronize(ctx->stream)); CK(cudaStreamSynchronize(ctx->copyStream));
+		if (!reuse) FreeView(*v);
+	}
 	v->w = W; v->h = H;
 	std::memcpy(v->K, K, 72); std::memcpy(v->R, R, 72); std::memcpy(v->C, C, 24);
 	ComposeP(K, R, C, v->P);
 	const size_t n = (size_t)W*H;
-	cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
-	CK(cudaMallocArray(&v->arr, &desc, W, H, cudaArrayTextureGather));
-	CK(cudaMemcpy2DToArrayAsync(v->arr, 0, 0, gray, (size_t)W*4, (size_t)W*4, H, cudaMemcpyHostToDevice, ctx->stream));
-	cudaResourceDesc rd; std::memset(&rd, 0, sizeof(rd)); rd.resType = cudaResourceTypeArray; rd.res.array.array = v->arr;
-	cudaTextureDesc td; std::memset(&td, 0, sizeof(td));
-	td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp; td.filterMode = cudaFilterModePoint;
-	td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
-	CK(cudaCreateTextureObject(&v->tex, &rd, &td, nullptr));
-	CK(cudaMalloc(&v->img_d, n*4));
-	CK(cudaMemcpyAsync(v->img_d, gray, n*4, cudaMemcpyHostToDevice, ctx->stream));
-	if (bgr) {
-		CK(cudaMalloc(&v->bgr_d, n*3));
-		CK(cudaMemcpyAsync(v->bgr_d, bgr, n*3, cudaMemcpyHostToDevice, ctx->stream));
+	if (!reuse) {
+		cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
+		CK(cudaMallocArray(&v->arr, &desc, W, H, cudaArrayTextureGather));
+		cudaResourceDesc rd; std::memset(&rd, 0, sizeof(rd)); rd.resType = cudaResourceTypeArray; rd.res.array.array = v->arr;
+		cudaTextureDesc td; std::memset(&td, 0, sizeof(td));
+		td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp; td.filterMode = cudaFilterModePoint;
+		td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+		CK(cudaCreateTextureObject(&v->tex, &rd, &td, nullptr));
+		CK(cudaMalloc(&v->img_d, n*4));
+		if (bgr) CK(cudaMalloc(&v->bgr_d, n*3));
+	} else {
+		v->graValid = false; // a new image invalidates the derived gradient map (rebuilt by the next hcmvs_init_depthmap)
 	}
+	CK(cudaMemcpy2DToArrayAsync(v->arr, 0, 0, gray, (size_t)W*4, (size_t)W*4, H, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(v->img_d, gray, n*4, cudaMemcpyHostToDevice, ctx->stream));
+	if (bgr) CK(cudaMemcpyAsync(v->bgr_d, bgr, n*3, cudaMemcpyHostToDevice, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream)); // host buffers may be released by the caller
 	v->set = true;
 	return HCMVS_OK;
@@ -235,16 +245,33 @@ static int AllocMaps(hcmvs_ctx* ctx, View* v) {
 	return HCMVS_OK;
 }
 
+// Upload a view's maps on the COPY stream (H2D + packing kernel), so that it overlaps whatever the compute stream is doing
+// for other views; consumers on the compute stream wait on v->ready. Returns once the host buffers may be reused.
 static int UploadMaps(hcmvs_ctx* ctx, View* v, const float* depth, const float* normal, const float* conf) {
 	const size_t n = (size_t)v->w*v->h;
-	int r = AllocMaps(ctx, v); if (r) return r;
-	float* tmp; r = hcmvs_scratch(ctx, n*16, (void**)&tmp); if (r) return r;
-	CK(cudaMemcpyAsync(tmp, depth, n*4, cudaMemcpyHostToDevice, ctx->stream));
-	if (normal) CK(cudaMemcpyAsync(tmp+n, normal, n*12, cudaMemcpyHostToDevice, ctx->stream));
-	CK(hcmvs_launch_pack(tmp, normal ? tmp+n : nullptr, v->dn_d, n, ctx->stream)); ++ctx->nLaunches;
-	if (conf) CK(cudaMemcpyAsync(v->conf_d, conf, n*4, cudaMemcpyHostToDevice, ctx->stream));
-	else CK(cudaMemsetAsync(v->conf_d, 0, n*4, ctx->stream));
-	CK(cudaStreamSynchronize(ctx->stream));
+	cudaStream_t cs = ctx->copyStream;
+	// the view's buffers may still be in use by earlier compute work (re-initialisation of an estimated view)
+	if (v->dn_d) { cudaEvent_t done; CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming)); CK(cudaEventRecord(done, ctx->stream)); CK(cudaStreamWaitEvent(cs, done, 0)); CK(cudaEventDestroy(done)); }
+	if (!v->dn_d) CK(cudaMalloc(&v->dn_d, n*sizeof(float4)));
+	if (!v->conf_d) CK(cudaMalloc(&v->conf_d, n*4));
+	if (ctx->uploadBytes < n*16) {
+		CK(cudaStreamSynchronize(cs));
+		cudaFree(ctx->upload_d); ctx->upload_d = nullptr; ctx->uploadBytes = 0;
+		CK(cudaMalloc(&ctx->upload_d, n*16)); ctx->uploadBytes = n*16;
+	}
+	float* tmp = (float*)ctx->upload_d;
+	CK(cudaMemcpyAsync(tmp, depth, n*4, cudaMemcpyHostToDevice, cs));
+	if (normal) CK(cudaMemcpyAsync(tmp+n, normal, n*12, cudaMemcpyHostToDevice, cs));
+	CK(hcmvs_launch_pack(tmp, normal ? tmp+n : nullptr, v->dn_d, n, cs)); ++ctx->nLaunches;
+	if (conf) CK(cudaMemcpyAsync(v->conf_d, conf, n*4, cudaMemcpyHostToDevice, cs));
+	else CK(cudaMemsetAsync(v->conf_d, 0, n*4, cs));
+	return HCMVS_OK;
+}
+static int FinishUpload(hcmvs_ctx* ctx, View* v) {
+	if (!v->ready) CK(cudaEventCreateWithFlags(&v->ready, cudaEventDisableTiming));
+	CK(cudaEventRecord(v->ready, ctx->copyStream));
+	CK(cudaStreamWaitEvent(ctx->stream, v->ready, 0)); // later compute-stream work sees the uploaded maps
+	CK(cudaStreamSynchronize(ctx->copyStream));        // host buffers are free again; does not wait for compute
 	return HCMVS_OK;
 }
 
@@ -253,15 +280,16 @@ extern "C" int hcmvs_init_depthmap(hcmvs_ctx* ctx, uint32_t ref, const float* de
 	if (!depth0 || !(dMin > 0.f) || !(dMin < dMax)) { hcmvs_set_error("bad depth range [%g,%g)", dMin, dMax); return HCMVS_ERR_ARG; }
 	cudaSetDevice(ctx->device);
 	const size_t n = (size_t)v->w*v->h;
-	hcmvs_time_begin(ctx, ST_PREP);
 	int r = UploadMaps(ctx, v, depth0, normal0, nullptr); if (r) return r;
 	v->dMin = dMin; v->dMax = dMax; v->hasMaps = true;
-	// InitGraMap, SceneDensify.cpp:815-819
+	// InitGraMap, SceneDensify.cpp:815-819 (once per view; also on the copy stream)
 	if (!v->gra_d) CK(cudaMalloc(&v->gra_d, n));
-	if (v->bgr_d) { CK(hcmvs_launch_gramap(v->bgr_d, v->gra_d, v->w, v->h, ctx->stream)); ++ctx->nLaunches; }
-	else CK(cudaMemsetAsync(v->gra_d, 0, n, ctx->stream));
-	hcmvs_time_end(ctx);
-	return HCMVS_OK;
+	if (!v->graValid) {
+		if (v->bgr_d) { CK(hcmvs_launch_gramap(v->bgr_d, v->gra_d, v->w, v->h, ctx->copyStream)); ++ctx->nLaunches; }
+		else CK(cudaMemsetAsync(v->gra_d, 0, n, ctx->copyStream));
+		v->graValid = true;
+	}
+	return FinishUpload(ctx, v);
 }
 
 extern "C" int hcmvs_set_depthmap(hcmvs_ctx* ctx, uint32_t view, const float* depth, const float* normal, const float* conf, float dMin, float dMax) {
@@ -270,7 +298,7 @@ extern "C" int hcmvs_set_depthmap(hcmvs_ctx* ctx, uint32_t view, const float* de
 	cudaSetDevice(ctx->device);
 	int r = UploadMaps(ctx, v, depth, normal, conf); if (r) return r;
 	v->dMin = dMin; v->dMax = dMax; v->hasMaps = true;
-	return HCMVS_OK;
+	return FinishUpload(ctx, v);
 }
 
 extern "C" int hcmvs_alloc_depthmap(hcmvs_ctx* ctx, uint32_t view) {
@@ -477,10 +505,11 @@ extern "C" int hcmvs_score_hypotheses(hcmvs_ctx* ctx, uint32_t ref, const float*
 	RefConst rc; int r = BuildRefConst(ctx, v, ref, 0, 0, rc);
 	if (!hadRange) { v->dMin = 0.f; v->dMax = 0.f; }
 	if (r) return r;
-	if (!v->gra_d) {
-		CK(cudaMalloc(&v->gra_d, n));
+	if (!v->gra_d || !v->graValid) {
+		if (!v->gra_d) CK(cudaMalloc(&v->gra_d, n));
 		if (v->bgr_d) { CK(hcmvs_launch_gramap(v->bgr_d, v->gra_d, v->w, v->h, ctx->stream)); ++ctx->nLaunches; }
 		else CK(cudaMemsetAsync(v->gra_d, 0, n, ctx->stream));
+		v->graValid = true;
 		rc.gra = v->gra_d;
 	}
 	char* buf; r = hcmvs_scratch(ctx, n*(16+16+4), (void**)&buf); if (r) return r;

@@ -295,13 +295,11 @@ struct FuseState {
 	uint32_t* oviews = nullptr; float* weights = nullptr; size_t capViews = 0;
 	int coopBlocks = 0;
 	size_t nPoints = 0, nViewRefs = 0; bool hasColor = false, hasNormal = false; // last fused cloud (device resident)
-	char* hostPool = nullptr; size_t hostPoolBytes = 0;                         // pinned staging for the download
 };
 
 void hcmvs_fuse_release(hcmvs_ctx* ctx) {
 	FuseState* f = ctx->fuse; if (!f) return;
 	cudaFree(f->views_d); cudaFree(f->state_d); cudaFree(f->mask_d); cudaFree(f->blockSums_d); cudaFree(f->counters_d);
-	cudaFreeHost(f->hostPool);
 	cudaFree(f->points); cudaFree(f->normals); cudaFree(f->colors); cudaFree(f->viewOffsets); cudaFree(f->oviews); cudaFree(f->weights);
 	delete f; ctx->fuse = nullptr;
 }
@@ -427,32 +425,36 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 		CK(cudaMemcpyAsync(f->viewOffsets+nPoints, &last, 4, cudaMemcpyHostToDevice, ctx->stream));
 	}
 	CK(cudaStreamSynchronize(ctx->stream));
-	if (!out) return HCMVS_OK; // cloud stays on the device (hcmvs_get_fused_device)
-	// hand the cloud to the host through a context-owned pinned pool (pageable D2H of ~1 GB costs more than the fusion)
+	if (!out) return HCMVS_OK; // cloud stays on the device (hcmvs_get_fused_device / hcmvs_download_fused)
 	out->n_points = nPoints;
 	if (nPoints) {
-		auto al = [](size_t b) { return (b+255)&~(size_t)255; };
-		const size_t need = al(nPoints*12)*2+al(nPoints*3)+al((nPoints+1)*4)+al(nViewRefs*4)*2;
-		if (f->hostPoolBytes < need) {
-			cudaFreeHost(f->hostPool); f->hostPool = nullptr; f->hostPoolBytes = 0;
-			CK(cudaMallocHost((void**)&f->hostPool, need+need/4));
-			f->hostPoolBytes = need+need/4;
+		out->points = (float*)malloc(nPoints*12);
+		out->view_offsets = (uint32_t*)malloc((nPoints+1)*4);
+		out->views = (uint32_t*)malloc(nViewRefs*4);
+		out->weights = (float*)malloc(nViewRefs*4);
+		if (estimate_normal) out->normals = (float*)malloc(nPoints*12);
+		if (estimate_color) out->colors = (uint8_t*)malloc(nPoints*3);
+		if (!out->points || !out->view_offsets || !out->views || !out->weights || (estimate_normal && !out->normals) || (estimate_color && !out->colors)) {
+			hcmvs_free_pointcloud(out); hcmvs_set_error("out of host memory"); return HCMVS_ERR_ARG;
 		}
-		char* q = f->hostPool;
-		out->points = (float*)q; q += al(nPoints*12);
-		out->normals = estimate_normal ? (float*)q : nullptr; q += al(nPoints*12);
-		out->colors = estimate_color ? (uint8_t*)q : nullptr; q += al(nPoints*3);
-		out->view_offsets = (uint32_t*)q; q += al((nPoints+1)*4);
-		out->views = (uint32_t*)q; q += al(nViewRefs*4);
-		out->weights = (float*)q;
-		CK(cudaMemcpyAsync(out->points, f->points, nPoints*12, cudaMemcpyDeviceToHost, ctx->stream));
-		CK(cudaMemcpyAsync(out->view_offsets, f->viewOffsets, (nPoints+1)*4, cudaMemcpyDeviceToHost, ctx->stream));
-		CK(cudaMemcpyAsync(out->views, f->oviews, nViewRefs*4, cudaMemcpyDeviceToHost, ctx->stream));
-		CK(cudaMemcpyAsync(out->weights, f->weights, nViewRefs*4, cudaMemcpyDeviceToHost, ctx->stream));
-		if (estimate_normal) CK(cudaMemcpyAsync(out->normals, f->normals, nPoints*12, cudaMemcpyDeviceToHost, ctx->stream));
-		if (estimate_color) CK(cudaMemcpyAsync(out->colors, f->colors, nPoints*3, cudaMemcpyDeviceToHost, ctx->stream));
-		CK(cudaStreamSynchronize(ctx->stream));
+		return hcmvs_download_fused(ctx, out->points, out->normals, out->colors, out->view_offsets, out->views, out->weights);
 	}
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_download_fused(hcmvs_ctx* ctx, float* points, float* normals, uint8_t* colors, uint32_t* view_offsets, uint32_t* views, float* weights) {
+	if (!ctx || !ctx->fuse) { hcmvs_set_error("no fused cloud"); return HCMVS_ERR_STATE; }
+	FuseState* f = ctx->fuse;
+	cudaSetDevice(ctx->device);
+	const size_t n = f->nPoints, m = f->nViewRefs;
+	if (!n) return HCMVS_OK;
+	if (points) CK(cudaMemcpyAsync(points, f->points, n*12, cudaMemcpyDeviceToHost, ctx->stream));
+	if (normals && f->hasNormal) CK(cudaMemcpyAsync(normals, f->normals, n*12, cudaMemcpyDeviceToHost, ctx->stream));
+	if (colors && f->hasColor) CK(cudaMemcpyAsync(colors, f->colors, n*3, cudaMemcpyDeviceToHost, ctx->stream));
+	if (view_offsets) CK(cudaMemcpyAsync(view_offsets, f->viewOffsets, (n+1)*4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (views) CK(cudaMemcpyAsync(views, f->oviews, m*4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (weights) CK(cudaMemcpyAsync(weights, f->weights, m*4, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
 	return HCMVS_OK;
 }
 
@@ -473,6 +475,7 @@ extern "C" int hcmvs_get_fused_device(hcmvs_ctx* ctx, uint64_t* n_points, uint64
 }
 
 extern "C" void hcmvs_free_pointcloud(hcmvs_pointcloud* pc) {
-	// the arrays live in the context's pinned pool (released by hcmvs_destroy / reused by the next fusion)
-	if (pc) memset(pc, 0, sizeof(*pc));
+	if (!pc) return;
+	free(pc->points); free(pc->normals); free(pc->colors); free(pc->view_offsets); free(pc->views); free(pc->weights);
+	memset(pc, 0, sizeof(*pc));
 }

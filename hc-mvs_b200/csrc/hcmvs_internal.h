@@ -13,6 +13,7 @@ struct View { // one scene image + its DepthData (libs/MVS/DepthMap.h:214-347)
 	float* img_d = nullptr;       // gray image, linear
 	uint8_t* bgr_d = nullptr;     // colour image (fusion colours, gradient map)
 	uint8_t* gra_d = nullptr;     // DepthData::graMap
+	bool graValid = false;        // gra_d matches the current image
 	float4* dn_d = nullptr;       // (normal.xyz, depth)
 	float* conf_d = nullptr;
 	float* prior_d = nullptr;     // DepthData::depthMapPrior
@@ -22,6 +23,7 @@ struct View { // one scene image + its DepthData (libs/MVS/DepthMap.h:214-347)
 	std::vector<uint32_t> nbIds;  // DepthData::neighbors (sorted by score)
 	std::vector<float> nbScores;
 	int nMatch = 0;               // first nMatch ids = DepthData::images[1..]
+	cudaEvent_t ready = nullptr;  // upload of this view's maps finished (recorded on the copy stream)
 	float fusePriority = 0.f; bool hasFusePriority = false; // #scored neighbours (FuseDepthMaps connection score)
 };
 
@@ -32,6 +34,8 @@ struct FuseState; // fuse.cu
 struct hcmvs_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
+	cudaStream_t copyStream = nullptr;   // H2D uploads + layout kernels, overlapping the compute stream
+	void* upload_d = nullptr; size_t uploadBytes = 0; // staging for uploads (copy stream only)
 	hcmvs_params P;
 	std::vector<View> views;
 	void* scratch_d = nullptr; size_t scratchBytes = 0;

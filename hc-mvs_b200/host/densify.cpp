@@ -6,6 +6,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
+#include <thread>
 
 namespace hcmvs_host {
 
@@ -240,20 +242,17 @@ bool DepthMapsData::FilterDepthMap(uint32_t idxImage, const std::vector<uint32_t
 }
 
 bool DepthMapsData::FuseDepthMaps(PointCloud& pc, bool bEstimateColor, bool bEstimateNormal) {
-	hcmvs_pointcloud out;
-	if (hcmvs_fuse_depthmaps(ctx, bEstimateColor, bEstimateNormal, &out) != HCMVS_OK) return Fail("hcmvs_fuse_depthmaps");
-	const size_t n = (size_t)out.n_points;
+	// fuse on the device, then download straight into the PointCloud's arrays (one copy)
+	if (hcmvs_fuse_depthmaps(ctx, bEstimateColor, bEstimateNormal, nullptr) != HCMVS_OK) return Fail("hcmvs_fuse_depthmaps");
+	uint64_t n = 0, m = 0; void* nd = nullptr; void* cd = nullptr;
+	if (hcmvs_get_fused_device(ctx, &n, &m, nullptr, &nd, &cd, nullptr, nullptr, nullptr) != HCMVS_OK) return Fail("hcmvs_get_fused_device");
 	pc = PointCloud();
-	if (n) {
-		pc.points.assign(out.points, out.points+n*3);
-		pc.viewOffsets.assign(out.view_offsets, out.view_offsets+n+1);
-		const size_t m = out.view_offsets[n];
-		pc.views.assign(out.views, out.views+m);
-		pc.weights.assign(out.weights, out.weights+m);
-		if (out.normals) pc.normals.assign(out.normals, out.normals+n*3);
-		if (out.colors) pc.colors.assign(out.colors, out.colors+n*3);
-	}
-	hcmvs_free_pointcloud(&out);
+	if (!n) return true;
+	pc.points.resize(n*3); pc.viewOffsets.resize(n+1); pc.views.resize(m); pc.weights.resize(m);
+	if (nd) pc.normals.resize(n*3);
+	if (cd) pc.colors.resize(n*3);
+	if (hcmvs_download_fused(ctx, pc.points.data(), nd ? pc.normals.data() : nullptr, cd ? pc.colors.data() : nullptr,
+	                         pc.viewOffsets.data(), pc.views.data(), pc.weights.data()) != HCMVS_OK) return Fail("hcmvs_download_fused");
 	return true;
 }
 
@@ -364,7 +363,15 @@ bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, co
 	const uint32_t nImages = (uint32_t)scene.images.size();
 	for (Image& im: scene.images) im.camera.ComposeP();
 	std::vector<uint32_t> valid;
-	for (uint32_t i=0; i<nImages; ++i) if (data.SelectViews(i)) valid.push_back(i); // :3652-3667
+	{ // the reference selects views with `#pragma omp parallel for` over the images (:3652-3667); each call only writes image i's state
+		std::vector<char> okv(nImages, 0);
+		const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), nImages));
+		std::atomic<uint32_t> next{0};
+		std::vector<std::thread> pool;
+		for (unsigned t=0; t<nt; ++t) pool.emplace_back([&]() { uint32_t i; while ((i = next.fetch_add(1)) < nImages) okv[i] = data.SelectViews(i) ? 1 : 0; });
+		for (std::thread& th: pool) th.join();
+		for (uint32_t i=0; i<nImages; ++i) if (okv[i]) valid.push_back(i);
+	}
 	if (valid.empty()) return fail("no image has enough neighbour views");
 	double t1 = Now(); st.secSelect = t1-t0;
 	for (uint32_t i: valid) {

@@ -46,8 +46,7 @@ typedef struct hcmvs_params {
 
 typedef struct hcmvs_ctx hcmvs_ctx;
 
-/* Fused point cloud (libs/MVS/PointCloud.h:49-109). The arrays live in pinned host memory owned by the context: they stay
- * valid until the next hcmvs_fuse_depthmaps / hcmvs_destroy on that context; hcmvs_free_pointcloud only clears the struct. */
+/* Fused point cloud (libs/MVS/PointCloud.h:49-109). Arrays are allocated by the library; release with hcmvs_free_pointcloud. */
 typedef struct hcmvs_pointcloud {
 	uint64_t n_points;
 	float*   points;      /* n*3 */
@@ -126,6 +125,8 @@ int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int estimate_normal
 void hcmvs_free_pointcloud(hcmvs_pointcloud* pc);
 /* hcmvs_fuse_depthmaps with out == NULL leaves the cloud on the device; this returns its device arrays
  * (points/normals float[3n], colors u8[3n], view_offsets u32[n+1], views u32[m], weights float[m]). */
+/* Copy the last fused cloud into caller-owned host arrays (sizes from hcmvs_get_fused_device); any pointer may be NULL. */
+int hcmvs_download_fused(hcmvs_ctx* ctx, float* points, float* normals, uint8_t* colors, uint32_t* view_offsets, uint32_t* views, float* weights);
 int hcmvs_get_fused_device(hcmvs_ctx* ctx, uint64_t* n_points, uint64_t* n_view_refs, void** points_d, void** normals_d, void** colors_d,
                            void** view_offsets_d, void** views_d, void** weights_d);
 
