@@ -350,7 +350,7 @@ def run_b200(args):
             "config": {"workload": WORKLOADS[args.config], "scale": args.scale, "views": V, "image": [W, H], "neighbours": 5,
                        "patchmatch_iters": int(P.nEstimationIters), "stages": "estimate(A+B+C) + filter + fuse", "parallelism": f"view-sharded x{world}",
                        "l2": "inputs per view (5 neighbour images + maps, ~77 MB) re-read per launch; 49-view working set 2.3 GB > 126 MB L2"},
-            "scene_seconds": sec_step, "fused_points": npoints, "stage_ms_per_step_rank0": stages,
+            "scene_seconds": sec_step, "fused_points": npoints, "fuse_rounds": int(tm["n_fuse_rounds"]), "stage_ms_per_step_rank0": stages,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         }
         print(json.dumps(line))

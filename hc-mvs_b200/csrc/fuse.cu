@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
+#include <cstdio>
 
 namespace cg = cooperative_groups;
 
@@ -42,6 +43,8 @@ struct FuseArgs {
 	uint8_t* state;   // per ref pixel: 0 not a seed / removed, 1 undecided, 2 emitted
 	uint32_t* mask;   // merged neighbours (bit k = nb[k]) of emitted seeds
 	int* counters;    // [0] undecided seeds, [1] rounds, [2] seeds
+	int* trace;       // optional: undecided seeds after each round (debug)
+	uint32_t* probes; size_t probeStride; // [neighbour][pixel] probe cache
 };
 
 struct Probe { int q; float z; };
@@ -65,17 +68,52 @@ __device__ __forceinline__ float conf2weight(float conf, float depth) { // Conf2
 }
 __device__ __forceinline__ float dot3f(const float3 a, const float3 b) { return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z)); }
 
+// per-(seed, neighbour) probe, computed once: pixel index in the neighbour view | class << 30
+#define PROBE_NONE  0u   // neither similar nor occluding: the seed never touches this pixel (no dependency through it)
+#define PROBE_MERGE 1u   // depth and normal agree (SceneDensify.cpp:3400-3423): claimed if the seed survives
+#define PROBE_INVAL 2u   // occluded by the seed (:3424-3427): zeroed if the seed survives
+#define PROBE_DEAD  0xFFFFFFFFu
+
 __global__ void __launch_bounds__(256) k_fuse_view(const FuseArgs a) {
 	cg::grid_group grid = cg::this_grid();
 	const FuseView& R = a.views[a.ref];
 	const int nPix = R.w*R.h;
 	const int tid = blockIdx.x*blockDim.x+threadIdx.x, nThreads = gridDim.x*blockDim.x;
-	// ---- phase 0: find the seeds (valid depth, not yet claimed), SceneDensify.cpp:3347-3354
+	// ---- phase 0: find the seeds (valid depth, not yet claimed, SceneDensify.cpp:3347-3354) and classify their probes.
+	// The geometry of a probe is static: the seed's 3-D point, the pixel it hits in each neighbour view, and — while that
+	// pixel is alive (depth != 0, not claimed) — whether it would merge, be invalidated, or be left alone. Only liveness
+	// changes during the fusion of this view, so the f64 projections are done once and the rounds below are integer work.
 	int mySeeds = 0;
 	for (int p=tid; p<nPix; p+=nThreads) {
-		const bool seed = R.dn[p].w != 0.f && R.claim[p] != CLAIM_TAKEN;
+		const float4 e = R.dn[p];
+		const bool seed = e.w != 0.f && R.claim[p] != CLAIM_TAKEN;
 		a.state[p] = seed ? 1 : 0;
 		mySeeds += seed;
+		if (!seed) continue;
+		const int x = p%R.w, y = p/R.w;
+		const float3 point = seed_point(R, x, y, e.w);
+		const float3 normal = cam_NormalC2W(R.cam, make_float3(e.x, e.y, e.z));
+		for (int k=0; k<a.nNb; ++k) {
+			uint32_t code = PROBE_DEAD;
+			const FuseView& B = a.views[a.nb[k]];
+			if (B.hasMaps) {
+				const Probe pr = probe_view(B, point);
+				if (pr.q >= 0) {
+					const float4 eB = B.dn[pr.q];
+					if (eB.w != 0.f && B.claim[pr.q] != CLAIM_TAKEN) {
+						uint32_t cls = PROBE_NONE;
+						bool merge = false;
+						if (depth_similar(pr.z, eB.w, a.depthTh)) {
+							const float3 normalB = cam_NormalC2W(B.cam, make_float3(eB.x, eB.y, eB.z));
+							merge = dot3f(normal, normalB) > a.normalError;
+						}
+						if (merge) cls = PROBE_MERGE; else if (pr.z < eB.w) cls = PROBE_INVAL;
+						code = (uint32_t)pr.q | (cls<<30);
+					}
+				}
+			}
+			a.probes[(size_t)k*a.probeStride+p] = code;
+		}
 	}
 	mySeeds = cg::reduce(cg::tiled_partition<32>(cg::this_thread_block()), mySeeds, cg::plus<int>());
 	if ((threadIdx.x&31) == 0 && mySeeds) { atomicAdd(&a.counters[0], mySeeds); atomicAdd(&a.counters[2], mySeeds); }
@@ -83,19 +121,17 @@ __global__ void __launch_bounds__(256) k_fuse_view(const FuseArgs a) {
 	int undecided = *(volatile int*)&a.counters[0];
 	int round = 0;
 	while (undecided > 0) {
-		// ---- phase 1: reserve every live neighbour pixel this seed would touch
+		// ---- phase 1: reserve every live neighbour pixel this seed would modify
 		for (int p=tid; p<nPix; p+=nThreads) {
 			if (a.state[p] != 1) continue;
-			const int x = p%R.w, y = p/R.w;
-			const float3 point = seed_point(R, x, y, R.dn[p].w);
 			for (int k=0; k<a.nNb; ++k) {
+				const uint32_t code = a.probes[(size_t)k*a.probeStride+p];
+				if (code == PROBE_DEAD || (code>>30) == PROBE_NONE) continue;
 				const FuseView& B = a.views[a.nb[k]];
-				if (!B.hasMaps) continue;
-				const Probe pr = probe_view(B, point);
-				if (pr.q < 0) continue;
-				if (B.dn[pr.q].w == 0.f) continue;
-				if (B.claim[pr.q] == CLAIM_TAKEN) continue;
-				atomicMin(&B.claim[pr.q], (uint32_t)p);
+				const uint32_t q = code & 0x3FFFFFFFu;
+				if (B.dn[q].w == 0.f) continue;
+				if (B.claim[q] == CLAIM_TAKEN) continue;
+				atomicMin(&B.claim[q], (uint32_t)p);
 			}
 		}
 		grid.sync();
@@ -103,42 +139,31 @@ __global__ void __launch_bounds__(256) k_fuse_view(const FuseArgs a) {
 		int nDone = 0;
 		for (int p=tid; p<nPix; p+=nThreads) {
 			if (a.state[p] != 1) continue;
-			const int x = p%R.w, y = p/R.w;
-			const float4 e = R.dn[p];
-			const float3 point = seed_point(R, x, y, e.w);
-			const float3 normal = cam_NormalC2W(R.cam, make_float3(e.x, e.y, e.z));
-			int qs[HCMVS_MAX_FUSE_VIEWS];
 			uint32_t live = 0, merged = 0, inval = 0;
 			unsigned nViews = 1;
 			bool ready = true;
-			for (int k=0; k<a.nNb && ready; ++k) {
-				qs[k] = -1;
+			for (int k=0; k<a.nNb; ++k) {
+				const uint32_t code = a.probes[(size_t)k*a.probeStride+p];
+				if (code == PROBE_DEAD || (code>>30) == PROBE_NONE) continue;
 				const FuseView& B = a.views[a.nb[k]];
-				if (!B.hasMaps) continue;
-				const Probe pr = probe_view(B, point);
-				if (pr.q < 0) continue;
-				const float4 eB = B.dn[pr.q];
-				const float depthB = eB.w;
-				if (depthB == 0.f) continue;
-				const uint32_t c = *(volatile uint32_t*)&B.claim[pr.q];
+				const uint32_t q = code & 0x3FFFFFFFu;
+				if (*(volatile float*)&B.dn[q].w == 0.f) continue;
+				const uint32_t c = *(volatile uint32_t*)&B.claim[q];
 				if (c == CLAIM_TAKEN) continue;
 				if (c != (uint32_t)p) { ready = false; break; }
-				qs[k] = pr.q; live |= 1u<<k;
-				if (depth_similar(pr.z, depthB, a.depthTh)) { // SceneDensify.cpp:3400-3423
-					const float3 normalB = cam_NormalC2W(B.cam, make_float3(eB.x, eB.y, eB.z));
-					if (dot3f(normal, normalB) > a.normalError) { merged |= 1u<<k; ++nViews; continue; }
-				}
-				if (pr.z < depthB) inval |= 1u<<k; // :3424-3427
+				live |= 1u<<k;
+				if ((code>>30) == PROBE_MERGE) { merged |= 1u<<k; ++nViews; } else inval |= 1u<<k;
 			}
 			if (!ready) continue;
 			const bool emit = nViews >= a.nMinViewsFuse; // :3429
 			for (int k=0; k<a.nNb; ++k) {
 				if (!(live & (1u<<k))) continue;
 				const FuseView& B = a.views[a.nb[k]];
-				if (emit && (merged & (1u<<k))) B.claim[qs[k]] = CLAIM_TAKEN;
+				const uint32_t q = a.probes[(size_t)k*a.probeStride+p] & 0x3FFFFFFFu;
+				if (emit && (merged & (1u<<k))) B.claim[q] = CLAIM_TAKEN;
 				else {
-					if (emit && (inval & (1u<<k))) B.dn[qs[k]].w = 0.f; // invalidate occluded depths, :3447-3449
-					B.claim[qs[k]] = CLAIM_FREE;
+					if (emit && (inval & (1u<<k))) B.dn[q].w = 0.f; // invalidate occluded depths, :3447-3449
+					B.claim[q] = CLAIM_FREE;
 				}
 			}
 			if (emit) { R.claim[p] = CLAIM_TAKEN; a.mask[p] = merged; a.state[p] = 2; }
@@ -149,6 +174,7 @@ __global__ void __launch_bounds__(256) k_fuse_view(const FuseArgs a) {
 		if ((threadIdx.x&31) == 0 && nDone) atomicSub(&a.counters[0], nDone);
 		grid.sync();
 		undecided = *(volatile int*)&a.counters[0];
+		if (tid == 0 && a.trace && round < 256) a.trace[round] = undecided;
 		++round;
 	}
 	if (tid == 0) a.counters[1] = round;
@@ -245,7 +271,7 @@ __global__ void __launch_bounds__(256) k_fuse_emit(const FuseArgs a, const uint2
 		for (int k=0; k<a.nNb; ++k) {
 			if (!(merged & (1u<<k))) continue;
 			const FuseView& B = a.views[a.nb[k]];
-			const Probe pr = probe_view(B, point);
+			Probe pr; pr.q = (int)(a.probes[(size_t)k*a.probeStride+p] & 0x3FFFFFFFu); pr.z = 0.f;
 			const int xB = pr.q%B.w, yB = pr.q/B.w;
 			const float4 eB = B.dn[pr.q];
 			const float depthB = eB.w;
@@ -289,7 +315,8 @@ struct FuseState {
 	FuseView* views_d = nullptr; size_t nViews = 0;
 	uint8_t* state_d = nullptr; uint32_t* mask_d = nullptr; size_t pixCap = 0;
 	uint2* blockSums_d = nullptr; size_t blockCap = 0;
-	int* counters_d = nullptr;
+	int* counters_d = nullptr; int* trace_d = nullptr;
+	uint32_t* probes_d = nullptr; size_t probeCap = 0;
 	// growing output
 	float* points = nullptr; float* normals = nullptr; uint8_t* colors = nullptr; uint32_t* viewOffsets = nullptr; size_t capPoints = 0;
 	uint32_t* oviews = nullptr; float* weights = nullptr; size_t capViews = 0;
@@ -299,6 +326,7 @@ struct FuseState {
 
 void hcmvs_fuse_release(hcmvs_ctx* ctx) {
 	FuseState* f = ctx->fuse; if (!f) return;
+	cudaFree(f->trace_d); cudaFree(f->probes_d);
 	cudaFree(f->views_d); cudaFree(f->state_d); cudaFree(f->mask_d); cudaFree(f->blockSums_d); cudaFree(f->counters_d);
 	cudaFree(f->points); cudaFree(f->normals); cudaFree(f->colors); cudaFree(f->viewOffsets); cudaFree(f->oviews); cudaFree(f->weights);
 	delete f; ctx->fuse = nullptr;
@@ -328,6 +356,7 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 	const size_t V = ctx->views.size();
 	if (!ctx->fuse) ctx->fuse = new FuseState();
 	FuseState* f = ctx->fuse;
+	const bool debug = getenv("HCMVS_FUSE_DEBUG") != nullptr;
 	// connections: valid views sorted by the size of their scored-neighbour list, SceneDensify.cpp:3286-3303 (ties by index)
 	struct Conn { uint32_t idx; float score; };
 	std::vector<Conn> conns;
@@ -358,6 +387,10 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 	const size_t maxBlocks = (maxPix+FUSE_CHUNK-1)/FUSE_CHUNK;
 	if (f->blockCap < maxBlocks+1) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(f->blockSums_d); CK(cudaMalloc(&f->blockSums_d, (maxBlocks+1)*sizeof(uint2))); f->blockCap = maxBlocks+1; }
 	if (!f->counters_d) CK(cudaMalloc(&f->counters_d, 4*sizeof(int)));
+	if (!f->trace_d) CK(cudaMalloc(&f->trace_d, 256*sizeof(int)));
+	size_t maxNb = 1; for (const Conn& c: conns) maxNb = std::max(maxNb, ctx->views[c.idx].nbIds.size());
+	if (f->probeCap < maxNb*maxPix) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(f->probes_d); CK(cudaMalloc(&f->probes_d, maxNb*maxPix*4)); f->probeCap = maxNb*maxPix; }
+	if (maxPix >= (1u<<30)) { hcmvs_set_error("depth maps above 2^30 pixels are not supported by the fusion probe cache"); return HCMVS_ERR_UNSUPPORTED; }
 	if (!f->coopBlocks) {
 		int dev = ctx->device, coop = 0, sms = 0, perSm = 0;
 		cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
@@ -381,7 +414,8 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 		for (uint32_t id: v.nbIds) { if (id < V) a.nb[a.nNb++] = (int)id; }
 		a.nMinViewsFuse = nMinViewsFuse;
 		a.depthTh = P.fDepthDiffThreshold*P.depthweight; a.normalError = normalError;
-		a.state = f->state_d; a.mask = f->mask_d; a.counters = f->counters_d;
+		a.state = f->state_d; a.mask = f->mask_d; a.counters = f->counters_d; a.trace = debug ? f->trace_d : nullptr;
+		a.probes = f->probes_d; a.probeStride = maxPix;
 		const int nPix = v.w*v.h;
 		CK(cudaMemsetAsync(f->counters_d, 0, 4*sizeof(int), ctx->stream));
 		void* args[] = {(void*)&a};
@@ -394,6 +428,12 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 		CK(cudaMemcpyAsync(cnt, f->counters_d, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
 		CK(cudaStreamSynchronize(ctx->stream));
 		totalRounds += (uint64_t)cnt[1];
+		if (debug) {
+			int tr[256]; cudaMemcpy(tr, f->trace_d, sizeof(tr), cudaMemcpyDeviceToHost);
+			fprintf(stderr, "[fuse] view %u: %d seeds, %d rounds, %u points, %u view refs; undecided after round:", conn.idx, cnt[2], cnt[1], tot.x, tot.y);
+			for (int k=0; k<std::min(cnt[1], 12); ++k) fprintf(stderr, " %d", tr[k]);
+			fprintf(stderr, "\n");
+		}
 		if (tot.x == 0) continue;
 		if (nPoints+tot.x > f->capPoints) {
 			const size_t nc = std::max<size_t>((nPoints+tot.x)*2, (size_t)1<<20);
