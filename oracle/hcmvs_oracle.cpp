@@ -990,6 +990,31 @@ static void RBProcessPixel(DepthEstimator& est, int px, int py, const uint32_t k
 	}
 }
 
+// the block-best plane offered to pixel (px,py): interpolate it to the pixel, score with the pixel's own smoothness set
+static void RBTestShared(DepthEstimator& est, int px, int py, int sx, int sy, Depth sd, Vec3f sn) {
+	if (!est.PreparePixelPatch(px, py) || !est.FillPixelPatch()) return;
+	DepthData& dd = est.dd;
+	const int w = est.w, h = est.h, hw = 7;
+	est.neighborsClose.clear();
+	auto addClose = [&](int nx, int ny) {
+		const Depth nd = dd.depthMap.at(nx, ny);
+		if (nd > 0) {
+			const Vec3d Xd = est.image0.cam.TransformPointI2C((double)nx, (double)ny, (double)nd);
+			est.neighborsClose.push_back(NeighborEstimate{nd, dd.normalMap[(size_t)ny*w+nx], Vec3f{(float)Xd.x, (float)Xd.y, (float)Xd.z}});
+		}
+	};
+	if (px > hw) addClose(px-1, py);
+	if (py > hw) addClose(px, py-1);
+	if (px < w-hw) addClose(px+1, py);
+	if (py < h-hw) addClose(px, py+1);
+	Depth nd = est.InterpolatePixel(sx, sy, sd, sn);
+	est.CorrectNormal(sn);
+	est.InitPlane(nd, sn);
+	const float nconf = est.ScorePixel(nd, sn);
+	float& conf = dd.confMap.d[(size_t)py*w+px];
+	if (conf > nconf) { conf = nconf; dd.depthMap.d[(size_t)py*w+px] = nd; dd.normalMap[(size_t)py*w+px] = sn; }
+}
+
 bool EstimateDepthMapRedBlack(Scene& scene, uint32_t idxImage, int it_external, uint64_t seed, unsigned nThreads,
 	const RedBlackCfg& cfg, EstimateStats* stats, bool runEnd)
 {
@@ -1012,6 +1037,34 @@ bool EstimateDepthMapRedBlack(Scene& scene, uint32_t idxImage, int it_external, 
 	for (unsigned iter=0; iter<P.nEstimationIters; ++iter) {
 		for (int colour=0; colour<2; ++colour) {
 			std::atomic<int> row{0};
+			if (cfg.blockShare) {
+				// warp-cooperative variant: the pixels of an 8x8 block (one GPU warp) first run ProcessPixel, then the pixel with
+				// the lowest score offers its refined plane to the other active pixels of the block (one more hypothesis each)
+				const int nby = (h+7)/8, nbx = (w+7)/8;
+				std::atomic<int> blk{0};
+				RunThreads(nThreads, [&](unsigned) {
+					DepthEstimator est(iter, it_external, scene, dd, 0);
+					int b;
+					while ((b = blk.fetch_add(1)) < nby*nbx) {
+						const int by0 = (b/nbx)*8, bx0 = (b%nbx)*8;
+						int bestX = -1, bestY = -1; float bestC = 3.f;
+						for (int ly=0; ly<8; ++ly) for (int lx=0; lx<4; ++lx) { // lane = ly*4+lx
+							const int y = by0+ly, x = bx0+lx*2+((y+colour)&1);
+							if (x >= w || y >= h) continue;
+							RBProcessPixel(est, x, y, key, 1+iter+it_external*64u, cfg);
+							if (est.PreparePixelPatch(x, y)) { const float c = dd.confMap.at(x, y); if (c < bestC) { bestC = c; bestX = x; bestY = y; } }
+						}
+						if (bestX < 0 || bestC >= P.fNCCThresholdKeep) continue;
+						const Depth bd = dd.depthMap.at(bestX, bestY); const Vec3f bn = dd.normalMap[(size_t)bestY*w+bestX];
+						for (int ly=0; ly<8; ++ly) for (int lx=0; lx<4; ++lx) {
+							const int y = by0+ly, x = bx0+lx*2+((y+colour)&1);
+							if (x >= w || y >= h || (x == bestX && y == bestY)) continue;
+							RBTestShared(est, x, y, bestX, bestY, bd, bn);
+						}
+					}
+					nHyp += est.nScored;
+				});
+			} else
 			RunThreads(nThreads, [&](unsigned) {
 				DepthEstimator est(iter, it_external, scene, dd, 0);
 				int y;

@@ -230,7 +230,7 @@ void EndDepthMap(Scene& scene, uint32_t idxImage);
 
 // Red-black restatement of the sweep: SAME scoring functions, checkerboard order and the counter-based
 // Philox RNG the CUDA kernels use. This is the CPU statement of what the GPU computes.
-struct RedBlackCfg { int farReach = 11; int useFar = 1; int nDirs = 4; };
+struct RedBlackCfg { int farReach = 11; int useFar = 1; int nDirs = 4; int blockShare = 0; };
 bool EstimateDepthMapRedBlack(Scene& scene, uint32_t idxImage, int it_external, uint64_t seed, unsigned nThreads,
 	const RedBlackCfg& cfg, EstimateStats* stats = nullptr, bool runEnd = true);
 

@@ -157,7 +157,7 @@ int orc_estimate_depthmap(orc_scene* s, int idx, int it_external, uint64_t seed,
 	EstimateStats st;
 	bool ok;
 	if (mode == 0) ok = EstimateDepthMap(s->scene, (uint32_t)idx, it_external, seed, (unsigned)std::max(nThreads, 1), &st, runEnd != 0);
-	else { RedBlackCfg cfg; cfg.nDirs = (mode == 2) ? 2 : 4; cfg.farReach = farReach > 0 ? farReach : 1; cfg.useFar = farReach > 1; ok = EstimateDepthMapRedBlack(s->scene, (uint32_t)idx, it_external, seed, (unsigned)std::max(nThreads, 1), cfg, &st, runEnd != 0); }
+	else { RedBlackCfg cfg; cfg.nDirs = (mode == 2 || mode == 3) ? 2 : 4; cfg.blockShare = (mode == 3 || mode == 4) ? 1 : 0; cfg.farReach = farReach > 0 ? farReach : 1; cfg.useFar = farReach > 1; ok = EstimateDepthMapRedBlack(s->scene, (uint32_t)idx, it_external, seed, (unsigned)std::max(nThreads, 1), cfg, &st, runEnd != 0); }
 	if (stats) { stats[0] = st.secScore; stats[1] = st.secSweeps; stats[2] = st.secEnd; stats[3] = (double)st.nHypotheses; stats[4] = (double)st.nPixelIters; }
 	return ok ? 0 : -1;
 }
