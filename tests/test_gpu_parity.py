@@ -163,3 +163,32 @@ def test_outer_iteration_plus_pattern_matches_oracle(scene, ctx):
     with pytest.raises(Exception, match="checkerboard"):
         ctx.estimate_depthmap(ref, 1, seed=1)
     ctx.set_params(**back)
+
+
+@pytest.mark.parametrize("sampler", [0, 1])
+def test_score_hypotheses_adapthalfwin7(scene, sampler):
+    """The authors' run value adapthalfwin = 7 (data/frame_main/resize3/run.py): 8x8 texels, or 6x6 where the gradient map
+    exceeds 100 (DepthMap.cpp:454-461) — the compile-time 8x8 walk chosen per pixel must match the oracle's runtime-side loop."""
+    syn, osc, gt, imgs, ok = scene
+    osc.set_params(adapthalfwin=7)
+    c = common.make_context(syn, osc, imgs, ok, adapthalfwin=7, sampler=sampler)
+    try:
+        for ref in (1, 5):
+            # the gradient map switches the window per pixel: it has to exist on both sides
+            osc.init_depth_sparse(ref)
+            d0, n0, c0, dmin, dmax = osc.get_depthmap(ref)
+            c.init_depthmap(ref, d0, None, dmin, dmax)
+            gra = osc.gramap(ref)
+            assert np.array_equal(c.gradient_map(ref), gra)
+            for k, (ds, ang) in enumerate(((0.0, 0.0), (0.01, 8.0))):
+                d, n = common.perturbed_hypotheses(gt[ref][0], gt[ref][1], syn.K[ref], seed=70 + 10 * ref + k, depth_sigma=ds, angle_deg=ang)
+                for smooth in (0, 1):
+                    want = osc.score_hypotheses(ref, d, n, smooth)
+                    got = c.score_hypotheses(ref, d, n, smooth)
+                    err = np.abs(want - got)
+                    assert err.max() <= NCC_TOL, f"ref {ref} case {k} smooth {smooth}: max |Δ| {err.max():.3e}"
+            inner = gra[7:-7, 7:-7]
+            print(f"\nahw7 ref {ref}: {100.0 * np.mean(inner > 100):.1f} % of pixels use the 6x6 window")
+    finally:
+        osc.set_params(adapthalfwin=5)
+        c.close()
