@@ -121,9 +121,10 @@ __global__ void __launch_bounds__(256) k_fuse_view(const FuseArgs a) {
 	int undecided = *(volatile int*)&a.counters[0];
 	int round = 0;
 	while (undecided > 0) {
-		// ---- phase 1: reserve every live neighbour pixel this seed would modify
+		// ---- phase 1: every unfinished seed reserves each live neighbour pixel it has not dealt with yet
 		for (int p=tid; p<nPix; p+=nThreads) {
-			if (a.state[p] != 1) continue;
+			const uint8_t st = a.state[p];
+			if (st != 1 && st != 3) continue;
 			for (int k=0; k<a.nNb; ++k) {
 				const uint32_t code = a.probes[(size_t)k*a.probeStride+p];
 				if (code == PROBE_DEAD || (code>>30) == PROBE_NONE) continue;
@@ -135,40 +136,57 @@ __global__ void __launch_bounds__(256) k_fuse_view(const FuseArgs a) {
 			}
 		}
 		grid.sync();
-		// ---- phase 2: seeds holding all their reservations run the reference's per-pixel action
+		// ---- phase 2: resolve what the raster order already fixes.
+		// A seed holding a reservation precedes every unfinished seed that touches the same pixel, so that pixel is in
+		// the state the seed would find it in at its turn of the raster scan. Hence:
+		//  * a seed whose own view + already merged + held agreeing pixels reach nMinViewsFuse WILL be emitted (:3429)
+		//    whatever its contested probes turn into: it acts on the pixels it holds at once (claim / zero them) and only
+		//    keeps waiting for the contested ones — this is what cuts the dependency chains along the rows;
+		//  * a seed that cannot reach nMinViewsFuse even if every contested agreeing pixel were still alive at its turn
+		//    will NOT be emitted: it releases everything;
+		//  * otherwise it waits for the lower seeds it conflicts with (the lowest unfinished seed never waits).
 		int nDone = 0;
 		for (int p=tid; p<nPix; p+=nThreads) {
-			if (a.state[p] != 1) continue;
-			uint32_t live = 0, merged = 0, inval = 0;
-			unsigned nViews = 1;
-			bool ready = true;
+			const uint8_t st = a.state[p];
+			if (st != 1 && st != 3) continue;
+			uint32_t merged = st == 3 ? a.mask[p] : 0u;
+			uint32_t heldMerge = 0, heldInval = 0;
+			unsigned nContested = 0, nContestedMerge = 0;
 			for (int k=0; k<a.nNb; ++k) {
 				const uint32_t code = a.probes[(size_t)k*a.probeStride+p];
 				if (code == PROBE_DEAD || (code>>30) == PROBE_NONE) continue;
 				const FuseView& B = a.views[a.nb[k]];
 				const uint32_t q = code & 0x3FFFFFFFu;
-				if (*(volatile float*)&B.dn[q].w == 0.f) continue;
 				const uint32_t c = *(volatile uint32_t*)&B.claim[q];
-				if (c == CLAIM_TAKEN) continue;
-				if (c != (uint32_t)p) { ready = false; break; }
-				live |= 1u<<k;
-				if ((code>>30) == PROBE_MERGE) { merged |= 1u<<k; ++nViews; } else inval |= 1u<<k;
+				if (c == CLAIM_TAKEN || *(volatile float*)&B.dn[q].w == 0.f) { a.probes[(size_t)k*a.probeStride+p] = PROBE_DEAD; continue; }
+				if (c == (uint32_t)p) { if ((code>>30) == PROBE_MERGE) heldMerge |= 1u<<k; else heldInval |= 1u<<k; }
+				else { ++nContested; nContestedMerge += (code>>30) == PROBE_MERGE; }
 			}
-			if (!ready) continue;
-			const bool emit = nViews >= a.nMinViewsFuse; // :3429
-			for (int k=0; k<a.nNb; ++k) {
-				if (!(live & (1u<<k))) continue;
-				const FuseView& B = a.views[a.nb[k]];
-				const uint32_t q = a.probes[(size_t)k*a.probeStride+p] & 0x3FFFFFFFu;
-				if (emit && (merged & (1u<<k))) B.claim[q] = CLAIM_TAKEN;
-				else {
-					if (emit && (inval & (1u<<k))) B.dn[q].w = 0.f; // invalidate occluded depths, :3447-3449
-					B.claim[q] = CLAIM_FREE;
+			const unsigned nViews = 1u+__popc(merged)+__popc(heldMerge);
+			if (st == 3 || nViews >= a.nMinViewsFuse) {
+				for (int k=0; k<a.nNb; ++k) {
+					const uint32_t bit = 1u<<k;
+					if (!((heldMerge|heldInval) & bit)) continue;
+					const FuseView& B = a.views[a.nb[k]];
+					const size_t pi = (size_t)k*a.probeStride+p;
+					const uint32_t q = a.probes[pi] & 0x3FFFFFFFu;
+					if (heldMerge & bit) B.claim[q] = CLAIM_TAKEN; // merged probes keep their pixel index for k_fuse_emit
+					else { B.dn[q].w = 0.f; __threadfence(); B.claim[q] = CLAIM_FREE; a.probes[pi] = PROBE_DEAD; } // :3447-3449
 				}
+				merged |= heldMerge;
+				// a merged probe must not be looked at again: park it as PROBE_NONE (pixel index kept)
+				for (int k=0; k<a.nNb; ++k) if (heldMerge & (1u<<k)) { const size_t pi = (size_t)k*a.probeStride+p; a.probes[pi] = (a.probes[pi] & 0x3FFFFFFFu) | (PROBE_NONE<<30); }
+				a.mask[p] = merged;
+				if (nContested == 0) { R.claim[p] = CLAIM_TAKEN; a.state[p] = 2; ++nDone; }
+				else a.state[p] = 3;
+			} else if (nViews+nContestedMerge < a.nMinViewsFuse) {
+				for (int k=0; k<a.nNb; ++k) {
+					if (!((heldMerge|heldInval) & (1u<<k))) continue;
+					const FuseView& B = a.views[a.nb[k]];
+					B.claim[a.probes[(size_t)k*a.probeStride+p] & 0x3FFFFFFFu] = CLAIM_FREE;
+				}
+				a.state[p] = 0; ++nDone;
 			}
-			if (emit) { R.claim[p] = CLAIM_TAKEN; a.mask[p] = merged; a.state[p] = 2; }
-			else a.state[p] = 0;
-			++nDone;
 		}
 		nDone = cg::reduce(cg::tiled_partition<32>(cg::this_thread_block()), nDone, cg::plus<int>());
 		if ((threadIdx.x&31) == 0 && nDone) atomicSub(&a.counters[0], nDone);

@@ -58,11 +58,17 @@ def test_filter_depthmap_bit_exact(loaded, adjust):
         assert (want[0] > 0).sum() > 1000  # the case is not vacuous
 
 
-def test_fuse_depthmaps_identical_cloud(loaded):
+@pytest.mark.parametrize("min_views_fuse", [2, 3, 1])
+def test_fuse_depthmaps_identical_cloud(loaded, min_views_fuse):
+    """nMinViewsFuse 2 is the shipped value; 3 and 1 exercise the "will / will not be emitted" early decisions of k_fuse_view."""
     syn, osc, ctx, maps, ok = loaded
     load_maps(syn, osc, ctx, maps)
-    want = osc.fuse(True, True)
-    got = ctx.fuse_depthmaps(True, True)
+    osc.set_params(nMinViewsFuse=min_views_fuse); ctx.set_params(nMinViewsFuse=min_views_fuse)
+    try:
+        want = osc.fuse(True, True)
+        got = ctx.fuse_depthmaps(True, True)
+    finally:
+        osc.set_params(nMinViewsFuse=2); ctx.set_params(nMinViewsFuse=2)
     assert len(want["xyz"]) > 10000
     assert len(want["xyz"]) == len(got["xyz"]), (len(want["xyz"]), len(got["xyz"]))
     assert np.array_equal(want["n_views"], got["n_views"])
