@@ -10,6 +10,9 @@
 #ifndef HCMVS_MINB
 #define HCMVS_MINB 3
 #endif
+#ifndef HCMVS_RB6
+#define HCMVS_RB6 2                     // rows of a 6x6 patch whose texture gathers are in flight together (k_sweep batches)
+#endif
 #ifndef HCMVS_EARLY_REJECT
 #define HCMVS_EARLY_REJECT 0
 #endif
