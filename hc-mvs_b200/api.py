@@ -16,7 +16,7 @@ EXPORTS = [
     "hcmvs_set_view", "hcmvs_set_neighbors", "hcmvs_init_depthmap", "hcmvs_set_depthmap", "hcmvs_get_depthmap",
     "hcmvs_set_prior", "hcmvs_get_gradient_map", "hcmvs_score_depthmap", "hcmvs_estimate_depthmap", "hcmvs_end_depthmap", "hcmvs_score_hypotheses",
     "hcmvs_filter_depthmap", "hcmvs_commit_filtered", "hcmvs_set_fuse_priority", "hcmvs_fuse_depthmaps",
-    "hcmvs_free_pointcloud", "hcmvs_get_fused_device", "hcmvs_download_fused", "hcmvs_get_depthmap_device", "hcmvs_set_depth_range", "hcmvs_alloc_depthmap",
+    "hcmvs_free_pointcloud", "hcmvs_get_fused_device", "hcmvs_download_fused", "hcmvs_download_fused_pinned", "hcmvs_get_depthmap_device", "hcmvs_set_depth_range", "hcmvs_alloc_depthmap",
     "hcmvs_export_maps_d", "hcmvs_import_maps_d", "hcmvs_get_timers", "hcmvs_reset_timers", "hcmvs_stream",
 ]
 

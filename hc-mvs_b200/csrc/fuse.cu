@@ -339,12 +339,14 @@ struct FuseState {
 	float* points = nullptr; float* normals = nullptr; uint8_t* colors = nullptr; uint32_t* viewOffsets = nullptr; size_t capPoints = 0;
 	uint32_t* oviews = nullptr; float* weights = nullptr; size_t capViews = 0;
 	int coopBlocks = 0;
+	void* pinned = nullptr; size_t pinnedBytes = 0; // page-locked host arena of hcmvs_download_fused_pinned (grow-only)
 	size_t nPoints = 0, nViewRefs = 0; bool hasColor = false, hasNormal = false; // last fused cloud (device resident)
 };
 
 void hcmvs_fuse_release(hcmvs_ctx* ctx) {
 	FuseState* f = ctx->fuse; if (!f) return;
 	cudaFree(f->trace_d); cudaFree(f->probes_d);
+	if (f->pinned) cudaFreeHost(f->pinned);
 	cudaFree(f->views_d); cudaFree(f->state_d); cudaFree(f->mask_d); cudaFree(f->blockSums_d); cudaFree(f->counters_d);
 	cudaFree(f->points); cudaFree(f->normals); cudaFree(f->colors); cudaFree(f->viewOffsets); cudaFree(f->oviews); cudaFree(f->weights);
 	delete f; ctx->fuse = nullptr;
@@ -514,6 +516,31 @@ extern "C" int hcmvs_download_fused(hcmvs_ctx* ctx, float* points, float* normal
 	if (weights) CK(cudaMemcpyAsync(weights, f->weights, m*4, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
 	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_download_fused_pinned(hcmvs_ctx* ctx, hcmvs_pointcloud* out) {
+	if (!ctx || !ctx->fuse || !out) { hcmvs_set_error("no fused cloud"); return HCMVS_ERR_STATE; }
+	FuseState* f = ctx->fuse;
+	cudaSetDevice(ctx->device);
+	memset(out, 0, sizeof(*out));
+	const size_t n = f->nPoints, m = f->nViewRefs;
+	if (!n) return HCMVS_OK;
+	auto al = [](size_t b) { return (b+255)&~(size_t)255; };
+	const size_t oPts = 0, oNrm = oPts+al(n*12), oCol = oNrm+al(f->hasNormal ? n*12 : 0), oOff = oCol+al(f->hasColor ? n*3 : 0),
+		oViews = oOff+al((n+1)*4), oW = oViews+al(m*4), total = oW+al(m*4);
+	if (f->pinnedBytes < total) {
+		if (f->pinned) cudaFreeHost(f->pinned);
+		f->pinned = nullptr; f->pinnedBytes = 0;
+		const size_t cap = total+total/8; // head-room: the next scene of the same size does not re-pin
+		CK(cudaHostAlloc(&f->pinned, cap, cudaHostAllocDefault));
+		f->pinnedBytes = cap;
+	}
+	char* base = (char*)f->pinned;
+	out->n_points = n;
+	out->points = (float*)(base+oPts); out->view_offsets = (uint32_t*)(base+oOff); out->views = (uint32_t*)(base+oViews); out->weights = (float*)(base+oW);
+	if (f->hasNormal) out->normals = (float*)(base+oNrm);
+	if (f->hasColor) out->colors = (uint8_t*)(base+oCol);
+	return hcmvs_download_fused(ctx, out->points, out->normals, out->colors, out->view_offsets, out->views, out->weights);
 }
 
 extern "C" int hcmvs_get_fused_device(hcmvs_ctx* ctx, uint64_t* n_points, uint64_t* n_view_refs, void** points_d, void** normals_d, void** colors_d,

@@ -242,17 +242,18 @@ bool DepthMapsData::FilterDepthMap(uint32_t idxImage, const std::vector<uint32_t
 }
 
 bool DepthMapsData::FuseDepthMaps(PointCloud& pc, bool bEstimateColor, bool bEstimateNormal) {
-	// fuse on the device, then download straight into the PointCloud's arrays (one copy)
+	// fuse on the device, then ONE copy into the context's page-locked arena; the PointCloud borrows those arrays
+	// (valid until the next FuseDepthMaps on this context or hcmvs_destroy — see hcmvs_download_fused_pinned)
 	if (hcmvs_fuse_depthmaps(ctx, bEstimateColor, bEstimateNormal, nullptr) != HCMVS_OK) return Fail("hcmvs_fuse_depthmaps");
-	uint64_t n = 0, m = 0; void* nd = nullptr; void* cd = nullptr;
-	if (hcmvs_get_fused_device(ctx, &n, &m, nullptr, &nd, &cd, nullptr, nullptr, nullptr) != HCMVS_OK) return Fail("hcmvs_get_fused_device");
+	uint64_t n = 0, m = 0;
+	if (hcmvs_get_fused_device(ctx, &n, &m, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr) != HCMVS_OK) return Fail("hcmvs_get_fused_device");
 	pc = PointCloud();
 	if (!n) return true;
-	pc.points.resize(n*3); pc.viewOffsets.resize(n+1); pc.views.resize(m); pc.weights.resize(m);
-	if (nd) pc.normals.resize(n*3);
-	if (cd) pc.colors.resize(n*3);
-	if (hcmvs_download_fused(ctx, pc.points.data(), nd ? pc.normals.data() : nullptr, cd ? pc.colors.data() : nullptr,
-	                         pc.viewOffsets.data(), pc.views.data(), pc.weights.data()) != HCMVS_OK) return Fail("hcmvs_download_fused");
+	hcmvs_pointcloud host;
+	if (hcmvs_download_fused_pinned(ctx, &host) != HCMVS_OK) return Fail("hcmvs_download_fused_pinned");
+	pc.points.borrow(host.points, n*3); pc.viewOffsets.borrow(host.view_offsets, n+1); pc.views.borrow(host.views, m); pc.weights.borrow(host.weights, m);
+	if (host.normals) pc.normals.borrow(host.normals, n*3);
+	if (host.colors) pc.colors.borrow(host.colors, n*3);
 	return true;
 }
 
@@ -362,34 +363,64 @@ bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, co
 	double t0 = Now();
 	const uint32_t nImages = (uint32_t)scene.images.size();
 	for (Image& im: scene.images) im.camera.ComposeP();
-	std::vector<uint32_t> valid;
-	{ // the reference selects views with `#pragma omp parallel for` over the images (:3652-3667); each call only writes image i's state
-		std::vector<char> okv(nImages, 0);
-		const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), nImages));
-		std::atomic<uint32_t> next{0};
-		std::vector<std::thread> pool;
-		for (unsigned t=0; t<nt; ++t) pool.emplace_back([&]() { uint32_t i; while ((i = next.fetch_add(1)) < nImages) okv[i] = data.SelectViews(i) ? 1 : 0; });
-		for (std::thread& th: pool) th.join();
-		for (uint32_t i=0; i<nImages; ++i) if (okv[i]) valid.push_back(i);
-	}
-	if (valid.empty()) return fail("no image has enough neighbour views");
-	double t1 = Now(); st.secSelect = t1-t0;
-	for (uint32_t i: valid) {
-		if (!data.InitViews(i, P.nNumViews)) { if (!data.lastError.empty()) return fail(data.lastError); data.arrDepthData[i].valid = false; }
-	}
+	// Host workers select the neighbour views (the reference does it with `#pragma omp parallel for`, :3652-3667 — each call only
+	// writes image i's state) and splat the sparse points into the initial depth map (:783-808), in image order, while this
+	// thread uploads the images and then feeds the GPU: view i is estimated as soon as ITS selection is done, so the host work
+	// of the later views hides behind the kernels of the earlier ones. All hcmvs_* calls stay on this thread.
+	struct Prepared { std::vector<float> depth; float dMin = 0, dMax = 0; };
+	std::vector<Prepared> prep(nImages);
+	std::vector<std::atomic<int>> state(nImages); // 0 pending, 1 selected + initial depth ready, -1 rejected
+	for (auto& s: state) s.store(0);
+	std::atomic<uint32_t> next{0}, consumed{0};
+	std::atomic<double> tSelectEnd{t0};
+	const uint32_t lookahead = 24; // bounds the host memory held by prepared depth maps
+	const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), nImages));
+	std::vector<std::thread> pool;
+	for (unsigned t=0; t<nt; ++t) pool.emplace_back([&]() {
+		uint32_t i;
+		while ((i = next.fetch_add(1)) < nImages) {
+			while (i >= consumed.load(std::memory_order_acquire)+lookahead) std::this_thread::yield();
+			const bool ok = data.SelectViews(i);
+			if (ok) SparseInitDepth(scene, i, data.arrDepthData[i].points, prep[i].depth, prep[i].dMin, prep[i].dMax);
+			tSelectEnd.store(Now());
+			state[i].store(ok ? 1 : -1, std::memory_order_release);
+		}
+	});
+	struct Joiner { std::vector<std::thread>& p; std::atomic<uint32_t>& c; ~Joiner() { c.store(0x7fffffffu); for (std::thread& th: p) if (th.joinable()) th.join(); } } joiner{pool, consumed};
+	// upload every image (each one is the reference view of its own depth map and a neighbour of others)
 	for (uint32_t i=0; i<nImages; ++i) {
+		if (!data.UploadView(i)) return fail(data.lastError);
 		const Image& im = scene.images[i];
-		if (data.arrDepthData[i].uploaded) st.h2dBytes += (uint64_t)im.width*im.height*(4+(im.bgr.empty() ? 0 : 3));
+		st.h2dBytes += (uint64_t)im.width*im.height*(4+(im.bgr.empty() ? 0 : 3));
 	}
-	double t2 = Now(); st.secUpload = t2-t1;
-	for (unsigned it=0; it<P.nEstimationIters_external; ++it) // :3684
+	double t1 = Now(); st.secUpload = t1-t0;
+	std::vector<uint32_t> valid;
+	for (uint32_t i=0; i<nImages; ++i) {
+		int s;
+		while ((s = state[i].load(std::memory_order_acquire)) == 0) std::this_thread::yield();
+		if (s > 0) {
+			valid.push_back(i);
+			DepthData& dd = data.arrDepthData[i];
+			if (!data.InitViews(i, P.nNumViews)) { if (!data.lastError.empty()) return fail(data.lastError); dd.valid = false; }
+			else {
+				dd.dMin = prep[i].dMin; dd.dMax = prep[i].dMax;
+				if (hcmvs_init_depthmap(ctx, i, prep[i].depth.data(), nullptr, dd.dMin, dd.dMax) != HCMVS_OK) return fail(std::string("hcmvs_init_depthmap: ")+hcmvs_last_error());
+				st.h2dBytes += (uint64_t)scene.images[i].width*scene.images[i].height*4;
+				if (hcmvs_estimate_depthmap(ctx, i, 0, seed) != HCMVS_OK) return fail(std::string("hcmvs_estimate_depthmap: ")+hcmvs_last_error());
+			}
+		}
+		std::vector<float>().swap(prep[i].depth);
+		consumed.store(i+1, std::memory_order_release);
+	}
+	st.secSelect = tSelectEnd.load()-t0; // overlaps the upload and the estimation
+	if (valid.empty()) return fail("no image has enough neighbour views");
+	for (unsigned it=1; it<P.nEstimationIters_external; ++it) // :3684
 		for (uint32_t i: valid) {
 			if (!data.arrDepthData[i].valid) continue;
 			if (!data.EstimateDepthMap((int)it, i, seed)) return fail(data.lastError);
-			if (it == 0) st.h2dBytes += (uint64_t)scene.images[i].width*scene.images[i].height*4;
 		}
 	if (hcmvs_sync(ctx) != HCMVS_OK) return fail(hcmvs_last_error());
-	double t3 = Now(); st.secEstimate = t3-t2;
+	double t3 = Now(); st.secEstimate = t3-t1;
 	if (!dmapDir.empty())
 		for (uint32_t i: valid) if (data.arrDepthData[i].valid) {
 			char name[64]; snprintf(name, sizeof(name), "/depth%04u.dmap", i);

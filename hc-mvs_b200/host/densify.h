@@ -43,10 +43,25 @@ struct SparsePoints { // the part of MVS::PointCloud the densifier reads
 	size_t size() const { return views.size(); }
 };
 
+// Array that either owns its storage or borrows it (the fused cloud lives in the CUDA context's page-locked arena)
+template<typename T>
+struct Array {
+	const T* data() const { return p; }
+	T* data() { return own.empty() ? const_cast<T*>(p) : own.data(); }
+	size_t size() const { return n; }
+	bool empty() const { return n == 0; }
+	const T& operator[](size_t i) const { return p[i]; }
+	void resize(size_t k) { own.resize(k); p = own.data(); n = k; }
+	void borrow(const T* q, size_t k) { own.clear(); own.shrink_to_fit(); p = q; n = k; }
+	void clear() { own.clear(); p = nullptr; n = 0; }
+private:
+	const T* p = nullptr; size_t n = 0; std::vector<T> own;
+};
+
 struct PointCloud { // fused output, libs/MVS/PointCloud.h:49-109
-	std::vector<float> points, normals, weights;
-	std::vector<uint8_t> colors;
-	std::vector<uint32_t> viewOffsets, views;
+	Array<float> points, normals, weights;
+	Array<uint8_t> colors;
+	Array<uint32_t> viewOffsets, views;
 	size_t size() const { return points.size()/3; }
 	bool Save(const std::string& fileName) const; // PointCloud::Save, PointCloud.cpp:188-242 (binary little-endian PLY)
 };

@@ -127,6 +127,10 @@ void hcmvs_free_pointcloud(hcmvs_pointcloud* pc);
  * (points/normals float[3n], colors u8[3n], view_offsets u32[n+1], views u32[m], weights float[m]). */
 /* Copy the last fused cloud into caller-owned host arrays (sizes from hcmvs_get_fused_device); any pointer may be NULL. */
 int hcmvs_download_fused(hcmvs_ctx* ctx, float* points, float* normals, uint8_t* colors, uint32_t* view_offsets, uint32_t* views, float* weights);
+/* Same, into a page-locked host arena OWNED BY THE CONTEXT (PCIe-rate copy, no per-scene pinning): `out` receives pointers that
+ * stay valid until the next hcmvs_fuse_depthmaps / hcmvs_download_fused_pinned on this context or hcmvs_destroy.
+ * Do NOT pass `out` to hcmvs_free_pointcloud. Replaces the PointCloud& output of FuseDepthMaps (SceneDensify.cpp:3265). */
+int hcmvs_download_fused_pinned(hcmvs_ctx* ctx, hcmvs_pointcloud* out);
 int hcmvs_get_fused_device(hcmvs_ctx* ctx, uint64_t* n_points, uint64_t* n_view_refs, void** points_d, void** normals_d, void** colors_d,
                            void** view_offsets_d, void** views_d, void** weights_d);
 
