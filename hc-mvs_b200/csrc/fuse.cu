@@ -74,50 +74,67 @@ __device__ __forceinline__ float dot3f(const float3 a, const float3 b) { return 
 #define PROBE_INVAL 2u   // occluded by the seed (:3424-3427): zeroed if the seed survives
 #define PROBE_DEAD  0xFFFFFFFFu
 
+// ---- phase 0 (own kernel, full grid): find the seeds (valid depth, not yet claimed, SceneDensify.cpp:3347-3354) and classify
+// their probes. The geometry of a probe is static: the seed's 3-D point, the pixel it hits in each neighbour view, and — while
+// that pixel is alive (depth != 0, not claimed) — whether it would merge, be invalidated, or be left alone. Only liveness
+// changes during the fusion of this view, so the f64 projections are done once and the rounds below are integer work.
+__global__ void __launch_bounds__(256) k_fuse_probe(const FuseArgs a) {
+	const FuseView& R = a.views[a.ref];
+	const int nPix = R.w*R.h;
+	const int p = blockIdx.x*blockDim.x+threadIdx.x;
+	int mySeeds = 0;
+	if (p < nPix) {
+		const float4 e = R.dn[p];
+		const bool seed = e.w != 0.f && R.claim[p] != CLAIM_TAKEN;
+		a.state[p] = seed ? 1 : 0;
+		mySeeds = seed;
+		if (seed) {
+		const int x = p%R.w, y = p/R.w;
+		const float3 point = seed_point(R, x, y, e.w);
+		const float3 normal = cam_NormalC2W(R.cam, make_float3(e.x, e.y, e.z));
+		// neighbours in chunks of 4: the projections first, then the 4 independent gathers in flight together (the kernel is
+		// bound by gather latency, not bandwidth), then the classification
+		for (int k0=0; k0<a.nNb; k0+=4) {
+			Probe pr[4]; float4 eB[4]; uint32_t cB[4];
+			#pragma unroll
+			for (int j=0; j<4; ++j) {
+				pr[j].q = -1; pr[j].z = 0.f;
+				if (k0+j < a.nNb) { const FuseView& B = a.views[a.nb[k0+j]]; if (B.hasMaps) pr[j] = probe_view(B, point); }
+			}
+			#pragma unroll
+			for (int j=0; j<4; ++j) {
+				eB[j] = make_float4(0.f, 0.f, 0.f, 0.f); cB[j] = CLAIM_TAKEN;
+				if (pr[j].q >= 0) { const FuseView& B = a.views[a.nb[k0+j]]; eB[j] = B.dn[pr[j].q]; cB[j] = B.claim[pr[j].q]; }
+			}
+			#pragma unroll
+			for (int j=0; j<4; ++j) {
+				if (k0+j >= a.nNb) break;
+				uint32_t code = PROBE_DEAD;
+				if (pr[j].q >= 0 && eB[j].w != 0.f && cB[j] != CLAIM_TAKEN) {
+					uint32_t cls = PROBE_NONE;
+					bool merge = false;
+					if (depth_similar(pr[j].z, eB[j].w, a.depthTh)) {
+						const float3 normalB = cam_NormalC2W(a.views[a.nb[k0+j]].cam, make_float3(eB[j].x, eB[j].y, eB[j].z));
+						merge = dot3f(normal, normalB) > a.normalError;
+					}
+					if (merge) cls = PROBE_MERGE; else if (pr[j].z < eB[j].w) cls = PROBE_INVAL;
+					code = (uint32_t)pr[j].q | (cls<<30);
+				}
+				a.probes[(size_t)(k0+j)*a.probeStride+p] = code;
+			}
+		}
+		}
+	}
+	mySeeds = cg::reduce(cg::tiled_partition<32>(cg::this_thread_block()), mySeeds, cg::plus<int>());
+	if ((threadIdx.x&31) == 0 && mySeeds) { atomicAdd(&a.counters[0], mySeeds); atomicAdd(&a.counters[2], mySeeds); }
+}
+
+// ---- the reserve / resolve rounds (cooperative: grid.sync between the phases)
 __global__ void __launch_bounds__(256) k_fuse_view(const FuseArgs a) {
 	cg::grid_group grid = cg::this_grid();
 	const FuseView& R = a.views[a.ref];
 	const int nPix = R.w*R.h;
 	const int tid = blockIdx.x*blockDim.x+threadIdx.x, nThreads = gridDim.x*blockDim.x;
-	// ---- phase 0: find the seeds (valid depth, not yet claimed, SceneDensify.cpp:3347-3354) and classify their probes.
-	// The geometry of a probe is static: the seed's 3-D point, the pixel it hits in each neighbour view, and — while that
-	// pixel is alive (depth != 0, not claimed) — whether it would merge, be invalidated, or be left alone. Only liveness
-	// changes during the fusion of this view, so the f64 projections are done once and the rounds below are integer work.
-	int mySeeds = 0;
-	for (int p=tid; p<nPix; p+=nThreads) {
-		const float4 e = R.dn[p];
-		const bool seed = e.w != 0.f && R.claim[p] != CLAIM_TAKEN;
-		a.state[p] = seed ? 1 : 0;
-		mySeeds += seed;
-		if (!seed) continue;
-		const int x = p%R.w, y = p/R.w;
-		const float3 point = seed_point(R, x, y, e.w);
-		const float3 normal = cam_NormalC2W(R.cam, make_float3(e.x, e.y, e.z));
-		for (int k=0; k<a.nNb; ++k) {
-			uint32_t code = PROBE_DEAD;
-			const FuseView& B = a.views[a.nb[k]];
-			if (B.hasMaps) {
-				const Probe pr = probe_view(B, point);
-				if (pr.q >= 0) {
-					const float4 eB = B.dn[pr.q];
-					if (eB.w != 0.f && B.claim[pr.q] != CLAIM_TAKEN) {
-						uint32_t cls = PROBE_NONE;
-						bool merge = false;
-						if (depth_similar(pr.z, eB.w, a.depthTh)) {
-							const float3 normalB = cam_NormalC2W(B.cam, make_float3(eB.x, eB.y, eB.z));
-							merge = dot3f(normal, normalB) > a.normalError;
-						}
-						if (merge) cls = PROBE_MERGE; else if (pr.z < eB.w) cls = PROBE_INVAL;
-						code = (uint32_t)pr.q | (cls<<30);
-					}
-				}
-			}
-			a.probes[(size_t)k*a.probeStride+p] = code;
-		}
-	}
-	mySeeds = cg::reduce(cg::tiled_partition<32>(cg::this_thread_block()), mySeeds, cg::plus<int>());
-	if ((threadIdx.x&31) == 0 && mySeeds) { atomicAdd(&a.counters[0], mySeeds); atomicAdd(&a.counters[2], mySeeds); }
-	grid.sync();
 	int undecided = *(volatile int*)&a.counters[0];
 	int round = 0;
 	while (undecided > 0) {
@@ -125,14 +142,22 @@ __global__ void __launch_bounds__(256) k_fuse_view(const FuseArgs a) {
 		for (int p=tid; p<nPix; p+=nThreads) {
 			const uint8_t st = a.state[p];
 			if (st != 1 && st != 3) continue;
-			for (int k=0; k<a.nNb; ++k) {
-				const uint32_t code = a.probes[(size_t)k*a.probeStride+p];
-				if (code == PROBE_DEAD || (code>>30) == PROBE_NONE) continue;
-				const FuseView& B = a.views[a.nb[k]];
-				const uint32_t q = code & 0x3FFFFFFFu;
-				if (B.dn[q].w == 0.f) continue;
-				if (B.claim[q] == CLAIM_TAKEN) continue;
-				atomicMin(&B.claim[q], (uint32_t)p);
+			for (int k0=0; k0<a.nNb; k0+=4) { // 4 independent probe -> pixel gathers in flight
+				uint32_t code[4], cl[4]; float dz[4];
+				#pragma unroll
+				for (int j=0; j<4; ++j) code[j] = k0+j < a.nNb ? a.probes[(size_t)(k0+j)*a.probeStride+p] : PROBE_DEAD;
+				#pragma unroll
+				for (int j=0; j<4; ++j) {
+					dz[j] = 0.f; cl[j] = CLAIM_TAKEN;
+					if (code[j] != PROBE_DEAD && (code[j]>>30) != PROBE_NONE) {
+						const FuseView& B = a.views[a.nb[k0+j]];
+						const uint32_t q = code[j] & 0x3FFFFFFFu;
+						dz[j] = B.dn[q].w; cl[j] = B.claim[q];
+					}
+				}
+				#pragma unroll
+				for (int j=0; j<4; ++j)
+					if (dz[j] != 0.f && cl[j] != CLAIM_TAKEN && cl[j] > (uint32_t)p) atomicMin(&a.views[a.nb[k0+j]].claim[code[j] & 0x3FFFFFFFu], (uint32_t)p);
 			}
 		}
 		grid.sync();
@@ -152,15 +177,27 @@ __global__ void __launch_bounds__(256) k_fuse_view(const FuseArgs a) {
 			uint32_t merged = st == 3 ? a.mask[p] : 0u;
 			uint32_t heldMerge = 0, heldInval = 0;
 			unsigned nContested = 0, nContestedMerge = 0;
-			for (int k=0; k<a.nNb; ++k) {
-				const uint32_t code = a.probes[(size_t)k*a.probeStride+p];
-				if (code == PROBE_DEAD || (code>>30) == PROBE_NONE) continue;
-				const FuseView& B = a.views[a.nb[k]];
-				const uint32_t q = code & 0x3FFFFFFFu;
-				const uint32_t c = *(volatile uint32_t*)&B.claim[q];
-				if (c == CLAIM_TAKEN || *(volatile float*)&B.dn[q].w == 0.f) { a.probes[(size_t)k*a.probeStride+p] = PROBE_DEAD; continue; }
-				if (c == (uint32_t)p) { if ((code>>30) == PROBE_MERGE) heldMerge |= 1u<<k; else heldInval |= 1u<<k; }
-				else { ++nContested; nContestedMerge += (code>>30) == PROBE_MERGE; }
+			for (int k0=0; k0<a.nNb; k0+=4) {
+				uint32_t code[4], cl[4]; float dz[4];
+				#pragma unroll
+				for (int j=0; j<4; ++j) code[j] = k0+j < a.nNb ? a.probes[(size_t)(k0+j)*a.probeStride+p] : PROBE_DEAD;
+				#pragma unroll
+				for (int j=0; j<4; ++j) {
+					dz[j] = 0.f; cl[j] = CLAIM_TAKEN;
+					if (code[j] != PROBE_DEAD && (code[j]>>30) != PROBE_NONE) {
+						const FuseView& B = a.views[a.nb[k0+j]];
+						const uint32_t q = code[j] & 0x3FFFFFFFu;
+						cl[j] = *(volatile uint32_t*)&B.claim[q]; dz[j] = *(volatile float*)&B.dn[q].w;
+					}
+				}
+				#pragma unroll
+				for (int j=0; j<4; ++j) {
+					if (code[j] == PROBE_DEAD || (code[j]>>30) == PROBE_NONE) continue;
+					const int k = k0+j;
+					if (cl[j] == CLAIM_TAKEN || dz[j] == 0.f) { a.probes[(size_t)k*a.probeStride+p] = PROBE_DEAD; continue; }
+					if (cl[j] == (uint32_t)p) { if ((code[j]>>30) == PROBE_MERGE) heldMerge |= 1u<<k; else heldInval |= 1u<<k; }
+					else { ++nContested; nContestedMerge += (code[j]>>30) == PROBE_MERGE; }
+				}
 			}
 			const unsigned nViews = 1u+__popc(merged)+__popc(heldMerge);
 			if (st == 3 || nViews >= a.nMinViewsFuse) {
@@ -418,7 +455,7 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_fuse_view, 256, 0));
 		if (perSm < 1) { hcmvs_set_error("fuse kernel does not fit"); return HCMVS_ERR_CUDA; }
-		f->coopBlocks = sms*std::min(perSm, 4);
+		f->coopBlocks = sms*std::min(perSm, 8);
 	}
 	const unsigned nMinViewsFuse = std::min<unsigned>(P.nMinViewsFuse, (unsigned)std::count_if(ctx->views.begin(), ctx->views.end(), [](const View& v) { return v.set; }));
 	const float FPI = (float)3.14159265358979323846;
@@ -438,6 +475,7 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 		a.probes = f->probes_d; a.probeStride = maxPix;
 		const int nPix = v.w*v.h;
 		CK(cudaMemsetAsync(f->counters_d, 0, 4*sizeof(int), ctx->stream));
+		k_fuse_probe<<<(nPix+255)/256, 256, 0, ctx->stream>>>(a); ++ctx->nLaunches;
 		void* args[] = {(void*)&a};
 		CK(cudaLaunchCooperativeKernel((void*)k_fuse_view, dim3(f->coopBlocks), dim3(256), args, 0, ctx->stream)); ++ctx->nLaunches;
 		const int nBlocks = (nPix+FUSE_CHUNK-1)/FUSE_CHUNK;
