@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libhcmvs_b200.so")
 EXPORTS = [
     "hcmvs_default_params", "hcmvs_last_error", "hcmvs_create", "hcmvs_destroy", "hcmvs_set_params", "hcmvs_sync",
     "hcmvs_set_view", "hcmvs_set_neighbors", "hcmvs_init_depthmap", "hcmvs_set_depthmap", "hcmvs_get_depthmap",
-    "hcmvs_set_prior", "hcmvs_get_gradient_map", "hcmvs_score_depthmap", "hcmvs_estimate_depthmap", "hcmvs_end_depthmap", "hcmvs_score_hypotheses",
+    "hcmvs_set_prior", "hcmvs_set_coarse_estimate", "hcmvs_get_coarse_estimate", "hcmvs_snapshot_maps", "hcmvs_get_gradient_map", "hcmvs_score_depthmap", "hcmvs_estimate_depthmap", "hcmvs_end_depthmap", "hcmvs_score_hypotheses",
     "hcmvs_filter_depthmap", "hcmvs_commit_filtered", "hcmvs_set_fuse_priority", "hcmvs_fuse_depthmaps",
     "hcmvs_free_pointcloud", "hcmvs_get_fused_device", "hcmvs_download_fused", "hcmvs_download_fused_pinned", "hcmvs_get_depthmap_device", "hcmvs_set_depth_range", "hcmvs_alloc_depthmap",
     "hcmvs_export_maps_d", "hcmvs_import_maps_d", "hcmvs_get_timers", "hcmvs_reset_timers", "hcmvs_stream",
@@ -34,7 +34,7 @@ class Params(C.Structure):
         ("fDepthDiffThreshold", C.c_float), ("fNormalDiffThreshold", C.c_float), ("depthweight", C.c_float), ("normalweight", C.c_float),
         ("adapthalfwin", C.c_int32), ("propagatehalfwin", C.c_int32), ("propagatestep", C.c_int32), ("photo2geo", C.c_int32),
         ("photometric_flow", C.c_float), ("para_prior", C.c_float), ("fsigmaPrior", C.c_float),
-        ("rb_far_reach", C.c_int32), ("rb_prop_dirs", C.c_int32), ("sampler", C.c_int32),
+        ("rb_far_reach", C.c_int32), ("rb_prop_dirs", C.c_int32), ("sampler", C.c_int32), ("viewspread", C.c_int32),
     ]
 
 
@@ -86,6 +86,9 @@ def load():
     L.hcmvs_get_depthmap.argtypes = [vp, u32, vp, vp, vp, C.POINTER(f32), C.POINTER(f32)]
     L.hcmvs_set_prior.argtypes = [vp, u32, vp]
     L.hcmvs_get_gradient_map.argtypes = [vp, u32, vp]
+    L.hcmvs_set_coarse_estimate.argtypes = [vp, u32, i32, i32, vp, vp]
+    L.hcmvs_get_coarse_estimate.argtypes = [vp, u32, vp, vp]
+    L.hcmvs_snapshot_maps.argtypes = [vp]
     L.hcmvs_score_depthmap.argtypes = [vp, u32, i32, C.c_uint64]
     L.hcmvs_estimate_depthmap.argtypes = [vp, u32, i32, C.c_uint64]
     L.hcmvs_end_depthmap.argtypes = [vp, u32]
@@ -189,6 +192,24 @@ class Context:
     def set_prior(self, ref, prior):
         prior = np.ascontiguousarray(prior, np.float32) if prior is not None else None
         self._ck(self.L.hcmvs_set_prior(self.h, ref, _p(prior)))
+
+    def set_coarse_estimate(self, view, depth, normal):
+        """restore tree hand-off: coarse (depth, normal) maps of the previous level; None removes them."""
+        if depth is None:
+            self._ck(self.L.hcmvs_set_coarse_estimate(self.h, view, 0, 0, None, None))
+            return
+        depth = np.ascontiguousarray(depth, np.float32); normal = np.ascontiguousarray(normal, np.float32)
+        hc, wc = depth.shape
+        self._ck(self.L.hcmvs_set_coarse_estimate(self.h, view, wc, hc, _p(depth), _p(normal)))
+
+    def get_coarse_estimate(self, view):
+        h, w = self.sizes[view]
+        d = np.zeros((h, w), np.float32); n = np.zeros((h, w, 3), np.float32)
+        self._ck(self.L.hcmvs_get_coarse_estimate(self.h, view, _p(d), _p(n)))
+        return d, n
+
+    def snapshot_maps(self):
+        self._ck(self.L.hcmvs_snapshot_maps(self.h))
 
     def score_depthmap(self, ref, it_external=0, seed=1):
         self._ck(self.L.hcmvs_score_depthmap(self.h, ref, it_external, seed))

@@ -33,7 +33,7 @@ extern "C" void hcmvs_default_params(hcmvs_params* p) {
 	p->fDepthDiffThreshold = 0.01f; p->fNormalDiffThreshold = 25.f; p->depthweight = 1.f; p->normalweight = 1.f;
 	p->adapthalfwin = 5; p->propagatehalfwin = 1; p->propagatestep = 4; p->photo2geo = 2;
 	p->photometric_flow = 0.f; p->para_prior = 0.3f; p->fsigmaPrior = 0.2f;
-	p->rb_far_reach = 11; p->rb_prop_dirs = 2; p->sampler = 0;
+	p->rb_far_reach = 11; p->rb_prop_dirs = 2; p->sampler = 0; p->viewspread = 0;
 }
 
 // ------------------------------------------------------------------------------------------------ context
@@ -70,7 +70,7 @@ static void FreeView(View& v) {
 	if (v.tex) cudaDestroyTextureObject(v.tex);
 	if (v.arr) cudaFreeArray(v.arr);
 	if (v.ready) cudaEventDestroy(v.ready);
-	cudaFree(v.img_d); cudaFree(v.bgr_d); cudaFree(v.gra_d); cudaFree(v.dn_d); cudaFree(v.conf_d); cudaFree(v.prior_d); cudaFree(v.fdepth_d); cudaFree(v.fconf_d); cudaFree(v.claim_d);
+	cudaFree(v.img_d); cudaFree(v.bgr_d); cudaFree(v.gra_d); cudaFree(v.dn_d); cudaFree(v.conf_d); cudaFree(v.prior_d); cudaFree(v.coarse_d); cudaFree(v.dnPrev_d); cudaFree(v.confPrev_d); cudaFree(v.fdepth_d); cudaFree(v.fconf_d); cudaFree(v.claim_d);
 	v = View();
 }
 
@@ -81,7 +81,7 @@ extern "C" void hcmvs_destroy(hcmvs_ctx* ctx) {
 	for (View& v: ctx->views) FreeView(v);
 	for (auto& te: ctx->timed) { cudaEventDestroy(te.a); cudaEventDestroy(te.b); }
 	for (cudaEvent_t ev: ctx->eventPool) cudaEventDestroy(ev);
-	cudaFree(ctx->scratch_d); cudaFree(ctx->counters_d); cudaFree(ctx->upload_d);
+	cudaFree(ctx->scratch_d); cudaFree(ctx->counters_d); cudaFree(ctx->upload_d); cudaFree(ctx->spread_d);
 	if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
 	hcmvs_fuse_release(ctx);
 	cudaStreamDestroy(ctx->stream);
@@ -360,6 +360,58 @@ extern "C" int hcmvs_set_depth_range(hcmvs_ctx* ctx, uint32_t view, float dMin, 
 	v->dMin = dMin; v->dMax = dMax; return HCMVS_OK;
 }
 
+extern "C" int hcmvs_set_coarse_estimate(hcmvs_ctx* ctx, uint32_t view, int wc, int hc, const float* depth, const float* normal) {
+	View* v = GetView(ctx, view, true); if (!v) return HCMVS_ERR_ARG;
+	cudaSetDevice(ctx->device);
+	if (!depth) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(v->coarse_d); v->coarse_d = nullptr; return HCMVS_OK; }
+	if (!normal || wc < 2 || hc < 2) { hcmvs_set_error("coarse estimate needs depth and normal maps of at least 2x2"); return HCMVS_ERR_ARG; }
+	if (wc > v->w && hc > v->h) { hcmvs_set_error("coarse estimate %dx%d is larger than view %u (%dx%d): INTER_AREA decimation is not the hand-off the restore tree does", wc, hc, view, v->w, v->h); return HCMVS_ERR_UNSUPPORTED; }
+	if (!v->hasMaps) { hcmvs_set_error("view %u has no depth map / range yet (call hcmvs_init_depthmap first)", view); return HCMVS_ERR_STATE; }
+	const size_t nc = (size_t)wc*hc, n = (size_t)v->w*v->h;
+	float* tmp; int r = hcmvs_scratch(ctx, nc*16+64, (void**)&tmp); if (r) return r;
+	if (!v->coarse_d) CK(cudaMalloc(&v->coarse_d, n*sizeof(float4)));
+	float* mm_d = tmp+nc*4;
+	float mm[2] = {v->dMin, v->dMax};
+	CK(cudaMemcpyAsync(tmp, depth, nc*4, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(tmp+nc, normal, nc*12, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(mm_d, mm, 8, cudaMemcpyHostToDevice, ctx->stream));
+	CK(hcmvs_launch_resize_area_up(tmp, tmp+nc, wc, hc, v->coarse_d, v->w, v->h, ctx->stream)); ++ctx->nLaunches;
+	// widen the depth range with the resized depths, restore/.../SceneDensify.cpp:526-532
+	CK(hcmvs_launch_minmax_w(v->coarse_d, n, mm_d, ctx->stream)); ++ctx->nLaunches;
+	CK(cudaMemcpyAsync(mm, mm_d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	v->dMin = mm[0]; v->dMax = mm[1];
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_get_coarse_estimate(hcmvs_ctx* ctx, uint32_t view, float* depth, float* normal) {
+	View* v = GetView(ctx, view, true); if (!v) return HCMVS_ERR_ARG;
+	if (!v->coarse_d) { hcmvs_set_error("view %u has no coarse estimate", view); return HCMVS_ERR_STATE; }
+	cudaSetDevice(ctx->device);
+	const size_t n = (size_t)v->w*v->h;
+	float* tmp; int r = hcmvs_scratch(ctx, n*16, (void**)&tmp); if (r) return r;
+	CK(hcmvs_launch_unpack(v->coarse_d, tmp, tmp+n, n, ctx->stream)); ++ctx->nLaunches;
+	if (depth) CK(cudaMemcpyAsync(depth, tmp, n*4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (normal) CK(cudaMemcpyAsync(normal, tmp+n, n*12, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_snapshot_maps(hcmvs_ctx* ctx) {
+	if (!ctx) { hcmvs_set_error("null context"); return HCMVS_ERR_ARG; }
+	cudaSetDevice(ctx->device);
+	for (View& v: ctx->views) {
+		if (!v.set || !v.hasMaps || !v.dn_d) continue;
+		const size_t n = (size_t)v.w*v.h;
+		if (!v.dnPrev_d) CK(cudaMalloc(&v.dnPrev_d, n*sizeof(float4)));
+		if (!v.confPrev_d) CK(cudaMalloc(&v.confPrev_d, n*4));
+		CK(cudaMemcpyAsync(v.dnPrev_d, v.dn_d, n*sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+		CK(cudaMemcpyAsync(v.confPrev_d, v.conf_d, n*4, cudaMemcpyDeviceToDevice, ctx->stream));
+		v.hasPrev = true;
+	}
+	return HCMVS_OK;
+}
+
 extern "C" int hcmvs_get_gradient_map(hcmvs_ctx* ctx, uint32_t view, uint8_t* gra) {
 	View* v = GetView(ctx, view, true); if (!v) return HCMVS_ERR_ARG;
 	if (!gra || !v->gra_d) { hcmvs_set_error("view %u has no gradient map", view); return HCMVS_ERR_STATE; }
@@ -425,7 +477,8 @@ static int BuildRefConst(hcmvs_ctx* ctx, View* v, uint32_t ref, int it_external,
 
 static int RequireMaps(View* v, uint32_t ref) {
 	if (!v->hasMaps || !v->dn_d) { hcmvs_set_error("view %u has no depth map (call hcmvs_init_depthmap)", ref); return HCMVS_ERR_STATE; }
-	if (!(v->dMin > 0.f && v->dMin < v->dMax)) { hcmvs_set_error("view %u has no valid depth range", ref); return HCMVS_ERR_STATE; }
+	// dMin == 0 is legal: the restore tree widens the range with the coarse map's depths, zeros included (SceneDensify.cpp:526-532)
+	if (!(v->dMin >= 0.f && v->dMin < v->dMax)) { hcmvs_set_error("view %u has no valid depth range", ref); return HCMVS_ERR_STATE; }
 	return HCMVS_OK;
 }
 
@@ -468,6 +521,21 @@ extern "C" int hcmvs_estimate_depthmap(hcmvs_ctx* ctx, uint32_t ref, int it_exte
 	const size_t n = (size_t)v->w*v->h;
 	RefConst rc; r = BuildRefConst(ctx, v, ref, it_external, seed, rc); if (r) return r;
 	const bool tex = P.sampler == 0;
+	rc.coarse = v->coarse_d;
+	if (P.viewspread && it_external >= 1) {
+		// viewspread (DepthMap.cpp:1504-1608) reads the matching neighbours' maps of the previous outer iteration
+		SpreadConst sc; std::memset(&sc, 0, sizeof(sc));
+		hcmvs_fill_cam(*v, sc.camRef);
+		for (int i=0; i<v->nMatch; ++i) {
+			View* nb = GetView(ctx, v->nbIds[i], true);
+			if (!nb || !nb->hasPrev) { hcmvs_set_error("viewspread: neighbour view %u of %u has no snapshot of the previous outer iteration (call hcmvs_snapshot_maps)", v->nbIds[i], ref); return HCMVS_ERR_STATE; }
+			hcmvs_fill_cam(*nb, sc.nb[i].cam);
+			sc.nb[i].dn = nb->dnPrev_d; sc.nb[i].conf = nb->confPrev_d; sc.nb[i].w = nb->w; sc.nb[i].h = nb->h;
+		}
+		if (!ctx->spread_d) CK(cudaMalloc(&ctx->spread_d, sizeof(SpreadConst)));
+		CK(cudaMemcpyAsync(ctx->spread_d, &sc, sizeof(sc), cudaMemcpyHostToDevice, ctx->stream)); // pageable source: staged before the call returns
+		rc.viewspread = 1; rc.spread = ctx->spread_d;
+	}
 	// cv::medianBlur(depthMap, depthMap, 3), SceneDensify.cpp:859
 	hcmvs_time_begin(ctx, ST_PREP);
 	float4* tmp; r = hcmvs_scratch(ctx, n*sizeof(float4), (void**)&tmp); if (r) return r;
@@ -482,6 +550,7 @@ extern "C" int hcmvs_estimate_depthmap(hcmvs_ctx* ctx, uint32_t ref, int it_exte
 	hcmvs_time_begin(ctx, ST_SWEEPS);
 	for (unsigned iter=0; iter<P.nEstimationIters; ++iter) {
 		rc.pass = 1u+iter+(uint32_t)it_external*64u;
+		rc.lastPass = it_external == (int)P.nEstimationIters_external-1 && iter == P.nEstimationIters-1;
 		for (int colour=0; colour<2; ++colour) { CK(hcmvs_launch_sweep(rc, colour, tex, ctx->stream)); ++ctx->nLaunches; }
 	}
 	hcmvs_time_end(ctx);

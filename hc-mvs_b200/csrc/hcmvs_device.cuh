@@ -47,8 +47,19 @@ struct RefConst {
 	float photometric_flow, para_prior, sigmaPrior;
 	uint32_t key0, key1, pass;
 	unsigned long long* counters; // [0] hypotheses, [1] view scores, [2] pixel-iterations
+	// extra hypotheses after the refinement (k_sweep<.., XTRA = true> only)
+	const float4* coarse;         // restore tree: the previous level's estimate resized to this view (nresize maps), or nullptr
+	int lastPass;                 // last PatchMatch iteration of the last outer iteration (restore/.../DepthMap.cpp:1527)
+	int viewspread;               // cross-view propagation (DepthMap.cpp:1504-1608)
+	const struct SpreadConst* spread; // device memory; valid when viewspread && it_external >= 1
 };
 
 struct CamConst { // f64 camera for the filter / fuse kernels (libs/MVS/Camera.h)
 	double K[9], R[9], C[3], P[12];
+};
+
+// what viewspread reads from the matching neighbours: their camera and their maps of the previous outer iteration
+struct SpreadConst {
+	CamConst camRef;
+	struct Nb { CamConst cam; const float4* dn; const float* conf; int w, h; } nb[HCMVS_MAXV];
 };

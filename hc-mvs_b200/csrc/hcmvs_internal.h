@@ -17,6 +17,8 @@ struct View { // one scene image + its DepthData (libs/MVS/DepthMap.h:214-347)
 	float4* dn_d = nullptr;       // (normal.xyz, depth)
 	float* conf_d = nullptr;
 	float* prior_d = nullptr;     // DepthData::depthMapPrior
+	float4* coarse_d = nullptr;   // restore tree: nresize_normalMap / nresize_depthMap packed like dn
+	float4* dnPrev_d = nullptr; float* confPrev_d = nullptr; bool hasPrev = false; // maps of the previous outer iteration (viewspread)
 	float* fdepth_d = nullptr; float* fconf_d = nullptr; bool hasFiltered = false; // pending FilterDepthMap output
 	uint32_t* claim_d = nullptr;  // FuseDepthMaps' arrDepthIdx (claim / reservation word per pixel)
 	float dMin = 0.f, dMax = 0.f;
@@ -45,6 +47,7 @@ struct hcmvs_ctx {
 	uint32_t nLaunches = 0;
 	uint64_t fuseRounds = 0;
 	FuseState* fuse = nullptr;
+	SpreadConst* spread_d = nullptr; // viewspread constants of the view being estimated
 };
 
 void hcmvs_set_error(const char* fmt, ...);
@@ -62,4 +65,6 @@ cudaError_t hcmvs_launch_end(float4* dn, float* conf, size_t n, float keep, cuda
 cudaError_t hcmvs_launch_median3(const float4* in, float4* out, int w, int h, cudaStream_t st);
 cudaError_t hcmvs_launch_gramap(const uint8_t* bgr, uint8_t* gra, int w, int h, cudaStream_t st);
 cudaError_t hcmvs_launch_pack(const float* depth, const float* normal, float4* dn, size_t n, cudaStream_t st);
+cudaError_t hcmvs_launch_resize_area_up(const float* depth, const float* normal, int sw, int sh, float4* dst, int dw, int dh, cudaStream_t st);
+cudaError_t hcmvs_launch_minmax_w(const float4* dn, size_t n, float* minmax_d, cudaStream_t st);
 cudaError_t hcmvs_launch_unpack(const float4* dn, float* depth, float* normal, size_t n, cudaStream_t st);

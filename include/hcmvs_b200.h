@@ -42,6 +42,7 @@ typedef struct hcmvs_params {
 	int32_t rb_far_reach;   /* red-black propagation: per direction the best-confidence pixel among odd offsets 1..rb_far_reach */
 	int32_t rb_prop_dirs;   /* 2 (default): one source per image axis = the reference's 2 propagation hypotheses per pixel-iteration; 4: one per direction */
 	int32_t sampler;        /* 0 = texture gather path (default), 1 = global-memory loads */
+	int32_t viewspread;     /* OPTDENSE::viewspread (DepthMap.cpp:102): cross-view propagation at outer iterations >= 1 (DepthMap.cpp:1504-1608); 0 in every shipped run */
 } hcmvs_params;
 
 typedef struct hcmvs_ctx hcmvs_ctx;
@@ -125,6 +126,19 @@ int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int estimate_normal
 void hcmvs_free_pointcloud(hcmvs_pointcloud* pc);
 /* hcmvs_fuse_depthmaps with out == NULL leaves the cloud on the device; this returns its device arrays
  * (points/normals float[3n], colors u8[3n], view_offsets u32[n+1], views u32[m], weights float[m]). */
+/* restore tree (restore/libs/MVS/SceneDensify.cpp:513-532, DepthMap.cpp:1527-1550): the previous pyramid level's estimate of this
+ * view, wc x hc (depth f32, normal 3 x f32, camera frame). The maps are resized on the device to the view's size exactly as
+ * cv::resize(.., INTER_AREA) enlarges them, [dMin, dMax) is widened by the resized depths (call after hcmvs_init_depthmap), and
+ * on the last PatchMatch iteration of the last outer iteration every pixel scores that estimate as one more hypothesis, kept
+ * unless clearly worse (conf > nconf - 0.1). depth == NULL removes it. */
+int hcmvs_set_coarse_estimate(hcmvs_ctx* ctx, uint32_t view, int wc, int hc, const float* depth, const float* normal);
+/* the resized coarse maps (nresize_depthMap / nresize_normalMap) back on the host, for parity checks; either pointer may be NULL */
+int hcmvs_get_coarse_estimate(hcmvs_ctx* ctx, uint32_t view, float* depth, float* normal);
+/* Keep a copy of every view's (normal, depth, confidence) maps as "the previous outer iteration": what viewspread
+ * (hcmvs_params.viewspread) reads from the neighbour views. Call between outer iterations — after the map exchange when
+ * the scene is sharded over GPUs — so that the result does not depend on the order or placement of the views. */
+int hcmvs_snapshot_maps(hcmvs_ctx* ctx);
+
 /* Copy the last fused cloud into caller-owned host arrays (sizes from hcmvs_get_fused_device); any pointer may be NULL. */
 int hcmvs_download_fused(hcmvs_ctx* ctx, float* points, float* normals, uint8_t* colors, uint32_t* view_offsets, uint32_t* views, float* weights);
 /* Same, into a page-locked host arena OWNED BY THE CONTEXT (PCIe-rate copy, no per-scene pinning): `out` receives pointers that

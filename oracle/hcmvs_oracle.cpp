@@ -668,6 +668,124 @@ void DepthEstimator::ProcessPixel(int px, int py) {
 			scaleRange = scaleRanges[++idxScaleRange];
 		}
 	}
+	ViewSpreadAndCoarse(px, py, conf, depth, normal);
+}
+
+// Cross-view propagation (DepthMap.cpp:1504-1608) and the restore tree's coarse-estimate hypothesis
+// (restore/libs/MVS/DepthMap.cpp:1527-1550). Both sit after the perturbation loop, so the early `return` of a failed
+// fully-random search (:1463) skips them, as in the reference.
+// Defined behaviour where the reference is undefined or order dependent:
+//  q11 the neighbour's maps are those at the end of the PREVIOUS outer iteration (SnapshotMaps) — the reference reads
+//      whatever the neighbour holds at that moment, which depends on the order the views are processed in;
+//  q12 a projection that is not finite / outside the neighbour's map is skipped ((int) of such a float is UB, and the
+//      reference indexes the neighbour's map with the REFERENCE image's bounds, :1527);
+//  q13 the candidates' camera-space points use the neighbour's own intrinsics (the RB2LT branch, :1572; the LT2RB
+//      branch reads images[1] of the neighbour's DepthData, :1547 — another camera);
+//  the neighbour's normals are used as they are, in the NEIGHBOUR's camera frame (:1546) — kept, it is what the code does.
+void DepthEstimator::ViewSpreadAndCoarse(int, int, float& conf, Depth& depth, Vec3f& normal) {
+	const int hw = 7;
+	if (P.viewspread && nIteration_external >= 1) {
+		for (const EstimatorView& v: images) {
+			const uint32_t id1 = (uint32_t)(v.view - scene.images.data());
+			const DepthData& d1 = scene.arrDepthData[id1];
+			if (d1.prevDepth.d.empty()) continue;
+			float H[9]; ComputeHomography(v, depth, normal, H);
+			const float fx0 = (float)x0x, fy0 = (float)x0y;
+			const float X1x = H[0]*fx0 + H[1]*fy0 + H[2], X1y = H[3]*fx0 + H[4]*fy0 + H[5], X1z = H[6]*fx0 + H[7]*fy0 + H[8];
+			const float x1f = X1x/X1z, y1f = X1y/X1z;
+			if (!(std::fabs(x1f) < 1e9f) || !(std::fabs(y1f) < 1e9f)) continue; // q12
+			const int x1 = (int)x1f, y1 = (int)y1f;
+			if (!(x1 > hw && y1 > hw && x1 < w-hw && y1 < h-hw)) continue;
+			if (x1+1 >= d1.prevDepth.w || y1+1 >= d1.prevDepth.h) continue; // q12
+			const int cx[4] = {x1, x1, x1-1, x1+1}, cy[4] = {y1-1, y1+1, y1, y1};
+			neighborsClose.clear();
+			int candX[4], candY[4], nc = 0;
+			const Camera& cam1 = v.view->cam;
+			for (int k=0; k<4; ++k) {
+				const Depth nd = d1.prevDepth.at(cx[k], cy[k]);
+				if (nd > 0) {
+					const Vec3d Xd = cam1.TransformPointI2C((double)cx[k], (double)cy[k], (double)nd); // q13
+					neighborsClose.push_back(NeighborEstimate{nd, d1.prevNormal[(size_t)cy[k]*d1.prevDepth.w+cx[k]], Vec3f{(float)Xd.x, (float)Xd.y, (float)Xd.z}});
+					candX[nc] = cx[k]; candY[nc] = cy[k]; ++nc;
+				}
+			}
+			for (int n=0; n<nc; ++n) {
+				if (d1.prevConf.at(candX[n], candY[n]) >= P.fNCCThresholdKeep) continue;
+				const NeighborEstimate& ne = neighborsClose[n];
+				const Vec3d Xw = cam1.TransformPointI2W((double)candX[n], (double)candY[n], (double)ne.depth);
+				const Vec3f Xf{(float)Xw.x, (float)Xw.y, (float)Xw.z};
+				const Vec3d Xc = image0.cam.TransformPointW2C(Vec3d{(double)Xf.x, (double)Xf.y, (double)Xf.z});
+				const Depth nd = (float)Xc.z;
+				Vec3f nn = ne.normal;
+				CorrectNormal(nn);
+				InitPlane(nd, nn);
+				const float nconf = ScorePixel(nd, nn);
+				if (conf > nconf) { conf = nconf; depth = nd; normal = nn; }
+			}
+		}
+	}
+	if (!dd.coarseDepth.d.empty() && nIteration_external == (int)P.nEstimationIters_external-1 && nIteration == P.nEstimationIters-1) {
+		Depth nd = dd.coarseDepth.at(x0x, x0y);
+		Vec3f nn = dd.coarseNormal[(size_t)x0y*w+x0x];
+		nd = InterpolatePixel(x0x, x0y, nd, nn);
+		CorrectNormal(nn);
+		InitPlane(nd, nn);
+		const float nconf = ScorePixel(nd, nn);
+		if (conf > nconf-0.1f) { conf = nconf; depth = nd; normal = nn; } // the coarse level wins unless clearly worse
+	}
+}
+
+void ResizeAreaUp(const float* src, int sw, int sh, int cn, float* dst, int dw, int dh) {
+	// OpenCV resize(), interpolation INTER_AREA with the destination larger than the source in x or y: the linear kernel
+	// with area_mode coordinates (imgproc/src/resize.cpp: sx = floor(dx*scale), fx = (dx+1) - (sx+1)*inv_scale, clamped
+	// at 0 and reduced to its fraction; borders clamp), f32 taps, horizontal pass then vertical pass.
+	const double inv_scale_x = (double)dw/sw, inv_scale_y = (double)dh/sh;
+	const double scale_x = 1./inv_scale_x, scale_y = 1./inv_scale_y;
+	std::vector<int> xofs(dw), yofs(dh); std::vector<float> ax(dw), ay(dh);
+	auto tab = [](int d, int ssize, double scale, double inv_scale, int& so, float& f) {
+		int s = (int)std::floor(d*scale);
+		float fr = (float)((d+1) - (s+1)*inv_scale);
+		fr = fr <= 0 ? 0.f : fr - std::floor(fr);
+		if (s < 0) { fr = 0; s = 0; }
+		if (s >= ssize-1) { fr = 0; s = ssize-1; }
+		so = s; f = fr;
+	};
+	for (int dx=0; dx<dw; ++dx) tab(dx, sw, scale_x, inv_scale_x, xofs[dx], ax[dx]);
+	for (int dy=0; dy<dh; ++dy) tab(dy, sh, scale_y, inv_scale_y, yofs[dy], ay[dy]);
+	for (int dy=0; dy<dh; ++dy) {
+		const int y0 = yofs[dy], y1 = std::min(y0+1, sh-1);
+		const float b0 = 1.f-ay[dy], b1 = ay[dy];
+		for (int dx=0; dx<dw; ++dx) {
+			const int x0 = xofs[dx], x1 = std::min(x0+1, sw-1);
+			const float a0 = 1.f-ax[dx], a1 = ax[dx];
+			for (int c=0; c<cn; ++c) {
+				const float r0 = src[((size_t)y0*sw+x0)*cn+c]*a0 + src[((size_t)y0*sw+x1)*cn+c]*a1;
+				const float r1 = src[((size_t)y1*sw+x0)*cn+c]*a0 + src[((size_t)y1*sw+x1)*cn+c]*a1;
+				dst[((size_t)dy*dw+dx)*cn+c] = r0*b0 + r1*b1;
+			}
+		}
+	}
+}
+
+void SetCoarseEstimate(Scene& scene, uint32_t idxImage, const float* depth, const float* normal, int wc, int hc) {
+	DepthData& dd = scene.arrDepthData[idxImage];
+	const ImageData& image = scene.images[idxImage];
+	if (!depth) { dd.coarseDepth = Image32F(); dd.coarseNormal.clear(); return; }
+	dd.coarseDepth.w = image.w; dd.coarseDepth.h = image.h; dd.coarseDepth.d.assign((size_t)image.w*image.h, 0.f);
+	dd.coarseNormal.assign((size_t)image.w*image.h, Vec3f{0,0,0});
+	ResizeAreaUp(depth, wc, hc, 1, dd.coarseDepth.d.data(), image.w, image.h);
+	ResizeAreaUp(normal, wc, hc, 3, &dd.coarseNormal[0].x, image.w, image.h);
+	for (float value: dd.coarseDepth.d) { // restore/.../SceneDensify.cpp:526-532
+		dd.dMin = dd.dMin > value ? value : dd.dMin;
+		dd.dMax = dd.dMax > value ? dd.dMax : value;
+	}
+}
+
+void SnapshotMaps(Scene& scene) {
+	for (DepthData& dd: scene.arrDepthData) {
+		if (dd.IsEmpty()) continue;
+		dd.prevDepth = dd.depthMap; dd.prevConf = dd.confMap; dd.prevNormal = dd.normalMap;
+	}
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -988,6 +1106,7 @@ static void RBProcessPixel(DepthEstimator& est, int px, int py, const uint32_t k
 			scaleRange = scaleRanges[++idxScaleRange];
 		}
 	}
+	est.ViewSpreadAndCoarse(px, py, conf, depth, normal);
 }
 
 // the block-best plane offered to pixel (px,py): interpolate it to the pixel, score with the pixel's own smoothness set

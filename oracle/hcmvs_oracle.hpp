@@ -92,6 +92,7 @@ struct Params {
 	int   photo2geo = 2;
 	float photometric_flow = 0.f;         // benchmark setting
 	float para_prior = 0.3f, fsigmaPrior = 0.2f;
+	int   viewspread = 0;                 // cross-view propagation (DepthMap.cpp:1504-1608); off in every shipped config
 };
 
 // ---------------------------------------------------------------- scene
@@ -120,6 +121,10 @@ struct DepthData {
 	Image32F depthMap, confMap;
 	std::vector<Vec3f> normalMap;
 	Image32F depthMapPrior;            // optional
+	Image32F coarseDepth;              // restore tree: nresize_depthMap / nresize_normalMap (restore/.../DepthMap.h:294-295), optional
+	std::vector<Vec3f> coarseNormal;
+	Image32F prevDepth, prevConf;      // maps at the end of the previous outer iteration (what viewspread reads from the neighbours, q11)
+	std::vector<Vec3f> prevNormal;
 	Image8U  graMap;
 	float dMin = 0, dMax = 0;
 	bool valid = false;
@@ -203,6 +208,7 @@ struct DepthEstimator {
 	float ScorePixelImage(const EstimatorView& v, Depth d, const Vec3f& n); // DepthMap.cpp:522-616 + 890-955
 	float ScorePixel(Depth d, const Vec3f& n);                    // DepthMap.cpp:987-1046
 	void  ProcessPixel(int x, int y);                             // DepthMap.cpp:1050-1501
+	void  ViewSpreadAndCoarse(int px, int py, float& conf, Depth& depth, Vec3f& normal); // DepthMap.cpp:1504-1608 + restore/.../DepthMap.cpp:1527-1550
 	Depth InterpolatePixel(int nx, int ny, Depth d, const Vec3f& n) const; // DepthMap.cpp:1671-1726
 	void  InitPlane(Depth d, const Vec3f& n);                     // DepthMap.cpp:1730-1738
 	void  CorrectNormal(Vec3f& n) const;                          // DepthMap.h:629-634
@@ -227,6 +233,13 @@ bool EstimateDepthMap(Scene& scene, uint32_t idxImage, int it_external, uint64_t
 void ScoreHypotheses(Scene& scene, uint32_t idxImage, const float* depth, const float* normal, int smoothMode, float* scoreOut);
 // EndDepthMapTmp (SceneDensify.cpp:688-744)
 void EndDepthMap(Scene& scene, uint32_t idxImage);
+// cv::resize(src, dst, dsize, 0, 0, INTER_AREA) when ENLARGING (OpenCV imgproc/resize.cpp: bilinear with the "area mode"
+// source coordinates) — how the restore tree brings the previous level's maps to the current size (restore/.../SceneDensify.cpp:523-524)
+void ResizeAreaUp(const float* src, int sw, int sh, int cn, float* dst, int dw, int dh);
+// restore/.../SceneDensify.cpp:513-532: resize the coarse maps to the view's size and widen [dMin, dMax) with the resized depths
+void SetCoarseEstimate(Scene& scene, uint32_t idxImage, const float* depth, const float* normal, int wc, int hc);
+// snapshot every view's maps: viewspread reads the NEIGHBOURS' maps of the previous outer iteration (q11)
+void SnapshotMaps(Scene& scene);
 
 // Red-black restatement of the sweep: SAME scoring functions, checkerboard order and the counter-based
 // Philox RNG the CUDA kernels use. This is the CPU statement of what the GPU computes.

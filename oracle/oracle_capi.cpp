@@ -22,7 +22,7 @@ int orc_set_param(orc_scene* s, const char* name, double v) {
 	#define PU(f) if (n == #f) { P.f = (unsigned)v; return 0; }
 	#define PI(f) if (n == #f) { P.f = (int)v; return 0; }
 	#define PF(f) if (n == #f) { P.f = (float)v; return 0; }
-	PU(nNumViews) PU(nMaxViews) PU(nMinViews) PU(nMinViewsTrustPoint) PU(nMinViewsFuse) PU(nMinViewsFilter)
+	PU(nNumViews) PU(nMaxViews) PU(nMinViews) PU(nMinViewsTrustPoint) PU(nMinViewsFuse) PI(viewspread) PU(nMinViewsFilter)
 	PU(nMinViewsFilterAdjust) PI(bFilterAdjust) PF(fViewMinScore) PF(fViewMinScoreRatio) PF(fMinArea) PF(fMinAngle)
 	PF(fOptimAngle) PF(fMaxAngle) PF(fNCCThresholdKeep) PU(nEstimationIters) PU(nEstimationIters_external)
 	PU(nRandomIters) PF(fRandomDepthRatio) PF(fRandomAngle1Range) PF(fRandomAngle2Range) PF(fRandomSmoothDepth)
@@ -143,6 +143,19 @@ int orc_set_prior(orc_scene* s, int idx, const float* prior) {
 	if (prior) dd.depthMapPrior.d.assign(prior, prior+(size_t)w*h); else dd.depthMapPrior.d.clear();
 	return 0;
 }
+int orc_set_coarse(orc_scene* s, int idx, const float* depth, const float* normal, int wc, int hc) {
+	if (idx < 0 || idx >= (int)s->scene.images.size()) return -1;
+	SetCoarseEstimate(s->scene, (uint32_t)idx, depth, normal, wc, hc); return 0;
+}
+int orc_get_coarse(orc_scene* s, int idx, float* depth, float* normal) {
+	const DepthData& dd = s->scene.arrDepthData[idx];
+	if (dd.coarseDepth.d.empty()) return -1;
+	if (depth) std::memcpy(depth, dd.coarseDepth.d.data(), dd.coarseDepth.d.size()*4);
+	if (normal) std::memcpy(normal, dd.coarseNormal.data(), dd.coarseNormal.size()*12);
+	return 0;
+}
+void orc_snapshot_maps(orc_scene* s) { SnapshotMaps(s->scene); }
+void orc_resize_area_up(const float* src, int sw, int sh, int cn, float* dst, int dw, int dh) { ResizeAreaUp(src, sw, sh, cn, dst, dw, dh); }
 int orc_get_gramap(orc_scene* s, int idx, uint8_t* out) {
 	const Image8U& g = s->scene.arrDepthData[idx].graMap;
 	std::memcpy(out, g.d.data(), g.d.size());

@@ -40,6 +40,10 @@ def lib():
         L.orc_get_depthmap.argtypes = [vp, C.c_int, vp, vp, vp, vp]
         L.orc_set_prior.argtypes = [vp, C.c_int, vp]
         L.orc_get_gramap.argtypes = [vp, C.c_int, vp]
+        L.orc_set_coarse.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.c_int]
+        L.orc_get_coarse.argtypes = [vp, C.c_int, vp, vp]
+        L.orc_snapshot_maps.argtypes = [vp]
+        L.orc_resize_area_up.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int]
         L.orc_score_depthmap.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, C.c_int]
         L.orc_estimate_depthmap.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, vp]
         L.orc_score_hypotheses.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp]
@@ -65,6 +69,15 @@ def _p(a):
         return None
     assert a.flags["C_CONTIGUOUS"]
     return a.ctypes.data_as(C.c_void_p)
+
+
+def resize_area_up(src, dw, dh):
+    """cv::resize(src, (dw, dh), interpolation=INTER_AREA) for an enlargement, f32, 1 or 3 channels (oracle restatement)."""
+    src = np.ascontiguousarray(src, np.float32)
+    sh, sw = src.shape[:2]; cn = 1 if src.ndim == 2 else src.shape[2]
+    dst = np.zeros((dh, dw) if src.ndim == 2 else (dh, dw, cn), np.float32)
+    lib().orc_resize_area_up(_p(src), sw, sh, cn, _p(dst), dw, dh)
+    return dst
 
 
 class OracleScene:
@@ -142,6 +155,24 @@ class OracleScene:
         d = np.zeros((h, w), np.float32); n = np.zeros((h, w, 3), np.float32); c = np.zeros((h, w), np.float32); mm = np.zeros(2, np.float32)
         self.L.orc_get_depthmap(self.h, i, _p(d), _p(n), _p(c), _p(mm))
         return d, n, c, float(mm[0]), float(mm[1])
+
+    def set_coarse(self, i, depth, normal):
+        """restore tree: coarse maps of the previous level -> resized to the view, widen [dMin,dMax) (None clears)."""
+        if depth is None:
+            self.L.orc_set_coarse(self.h, i, None, None, 0, 0)
+            return
+        depth = np.ascontiguousarray(depth, np.float32); normal = np.ascontiguousarray(normal, np.float32)
+        hc, wc = depth.shape
+        assert self.L.orc_set_coarse(self.h, i, _p(depth), _p(normal), wc, hc) == 0
+
+    def get_coarse(self, i):
+        h, w = self.sizes[i]
+        d = np.zeros((h, w), np.float32); n = np.zeros((h, w, 3), np.float32)
+        assert self.L.orc_get_coarse(self.h, i, _p(d), _p(n)) == 0
+        return d, n
+
+    def snapshot_maps(self):
+        self.L.orc_snapshot_maps(self.h)
 
     def gramap(self, i):
         h, w = self.sizes[i]

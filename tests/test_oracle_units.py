@@ -186,3 +186,17 @@ def test_filter_and_fuse_on_ground_truth_maps():
     for k in range(0, len(off) - 1, 97):
         v = cloud["views"][off[k]:off[k + 1]]
         assert np.all(np.diff(v.astype(np.int64)) > 0)                        # PointCloud::pointViews sorted, unique
+
+
+def test_resize_area_up_matches_opencv():
+    """The restore tree brings the previous level's maps to the current size with cv::resize(INTER_AREA)
+    (restore/libs/MVS/SceneDensify.cpp:523-524); enlarging, OpenCV runs its linear kernel with "area mode" coordinates.
+    The oracle's restatement is compared bit for bit with the cv2 in this image — a third-party pin for that piece."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for (sh, sw, dh, dw) in ((30, 40, 60, 80), (37, 53, 120, 160), (100, 75, 101, 76), (48, 64, 480, 640), (5, 7, 33, 20), (60, 80, 120, 160)):
+        for cn in (1, 3):
+            src = rng.uniform(0.1, 10, (sh, sw) if cn == 1 else (sh, sw, cn)).astype(np.float32)
+            want = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_AREA)
+            got = O.resize_area_up(src, dw, dh)
+            assert np.array_equal(want, got), (sh, sw, dh, dw, cn, np.abs(want - got).max())
