@@ -108,6 +108,23 @@ def make_scene(args):
     return syn, imgs
 
 
+def ncu_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_sweep launch from the committed `ncu --set full` summary (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_k_sweep_v3_packed.txt")
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, found = 0.0, 0
+    try:
+        with open(path) as f:
+            for line in f:
+                for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    if line.startswith(key + " ["):
+                        u = line[line.index("[") + 1:line.index("]")]
+                        tot += float(line.split("=")[1].split(",")[0]) * unit[u]; found += 1
+    except OSError:
+        return None
+    return tot if found == 2 else None
+
+
 def flops_per_view_score(texels):
     # SURVEY §8(d): 24 flop per texel + ~110 per (hypothesis, view) for H, projections, normalisation
     return 24.0 * texels + 110.0
@@ -306,10 +323,17 @@ def run_b200(args):
         "algorithmic_flops_per_view_score": flops_per_view_score(texels),
         "hbm": {"achieved": hbm_bytes / sweep_s / 1e9 if sweep_s > 0 else 0.0, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                 "frac": (hbm_bytes / sweep_s / 1e9) / peaks.get("hbm_gbs", 1.0) if sweep_s > 0 else None, "bytes_per_pixel_iter": 64},
-        "traffic": None,
+        "traffic": ncu_traffic_per_launch(),
+        "traffic_note": "DRAM bytes of one k_sweep launch (ncu --set full, profiles/r01_ncu_k_sweep_v3_packed.txt) vs 0.96 Mpix x 64 B = 61 MB algorithmic",
         "sweep_mpix_iter_s": tm["n_pixel_iters"] / sweep_s / 1e6 if sweep_s > 0 else None,
         "hyp_per_pixel_iter": tm["n_hypotheses"] / max(tm["n_pixel_iters"], 1),
     }
+    # the unit that actually bounds k_sweep: a 4-tap texture gather costs 16 cycles of L1TEX write-back per warp
+    # => 2 bilinear samples / clk / SM; samples = view scores x texels
+    tex_peak = 2.0 * sms * peaks.get("sm_max_mhz", 1965.0) * 1e6
+    tex_rate = tm["n_view_scores"] * texels / sweep_s if sweep_s > 0 else 0.0
+    roofline["tex_wall"] = {"achieved": tex_rate / 1e9, "peak": tex_peak / 1e9, "unit": "Gsample/s", "frac": tex_rate / tex_peak if tex_peak else None,
+                            "note": "texture write-back 32 B/clk/SM, 16 B per bilinear sample (ncu l1tex__tex_writeback_active 79.6 %)"}
     stages = {k: tm[k] / args.steps for k in ("ms_prep", "ms_score", "ms_sweeps", "ms_end", "ms_filter", "ms_fuse")}
     launches = tm["n_launches"]
 

@@ -70,6 +70,8 @@ static void FreeView(View& v) {
 	if (v.tex) cudaDestroyTextureObject(v.tex);
 	if (v.arr) cudaFreeArray(v.arr);
 	if (v.ready) cudaEventDestroy(v.ready);
+	if (v.imgReady) cudaEventDestroy(v.imgReady);
+	if (v.lastUse) cudaEventDestroy(v.lastUse);
 	cudaFree(v.img_d); cudaFree(v.bgr_d); cudaFree(v.gra_d); cudaFree(v.dn_d); cudaFree(v.conf_d); cudaFree(v.prior_d); cudaFree(v.coarse_d); cudaFree(v.dnPrev_d); cudaFree(v.confPrev_d); cudaFree(v.fdepth_d); cudaFree(v.fconf_d); cudaFree(v.claim_d);
 	v = View();
 }
@@ -196,9 +198,10 @@ extern "C" int hcmvs_set_view(hcmvs_ctx* ctx, uint32_t view, int W, int H, const
 	View* v = GetView(ctx, view, false); if (!v) return HCMVS_ERR_ARG;
 	const bool reuse = v->set && v->w == W && v->h == H && (v->bgr_d != nullptr) == (bgr != nullptr);
 	if (v->set) {
-		// the image may still be read by queued kernels
-		CK(cudaStreamSynchronize(ctx->stream)); CK(cudaStreamSynchronize(ctx->copyStream));
-		if (!reuse) FreeView(*v);
+		// the image may still be read by queued kernels: same-size re-uploads wait for them on the device (copy stream),
+		// a change of size frees the buffers and has to wait on the host
+		if (reuse) { if (v->lastUse) CK(cudaStreamWaitEvent(ctx->copyStream, v->lastUse, 0)); }
+		else { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaStreamSynchronize(ctx->copyStream)); FreeView(*v); }
 	}
 	v->w = W; v->h = H;
 	std::memcpy(v->K, K, 72); std::memcpy(v->R, R, 72); std::memcpy(v->C, C, 24);
@@ -217,11 +220,35 @@ extern "C" int hcmvs_set_view(hcmvs_ctx* ctx, uint32_t view, int W, int H, const
 	} else {
 		v->graValid = false; // a new image invalidates the derived gradient map (rebuilt by the next hcmvs_init_depthmap)
 	}
-	CK(cudaMemcpy2DToArrayAsync(v->arr, 0, 0, gray, (size_t)W*4, (size_t)W*4, H, cudaMemcpyHostToDevice, ctx->stream));
-	CK(cudaMemcpyAsync(v->img_d, gray, n*4, cudaMemcpyHostToDevice, ctx->stream));
-	if (bgr) CK(cudaMemcpyAsync(v->bgr_d, bgr, n*3, cudaMemcpyHostToDevice, ctx->stream));
-	CK(cudaStreamSynchronize(ctx->stream)); // host buffers may be released by the caller
+	// uploads go on the COPY stream so that they overlap the kernels of other views; consumers wait on v->imgReady.
+	// The caller may release its buffers on return: cudaMemcpyAsync returns once a PAGEABLE source has been staged, and for a
+	// pinned source (read by the DMA engine itself) the copy stream is synchronised below.
+	cudaStream_t cs = ctx->copyStream;
+	CK(cudaMemcpy2DToArrayAsync(v->arr, 0, 0, gray, (size_t)W*4, (size_t)W*4, H, cudaMemcpyHostToDevice, cs));
+	CK(cudaMemcpyAsync(v->img_d, gray, n*4, cudaMemcpyHostToDevice, cs));
+	if (bgr) CK(cudaMemcpyAsync(v->bgr_d, bgr, n*3, cudaMemcpyHostToDevice, cs));
+	if (!v->imgReady) CK(cudaEventCreateWithFlags(&v->imgReady, cudaEventDisableTiming));
+	CK(cudaEventRecord(v->imgReady, cs));
+	cudaPointerAttributes pa; const bool pinned = cudaPointerGetAttributes(&pa, gray) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+	cudaGetLastError();
+	if (pinned) CK(cudaStreamSynchronize(cs)); // a pinned source is read by the DMA engine itself: wait before the caller reuses it
 	v->set = true;
+	return HCMVS_OK;
+}
+
+int hcmvs_mark_image_use(hcmvs_ctx* ctx, View& v) {
+	if (!v.lastUse) CK(cudaEventCreateWithFlags(&v.lastUse, cudaEventDisableTiming));
+	CK(cudaEventRecord(v.lastUse, ctx->stream));
+	return HCMVS_OK;
+}
+static int MarkUse(hcmvs_ctx* ctx, View* v) { // the reference view and its matching neighbours
+	int r = hcmvs_mark_image_use(ctx, *v); if (r) return r;
+	for (int i=0; i<v->nMatch; ++i) { r = hcmvs_mark_image_use(ctx, ctx->views[v->nbIds[i]]); if (r) return r; }
+	return HCMVS_OK;
+}
+
+int hcmvs_wait_image(hcmvs_ctx* ctx, const View& v) {
+	if (v.imgReady) CK(cudaStreamWaitEvent(ctx->stream, v.imgReady, 0));
 	return HCMVS_OK;
 }
 
@@ -443,9 +470,11 @@ static int BuildRefConst(hcmvs_ctx* ctx, View* v, uint32_t ref, int it_external,
 	rc.img0 = v->img_d; rc.pitch0 = v->w; rc.gra = v->gra_d; rc.prior = v->prior_d;
 	rc.dn = v->dn_d; rc.conf = v->conf_d;
 	rc.nViews = v->nMatch;
+	{ int r = hcmvs_wait_image(ctx, *v); if (r) return r; }
 	for (int i=0; i<v->nMatch; ++i) {
 		View* nb = GetView(ctx, v->nbIds[i], true);
 		if (!nb) { hcmvs_set_error("neighbour view %u of %u not set", v->nbIds[i], ref); return HCMVS_ERR_STATE; }
+		{ int r = hcmvs_wait_image(ctx, *nb); if (r) return r; }
 		NbViewConst& c = rc.nb[i];
 		// DepthEstimator::ViewData, DepthMap.h:430-433: Hl = K1 R1 R0^T, Hm = K1 R1 (C0-C1)
 		double KR[9]; Mul33(nb->K, nb->R, KR);
@@ -490,7 +519,7 @@ extern "C" int hcmvs_score_depthmap(hcmvs_ctx* ctx, uint32_t ref, int it_externa
 	hcmvs_time_begin(ctx, ST_SCORE);
 	CK(hcmvs_launch_score_init(rc, ctx->P.sampler == 0, ctx->stream)); ++ctx->nLaunches;
 	hcmvs_time_end(ctx);
-	return HCMVS_OK;
+	return MarkUse(ctx, v);
 }
 
 extern "C" int hcmvs_end_depthmap(hcmvs_ctx* ctx, uint32_t ref) {
@@ -560,7 +589,7 @@ extern "C" int hcmvs_estimate_depthmap(hcmvs_ctx* ctx, uint32_t ref, int it_exte
 		CK(hcmvs_launch_end(v->dn_d, v->conf_d, n, P.fNCCThresholdKeep, ctx->stream)); ++ctx->nLaunches;
 		hcmvs_time_end(ctx);
 	}
-	return HCMVS_OK;
+	return MarkUse(ctx, v);
 }
 
 extern "C" int hcmvs_score_hypotheses(hcmvs_ctx* ctx, uint32_t ref, const float* depth, const float* normal, int smooth_mode, float* score_out) {
@@ -590,5 +619,5 @@ extern "C" int hcmvs_score_hypotheses(hcmvs_ctx* ctx, uint32_t ref, const float*
 	CK(hcmvs_launch_score_hyp(rc, hyp, smooth_mode, out, ctx->P.sampler == 0, ctx->stream)); ++ctx->nLaunches;
 	CK(cudaMemcpyAsync(score_out, out, n*4, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
-	return HCMVS_OK;
+	return MarkUse(ctx, v);
 }

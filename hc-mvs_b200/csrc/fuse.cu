@@ -423,6 +423,7 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 		View& v = ctx->views[i];
 		FuseView& fv = hv[i]; memset(&fv, 0, sizeof(fv));
 		if (!v.set || !v.hasMaps) continue;
+		{ int r = hcmvs_wait_image(ctx, v); if (r) return r; } // colours
 		const size_t n = (size_t)v.w*v.h;
 		if (!v.claim_d) CK(cudaMalloc(&v.claim_d, n*4));
 		k_fill_u32<<<(unsigned)((n+255)/256), 256, 0, ctx->stream>>>(v.claim_d, CLAIM_FREE, n); ++ctx->nLaunches;
@@ -516,6 +517,7 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 		nPoints += tot.x; nViewRefs += tot.y;
 	}
 	hcmvs_time_end(ctx);
+	for (View& v: ctx->views) if (v.set && v.hasMaps) { int r = hcmvs_mark_image_use(ctx, v); if (r) return r; } // colours were read
 	ctx->fuseRounds = totalRounds;
 	f->nPoints = nPoints; f->nViewRefs = nViewRefs; f->hasColor = estimate_color != 0; f->hasNormal = estimate_normal != 0;
 	if (nPoints) { // close the CSR offsets on the device

@@ -26,6 +26,8 @@ struct View { // one scene image + its DepthData (libs/MVS/DepthMap.h:214-347)
 	std::vector<float> nbScores;
 	int nMatch = 0;               // first nMatch ids = DepthData::images[1..]
 	cudaEvent_t ready = nullptr;  // upload of this view's maps finished (recorded on the copy stream)
+	cudaEvent_t lastUse = nullptr;  // last kernel that reads this view's images was queued before this event (compute stream)
+	cudaEvent_t imgReady = nullptr; // upload of this view's images finished (copy stream); compute entry points wait on it
 	float fusePriority = 0.f; bool hasFusePriority = false; // #scored neighbours (FuseDepthMaps connection score)
 };
 
@@ -56,6 +58,8 @@ void hcmvs_time_begin(hcmvs_ctx* ctx, int stage);
 void hcmvs_time_end(hcmvs_ctx* ctx);
 void hcmvs_fuse_release(hcmvs_ctx* ctx);
 void hcmvs_fill_cam(const View& v, CamConst& c);
+int  hcmvs_mark_image_use(hcmvs_ctx* ctx, View& v);   // record v.lastUse on the compute stream
+int  hcmvs_wait_image(hcmvs_ctx* ctx, const View& v); // make the compute stream wait for the view's image upload
 
 // patchmatch.cu
 cudaError_t hcmvs_launch_score_init(const RefConst& rc, bool tex, cudaStream_t st);

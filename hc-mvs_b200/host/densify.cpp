@@ -387,13 +387,8 @@ bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, co
 		}
 	});
 	struct Joiner { std::vector<std::thread>& p; std::atomic<uint32_t>& c; ~Joiner() { c.store(0x7fffffffu); for (std::thread& th: p) if (th.joinable()) th.join(); } } joiner{pool, consumed};
-	// upload every image (each one is the reference view of its own depth map and a neighbour of others)
-	for (uint32_t i=0; i<nImages; ++i) {
-		if (!data.UploadView(i)) return fail(data.lastError);
-		const Image& im = scene.images[i];
-		st.h2dBytes += (uint64_t)im.width*im.height*(4+(im.bgr.empty() ? 0 : 3));
-	}
-	double t1 = Now(); st.secUpload = t1-t0;
+	// images are uploaded on first use by InitViews (copy stream), so the uploads of later views overlap the kernels of earlier ones
+	double t1 = Now();
 	std::vector<uint32_t> valid;
 	for (uint32_t i=0; i<nImages; ++i) {
 		int s;
@@ -412,7 +407,12 @@ bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, co
 		std::vector<float>().swap(prep[i].depth);
 		consumed.store(i+1, std::memory_order_release);
 	}
-	st.secSelect = tSelectEnd.load()-t0; // overlaps the upload and the estimation
+	for (uint32_t i=0; i<nImages; ++i) {
+		const Image& im = scene.images[i];
+		if (data.arrDepthData[i].uploaded) st.h2dBytes += (uint64_t)im.width*im.height*(4+(im.bgr.empty() ? 0 : 3));
+	}
+	st.secSelect = tSelectEnd.load()-t0; // overlaps the uploads and the estimation
+	st.secUpload = 0; // image uploads ride the copy stream inside the estimation loop
 	if (valid.empty()) return fail("no image has enough neighbour views");
 	for (unsigned it=1; it<P.nEstimationIters_external; ++it) // :3684
 		for (uint32_t i: valid) {
