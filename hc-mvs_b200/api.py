@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libhcmvs_b200.so")
 
 EXPORTS = [
     "hcmvs_default_params", "hcmvs_last_error", "hcmvs_create", "hcmvs_destroy", "hcmvs_set_params", "hcmvs_sync",
-    "hcmvs_set_view", "hcmvs_set_neighbors", "hcmvs_init_depthmap", "hcmvs_set_depthmap", "hcmvs_get_depthmap",
+    "hcmvs_set_view", "hcmvs_set_neighbors", "hcmvs_set_neighbor_image", "hcmvs_init_depthmap", "hcmvs_set_depthmap", "hcmvs_get_depthmap",
     "hcmvs_set_prior", "hcmvs_set_coarse_estimate", "hcmvs_get_coarse_estimate", "hcmvs_snapshot_maps", "hcmvs_get_gradient_map", "hcmvs_score_depthmap", "hcmvs_estimate_depthmap", "hcmvs_end_depthmap", "hcmvs_score_hypotheses",
     "hcmvs_filter_depthmap", "hcmvs_commit_filtered", "hcmvs_set_fuse_priority", "hcmvs_fuse_depthmaps",
     "hcmvs_free_pointcloud", "hcmvs_get_fused_device", "hcmvs_download_fused", "hcmvs_download_fused_pinned", "hcmvs_get_depthmap_device", "hcmvs_set_depth_range", "hcmvs_alloc_depthmap",
@@ -81,6 +81,7 @@ def load():
     L.hcmvs_sync.argtypes = [vp]
     L.hcmvs_set_view.argtypes = [vp, u32, i32, i32, vp, vp, vp, vp, vp]
     L.hcmvs_set_neighbors.argtypes = [vp, u32, vp, vp, i32, i32]
+    L.hcmvs_set_neighbor_image.argtypes = [vp, u32, i32, i32, i32, vp, vp]
     L.hcmvs_init_depthmap.argtypes = [vp, u32, vp, vp, f32, f32]
     L.hcmvs_set_depthmap.argtypes = [vp, u32, vp, vp, vp, f32, f32]
     L.hcmvs_get_depthmap.argtypes = [vp, u32, vp, vp, vp, C.POINTER(f32), C.POINTER(f32)]
@@ -164,6 +165,15 @@ class Context:
         ids = np.ascontiguousarray(ids, np.uint32)
         sc = np.ascontiguousarray(scores, np.float32) if scores is not None else None
         self._ck(self.L.hcmvs_set_neighbors(self.h, ref, _p(ids), _p(sc), int(n_match), len(ids)))
+
+    def set_neighbor_image(self, ref, slot, K, gray):
+        """ViewData::ScaleImage: matching view `slot` of `ref` is matched against this rescaled image / intrinsics (None: its own image)."""
+        if gray is None:
+            self._ck(self.L.hcmvs_set_neighbor_image(self.h, ref, slot, 0, 0, None, None))
+            return
+        gray = np.ascontiguousarray(gray, np.float32); K = np.ascontiguousarray(K, np.float64)
+        h, w = gray.shape
+        self._ck(self.L.hcmvs_set_neighbor_image(self.h, ref, slot, w, h, _p(K), _p(gray)))
 
     def init_depthmap(self, ref, depth0, normal0, dmin, dmax):
         depth0 = np.ascontiguousarray(depth0, np.float32)

@@ -66,7 +66,14 @@ extern "C" hcmvs_ctx* hcmvs_create(int device, const hcmvs_params* p) {
 	return ctx;
 }
 
+static void FreeNbImage(NbImage& o) {
+	if (o.tex) cudaDestroyTextureObject(o.tex);
+	if (o.arr) cudaFreeArray(o.arr);
+	cudaFree(o.img_d);
+	o = NbImage();
+}
 static void FreeView(View& v) {
+	for (NbImage& o: v.nbImages) FreeNbImage(o);
 	if (v.tex) cudaDestroyTextureObject(v.tex);
 	if (v.arr) cudaFreeArray(v.arr);
 	if (v.ready) cudaEventDestroy(v.ready);
@@ -188,6 +195,17 @@ static View* GetView(hcmvs_ctx* ctx, uint32_t view, bool mustExist) {
 	return v;
 }
 
+static int CreateGrayTexture(int W, int H, cudaArray_t& arr, cudaTextureObject_t& tex) {
+	cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
+	CK(cudaMallocArray(&arr, &desc, W, H, cudaArrayTextureGather));
+	cudaResourceDesc rd; std::memset(&rd, 0, sizeof(rd)); rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
+	cudaTextureDesc td; std::memset(&td, 0, sizeof(td));
+	td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp; td.filterMode = cudaFilterModePoint;
+	td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+	CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+	return HCMVS_OK;
+}
+
 extern "C" int hcmvs_set_view(hcmvs_ctx* ctx, uint32_t view, int W, int H, const double K[9], const double R[9], const double C[3],
 	const float* gray, const uint8_t* bgr)
 {
@@ -208,13 +226,7 @@ extern "C" int hcmvs_set_view(hcmvs_ctx* ctx, uint32_t view, int W, int H, const
 	ComposeP(K, R, C, v->P);
 	const size_t n = (size_t)W*H;
 	if (!reuse) {
-		cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
-		CK(cudaMallocArray(&v->arr, &desc, W, H, cudaArrayTextureGather));
-		cudaResourceDesc rd; std::memset(&rd, 0, sizeof(rd)); rd.resType = cudaResourceTypeArray; rd.res.array.array = v->arr;
-		cudaTextureDesc td; std::memset(&td, 0, sizeof(td));
-		td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp; td.filterMode = cudaFilterModePoint;
-		td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
-		CK(cudaCreateTextureObject(&v->tex, &rd, &td, nullptr));
+		{ int r = CreateGrayTexture(W, H, v->arr, v->tex); if (r) return r; }
 		CK(cudaMalloc(&v->img_d, n*4));
 		if (bgr) CK(cudaMalloc(&v->bgr_d, n*3));
 	} else {
@@ -258,10 +270,36 @@ extern "C" int hcmvs_set_neighbors(hcmvs_ctx* ctx, uint32_t ref, const uint32_t*
 		hcmvs_set_error("bad neighbour list (n_match %d <= %d, n_all %d <= %d)", n_match, HCMVS_MAX_MATCH_VIEWS, n_all, HCMVS_MAX_FUSE_VIEWS); return HCMVS_ERR_ARG;
 	}
 	for (int i=0; i<n_all; ++i) if (ids[i] == ref) { hcmvs_set_error("view %u lists itself as neighbour", ref); return HCMVS_ERR_ARG; }
+	if (!v->nbImages.empty()) { // a new neighbour list drops the per-pair rescaled images
+		cudaSetDevice(ctx->device);
+		CK(cudaStreamSynchronize(ctx->stream));
+		for (NbImage& o: v->nbImages) FreeNbImage(o);
+		v->nbImages.clear();
+	}
 	v->nbIds.assign(ids, ids+n_all);
 	v->nbScores.assign(n_all, 0.f);
 	if (scores) v->nbScores.assign(scores, scores+n_all);
 	v->nMatch = n_match;
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_set_neighbor_image(hcmvs_ctx* ctx, uint32_t ref, int slot, int W, int H, const double K[9], const float* gray) {
+	View* v = GetView(ctx, ref, true); if (!v) return HCMVS_ERR_ARG;
+	if (slot < 0 || slot >= v->nMatch) { hcmvs_set_error("view %u has no matching neighbour %d (call hcmvs_set_neighbors first)", ref, slot); return HCMVS_ERR_ARG; }
+	cudaSetDevice(ctx->device);
+	if (v->nbImages.size() < (size_t)v->nMatch) v->nbImages.resize(v->nMatch);
+	NbImage& o = v->nbImages[slot];
+	CK(cudaStreamSynchronize(ctx->stream)); // queued kernels may still sample the previous image
+	FreeNbImage(o);
+	if (!gray) return HCMVS_OK;
+	if (!K || W < 4 || H < 4 || W > 65535 || H > 65535) { hcmvs_set_error("bad rescaled image %dx%d", W, H); return HCMVS_ERR_ARG; }
+	if (K[1] != 0.0 || K[3] != 0.0 || K[6] != 0.0 || K[7] != 0.0) { hcmvs_set_error("K must be upper triangular with zero skew"); return HCMVS_ERR_UNSUPPORTED; }
+	{ int r = CreateGrayTexture(W, H, o.arr, o.tex); if (r) return r; }
+	CK(cudaMalloc(&o.img_d, (size_t)W*H*4));
+	CK(cudaMemcpy2DToArrayAsync(o.arr, 0, 0, gray, (size_t)W*4, (size_t)W*4, H, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(o.img_d, gray, (size_t)W*H*4, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	o.w = W; o.h = H; std::memcpy(o.K, K, 72);
 	return HCMVS_OK;
 }
 
@@ -476,12 +514,15 @@ static int BuildRefConst(hcmvs_ctx* ctx, View* v, uint32_t ref, int it_external,
 		if (!nb) { hcmvs_set_error("neighbour view %u of %u not set", v->nbIds[i], ref); return HCMVS_ERR_STATE; }
 		{ int r = hcmvs_wait_image(ctx, *nb); if (r) return r; }
 		NbViewConst& c = rc.nb[i];
-		// DepthEstimator::ViewData, DepthMap.h:430-433: Hl = K1 R1 R0^T, Hm = K1 R1 (C0-C1)
-		double KR[9]; Mul33(nb->K, nb->R, KR);
+		// DepthEstimator::ViewData, DepthMap.h:430-433: Hl = K1 R1 R0^T, Hm = K1 R1 (C0-C1); a neighbour rescaled for this
+		// reference view (ViewData::ScaleImage, SceneDensify.cpp:370-376) brings its own image and intrinsics
+		const NbImage* ov = (i < (int)v->nbImages.size() && v->nbImages[i].w) ? &v->nbImages[i] : nullptr;
+		double KR[9]; Mul33(ov ? ov->K : nb->K, nb->R, KR);
 		Mul33Bt(KR, v->R, c.Hl);
 		const double dC[3] = {v->C[0]-nb->C[0], v->C[1]-nb->C[1], v->C[2]-nb->C[2]};
 		Mul3v(KR, dC, c.Hm);
-		c.tex = nb->tex; c.img = nb->img_d; c.pitch = nb->w; c.w = nb->w; c.h = nb->h;
+		if (ov) { c.tex = ov->tex; c.img = ov->img_d; c.pitch = ov->w; c.w = ov->w; c.h = ov->h; }
+		else { c.tex = nb->tex; c.img = nb->img_d; c.pitch = nb->w; c.w = nb->w; c.h = nb->h; }
 	}
 	// DepthEstimator constants, DepthMap.cpp:413-433
 	const float FPI = (float)3.14159265358979323846;

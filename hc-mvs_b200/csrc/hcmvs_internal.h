@@ -5,6 +5,11 @@
 
 enum { ST_SCORE = 0, ST_SWEEPS, ST_END, ST_PREP, ST_FILTER, ST_FUSE, ST_COUNT };
 
+struct NbImage { // a matching view's image rescaled for ONE reference view (ViewData::ScaleImage, DepthMap.h:232-238)
+	int w = 0, h = 0; double K[9];
+	cudaArray_t arr = nullptr; cudaTextureObject_t tex = 0; float* img_d = nullptr;
+};
+
 struct View { // one scene image + its DepthData (libs/MVS/DepthMap.h:214-347)
 	bool set = false, hasMaps = false;
 	int w = 0, h = 0;
@@ -25,6 +30,7 @@ struct View { // one scene image + its DepthData (libs/MVS/DepthMap.h:214-347)
 	std::vector<uint32_t> nbIds;  // DepthData::neighbors (sorted by score)
 	std::vector<float> nbScores;
 	int nMatch = 0;               // first nMatch ids = DepthData::images[1..]
+	std::vector<NbImage> nbImages; // per matching slot; w == 0: the neighbour's own image is used
 	cudaEvent_t ready = nullptr;  // upload of this view's maps finished (recorded on the copy stream)
 	cudaEvent_t lastUse = nullptr;  // last kernel that reads this view's images was queued before this event (compute stream)
 	cudaEvent_t imgReady = nullptr; // upload of this view's images finished (copy stream); compute entry points wait on it

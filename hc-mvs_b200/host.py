@@ -32,6 +32,7 @@ def lib():
         L.hcmvs_host_select_views.argtypes = [vp, C.POINTER(api.Params), i32]
         L.hcmvs_host_get_neighbors.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, i32]
         L.hcmvs_host_get_gray.argtypes = [vp, i32, vp]
+        L.hcmvs_host_scale_image.argtypes = [vp, i32, i32, C.c_float, vp, C.POINTER(i32), C.POINTER(i32), vp, vp]
         L.hcmvs_host_init_depth.argtypes = [vp, i32, vp, vp]
         L.hcmvs_host_dense_reconstruction.argtypes = [vp, vp, C.POINTER(api.Params), C.c_uint64, i32, C.c_char_p, vp]
         L.hcmvs_host_cloud_size.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -139,6 +140,19 @@ class HostScene:
             self.close()
         except Exception:
             pass
+
+
+def scale_image(gray, scale, K=None):
+    """ViewData::ScaleImage on an f32 gray image -> (scaled image, K of the new resolution) or None when |scale-1| < 0.15."""
+    gray = np.ascontiguousarray(gray, np.float32); sh, sw = gray.shape
+    dw = C.c_int(); dh = C.c_int()
+    if lib().hcmvs_host_scale_image(_p(gray), sw, sh, float(scale), None, C.byref(dw), C.byref(dh), None, None) != 0:
+        return None
+    out = np.zeros((dh.value, dw.value), np.float32)
+    Kin = np.ascontiguousarray(K, np.float64) if K is not None else None
+    Kout = np.zeros(9) if K is not None else None
+    lib().hcmvs_host_scale_image(_p(gray), sw, sh, float(scale), _p(out), C.byref(dw), C.byref(dh), _p(Kin), _p(Kout))
+    return out, Kout
 
 
 def write_dmap(path, image_name, ids, image_size, K, R, Cc, dmin, dmax, depth, normal=None, conf=None):

@@ -51,6 +51,116 @@ void ToGray(const uint8_t* bgr, int w, int h, float* gray) {
 		gray[i] = 0.114f*(float(bgr[i*3])*inv255) + 0.587f*(float(bgr[i*3+1])*inv255) + 0.299f*(float(bgr[i*3+2])*inv255);
 }
 
+// ------------------------------------------------------------------------------------------------ image rescaling
+namespace {
+struct DecimateAlpha { int si, di; float alpha; };
+// computeResizeAreaTab, OpenCV imgproc/src/resize.cpp
+void AreaTab(int ssize, int dsize, double scale, std::vector<DecimateAlpha>& tab) {
+	tab.clear();
+	for (int dx=0; dx<dsize; ++dx) {
+		const double fsx1 = dx*scale, fsx2 = fsx1+scale;
+		const double cellWidth = std::min(scale, ssize-fsx1);
+		int sx1 = (int)std::ceil(fsx1), sx2 = (int)std::floor(fsx2);
+		sx2 = std::min(sx2, ssize-1);
+		sx1 = std::min(sx1, sx2);
+		if (sx1-fsx1 > 1e-3) tab.push_back({sx1-1, dx, (float)((sx1-fsx1)/cellWidth)});
+		for (int sx=sx1; sx<sx2; ++sx) tab.push_back({sx, dx, float(1.0/cellWidth)});
+		if (fsx2-sx2 > 1e-3) tab.push_back({sx2, dx, (float)(std::min(std::min(fsx2-sx2, 1.), cellWidth)/cellWidth)});
+	}
+}
+// interpolateCubic, A = -0.75
+void CubicCoeffs(float x, float c[4]) {
+	const float A = -0.75f;
+	c[0] = ((A*(x+1)-5*A)*(x+1)+8*A)*(x+1)-4*A;
+	c[1] = ((A+2)*x-(A+3))*x*x+1;
+	c[2] = ((A+2)*(1-x)-(A+3))*(1-x)*(1-x)+1;
+	c[3] = 1.f-c[0]-c[1]-c[2];
+}
+inline int RoundHalfEven(double v) { return (int)std::nearbyint(v); } // cvRound / saturate_cast<int>(double)
+}
+
+bool ScaleImage(const std::vector<float>& src, int sw, int sh, float scale, std::vector<float>& dst, int& dw, int& dh) {
+	if (std::abs(scale-1.f) < 0.15f) return false;
+	const double inv_scale = (double)scale, sc = 1./inv_scale; // resize(): scale_x = 1/inv_scale_x, dsize from inv_scale
+	dw = RoundHalfEven(sw*inv_scale); dh = RoundHalfEven(sh*inv_scale);
+	if (dw < 1 || dh < 1) return false;
+	dst.assign((size_t)dw*dh, 0.f);
+	if (scale < 1.f) {
+		// INTER_AREA, shrinking
+		const int isc = RoundHalfEven(sc);
+		if (std::abs(sc-isc) < 2.220446049250313e-16) {
+			// ResizeAreaFast: block mean, f32 accumulation in raster order of the block, x (1/area)
+			const float inv = 1.f/(float)(isc*isc);
+			for (int dy=0; dy<dh; ++dy) for (int dx=0; dx<dw; ++dx) {
+				const int sy0 = dy*isc, sx0 = dx*isc;
+				if (sy0+isc <= sh && sx0+isc <= sw) {
+					float sum = 0;
+					for (int y=0; y<isc; ++y) for (int x=0; x<isc; ++x) sum += src[(size_t)(sy0+y)*sw+sx0+x];
+					dst[(size_t)dy*dw+dx] = sum*inv;
+				} else { // partial block at the border: mean of what exists
+					float sum = 0; int cnt = 0;
+					for (int y=0; y<isc && sy0+y<sh; ++y) for (int x=0; x<isc && sx0+x<sw; ++x) { sum += src[(size_t)(sy0+y)*sw+sx0+x]; ++cnt; }
+					dst[(size_t)dy*dw+dx] = cnt ? (float)((double)sum/cnt) : 0.f;
+				}
+			}
+			return true;
+		}
+		std::vector<DecimateAlpha> xtab, ytab;
+		AreaTab(sw, dw, sc, xtab); AreaTab(sh, dh, sc, ytab);
+		std::vector<float> buf(dw), sum(dw, 0.f);
+		int prev_dy = ytab.empty() ? 0 : ytab[0].di;
+		for (size_t j=0; j<ytab.size(); ++j) { // ResizeArea_Invoker
+			const float beta = ytab[j].alpha; const int dy = ytab[j].di, sy = ytab[j].si;
+			const float* S = &src[(size_t)sy*sw];
+			std::fill(buf.begin(), buf.end(), 0.f);
+			for (const DecimateAlpha& t: xtab) buf[t.di] += S[t.si]*t.alpha;
+			if (dy != prev_dy) {
+				float* D = &dst[(size_t)prev_dy*dw];
+				for (int dx=0; dx<dw; ++dx) { D[dx] = sum[dx]; sum[dx] = beta*buf[dx]; }
+				prev_dy = dy;
+			} else for (int dx=0; dx<dw; ++dx) sum[dx] += beta*buf[dx];
+		}
+		if (!ytab.empty()) { float* D = &dst[(size_t)prev_dy*dw]; for (int dx=0; dx<dw; ++dx) D[dx] = sum[dx]; }
+		return true;
+	}
+	// INTER_CUBIC, enlarging: taps sx-1..sx+2 / sy-1..sy+2 with replicated borders, horizontal pass then vertical pass, f32
+	std::vector<int> xofs(dw), yofs(dh); std::vector<float> ax((size_t)dw*4), ay((size_t)dh*4);
+	for (int dx=0; dx<dw; ++dx) { float fx = (float)((dx+0.5)*sc-0.5); const int sx = (int)std::floor(fx); fx -= sx; xofs[dx] = sx; CubicCoeffs(fx, &ax[(size_t)dx*4]); }
+	for (int dy=0; dy<dh; ++dy) { float fy = (float)((dy+0.5)*sc-0.5); const int sy = (int)std::floor(fy); fy -= sy; yofs[dy] = sy; CubicCoeffs(fy, &ay[(size_t)dy*4]); }
+	auto clampi = [](int v, int n) { return v < 0 ? 0 : (v >= n ? n-1 : v); };
+	std::vector<float> rows[4]; for (auto& r: rows) r.resize(dw);
+	int rowOf[4] = {-1000000, -1000000, -1000000, -1000000};
+	for (int dy=0; dy<dh; ++dy) {
+		const float* b = &ay[(size_t)dy*4];
+		const float* R[4];
+		for (int k=0; k<4; ++k) {
+			const int sy = clampi(yofs[dy]-1+k, sh);
+			int slot = -1;
+			for (int q=0; q<4; ++q) if (rowOf[q] == sy) slot = q;
+			if (slot < 0) { // horizontal pass of source row sy into a free slot
+				for (int q=0; q<4 && slot<0; ++q) { bool used = false; for (int kk=0; kk<4; ++kk) if (rowOf[q] == clampi(yofs[dy]-1+kk, sh)) used = true; if (!used) slot = q; }
+				const float* S = &src[(size_t)sy*sw];
+				float* D = rows[slot].data();
+				for (int dx=0; dx<dw; ++dx) {
+					const float* a = &ax[(size_t)dx*4]; const int sx = xofs[dx];
+					D[dx] = S[clampi(sx-1, sw)]*a[0] + S[clampi(sx, sw)]*a[1] + S[clampi(sx+1, sw)]*a[2] + S[clampi(sx+2, sw)]*a[3];
+				}
+				rowOf[slot] = sy;
+			}
+			R[k] = rows[slot].data();
+		}
+		float* D = &dst[(size_t)dy*dw];
+		for (int dx=0; dx<dw; ++dx) D[dx] = R[0][dx]*b[0] + R[1][dx]*b[1] + R[2][dx]*b[2] + R[3][dx]*b[3];
+	}
+	return true;
+}
+
+void ScaleK(const double K[9], int w, int h, int newW, int newH, double Kout[9]) {
+	const double s = (double)(float)std::max(newW, newH)/(double)(float)std::max(w, h);
+	for (int i=0; i<9; ++i) Kout[i] = K[i];
+	Kout[0] = K[0]*s; Kout[4] = K[4]*s; Kout[2] = K[2]*s; Kout[5] = K[5]*s;
+}
+
 // ------------------------------------------------------------------------------------------------ view selection
 static inline float CosAngle(const float* a, const float* b) { // ComputeAngle<float,float>, Common/Util.inl:416-420
 	const float c = (a[0]*b[0]+a[1]*b[1]+a[2]*b[2])/std::sqrt((a[0]*a[0]+a[1]*a[1]+a[2]*a[2])*(b[0]*b[0]+b[1]*b[1]+b[2]*b[2]));
@@ -176,15 +286,13 @@ bool DepthMapsData::UploadView(uint32_t idxImage) {
 }
 
 bool DepthMapsData::InitViews(uint32_t idxImage, uint32_t numNeighbors) {
-	// SceneDensify.cpp:336-397 (idxNeighbor == NO_ID branch). Neighbour rescaling for |scale-1| >= 0.15
-	// (DepthMap.h:232-238) is not built: such neighbours are rejected with an error instead of silently mis-scored.
+	// SceneDensify.cpp:336-397 (idxNeighbor == NO_ID branch), including the rescaling of neighbours with |scale-1| >= 0.15
 	DepthData& dd = arrDepthData[idxImage];
 	if (dd.neighbors.empty()) { lastError = "InitViews before SelectViews"; return false; }
 	dd.images.assign(1, idxImage);
 	const float fMinScore = std::max(dd.neighbors.front().score*(VS.fViewMinScoreRatio*0.1f), VS.fViewMinScore);
 	for (const ViewScore& nb: dd.neighbors) {
 		if ((numNeighbors && dd.images.size() > numNeighbors) || nb.score < fMinScore) break;
-		if (std::abs(nb.scale-1.f) >= 0.15f) { lastError = "neighbour needs rescaling (|scale-1| >= 0.15): not supported"; dd.images.clear(); return false; }
 		dd.images.push_back(nb.ID);
 	}
 	if (dd.images.size() < 2) { dd.images.clear(); return false; }
@@ -195,6 +303,16 @@ bool DepthMapsData::InitViews(uint32_t idxImage, uint32_t numNeighbors) {
 	// matching views are the first entries of the (sorted) neighbour list
 	if (hcmvs_set_neighbors(ctx, idxImage, ids.data(), scores.data(), (int)dd.images.size()-1, (int)ids.size()) != HCMVS_OK) return Fail("hcmvs_set_neighbors");
 	if (hcmvs_set_fuse_priority(ctx, idxImage, (float)scene.images[idxImage].neighbors.size()) != HCMVS_OK) return Fail("hcmvs_set_fuse_priority");
+	// ViewData::ScaleImage (SceneDensify.cpp:370-376): a matching view whose footprint differs by |scale-1| >= 0.15 is matched against a
+	// resized copy of its image, with the camera of the new resolution
+	for (size_t k=1; k<dd.images.size(); ++k) {
+		const ViewScore& nb = dd.neighbors[k-1];
+		Image& im = scene.images[nb.ID];
+		std::vector<float> scaled; int sw = 0, sh = 0;
+		if (!ScaleImage(im.gray, im.width, im.height, nb.scale, scaled, sw, sh)) continue;
+		double Ks[9]; ScaleK(im.camera.K, im.width, im.height, sw, sh, Ks);
+		if (hcmvs_set_neighbor_image(ctx, idxImage, (int)k-1, sw, sh, Ks, scaled.data()) != HCMVS_OK) return Fail("hcmvs_set_neighbor_image");
+	}
 	return true;
 }
 
@@ -414,11 +532,14 @@ bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, co
 	st.secSelect = tSelectEnd.load()-t0; // overlaps the uploads and the estimation
 	st.secUpload = 0; // image uploads ride the copy stream inside the estimation loop
 	if (valid.empty()) return fail("no image has enough neighbour views");
-	for (unsigned it=1; it<P.nEstimationIters_external; ++it) // :3684
+	for (unsigned it=1; it<P.nEstimationIters_external; ++it) { // :3684
+		// viewspread reads the neighbours' maps of the previous outer iteration (hcmvs_snapshot_maps)
+		if (P.viewspread && hcmvs_snapshot_maps(ctx) != HCMVS_OK) return fail(std::string("hcmvs_snapshot_maps: ")+hcmvs_last_error());
 		for (uint32_t i: valid) {
 			if (!data.arrDepthData[i].valid) continue;
 			if (!data.EstimateDepthMap((int)it, i, seed)) return fail(data.lastError);
 		}
+	}
 	if (hcmvs_sync(ctx) != HCMVS_OK) return fail(hcmvs_last_error());
 	double t3 = Now(); st.secEstimate = t3-t1;
 	if (!dmapDir.empty())

@@ -90,6 +90,13 @@ struct ViewSelectionParams { // OPTDENSE fields SelectViews reads, DepthMap.cpp:
 };
 
 void ToGray(const uint8_t* bgr, int w, int h, float* gray);
+// DepthData::ViewData::ScaleImage (DepthMap.h:232-238): cv::resize(image, scaled, Size(), scale, scale, scale > 1 ? INTER_CUBIC : INTER_AREA)
+// on the f32 gray image, restated from OpenCV's scalar code paths (imgproc/src/resize.cpp; cross-checked with cv2 in the CPU tests).
+// Returns false (and leaves dst alone) when |scale-1| < 0.15, like the reference.
+bool ScaleImage(const std::vector<float>& src, int sw, int sh, float scale, std::vector<float>& dst, int& dw, int& dh);
+// Image::GetCamera(platforms, newSize) (Image.cpp:194-209): the intrinsics of the same camera at another resolution —
+// K scales with the normalisation length max(width, height) (Camera.h:105-108, 167-180)
+void ScaleK(const double K[9], int w, int h, int newW, int newH, double Kout[9]);
 // sparse-point initialisation of a depth map (SceneDensify.cpp:783-808)
 void SparseInitDepth(const Scene& scene, uint32_t idxImage, const std::vector<uint32_t>& points, std::vector<float>& depth, float& dMin, float& dMax);
 

@@ -73,6 +73,16 @@ int hcmvs_host_init_depth(hcmvs_host_scene* s, int idx, float* depth, float* dmi
 	return 0;
 }
 
+int hcmvs_host_scale_image(const float* src, int sw, int sh, float scale, float* dst, int* dw, int* dh, const double* K, double* Kout) {
+	if (!src || !dw || !dh) return -1;
+	std::vector<float> in(src, src+(size_t)sw*sh), out; int w = 0, h = 0;
+	if (!ScaleImage(in, sw, sh, scale, out, w, h)) return 1; // |scale-1| < 0.15: not rescaled
+	*dw = w; *dh = h;
+	if (dst) memcpy(dst, out.data(), out.size()*4);
+	if (K && Kout) ScaleK(K, sw, sh, w, h, Kout);
+	return 0;
+}
+
 int hcmvs_host_get_gray(hcmvs_host_scene* s, int idx, float* gray) {
 	if (!s || idx < 0 || idx >= (int)s->scene.images.size()) return -1;
 	const Image& im = s->scene.images[idx];

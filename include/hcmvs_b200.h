@@ -126,6 +126,13 @@ int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int estimate_normal
 void hcmvs_free_pointcloud(hcmvs_pointcloud* pc);
 /* hcmvs_fuse_depthmaps with out == NULL leaves the cloud on the device; this returns its device arrays
  * (points/normals float[3n], colors u8[3n], view_offsets u32[n+1], views u32[m], weights float[m]). */
+/* DepthData::ViewData::ScaleImage (DepthMap.h:232-238) as used by InitViews (SceneDensify.cpp:370-376): when a matching view's
+ * footprint differs from the reference view's by |scale-1| >= 0.15 the reference matches against a RESIZED copy of that image with
+ * the camera of the new resolution. `slot` is the 0-based index into the matching views given to hcmvs_set_neighbors; gray is the
+ * resized image (H x W, [0,1]) and K its intrinsics (R, C stay the neighbour's). gray == NULL returns to the neighbour's own image.
+ * Only the PatchMatch cost reads it; filter and fusion work on the neighbour's maps at their own resolution, as in the reference. */
+int hcmvs_set_neighbor_image(hcmvs_ctx* ctx, uint32_t ref, int slot, int W, int H, const double K[9], const float* gray);
+
 /* restore tree (restore/libs/MVS/SceneDensify.cpp:513-532, DepthMap.cpp:1527-1550): the previous pyramid level's estimate of this
  * view, wc x hc (depth f32, normal 3 x f32, camera frame). The maps are resized on the device to the view's size exactly as
  * cv::resize(.., INTER_AREA) enlarges them, [dMin, dMax) is widened by the resized depths (call after hcmvs_init_depthmap), and

@@ -24,6 +24,9 @@ int hcmvs_host_get_neighbors(hcmvs_host_scene* s, int idx, int which, uint32_t* 
 /* sparse-point initial depth map + depth range of a selected view (SceneDensify.cpp:783-808) */
 int hcmvs_host_init_depth(hcmvs_host_scene* s, int idx, float* depth, float* dminmax);
 int hcmvs_host_get_gray(hcmvs_host_scene* s, int idx, float* gray);
+/* DepthData::ViewData::ScaleImage (DepthMap.h:232-238) on an f32 gray image + the intrinsics of the new resolution (Image::GetCamera).
+ * Call with dst == NULL first to learn dw x dh. Returns 1 (nothing written) when |scale-1| < 0.15, like the reference. */
+int hcmvs_host_scale_image(const float* src, int sw, int sh, float scale, float* dst, int* dw, int* dh, const double* K, double* Kout);
 /* Scene::DenseReconstruction (SceneDensify.cpp:3532-3574) through the C ABI with HOST buffers.
  * stats[8] = sec select, upload, estimate, filter, fuse, h2d bytes, d2h bytes, #points. dmap_dir may be NULL. */
 int hcmvs_host_dense_reconstruction(hcmvs_host_scene* s, hcmvs_ctx* ctx, const hcmvs_params* p, uint64_t seed, int run_filter, const char* dmap_dir, double* stats);

@@ -375,8 +375,8 @@ DepthEstimator::DepthEstimator(unsigned nIter, int nIterExternal, Scene& _scene,
 	thConfSmall = P.fNCCThresholdKeep*0.2f; thConfBig = P.fNCCThresholdKeep*0.4f;
 	thConfRand = P.fNCCThresholdKeep*0.9f; thRobust = P.fNCCThresholdKeep*1.2f;
 	for (size_t i=1; i<dd.images.size(); ++i) {
-		const ImageData& image1 = scene.images[dd.images[i]];
-		EstimatorView v; v.view = &image1;
+		const ImageData& image1 = (i-1 < dd.scaledImages.size() && dd.scaledImages[i-1].w) ? dd.scaledImages[i-1] : scene.images[dd.images[i]];
+		EstimatorView v; v.view = &image1; v.id = dd.images[i];
 		double KR[9]; Mul33(image1.cam.K, image1.cam.R, KR);
 		Mul33T(KR, image0.cam.R, v.Hl);                                    // K1 R1 R0^T
 		const double dC[3] = {image0.cam.C[0]-image1.cam.C[0], image0.cam.C[1]-image1.cam.C[1], image0.cam.C[2]-image1.cam.C[2]};
@@ -686,7 +686,7 @@ void DepthEstimator::ViewSpreadAndCoarse(int, int, float& conf, Depth& depth, Ve
 	const int hw = 7;
 	if (P.viewspread && nIteration_external >= 1) {
 		for (const EstimatorView& v: images) {
-			const uint32_t id1 = (uint32_t)(v.view - scene.images.data());
+			const uint32_t id1 = v.id;
 			const DepthData& d1 = scene.arrDepthData[id1];
 			if (d1.prevDepth.d.empty()) continue;
 			float H[9]; ComputeHomography(v, depth, normal, H);
@@ -700,7 +700,7 @@ void DepthEstimator::ViewSpreadAndCoarse(int, int, float& conf, Depth& depth, Ve
 			const int cx[4] = {x1, x1, x1-1, x1+1}, cy[4] = {y1-1, y1+1, y1, y1};
 			neighborsClose.clear();
 			int candX[4], candY[4], nc = 0;
-			const Camera& cam1 = v.view->cam;
+			const Camera& cam1 = scene.images[id1].cam; // the neighbour's maps live at its own resolution
 			for (int k=0; k<4; ++k) {
 				const Depth nd = d1.prevDepth.at(cx[k], cy[k]);
 				if (nd > 0) {

@@ -120,6 +120,8 @@ struct DepthData {
 	std::vector<uint32_t> points;      // sparse point ids seen
 	Image32F depthMap, confMap;
 	std::vector<Vec3f> normalMap;
+	std::vector<ImageData> scaledImages; // per matching view (images[1..]): its image resized by ViewData::ScaleImage with the camera of the new
+	                                   // resolution (InitViews, SceneDensify.cpp:370-376); an entry with w == 0 means "not rescaled"
 	Image32F depthMapPrior;            // optional
 	Image32F coarseDepth;              // restore tree: nresize_depthMap / nresize_normalMap (restore/.../DepthMap.h:294-295), optional
 	std::vector<Vec3f> coarseNormal;
@@ -169,7 +171,8 @@ bool InitViews(Scene& scene, uint32_t idxImage, unsigned numNeighbors); // Scene
 enum RngKind { RNG_MT19937 = 0, RNG_PHILOX = 1 };
 
 struct EstimatorView { // DepthMap.h:412-444
-	const ImageData* view;
+	const ImageData* view;   // the matching view's image + camera: the scene image, or its rescaled copy (DepthData::scaledImages)
+	uint32_t id;             // scene image index
 	double Hl[9], Hm[3], Hr[9];
 };
 

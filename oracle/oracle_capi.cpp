@@ -109,6 +109,23 @@ int orc_set_neighbors(orc_scene* s, int idx, const uint32_t* ids, const float* s
 	return 0;
 }
 
+// InitViews with ViewData::ScaleImage (SceneDensify.cpp:370-376, DepthMap.h:232-238): matching view `slot` (0-based) of `idx` uses this
+// resized gray image and the K of the new resolution (R, C unchanged). The resize itself is OpenCV's; the tests produce it with cv2.
+int orc_set_neighbor_image(orc_scene* s, int idx, int slot, int w, int h, const double* K, const float* gray) {
+	Scene& sc = s->scene;
+	DepthData& dd = sc.arrDepthData[idx];
+	if (slot < 0 || slot+1 >= (int)dd.images.size()) return -1;
+	if (dd.scaledImages.size() < dd.images.size()-1) dd.scaledImages.resize(dd.images.size()-1);
+	ImageData& im = dd.scaledImages[slot];
+	if (!gray) { im = ImageData(); return 0; }
+	im = ImageData();
+	im.w = w; im.h = h;
+	im.cam = sc.images[dd.images[slot+1]].cam;
+	std::memcpy(im.cam.K, K, 72);
+	im.cam.ComposeP();
+	im.gray.w = w; im.gray.h = h; im.gray.d.assign(gray, gray+(size_t)w*h);
+	return 0;
+}
 int orc_init_depth_sparse(orc_scene* s, int idx) { InitDepthMapFromSparse(s->scene, (uint32_t)idx); return 0; }
 
 int orc_set_depthmap(orc_scene* s, int idx, const float* depth, const float* normal, const float* conf, float dMin, float dMax) {

@@ -36,6 +36,7 @@ def lib():
         L.orc_get_points.argtypes = [vp, C.c_int, vp, C.c_int]
         L.orc_set_neighbors.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.c_int]
         L.orc_init_depth_sparse.argtypes = [vp, C.c_int]
+        L.orc_set_neighbor_image.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
         L.orc_set_depthmap.argtypes = [vp, C.c_int, vp, vp, vp, C.c_float, C.c_float]
         L.orc_get_depthmap.argtypes = [vp, C.c_int, vp, vp, vp, vp]
         L.orc_set_prior.argtypes = [vp, C.c_int, vp]
@@ -140,6 +141,15 @@ class OracleScene:
         ids = np.ascontiguousarray(ids, np.uint32)
         sc = np.ascontiguousarray(scores, np.float32) if scores is not None else None
         self.L.orc_set_neighbors(self.h, i, _p(ids), _p(sc), n_match, len(ids))
+
+    def set_neighbor_image(self, i, slot, K, gray):
+        """matching view `slot` of view i uses this rescaled gray image and intrinsics (None restores the scene image)."""
+        if gray is None:
+            assert self.L.orc_set_neighbor_image(self.h, i, slot, 0, 0, None, None) == 0
+            return
+        gray = np.ascontiguousarray(gray, np.float32); K = np.ascontiguousarray(K, np.float64)
+        h, w = gray.shape
+        assert self.L.orc_set_neighbor_image(self.h, i, slot, w, h, _p(K), _p(gray)) == 0
 
     def init_depth_sparse(self, i):
         self.L.orc_init_depth_sparse(self.h, i)

@@ -278,3 +278,42 @@ def test_viewspread_matches_oracle(scene, ctx):
     finally:
         back = dict(nEstimationIters=3, nEstimationIters_external=1, propagatehalfwin=1, propagatestep=4, viewspread=0)
         osc.set_params(**back); ctx.set_params(**back)
+
+
+@pytest.mark.parametrize("scale", [0.8, 1.25])
+def test_rescaled_neighbour_image_matches_oracle(scene, ctx, scale):
+    """ViewData::ScaleImage (DepthMap.h:232-238, SceneDensify.cpp:370-376): a matching view with |scale-1| >= 0.15 is matched against a
+    resized copy of its image with the intrinsics of the new resolution. The resized image comes from the product's host code
+    (pinned against cv2 in the CPU tests); kernel and oracle must score it identically, also through a whole estimation."""
+    from hcmvs_b200 import host
+    syn, osc, gt, imgs, ok = scene
+    ref = 5
+    match = [int(v) for v in osc.match_views(ref)]
+    slot = 1
+    nb = match[slot]
+    g, Ks = host.scale_image(osc.gray(nb), scale, syn.K[nb])
+    assert g.shape != osc.gray(nb).shape
+    osc.set_neighbor_image(ref, slot, Ks, g); ctx.set_neighbor_image(ref, slot, Ks, g)
+    try:
+        for k, (ds, ang) in enumerate(((0.0, 0.0), (0.01, 8.0))):
+            d, n = common.perturbed_hypotheses(gt[ref][0], gt[ref][1], syn.K[ref], seed=900 + k, depth_sigma=ds, angle_deg=ang)
+            want = osc.score_hypotheses(ref, d, n, 1)
+            got = ctx.score_hypotheses(ref, d, n, 1)
+            assert np.abs(want - got).max() <= NCC_TOL, np.abs(want - got).max()
+        # the rescaled view really is what gets sampled: with the original image the scores are different
+        osc.set_neighbor_image(ref, slot, None, None)
+        plain = osc.score_hypotheses(ref, d, n, 1)
+        osc.set_neighbor_image(ref, slot, Ks, g)
+        assert np.mean(np.abs(plain - want) > 1e-3) > 0.2
+        osc.init_depth_sparse(ref)
+        d0, n0, c0, dmin, dmax = osc.get_depthmap(ref)
+        ctx.init_depthmap(ref, d0, None, dmin, dmax)
+        ctx.estimate_depthmap(ref, 0, seed=77)
+        osc.estimate(ref, seed=77, threads=8, mode=2, far_reach=11)
+        gd = ctx.get_depthmap(ref)[0]; od = osc.get_depthmap(ref)[0]
+        a = common.agreement(od, gd)
+        print(f"\nrescaled neighbour x{scale}: {g.shape[1]}x{g.shape[0]}, GPU vs oracle-redblack {a:.4f}, within 1% of GT {common.agreement(gt[ref][0], gd, mask=gd > 0):.4f}")
+        assert a >= 0.995
+        assert common.agreement(gt[ref][0], gd, mask=gd > 0) >= 0.96
+    finally:
+        osc.set_neighbor_image(ref, slot, None, None); ctx.set_neighbor_image(ref, slot, None, None)

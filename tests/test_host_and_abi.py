@@ -111,3 +111,24 @@ def test_shard_plan_covers_every_view_once():
         assert [nall[v] for v in plan.order] == sorted((nall[v] for v in valid), reverse=True)
         loc = plan.location()
         assert len({loc[v] for v in valid}) == len(valid) and all(s < plan.slots for _, s in loc.values())
+
+
+def test_scale_image_matches_opencv(built):
+    """ViewData::ScaleImage (DepthMap.h:232-238) = cv::resize INTER_AREA (shrinking) / INTER_CUBIC (enlarging) on the f32 gray image.
+    The host restatement follows OpenCV's scalar code: bit-equal to cv2 for the general area decimation; the vectorised kernels cv2
+    runs for integer factors and for the cubic taps associate the sums differently (<= 1e-6 on [0,1] images)."""
+    cv2 = pytest.importorskip("cv2")
+    from hcmvs_b200 import host
+    rng = np.random.default_rng(0)
+    img = cv2.GaussianBlur(rng.uniform(0, 1, (240, 320)).astype(np.float32), (0, 0), 2.0)
+    K = np.array([600.0, 0, 159.5, 0, 600.0, 119.5, 0, 0, 1])
+    for sc, tol in ((0.7, 0.0), (0.83, 0.0), (0.6180339, 0.0), (0.5, 2e-7), (0.25, 2e-7), (1.2, 1e-6), (1.5, 1e-6), (2.0, 1e-6), (1.37, 1e-6)):
+        got, Ks = host.scale_image(img, sc, K)
+        f = np.float32(sc).item()
+        want = cv2.resize(img, None, fx=f, fy=f, interpolation=cv2.INTER_CUBIC if sc > 1 else cv2.INTER_AREA)
+        assert got.shape == want.shape, (sc, got.shape, want.shape)
+        assert np.abs(got - want).max() <= tol, (sc, np.abs(got - want).max())
+        s = max(got.shape) / 320.0                                    # Image::GetCamera: K scales with max(width, height)
+        assert np.allclose(Ks[[0, 4, 2, 5]], K[[0, 4, 2, 5]] * s, rtol=1e-7) and Ks[8] == 1
+    for sc in (1.0, 0.9, 1.14):                                       # |scale-1| < 0.15: the reference keeps the image
+        assert host.scale_image(img, sc) is None
