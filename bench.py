@@ -131,7 +131,7 @@ def flops_per_view_score(texels):
 
 
 # ------------------------------------------------------------------------------------------------ CPU oracle arm
-def cpu_oracle_sample(args, syn, imgs, seconds_budget=25.0):
+def cpu_oracle_sample(args, syn, imgs, seconds_budget=25.0, stages=True):
     """Time the CPU restatement of the reference path (oracle/) on a bounded sample of the workload."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
@@ -145,6 +145,7 @@ def cpu_oracle_sample(args, syn, imgs, seconds_budget=25.0):
         raise RuntimeError("oracle view selection failed")
     # bounded sample: as many PatchMatch iterations of ONE reference view as fit the budget (at least 1)
     h, w = osc.sizes[ref]
+    inner_pix = (w - 14) * (h - 14)
     osc.init_depth_sparse(ref)
     osc.set_params(nEstimationIters=1)
     t0 = time.time()
@@ -162,8 +163,33 @@ def cpu_oracle_sample(args, syn, imgs, seconds_budget=25.0):
         pix_iters = st["n_pixel_iters"]
     value = pix_iters / total_s / 1e6
     sample = f"1 of {syn.n_views} reference views ({w}x{h}, 5 neighbours), PASS A + {iters} raster PatchMatch iteration(s), {cores} threads"
-    return {"value": value, "unit": "Mpix*iter/s", "cores": cores, "kind": "port", "sample": sample,
-            "hyp_per_pixel_iter": st["n_hyp"] / max(st["n_pixel_iters"], 1), "seconds": total_s}
+    out = {"value": value, "unit": "Mpix*iter/s", "cores": cores, "kind": "port", "sample": sample,
+           "hyp_per_pixel_iter": st["n_hyp"] / max(st["n_pixel_iters"], 1), "seconds": total_s}
+    if stages:
+        # the other two stages of the scene time, single-threaded as in the reference (FilterDepthMap: one thread per view; FuseDepthMaps:
+        # main thread only): FilterDepthMap of that view against 8 neighbours and FuseDepthMaps over the same 9 views, on maps derived
+        # from the analytic depth (the CPU cannot estimate 9 views within the sample budget)
+        try:
+            nb = [int(v) for v in osc.neighbors(ref, 1)["ids"][:8]]
+            rng = np.random.default_rng(7)
+            for v in [ref] + nb:
+                _, d, n = syn.render(v, want_bgr=False)
+                dn = (d * (1 + 0.002 * rng.standard_normal(d.shape, dtype=np.float32))).astype(np.float32)
+                cf = np.where(d > 0, rng.uniform(0.5, 1, d.shape).astype(np.float32), 0).astype(np.float32)
+                if osc.select_views(v) <= 0:
+                    continue
+                osc.init_views(v, 5)
+                osc.set_depthmap(v, dn, n, cf, float(d[d > 0].min() * 0.5), float(d.max() * 2))
+            t0 = time.time(); osc.filter(ref, list(range(len(nb))), True); t_filter = time.time() - t0
+            t0 = time.time(); cloud = osc.fuse(True, True); t_fuse = (time.time() - t0) / (1 + len(nb))
+            per_view = total_s * (3.0 / iters) + t_filter + t_fuse
+            out["stage_seconds_per_view"] = {"estimate": total_s * (3.0 / iters), "filter": t_filter, "fuse": t_fuse}
+            out["scene_seconds_extrapolated"] = per_view * syn.n_views
+            out["scene_equivalent_value"] = inner_pix * 3 * syn.n_views / (per_view * syn.n_views) / 1e6
+            out["sample"] += f"; + FilterDepthMap of that view (8 neighbours) and FuseDepthMaps over {1 + len(nb)} views ({len(cloud['xyz'])} points), 1 thread each"
+        except Exception as e:  # the stage timings are additional information only
+            out["stage_seconds_per_view"] = f"failed: {e}"
+    return out
 
 
 def run_reference(args):
@@ -175,7 +201,7 @@ def run_reference(args):
     vals, secs = [], []
     base = None
     for s in range(args.warmup + args.steps):
-        base = cpu_oracle_sample(args, syn, imgs, seconds_budget=20.0 if args.steps + args.warmup <= 3 else 8.0)
+        base = cpu_oracle_sample(args, syn, imgs, seconds_budget=20.0 if args.steps + args.warmup <= 3 else 8.0, stages=(s == args.warmup + args.steps - 1))
         if s >= args.warmup:
             vals.append(base["value"]); secs.append(base["seconds"])
         if sum(secs) > 150:  # keep the whole run within a few minutes
@@ -186,7 +212,8 @@ def run_reference(args):
         "steps": len(vals), "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3 if secs else None,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.config], "scale": args.scale, "views": syn.n_views, "neighbours": 5, "patchmatch_iters": 3},
-        "cpu_baseline": {"value": value, "unit": "Mpix*iter/s", "cores": base["cores"], "kind": "port", "sample": base["sample"]},
+        "cpu_baseline": {"value": value, "unit": "Mpix*iter/s", "cores": base["cores"], "kind": "port", "sample": base["sample"],
+                         **{k: base[k] for k in ("stage_seconds_per_view", "scene_seconds_extrapolated", "scene_equivalent_value") if k in base}},
         "e2e": {"value": value, "unit": "Mpix*iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

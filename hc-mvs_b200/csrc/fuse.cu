@@ -359,6 +359,17 @@ __global__ void __launch_bounds__(256) k_fuse_emit(const FuseArgs a, const uint2
 	}
 }
 
+// The fork's RemoveSmallSegments (SceneDensify.cpp:2228-2260): depthMap_fuse / normalMap_fuse = the view's estimate where the pixel
+// became part of a fused point (arrDepthIdx != NO_ID), 0 elsewhere
+__global__ void k_fused_support(const float4* __restrict__ dn, const uint32_t* __restrict__ claim, float* __restrict__ depth, float* __restrict__ normal, size_t n) {
+	const size_t i = (size_t)blockIdx.x*blockDim.x+threadIdx.x;
+	if (i >= n) return;
+	const bool in = claim[i] == CLAIM_TAKEN;
+	const float4 e = in ? dn[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+	if (depth) depth[i] = e.w;
+	if (normal) { normal[i*3] = e.x; normal[i*3+1] = e.y; normal[i*3+2] = e.z; }
+}
+
 __global__ void k_fill_u32(uint32_t* p, uint32_t v, size_t n) { const size_t i = (size_t)blockIdx.x*blockDim.x+threadIdx.x; if (i < n) p[i] = v; }
 
 } // namespace hcmvs
@@ -581,6 +592,20 @@ extern "C" int hcmvs_download_fused_pinned(hcmvs_ctx* ctx, hcmvs_pointcloud* out
 	if (f->hasNormal) out->normals = (float*)(base+oNrm);
 	if (f->hasColor) out->colors = (uint8_t*)(base+oCol);
 	return hcmvs_download_fused(ctx, out->points, out->normals, out->colors, out->view_offsets, out->views, out->weights);
+}
+
+extern "C" int hcmvs_get_fused_support(hcmvs_ctx* ctx, uint32_t view, float* depth_fuse, float* normal_fuse) {
+	if (!ctx || view >= ctx->views.size() || !ctx->views[view].set) { hcmvs_set_error("view %u not set", view); return HCMVS_ERR_ARG; }
+	View& v = ctx->views[view];
+	if (!v.hasMaps || !v.claim_d) { hcmvs_set_error("view %u took no part in a fusion yet (call hcmvs_fuse_depthmaps)", view); return HCMVS_ERR_STATE; }
+	cudaSetDevice(ctx->device);
+	const size_t n = (size_t)v.w*v.h;
+	float* tmp; int r = hcmvs_scratch(ctx, n*16, (void**)&tmp); if (r) return r;
+	k_fused_support<<<(unsigned)((n+255)/256), 256, 0, ctx->stream>>>(v.dn_d, v.claim_d, tmp, tmp+n, n); ++ctx->nLaunches;
+	if (depth_fuse) CK(cudaMemcpyAsync(depth_fuse, tmp, n*4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (normal_fuse) CK(cudaMemcpyAsync(normal_fuse, tmp+n, n*12, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return HCMVS_OK;
 }
 
 extern "C" int hcmvs_get_fused_device(hcmvs_ctx* ctx, uint64_t* n_points, uint64_t* n_view_refs, void** points_d, void** normals_d, void** colors_d,

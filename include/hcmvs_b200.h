@@ -152,6 +152,10 @@ int hcmvs_download_fused(hcmvs_ctx* ctx, float* points, float* normals, uint8_t*
  * stay valid until the next hcmvs_fuse_depthmaps / hcmvs_download_fused_pinned on this context or hcmvs_destroy.
  * Do NOT pass `out` to hcmvs_free_pointcloud. Replaces the PointCloud& output of FuseDepthMaps (SceneDensify.cpp:3265). */
 int hcmvs_download_fused_pinned(hcmvs_ctx* ctx, hcmvs_pointcloud* out);
+/* The fork's RemoveSmallSegments (SceneDensify.cpp:1953-2276, live branch): a whole-scene fusion whose only product is, per view,
+ * depthMap_fuse / normalMap_fuse = the estimate where the pixel became part of a fused point, 0 elsewhere (:2228-2260) — the input
+ * of GapInterpolation. After hcmvs_fuse_depthmaps this returns those two maps for `view` (H*W and H*W*3 floats; either may be NULL). */
+int hcmvs_get_fused_support(hcmvs_ctx* ctx, uint32_t view, float* depth_fuse, float* normal_fuse);
 int hcmvs_get_fused_device(hcmvs_ctx* ctx, uint64_t* n_points, uint64_t* n_view_refs, void** points_d, void** normals_d, void** colors_d,
                            void** view_offsets_d, void** views_d, void** weights_d);
 

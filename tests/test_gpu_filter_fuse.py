@@ -80,6 +80,15 @@ def test_fuse_depthmaps_identical_cloud(loaded, min_views_fuse):
     # fusion zeroes occluded depths in place (SceneDensify.cpp:3447-3449): the maps must end up identical too
     for i in range(syn.n_views):
         assert np.array_equal(osc.get_depthmap(i)[0], ctx.get_depthmap(i)[0]), f"view {i}"
+    # the fork's RemoveSmallSegments product (SceneDensify.cpp:2228-2260): per view, the estimate where the pixel joined a fused point.
+    # Every claimed pixel is exactly one (point, view) entry of the cloud, so the per-view counts must equal the view-list histogram.
+    per_view = np.bincount(want["views"], minlength=syn.n_views)
+    for i in range(syn.n_views):
+        df, nf = ctx.fused_support(i)
+        after = ctx.get_depthmap(i)
+        sup = df > 0
+        assert int(sup.sum()) == int(per_view[i]), (i, int(sup.sum()), int(per_view[i]))
+        assert np.array_equal(df[sup], after[0][sup]) and np.array_equal(nf[sup], after[1][sup]) and np.all(nf[~sup] == 0)
     print(f"\nfused {len(got['xyz'])} points in {ctx.timers()['n_fuse_rounds']} reserve/commit rounds")
 
 
