@@ -62,3 +62,68 @@ def test_gpu_reproduces_golden():
     assert make_golden.sha(cloud["views"]) == G["fuse_views_sha"][0] and make_golden.sha(cloud["xyz"]) == G["fuse_xyz_sha"][0]
     assert np.array_equal(cloud["colors"][:2000], G["fuse_colors_head"])
     ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ second fixture: later-added paths
+import make_golden_ext  # noqa: E402
+
+GX = np.load(os.path.join(HERE, "golden", "c1_quarter_ext.npz"))
+
+
+def test_oracle_reproduces_extended_golden():
+    cur = make_golden_ext.build()
+    assert set(cur) == set(GX.files)
+    exact = ["resize_dst1", "resize_dst3_sha", "coarse_resized_depth", "coarse_range", "coarse_init_depth", "scaled_dn_gray_sha", "scaled_up_gray_sha",
+             "scaled_dn_K", "scaled_up_K", "scaled_dn_score0", "scaled_up_score0", "vs_views"]
+    for k in exact:
+        assert np.array_equal(cur[k], GX[k]), k
+    # PatchMatch runs draw through libm sin/cos: statistical agreement with the stored run
+    assert common.agreement(GX["coarse_redblack_depth"], cur["coarse_redblack_depth"]) > 0.97
+    assert common.agreement(GX["vs_redblack_depth"], cur["vs_redblack_depth"]) > 0.97
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_extended_golden():
+    from hcmvs_b200 import host
+    syn, osc, gt, imgs, ok = common.make_scene(1, 0.25)
+    ctx = common.make_context(syn, osc, imgs, ok)
+    try:
+        # coarse-level hand-off: resize, widened range, last-iteration hypothesis
+        ref = 3
+        ctx.set_params(nEstimationIters=2, nEstimationIters_external=1)
+        osc.init_depth_sparse(ref)
+        d0, _, _, lo, hi = osc.get_depthmap(ref)
+        assert np.array_equal(d0, GX["coarse_init_depth"])
+        ctx.init_depthmap(ref, GX["coarse_init_depth"], None, lo, hi)
+        ctx.set_coarse_estimate(ref, GX["coarse_depth"], GX["coarse_normal"])
+        assert np.array_equal(ctx.get_coarse_estimate(ref)[0], GX["coarse_resized_depth"])
+        assert np.array_equal(np.array(ctx.get_depthmap(ref)[3:], np.float32), GX["coarse_range"])
+        ctx.estimate_depthmap(ref, 0, seed=33)
+        assert common.agreement(GX["coarse_redblack_depth"], ctx.get_depthmap(ref)[0]) >= 0.99
+        ctx.set_coarse_estimate(ref, None, None)
+        ctx.set_params(nEstimationIters=3, nEstimationIters_external=1)
+        # rescaled matching view
+        ref, slot = 5, 1
+        nb = int(osc.match_views(ref)[slot])
+        for tag, scale in (("dn", 0.8), ("up", 1.25)):
+            g, Ks = host.scale_image(osc.gray(nb), scale, syn.K[nb])
+            assert make_golden_ext.sha(g) == GX[f"scaled_{tag}_gray_sha"][0] and np.array_equal(Ks, GX[f"scaled_{tag}_K"])
+            ctx.set_neighbor_image(ref, slot, Ks, g)
+            got = ctx.score_hypotheses(ref, GX["scaled_hyp_depth"], GX["scaled_hyp_normal"], 0)
+            assert np.abs(got - GX[f"scaled_{tag}_score0"]).max() <= 1e-4
+            ctx.set_neighbor_image(ref, slot, None, None)
+        # viewspread from stored neighbour maps
+        ref = 4
+        over = dict(nEstimationIters=1, nEstimationIters_external=2, propagatehalfwin=5, propagatestep=4, viewspread=1)
+        ctx.set_params(**over)
+        for v in GX["vs_views"]:
+            v = int(v)
+            r = GX[f"vs_view{v}_range"]
+            if v == ref:
+                ctx.init_depthmap(v, GX[f"vs_view{v}_depth"], GX[f"vs_view{v}_normal"], float(r[0]), float(r[1]))   # builds the gradient map
+            ctx.set_depthmap(v, GX[f"vs_view{v}_depth"], GX[f"vs_view{v}_normal"], GX[f"vs_view{v}_conf"], float(r[0]), float(r[1]))
+        ctx.snapshot_maps()
+        ctx.estimate_depthmap(ref, 1, seed=61)
+        assert common.agreement(GX["vs_redblack_depth"], ctx.get_depthmap(ref)[0]) >= 0.99
+    finally:
+        ctx.close()
