@@ -51,7 +51,7 @@ class Timers(C.Structure):
         ("ms_score", C.c_double), ("ms_sweeps", C.c_double), ("ms_end", C.c_double), ("ms_prep", C.c_double),
         ("ms_filter", C.c_double), ("ms_fuse", C.c_double),
         ("n_hypotheses", C.c_uint64), ("n_pixel_iters", C.c_uint64), ("n_view_scores", C.c_uint64), ("n_smooth_terms", C.c_uint64),
-        ("n_launches", C.c_uint32), ("n_fuse_rounds", C.c_uint64),
+        ("n_launches", C.c_uint32), ("n_fuse_rounds", C.c_uint64), ("n_window_walks", C.c_uint64),
     ]
 
 

@@ -5,6 +5,7 @@
 #include "hcmvs_internal.h"
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cstdarg>
 #include <string>
@@ -144,7 +145,7 @@ extern "C" int hcmvs_get_timers(hcmvs_ctx* ctx, hcmvs_timers* t) {
 	CK(cudaMemcpy(c, ctx->counters_d, sizeof(c), cudaMemcpyDeviceToHost));
 	t->ms_score = ctx->stageMs[ST_SCORE]; t->ms_sweeps = ctx->stageMs[ST_SWEEPS]; t->ms_end = ctx->stageMs[ST_END];
 	t->ms_prep = ctx->stageMs[ST_PREP]; t->ms_filter = ctx->stageMs[ST_FILTER]; t->ms_fuse = ctx->stageMs[ST_FUSE];
-	t->n_hypotheses = c[0]; t->n_view_scores = c[1]; t->n_pixel_iters = c[2]; t->n_smooth_terms = c[3];
+	t->n_hypotheses = c[0]; t->n_view_scores = c[1]; t->n_pixel_iters = c[2]; t->n_smooth_terms = c[3]; t->n_window_walks = c[4];
 	t->n_launches = ctx->nLaunches; t->n_fuse_rounds = ctx->fuseRounds;
 	return HCMVS_OK;
 }
@@ -558,7 +559,7 @@ extern "C" int hcmvs_score_depthmap(hcmvs_ctx* ctx, uint32_t ref, int it_externa
 	cudaSetDevice(ctx->device);
 	RefConst rc; r = BuildRefConst(ctx, v, ref, it_external, seed, rc); if (r) return r;
 	hcmvs_time_begin(ctx, ST_SCORE);
-	CK(hcmvs_launch_score_init(rc, ctx->P.sampler == 0, ctx->stream)); ++ctx->nLaunches;
+	CK(hcmvs_launch_score_init(rc, ctx->P.sampler != 1, ctx->stream)); ++ctx->nLaunches;
 	hcmvs_time_end(ctx);
 	return MarkUse(ctx, v);
 }
@@ -590,7 +591,7 @@ extern "C" int hcmvs_estimate_depthmap(hcmvs_ctx* ctx, uint32_t ref, int it_exte
 	const hcmvs_params& P = ctx->P;
 	const size_t n = (size_t)v->w*v->h;
 	RefConst rc; r = BuildRefConst(ctx, v, ref, it_external, seed, rc); if (r) return r;
-	const bool tex = P.sampler == 0;
+	const bool tex = P.sampler != 1;
 	rc.coarse = v->coarse_d;
 	if (P.viewspread && it_external >= 1) {
 		// viewspread (DepthMap.cpp:1504-1608) reads the matching neighbours' maps of the previous outer iteration
@@ -621,7 +622,7 @@ extern "C" int hcmvs_estimate_depthmap(hcmvs_ctx* ctx, uint32_t ref, int it_exte
 	for (unsigned iter=0; iter<P.nEstimationIters; ++iter) {
 		rc.pass = 1u+iter+(uint32_t)it_external*64u;
 		rc.lastPass = it_external == (int)P.nEstimationIters_external-1 && iter == P.nEstimationIters-1;
-		for (int colour=0; colour<2; ++colour) { CK(hcmvs_launch_sweep(rc, colour, tex, ctx->stream)); ++ctx->nLaunches; }
+		for (int colour=0; colour<2; ++colour) { CK(hcmvs_launch_sweep(rc, colour, tex, ctx->stream, P.sampler == 2)); ++ctx->nLaunches; }
 	}
 	hcmvs_time_end(ctx);
 	// PASS C, SceneDensify.cpp:1035-1056
@@ -657,7 +658,7 @@ extern "C" int hcmvs_score_hypotheses(hcmvs_ctx* ctx, uint32_t ref, const float*
 	CK(cudaMemcpyAsync(stage+n, normal, n*12, cudaMemcpyHostToDevice, ctx->stream));
 	CK(hcmvs_launch_pack(stage, stage+n, hyp, n, ctx->stream)); ++ctx->nLaunches;
 	rc.counters = nullptr;
-	CK(hcmvs_launch_score_hyp(rc, hyp, smooth_mode, out, ctx->P.sampler == 0, ctx->stream)); ++ctx->nLaunches;
+	CK(hcmvs_launch_score_hyp(rc, hyp, smooth_mode, out, ctx->P.sampler != 1, ctx->stream)); ++ctx->nLaunches;
 	CK(cudaMemcpyAsync(score_out, out, n*4, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
 	return MarkUse(ctx, v);

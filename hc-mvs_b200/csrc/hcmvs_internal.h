@@ -70,7 +70,7 @@ int  hcmvs_wait_image(hcmvs_ctx* ctx, const View& v); // make the compute stream
 // patchmatch.cu
 cudaError_t hcmvs_launch_score_init(const RefConst& rc, bool tex, cudaStream_t st);
 cudaError_t hcmvs_launch_score_hyp(const RefConst& rc, const float4* hyp, int smoothMode, float* out, bool tex, cudaStream_t st);
-cudaError_t hcmvs_launch_sweep(const RefConst& rc, int colour, bool tex, cudaStream_t st);
+cudaError_t hcmvs_launch_sweep(const RefConst& rc, int colour, bool tex, cudaStream_t st, bool window = false);
 cudaError_t hcmvs_launch_end(float4* dn, float* conf, size_t n, float keep, cudaStream_t st);
 cudaError_t hcmvs_launch_median3(const float4* in, float4* out, int w, int h, cudaStream_t st);
 cudaError_t hcmvs_launch_gramap(const uint8_t* bgr, uint8_t* gra, int w, int h, cudaStream_t st);

@@ -41,7 +41,7 @@ typedef struct hcmvs_params {
 	/* B200 reformulation knobs (no reference counterpart) */
 	int32_t rb_far_reach;   /* red-black propagation: per direction the best-confidence pixel among odd offsets 1..rb_far_reach */
 	int32_t rb_prop_dirs;   /* 2 (default): one source per image axis = the reference's 2 propagation hypotheses per pixel-iteration; 4: one per direction */
-	int32_t sampler;        /* 0 = texture gather path (default), 1 = global-memory loads */
+	int32_t sampler;        /* 0 = texture gather path (default), 1 = global-memory loads, 2 = texture gathers + shared-memory windows for the sweeps */
 	int32_t viewspread;     /* OPTDENSE::viewspread (DepthMap.cpp:102): cross-view propagation at outer iterations >= 1 (DepthMap.cpp:1504-1608); 0 in every shipped run */
 } hcmvs_params;
 
@@ -67,6 +67,7 @@ typedef struct hcmvs_timers {
 	uint64_t n_smooth_terms;   /* smoothness-neighbour terms evaluated inside the sweeps (sum over hypotheses) */
 	uint32_t n_launches;       /* kernels launched */
 	uint64_t n_fuse_rounds;    /* reserve/commit rounds of the last hcmvs_fuse_depthmaps */
+	uint64_t n_window_walks;   /* sampler 2: warp-level (hypothesis, view) patch walks served from the shared-memory windows */
 } hcmvs_timers;
 
 void hcmvs_default_params(hcmvs_params* p);              /* OPTDENSE defaults, DepthMap.cpp:69-143 */

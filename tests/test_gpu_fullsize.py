@@ -127,3 +127,22 @@ def test_dmap_roundtrip_of_gpu_maps(full, tmp_path):
     back = host.read_dmap(path)
     assert np.array_equal(back["depth"], d) and np.array_equal(back["normal"], n) and np.array_equal(back["conf"], c)
     assert back["dmin"] == np.float32(lo) and back["dmax"] == np.float32(hi)
+
+
+def test_window_sampler_is_bit_identical(full):
+    """sampler 2 serves the patches that fall inside the CTA's shared-memory window of a neighbour image with LDS instead of
+    texture gathers: same positions, same taps, same sums — the maps must be bit-identical to the texture-only path."""
+    syn, osc, gt, imgs, ok, ctx = full
+    ref = 3
+    ctx.set_params(sampler=0)
+    a = _estimate(ctx, osc, ref, seed=23)
+    ctx.set_params(sampler=2)
+    ctx.reset_timers()
+    b = _estimate(ctx, osc, ref, seed=23)
+    t = ctx.timers()
+    ctx.set_params(sampler=0)
+    for x, y in zip(a[:3], b[:3]):
+        assert np.array_equal(x, y)
+    share = t["n_window_walks"] * 32.0 / max(t["n_view_scores"], 1)
+    print(f"\nwindow sampler: {100 * share:.1f} % of the (hypothesis, view) walks served from shared memory")
+    assert share > 0.05
