@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sampler", type=int, default=0)
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "torch"],
+                    help="N>1 map exchange: 'nccl' = hcmvs_exchange_maps (in-place NCCL broadcasts inside the C ABI), 'torch' = torch.distributed all-gather through staging slots")
     return ap.parse_args()
 
 
@@ -265,16 +267,25 @@ def run_b200(args):
     inner = (W - 14) * (H - 14)
     pix_iters_step = inner * int(P.nEstimationIters) * len(valid)
 
-    # exchange buffers (one slot per view, replicated on every rank)
-    if world > 1:
+    lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+    filtered_views = {v for v in valid if min(8, len(nbs[v]["ids"])) >= 2}
+    use_lib_nccl = world > 1 and args.exchange == "nccl"
+    if use_lib_nccl:
+        # the library's own NCCL communicator: rank 0 creates the id, torch.distributed only carries its 128 bytes
+        ids = [api.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(ids[0], rank, world)
+        owner_all = plan.owner_array(V)
+        owner_filtered = plan.owner_array(V, only=filtered_views)
+    elif world > 1:
+        # exchange buffers (one slot per view, replicated on every rank)
         send_dn = torch.zeros((plan.slots, H, W, 4), dtype=torch.float32, device=dev)
         send_cf = torch.zeros((plan.slots, H, W), dtype=torch.float32, device=dev)
         recv_dn = torch.zeros((world, plan.slots, H, W, 4), dtype=torch.float32, device=dev)
         recv_cf = torch.zeros((world, plan.slots, H, W), dtype=torch.float32, device=dev)
-    lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
 
     def exchange():
-        """All-gather every rank's (normal, depth) and confidence maps over NCCL; import the others' maps."""
+        """torch path: all-gather every rank's (normal, depth) and confidence maps over NCCL; import the others' maps."""
         if world == 1:
             return
         shard.exchange_maps(
@@ -292,14 +303,20 @@ def run_b200(args):
     def hot_path():
         for v in mine:
             ctx.estimate_depthmap(v, 0, 1)
-        exchange()
+        if use_lib_nccl:
+            ctx.exchange_maps(owner_all, 0)          # (normal, depth, conf) of every view, in place, one NCCL group
+        else:
+            exchange()
         # FilterDepthMap: neighbours with maps, at most 8 (SceneDensify.cpp:4117-4130)
         for v in mine:
-            idx = list(range(min(8, len(nbs[v]["ids"]))))
-            if len(idx) >= 2:
-                ctx.filter_depthmap(v, idx, adjust=True, download=False)
-        ctx.commit_filtered()
-        exchange()
+            if v in filtered_views:
+                ctx.filter_depthmap(v, list(range(min(8, len(nbs[v]["ids"])))), adjust=True, download=False)
+        if use_lib_nccl:
+            ctx.exchange_maps(owner_filtered, 1)     # the pending filter output (8 B/px); committed on every rank below
+            ctx.commit_filtered()
+        else:
+            ctx.commit_filtered()
+            exchange()
         n = 0
         if rank == 0:
             n = ctx.fuse_depthmaps_device(True, True)[0]  # the fused cloud stays in HBM; e2e below downloads it
@@ -361,7 +378,7 @@ def run_b200(args):
     tex_rate = tm["n_view_scores"] * texels / sweep_s if sweep_s > 0 else 0.0
     roofline["tex_wall"] = {"achieved": tex_rate / 1e9, "peak": tex_peak / 1e9, "unit": "Gsample/s", "frac": tex_rate / tex_peak if tex_peak else None,
                             "note": "texture write-back 32 B/clk/SM, 16 B per bilinear sample (ncu l1tex__tex_writeback_active 79.6 %)"}
-    stages = {k: tm[k] / args.steps for k in ("ms_prep", "ms_score", "ms_sweeps", "ms_end", "ms_filter", "ms_fuse")}
+    stages = {k: tm[k] / args.steps for k in ("ms_prep", "ms_score", "ms_sweeps", "ms_end", "ms_filter", "ms_fuse", "ms_exchange")}
     launches = tm["n_launches"]
 
     # ---- e2e: the host-facing DenseReconstruction call with HOST buffers (uploads + downloads inside the timed region)
@@ -399,7 +416,7 @@ def run_b200(args):
             "metric": "PatchMatch Mpix*iter/s", "value": value, "unit": "Mpix*iter/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.config], "scale": args.scale, "views": V, "image": [W, H], "neighbours": 5,
-                       "patchmatch_iters": int(P.nEstimationIters), "stages": "estimate(A+B+C) + filter + fuse", "parallelism": f"view-sharded x{world}",
+                       "patchmatch_iters": int(P.nEstimationIters), "stages": "estimate(A+B+C) + filter + fuse", "parallelism": f"view-sharded x{world}" + (f", map exchange: {args.exchange}" if world > 1 else ""),
                        "l2": "inputs per view (5 neighbour images + maps, ~77 MB) re-read per launch; 49-view working set 2.3 GB > 126 MB L2"},
             "scene_seconds": sec_step, "fused_points": npoints, "fuse_rounds": int(tm["n_fuse_rounds"]), "stage_ms_per_step_rank0": stages,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,

@@ -17,7 +17,7 @@ EXPORTS = [
     "hcmvs_set_prior", "hcmvs_set_coarse_estimate", "hcmvs_get_coarse_estimate", "hcmvs_snapshot_maps", "hcmvs_get_gradient_map", "hcmvs_score_depthmap", "hcmvs_estimate_depthmap", "hcmvs_end_depthmap", "hcmvs_score_hypotheses",
     "hcmvs_filter_depthmap", "hcmvs_commit_filtered", "hcmvs_set_fuse_priority", "hcmvs_fuse_depthmaps",
     "hcmvs_free_pointcloud", "hcmvs_get_fused_device", "hcmvs_get_fused_support", "hcmvs_download_fused", "hcmvs_download_fused_pinned", "hcmvs_get_depthmap_device", "hcmvs_set_depth_range", "hcmvs_alloc_depthmap",
-    "hcmvs_export_maps_d", "hcmvs_import_maps_d", "hcmvs_get_timers", "hcmvs_reset_timers", "hcmvs_stream",
+    "hcmvs_comm_unique_id", "hcmvs_comm_init", "hcmvs_exchange_maps", "hcmvs_export_maps_d", "hcmvs_import_maps_d", "hcmvs_get_timers", "hcmvs_reset_timers", "hcmvs_stream",
 ]
 
 
@@ -51,7 +51,7 @@ class Timers(C.Structure):
         ("ms_score", C.c_double), ("ms_sweeps", C.c_double), ("ms_end", C.c_double), ("ms_prep", C.c_double),
         ("ms_filter", C.c_double), ("ms_fuse", C.c_double),
         ("n_hypotheses", C.c_uint64), ("n_pixel_iters", C.c_uint64), ("n_view_scores", C.c_uint64), ("n_smooth_terms", C.c_uint64),
-        ("n_launches", C.c_uint32), ("n_fuse_rounds", C.c_uint64), ("n_window_walks", C.c_uint64),
+        ("n_launches", C.c_uint32), ("n_fuse_rounds", C.c_uint64), ("n_window_walks", C.c_uint64), ("ms_exchange", C.c_double),
     ]
 
 
@@ -104,6 +104,9 @@ def load():
     L.hcmvs_get_depthmap_device.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(vp), C.POINTER(f32), C.POINTER(f32)]
     L.hcmvs_set_depth_range.argtypes = [vp, u32, f32, f32]
     L.hcmvs_alloc_depthmap.argtypes = [vp, u32]
+    L.hcmvs_comm_unique_id.argtypes = [vp]
+    L.hcmvs_comm_init.argtypes = [vp, vp, i32, i32]
+    L.hcmvs_exchange_maps.argtypes = [vp, vp, u32, i32]
     L.hcmvs_export_maps_d.argtypes = [vp, u32, vp, vp]
     L.hcmvs_import_maps_d.argtypes = [vp, u32, vp, vp, f32, f32]
     L.hcmvs_get_timers.argtypes = [vp, C.POINTER(Timers)]
@@ -112,6 +115,14 @@ def load():
     L.hcmvs_stream.argtypes = [vp]
     _lib = L
     return L
+
+
+def comm_unique_id():
+    """NCCL unique id (bytes) for Context.comm_init — create on rank 0 and hand to every rank."""
+    buf = (C.c_char * 128)()
+    if load().hcmvs_comm_unique_id(buf) != 0:
+        raise HcmvsError(load().hcmvs_last_error().decode())
+    return bytes(buf.raw)
 
 
 def default_params(**over):
@@ -305,6 +316,16 @@ class Context:
 
     def sync(self):
         self._ck(self.L.hcmvs_sync(self.h))
+
+    def comm_init(self, id_bytes, rank, world):
+        """Join the NCCL communicator of the map exchange (collective); id_bytes from comm_unique_id() on rank 0."""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(id_bytes))
+        self._ck(self.L.hcmvs_comm_init(self.h, buf, int(rank), int(world)))
+
+    def exchange_maps(self, owner, what=0):
+        """Broadcast every view's maps in place from its owning rank (what = 0 estimated maps, 1 pending filter output)."""
+        owner = np.ascontiguousarray(owner, np.int32)
+        self._ck(self.L.hcmvs_exchange_maps(self.h, _p(owner), len(owner), int(what)))
 
     def timers(self):
         t = Timers()

@@ -94,6 +94,7 @@ extern "C" void hcmvs_destroy(hcmvs_ctx* ctx) {
 	cudaFree(ctx->scratch_d); cudaFree(ctx->counters_d); cudaFree(ctx->upload_d); cudaFree(ctx->spread_d);
 	if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
 	hcmvs_fuse_release(ctx);
+	hcmvs_comm_release(ctx);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -144,7 +145,7 @@ extern "C" int hcmvs_get_timers(hcmvs_ctx* ctx, hcmvs_timers* t) {
 	unsigned long long c[8];
 	CK(cudaMemcpy(c, ctx->counters_d, sizeof(c), cudaMemcpyDeviceToHost));
 	t->ms_score = ctx->stageMs[ST_SCORE]; t->ms_sweeps = ctx->stageMs[ST_SWEEPS]; t->ms_end = ctx->stageMs[ST_END];
-	t->ms_prep = ctx->stageMs[ST_PREP]; t->ms_filter = ctx->stageMs[ST_FILTER]; t->ms_fuse = ctx->stageMs[ST_FUSE];
+	t->ms_prep = ctx->stageMs[ST_PREP]; t->ms_filter = ctx->stageMs[ST_FILTER]; t->ms_fuse = ctx->stageMs[ST_FUSE]; t->ms_exchange = ctx->stageMs[ST_EXCHANGE];
 	t->n_hypotheses = c[0]; t->n_view_scores = c[1]; t->n_pixel_iters = c[2]; t->n_smooth_terms = c[3]; t->n_window_walks = c[4];
 	t->n_launches = ctx->nLaunches; t->n_fuse_rounds = ctx->fuseRounds;
 	return HCMVS_OK;

@@ -1,0 +1,120 @@
+// Multi-GPU map exchange inside the C ABI: one process per GPU, NCCL over NVLink / NVSwitch.
+//
+// The scene shards by reference view: every rank estimates / filters its own views and the others need those
+// maps for FilterDepthMap and FuseDepthMaps. Each view's buffers are broadcast IN PLACE from its owner — all broadcasts of
+// one exchange in a single NCCL group, so they run as one fused transfer without staging copies — which makes the exchange
+// usable from a plain C++ host (the reference's language) with no Python / torch in the process.
+//
+// NCCL is loaded lazily with dlopen: a single-GPU user never needs the library, and in a process that already loaded an NCCL
+// (e.g. through torch) the same SONAME resolves to that copy.
+#include "hcmvs_internal.h"
+#include <dlfcn.h>
+#include <cstring>
+#include <nccl.h>
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { hcmvs_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return HCMVS_ERR_CUDA; } } while (0)
+
+namespace {
+struct Nccl {
+	void* lib = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
+	const char* (*GetErrorString)(ncclResult_t) = nullptr;
+	bool ok = false;
+};
+Nccl g_nccl;
+
+int LoadNccl() {
+	if (g_nccl.ok) return HCMVS_OK;
+	const char* names[] = {"libnccl.so.2", "libnccl.so"};
+	for (const char* n: names) { g_nccl.lib = dlopen(n, RTLD_NOW|RTLD_GLOBAL); if (g_nccl.lib) break; }
+	if (!g_nccl.lib) { hcmvs_set_error("NCCL not found (dlopen libnccl.so.2): %s", dlerror()); return HCMVS_ERR_UNSUPPORTED; }
+	#define SYM(field, name) *(void**)(&g_nccl.field) = dlsym(g_nccl.lib, name); if (!g_nccl.field) { hcmvs_set_error("NCCL symbol %s missing", name); return HCMVS_ERR_UNSUPPORTED; }
+	SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+	SYM(Broadcast, "ncclBroadcast") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
+	#undef SYM
+	g_nccl.ok = true;
+	return HCMVS_OK;
+}
+}
+
+#define NK(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) { hcmvs_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); return HCMVS_ERR_CUDA; } } while (0)
+
+extern "C" int hcmvs_comm_unique_id(void* id128) {
+	if (!id128) { hcmvs_set_error("null argument"); return HCMVS_ERR_ARG; }
+	int r = LoadNccl(); if (r) return r;
+	static_assert(HCMVS_COMM_ID_BYTES == NCCL_UNIQUE_ID_BYTES, "id size");
+	ncclUniqueId id;
+	NK(g_nccl.GetUniqueId(&id));
+	std::memcpy(id128, &id, sizeof(id));
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_comm_init(hcmvs_ctx* ctx, const void* id128, int rank, int world) {
+	if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) { hcmvs_set_error("bad communicator arguments (rank %d of %d)", rank, world); return HCMVS_ERR_ARG; }
+	int r = LoadNccl(); if (r) return r;
+	cudaSetDevice(ctx->device);
+	if (ctx->comm) { g_nccl.CommDestroy((ncclComm_t)ctx->comm); ctx->comm = nullptr; }
+	ncclUniqueId id; std::memcpy(&id, id128, sizeof(id));
+	ncclComm_t comm;
+	NK(g_nccl.CommInitRank(&comm, world, id, rank));
+	ctx->comm = comm; ctx->rank = rank; ctx->world = world;
+	return HCMVS_OK;
+}
+
+void hcmvs_comm_release(hcmvs_ctx* ctx) {
+	if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)ctx->comm);
+	ctx->comm = nullptr;
+}
+
+extern "C" int hcmvs_exchange_maps(hcmvs_ctx* ctx, const int32_t* owner, uint32_t n_views, int what) {
+	if (!ctx || !owner) { hcmvs_set_error("null argument"); return HCMVS_ERR_ARG; }
+	if (what != HCMVS_EXCHANGE_ESTIMATED && what != HCMVS_EXCHANGE_FILTERED) { hcmvs_set_error("unknown exchange kind %d", what); return HCMVS_ERR_ARG; }
+	if (!ctx->comm) { hcmvs_set_error("no communicator (call hcmvs_comm_init)"); return HCMVS_ERR_STATE; }
+	if (n_views > ctx->views.size()) { hcmvs_set_error("owner list longer than the scene (%u > %zu views)", n_views, ctx->views.size()); return HCMVS_ERR_ARG; }
+	cudaSetDevice(ctx->device);
+	// every rank walks the same list in the same order: the broadcasts pair up by position
+	for (uint32_t i=0; i<n_views; ++i) {
+		if (owner[i] < 0) continue;
+		if (owner[i] >= ctx->world) { hcmvs_set_error("view %u is owned by rank %d of %d", i, owner[i], ctx->world); return HCMVS_ERR_ARG; }
+		View& v = ctx->views[i];
+		if (!v.set) { hcmvs_set_error("view %u not set on rank %d (every rank holds every image)", i, ctx->rank); return HCMVS_ERR_STATE; }
+		const size_t n = (size_t)v.w*v.h;
+		if (owner[i] == ctx->rank) {
+			if (!v.hasMaps || !v.dn_d) { hcmvs_set_error("rank %d owns view %u but has no maps for it", ctx->rank, i); return HCMVS_ERR_STATE; }
+			if (what == HCMVS_EXCHANGE_FILTERED && !v.hasFiltered) { hcmvs_set_error("rank %d owns view %u but has not filtered it", ctx->rank, i); return HCMVS_ERR_STATE; }
+		} else if (what == HCMVS_EXCHANGE_ESTIMATED) {
+			if (!v.dn_d) { CK(cudaMalloc(&v.dn_d, n*sizeof(float4))); }
+			if (!v.conf_d) { CK(cudaMalloc(&v.conf_d, n*4)); }
+		} else {
+			if (!v.fdepth_d) CK(cudaMalloc(&v.fdepth_d, n*4));
+			if (!v.fconf_d) CK(cudaMalloc(&v.fconf_d, n*4));
+		}
+	}
+	hcmvs_time_begin(ctx, ST_EXCHANGE);
+	NK(g_nccl.GroupStart());
+	for (uint32_t i=0; i<n_views; ++i) {
+		if (owner[i] < 0) continue;
+		View& v = ctx->views[i];
+		const size_t n = (size_t)v.w*v.h;
+		if (what == HCMVS_EXCHANGE_ESTIMATED) {
+			NK(g_nccl.Broadcast(v.dn_d, v.dn_d, n*4, ncclFloat, owner[i], (ncclComm_t)ctx->comm, ctx->stream));
+			NK(g_nccl.Broadcast(v.conf_d, v.conf_d, n, ncclFloat, owner[i], (ncclComm_t)ctx->comm, ctx->stream));
+		} else {
+			NK(g_nccl.Broadcast(v.fdepth_d, v.fdepth_d, n, ncclFloat, owner[i], (ncclComm_t)ctx->comm, ctx->stream));
+			NK(g_nccl.Broadcast(v.fconf_d, v.fconf_d, n, ncclFloat, owner[i], (ncclComm_t)ctx->comm, ctx->stream));
+		}
+	}
+	NK(g_nccl.GroupEnd());
+	hcmvs_time_end(ctx);
+	for (uint32_t i=0; i<n_views; ++i) {
+		if (owner[i] < 0 || owner[i] == ctx->rank) continue;
+		View& v = ctx->views[i];
+		if (what == HCMVS_EXCHANGE_ESTIMATED) v.hasMaps = true; else v.hasFiltered = true; // hcmvs_commit_filtered applies it on this rank too
+	}
+	return HCMVS_OK;
+}

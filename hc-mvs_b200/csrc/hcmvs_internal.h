@@ -3,7 +3,7 @@
 #include "hcmvs_device.cuh"
 #include <vector>
 
-enum { ST_SCORE = 0, ST_SWEEPS, ST_END, ST_PREP, ST_FILTER, ST_FUSE, ST_COUNT };
+enum { ST_SCORE = 0, ST_SWEEPS, ST_END, ST_PREP, ST_FILTER, ST_FUSE, ST_EXCHANGE, ST_COUNT };
 
 struct NbImage { // a matching view's image rescaled for ONE reference view (ViewData::ScaleImage, DepthMap.h:232-238)
 	int w = 0, h = 0; double K[9];
@@ -51,11 +51,12 @@ struct hcmvs_ctx {
 	void* scratch_d = nullptr; size_t scratchBytes = 0;
 	unsigned long long* counters_d = nullptr;
 	std::vector<TimedSpan> timed; std::vector<cudaEvent_t> eventPool;
-	double stageMs[ST_COUNT] = {0, 0, 0, 0, 0, 0};
+	double stageMs[ST_COUNT] = {0, 0, 0, 0, 0, 0, 0};
 	uint32_t nLaunches = 0;
 	uint64_t fuseRounds = 0;
 	FuseState* fuse = nullptr;
 	SpreadConst* spread_d = nullptr; // viewspread constants of the view being estimated
+	void* comm = nullptr; int rank = 0, world = 1; // NCCL communicator of hcmvs_comm_init (exchange.cu)
 };
 
 void hcmvs_set_error(const char* fmt, ...);
@@ -63,6 +64,7 @@ int  hcmvs_scratch(hcmvs_ctx* ctx, size_t bytes, void** out);
 void hcmvs_time_begin(hcmvs_ctx* ctx, int stage);
 void hcmvs_time_end(hcmvs_ctx* ctx);
 void hcmvs_fuse_release(hcmvs_ctx* ctx);
+void hcmvs_comm_release(hcmvs_ctx* ctx);
 void hcmvs_fill_cam(const View& v, CamConst& c);
 int  hcmvs_mark_image_use(hcmvs_ctx* ctx, View& v);   // record v.lastUse on the compute stream
 int  hcmvs_wait_image(hcmvs_ctx* ctx, const View& v); // make the compute stream wait for the view's image upload

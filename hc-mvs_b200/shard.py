@@ -25,6 +25,16 @@ class ShardPlan:
     def views_of(self, rank: int) -> List[int]:
         return [v for k, v in enumerate(self.order) if k % self.world == rank]
 
+    def owner_array(self, n_views: int, only=None):
+        """owner[i] = rank that estimates view i, -1 for views outside the plan (or outside `only`): the list every rank hands to
+        hcmvs_exchange_maps."""
+        import numpy as np
+        o = np.full(n_views, -1, np.int32)
+        for k, v in enumerate(self.order):
+            if only is None or v in only:
+                o[v] = k % self.world
+        return o
+
     def location(self) -> Dict[int, tuple]:
         """view -> (rank, slot) of its maps in the gathered buffer."""
         return {v: (k % self.world, k // self.world) for k, v in enumerate(self.order)}

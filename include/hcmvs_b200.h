@@ -68,6 +68,7 @@ typedef struct hcmvs_timers {
 	uint32_t n_launches;       /* kernels launched */
 	uint64_t n_fuse_rounds;    /* reserve/commit rounds of the last hcmvs_fuse_depthmaps */
 	uint64_t n_window_walks;   /* sampler 2: warp-level (hypothesis, view) patch walks served from the shared-memory windows */
+	double ms_exchange;        /* hcmvs_exchange_maps (NCCL) */
 } hcmvs_timers;
 
 void hcmvs_default_params(hcmvs_params* p);              /* OPTDENSE defaults, DepthMap.cpp:69-143 */
@@ -159,6 +160,22 @@ int hcmvs_download_fused_pinned(hcmvs_ctx* ctx, hcmvs_pointcloud* out);
 int hcmvs_get_fused_support(hcmvs_ctx* ctx, uint32_t view, float* depth_fuse, float* normal_fuse);
 int hcmvs_get_fused_device(hcmvs_ctx* ctx, uint64_t* n_points, uint64_t* n_view_refs, void** points_d, void** normals_d, void** colors_d,
                            void** view_offsets_d, void** views_d, void** weights_d);
+
+/* ---- multi-GPU: one process (one context) per GPU, views sharded by reference view. No reference counterpart: the
+ * reference is single-node CPU code. Rank 0 creates an id (hcmvs_comm_unique_id), the host distributes its HCMVS_COMM_ID_BYTES bytes
+ * by any means (file, socket, MPI, torch.distributed), every rank calls hcmvs_comm_init (collective). hcmvs_exchange_maps then
+ * broadcasts, in place and in one NCCL group, the maps of every view i from rank owner[i] (owner[i] < 0: view not exchanged) to all
+ * other ranks, on the context's stream:
+ *   HCMVS_EXCHANGE_ESTIMATED  (normal, depth) + confidence of the estimated maps (20 B/px) — before FilterDepthMap / FuseDepthMaps
+ *   HCMVS_EXCHANGE_FILTERED   the pending FilterDepthMap output (depth + confidence, 8 B/px); hcmvs_commit_filtered then applies
+ *                             it on every rank
+ * Every rank passes the same owner list (n_views entries, indexed by view id) and must hold every view's image (hcmvs_set_view). */
+#define HCMVS_COMM_ID_BYTES 128
+#define HCMVS_EXCHANGE_ESTIMATED 0
+#define HCMVS_EXCHANGE_FILTERED 1
+int hcmvs_comm_unique_id(void* id128);
+int hcmvs_comm_init(hcmvs_ctx* ctx, const void* id128, int rank, int world);
+int hcmvs_exchange_maps(hcmvs_ctx* ctx, const int32_t* owner, uint32_t n_views, int what);
 
 /* Device pointers of a view's maps for GPU<->GPU exchange by the host plumbing (NCCL / P2P):
  * dn_d = float4 (nx,ny,nz,depth) per pixel, conf_d = float per pixel. */

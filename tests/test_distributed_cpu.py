@@ -64,3 +64,21 @@ def test_two_rank_map_exchange_gloo():
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(r[1] for r in res), "a rank did not end up with every view's maps"
     assert all(r[2] == 2.0 for r in res)
+
+
+def test_owner_arrays_are_consistent_across_ranks():
+    """hcmvs_exchange_maps takes one owner list that every rank must build identically: owner[v] = rank estimating view v."""
+    sys.path.insert(0, ROOT)
+    from hcmvs_b200 import shard
+    valid = [0, 1, 2, 4, 5, 7, 8, 9, 10]
+    nall = {v: 12 - (v % 5) for v in valid}
+    for world in (1, 2, 4, 8):
+        plan = shard.make_plan(valid, nall, world)
+        owner = plan.owner_array(11)
+        assert owner.dtype == np.int32 and list(np.where(owner < 0)[0]) == [3, 6]
+        for r in range(world):
+            assert sorted(plan.views_of(r)) == sorted(int(v) for v in np.where(owner == r)[0])
+        counts = np.bincount(owner[owner >= 0], minlength=world)
+        assert counts.max() - counts.min() <= 1                       # round-robin in connection order balances the ranks
+        sub = plan.owner_array(11, only={0, 5, 9})
+        assert set(np.where(sub >= 0)[0]) == {0, 5, 9} and all(sub[v] == owner[v] for v in (0, 5, 9))
