@@ -275,7 +275,7 @@ def run_b200(args):
         ids = [api.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         ctx.comm_init(ids[0], rank, world)
-        owner_all = plan.owner_array(V)
+        owner_rounds = plan.round_owner_arrays(V)
         owner_filtered = plan.owner_array(V, only=filtered_views)
     elif world > 1:
         # exchange buffers (one slot per view, replicated on every rank)
@@ -301,11 +301,17 @@ def run_b200(args):
         ctx.sync()
 
     def hot_path():
-        for v in mine:
-            ctx.estimate_depthmap(v, 0, 1)
         if use_lib_nccl:
-            ctx.exchange_maps(owner_all, 0)          # (normal, depth, conf) of every view, in place, one NCCL group
+            # round s: every rank estimates its s-th view, then those views are broadcast in place (one NCCL group) on the
+            # communication stream while round s+1 is being estimated
+            for s_, own in enumerate(owner_rounds):
+                if s_ < len(mine):
+                    ctx.estimate_depthmap(mine[s_], 0, 1)
+                ctx.exchange_maps(own, 0, overlap=True)
+            ctx.exchange_wait()
         else:
+            for v in mine:
+                ctx.estimate_depthmap(v, 0, 1)
             exchange()
         # FilterDepthMap: neighbours with maps, at most 8 (SceneDensify.cpp:4117-4130)
         for v in mine:

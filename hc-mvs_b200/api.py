@@ -17,7 +17,7 @@ EXPORTS = [
     "hcmvs_set_prior", "hcmvs_set_coarse_estimate", "hcmvs_get_coarse_estimate", "hcmvs_snapshot_maps", "hcmvs_get_gradient_map", "hcmvs_score_depthmap", "hcmvs_estimate_depthmap", "hcmvs_end_depthmap", "hcmvs_score_hypotheses",
     "hcmvs_filter_depthmap", "hcmvs_commit_filtered", "hcmvs_set_fuse_priority", "hcmvs_fuse_depthmaps",
     "hcmvs_free_pointcloud", "hcmvs_get_fused_device", "hcmvs_get_fused_support", "hcmvs_download_fused", "hcmvs_download_fused_pinned", "hcmvs_get_depthmap_device", "hcmvs_set_depth_range", "hcmvs_alloc_depthmap",
-    "hcmvs_comm_unique_id", "hcmvs_comm_init", "hcmvs_exchange_maps", "hcmvs_export_maps_d", "hcmvs_import_maps_d", "hcmvs_get_timers", "hcmvs_reset_timers", "hcmvs_stream",
+    "hcmvs_comm_unique_id", "hcmvs_comm_init", "hcmvs_exchange_maps", "hcmvs_exchange_wait", "hcmvs_export_maps_d", "hcmvs_import_maps_d", "hcmvs_get_timers", "hcmvs_reset_timers", "hcmvs_stream",
 ]
 
 
@@ -107,6 +107,7 @@ def load():
     L.hcmvs_comm_unique_id.argtypes = [vp]
     L.hcmvs_comm_init.argtypes = [vp, vp, i32, i32]
     L.hcmvs_exchange_maps.argtypes = [vp, vp, u32, i32]
+    L.hcmvs_exchange_wait.argtypes = [vp]
     L.hcmvs_export_maps_d.argtypes = [vp, u32, vp, vp]
     L.hcmvs_import_maps_d.argtypes = [vp, u32, vp, vp, f32, f32]
     L.hcmvs_get_timers.argtypes = [vp, C.POINTER(Timers)]
@@ -322,10 +323,14 @@ class Context:
         buf = (C.c_char * 128).from_buffer_copy(bytes(id_bytes))
         self._ck(self.L.hcmvs_comm_init(self.h, buf, int(rank), int(world)))
 
-    def exchange_maps(self, owner, what=0):
-        """Broadcast every view's maps in place from its owning rank (what = 0 estimated maps, 1 pending filter output)."""
+    def exchange_maps(self, owner, what=0, overlap=False):
+        """Broadcast every view's maps in place from its owning rank (what = 0 estimated maps, 1 pending filter output);
+        overlap=True runs it on the communication stream (join with exchange_wait)."""
         owner = np.ascontiguousarray(owner, np.int32)
-        self._ck(self.L.hcmvs_exchange_maps(self.h, _p(owner), len(owner), int(what)))
+        self._ck(self.L.hcmvs_exchange_maps(self.h, _p(owner), len(owner), int(what) | (0x100 if overlap else 0)))
+
+    def exchange_wait(self):
+        self._ck(self.L.hcmvs_exchange_wait(self.h))
 
     def timers(self):
         t = Timers()

@@ -67,12 +67,26 @@ extern "C" int hcmvs_comm_init(hcmvs_ctx* ctx, const void* id128, int rank, int 
 }
 
 void hcmvs_comm_release(hcmvs_ctx* ctx) {
+	if (ctx->commStream) { cudaStreamSynchronize(ctx->commStream); cudaStreamDestroy(ctx->commStream); cudaEventDestroy(ctx->commDone); cudaEventDestroy(ctx->commReady); ctx->commStream = nullptr; }
 	if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)ctx->comm);
 	ctx->comm = nullptr;
 }
 
+extern "C" int hcmvs_exchange_wait(hcmvs_ctx* ctx) {
+	if (!ctx) { hcmvs_set_error("null context"); return HCMVS_ERR_ARG; }
+	cudaSetDevice(ctx->device);
+	if (ctx->commPending) {
+		CK(cudaEventRecord(ctx->commDone, ctx->commStream));
+		CK(cudaStreamWaitEvent(ctx->stream, ctx->commDone, 0)); // later compute work sees the received maps
+		ctx->commPending = false;
+	}
+	return HCMVS_OK;
+}
+
 extern "C" int hcmvs_exchange_maps(hcmvs_ctx* ctx, const int32_t* owner, uint32_t n_views, int what) {
 	if (!ctx || !owner) { hcmvs_set_error("null argument"); return HCMVS_ERR_ARG; }
+	const bool async = (what & HCMVS_EXCHANGE_ASYNC) != 0;
+	what &= ~HCMVS_EXCHANGE_ASYNC;
 	if (what != HCMVS_EXCHANGE_ESTIMATED && what != HCMVS_EXCHANGE_FILTERED) { hcmvs_set_error("unknown exchange kind %d", what); return HCMVS_ERR_ARG; }
 	if (!ctx->comm) { hcmvs_set_error("no communicator (call hcmvs_comm_init)"); return HCMVS_ERR_STATE; }
 	if (n_views > ctx->views.size()) { hcmvs_set_error("owner list longer than the scene (%u > %zu views)", n_views, ctx->views.size()); return HCMVS_ERR_ARG; }
@@ -95,22 +109,30 @@ extern "C" int hcmvs_exchange_maps(hcmvs_ctx* ctx, const int32_t* owner, uint32_
 			if (!v.fconf_d) CK(cudaMalloc(&v.fconf_d, n*4));
 		}
 	}
-	hcmvs_time_begin(ctx, ST_EXCHANGE);
+	// async: the broadcasts run on the communication stream behind everything queued on the compute stream so far, and overlap
+	// whatever is queued on the compute stream afterwards (the next view's sweeps) until hcmvs_exchange_wait
+	cudaStream_t st = ctx->stream;
+	if (async) {
+		if (!ctx->commStream) { CK(cudaStreamCreateWithFlags(&ctx->commStream, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&ctx->commDone, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->commReady, cudaEventDisableTiming)); }
+		CK(cudaEventRecord(ctx->commReady, ctx->stream));
+		CK(cudaStreamWaitEvent(ctx->commStream, ctx->commReady, 0));
+		st = ctx->commStream; ctx->commPending = true;
+	} else hcmvs_time_begin(ctx, ST_EXCHANGE);
 	NK(g_nccl.GroupStart());
 	for (uint32_t i=0; i<n_views; ++i) {
 		if (owner[i] < 0) continue;
 		View& v = ctx->views[i];
 		const size_t n = (size_t)v.w*v.h;
 		if (what == HCMVS_EXCHANGE_ESTIMATED) {
-			NK(g_nccl.Broadcast(v.dn_d, v.dn_d, n*4, ncclFloat, owner[i], (ncclComm_t)ctx->comm, ctx->stream));
-			NK(g_nccl.Broadcast(v.conf_d, v.conf_d, n, ncclFloat, owner[i], (ncclComm_t)ctx->comm, ctx->stream));
+			NK(g_nccl.Broadcast(v.dn_d, v.dn_d, n*4, ncclFloat, owner[i], (ncclComm_t)ctx->comm, st));
+			NK(g_nccl.Broadcast(v.conf_d, v.conf_d, n, ncclFloat, owner[i], (ncclComm_t)ctx->comm, st));
 		} else {
-			NK(g_nccl.Broadcast(v.fdepth_d, v.fdepth_d, n, ncclFloat, owner[i], (ncclComm_t)ctx->comm, ctx->stream));
-			NK(g_nccl.Broadcast(v.fconf_d, v.fconf_d, n, ncclFloat, owner[i], (ncclComm_t)ctx->comm, ctx->stream));
+			NK(g_nccl.Broadcast(v.fdepth_d, v.fdepth_d, n, ncclFloat, owner[i], (ncclComm_t)ctx->comm, st));
+			NK(g_nccl.Broadcast(v.fconf_d, v.fconf_d, n, ncclFloat, owner[i], (ncclComm_t)ctx->comm, st));
 		}
 	}
 	NK(g_nccl.GroupEnd());
-	hcmvs_time_end(ctx);
+	if (!async) hcmvs_time_end(ctx);
 	for (uint32_t i=0; i<n_views; ++i) {
 		if (owner[i] < 0 || owner[i] == ctx->rank) continue;
 		View& v = ctx->views[i];

@@ -57,6 +57,7 @@ struct hcmvs_ctx {
 	FuseState* fuse = nullptr;
 	SpreadConst* spread_d = nullptr; // viewspread constants of the view being estimated
 	void* comm = nullptr; int rank = 0, world = 1; // NCCL communicator of hcmvs_comm_init (exchange.cu)
+	cudaStream_t commStream = nullptr; cudaEvent_t commDone = nullptr, commReady = nullptr; bool commPending = false; // asynchronous exchanges
 };
 
 void hcmvs_set_error(const char* fmt, ...);

@@ -35,6 +35,17 @@ class ShardPlan:
                 o[v] = k % self.world
         return o
 
+    def round_owner_arrays(self, n_views: int):
+        """One owner list per estimation round s (the s-th view of every rank): the exchange of round s overlaps round s+1."""
+        import numpy as np
+        out = []
+        for s in range(self.slots):
+            o = np.full(n_views, -1, np.int32)
+            for k in range(s*self.world, min((s+1)*self.world, len(self.order))):
+                o[self.order[k]] = k % self.world
+            out.append(o)
+        return out
+
     def location(self) -> Dict[int, tuple]:
         """view -> (rank, slot) of its maps in the gathered buffer."""
         return {v: (k % self.world, k // self.world) for k, v in enumerate(self.order)}

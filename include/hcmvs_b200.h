@@ -173,9 +173,12 @@ int hcmvs_get_fused_device(hcmvs_ctx* ctx, uint64_t* n_points, uint64_t* n_view_
 #define HCMVS_COMM_ID_BYTES 128
 #define HCMVS_EXCHANGE_ESTIMATED 0
 #define HCMVS_EXCHANGE_FILTERED 1
+#define HCMVS_EXCHANGE_ASYNC 0x100   /* OR into `what`: run the broadcasts on a communication stream, behind the work queued so far and
+                                        overlapping the work queued afterwards (the next view's sweeps); hcmvs_exchange_wait joins */
 int hcmvs_comm_unique_id(void* id128);
 int hcmvs_comm_init(hcmvs_ctx* ctx, const void* id128, int rank, int world);
 int hcmvs_exchange_maps(hcmvs_ctx* ctx, const int32_t* owner, uint32_t n_views, int what);
+int hcmvs_exchange_wait(hcmvs_ctx* ctx);   /* the compute stream waits for every asynchronous exchange issued so far */
 
 /* Device pointers of a view's maps for GPU<->GPU exchange by the host plumbing (NCCL / P2P):
  * dn_d = float4 (nx,ny,nz,depth) per pixel, conf_d = float per pixel. */

@@ -28,10 +28,18 @@ def run(ctx, world, rank, use_comm):
     plan = shard.make_plan(valid, nall, world)
     mine = plan.views_of(rank)
     filt = {v for v in valid if min(8, len(nbs[v]["ids"])) >= 2}
-    for v in mine:
-        d, lo, hi = hs.init_depth(v)
-        ctx.init_depthmap(v, d, None, lo, hi); ctx.estimate_depthmap(v, 0, 1)
-    if use_comm: ctx.exchange_maps(plan.owner_array(V), 0)
+    if use_comm:  # per-round exchange overlapped with the next round's estimation, as bench.py does
+        for s_, own in enumerate(plan.round_owner_arrays(V)):
+            if s_ < len(mine):
+                v = mine[s_]
+                d, lo, hi = hs.init_depth(v)
+                ctx.init_depthmap(v, d, None, lo, hi); ctx.estimate_depthmap(v, 0, 1)
+            ctx.exchange_maps(own, 0, overlap=True)
+        ctx.exchange_wait()
+    else:
+        for v in mine:
+            d, lo, hi = hs.init_depth(v)
+            ctx.init_depthmap(v, d, None, lo, hi); ctx.estimate_depthmap(v, 0, 1)
     for v in mine:
         if v in filt: ctx.filter_depthmap(v, list(range(min(8, len(nbs[v]["ids"])))), True, download=False)
     if use_comm: ctx.exchange_maps(plan.owner_array(V, only=filt), 1)
