@@ -41,6 +41,13 @@ def lib():
         L.hcmvs_host_write_dmap.argtypes = [C.c_char_p, C.c_char_p, vp, i32, i32, i32, vp, vp, vp, C.c_float, C.c_float, i32, i32, vp, vp, vp]
         L.hcmvs_host_read_dmap_header.argtypes = [C.c_char_p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
         L.hcmvs_host_read_dmap.argtypes = [C.c_char_p, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.hcmvs_host_scene_load_mvs.argtypes = [vp, C.c_char_p, i32]
+        L.hcmvs_host_scene_save_mvs.argtypes = [vp, C.c_char_p, i32, i32]
+        L.hcmvs_host_num_images.argtypes = [vp]
+        L.hcmvs_host_get_image_info.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_uint32), vp, vp, vp, C.c_char_p, i32]
+        L.hcmvs_host_get_image_bgr.argtypes = [vp, i32, vp]
+        L.hcmvs_host_get_sparse.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), vp, vp, vp, vp]
+        L.hcmvs_host_load_image.argtypes = [C.c_char_p, C.POINTER(i32), C.POINTER(i32), vp]
         _lib = L
     return _lib
 
@@ -126,6 +133,45 @@ class HostScene:
             self.L.hcmvs_host_cloud_get(self.h, _p(xyz), _p(nrm), _p(col), _p(off), _p(views), _p(wts))
         return dict(xyz=xyz, normals=nrm, colors=col, n_views=np.diff(off.astype(np.int64)).astype(np.int32), views=views, weights=wts)
 
+    # ---- MVSI project files (Scene::LoadInterface / SaveInterface, libs/MVS/Scene.cpp:62-286)
+    @classmethod
+    def load_mvs(cls, path, load_images=True):
+        s = cls()
+        if s.L.hcmvs_host_scene_load_mvs(s.h, str(path).encode(), int(load_images)) != 0:
+            raise RuntimeError("LoadInterface: " + s.L.hcmvs_host_last_error(s.h).decode())
+        s.sizes = [(im["height"], im["width"]) for im in (s.image_info(i) for i in range(s.num_images()))]
+        return s
+
+    def save_mvs(self, path, version=-1, dense=False):
+        if self.L.hcmvs_host_scene_save_mvs(self.h, str(path).encode(), version, int(dense)) != 0:
+            raise RuntimeError("SaveInterface: " + self.L.hcmvs_host_last_error(self.h).decode())
+
+    def num_images(self):
+        return self.L.hcmvs_host_num_images(self.h)
+
+    def image_info(self, idx):
+        w, h, cal, iid = C.c_int(), C.c_int(), C.c_int(), C.c_uint32()
+        K = np.zeros(9); R = np.zeros(9); Cc = np.zeros(3)
+        name = C.create_string_buffer(1024)
+        if self.L.hcmvs_host_get_image_info(self.h, idx, C.byref(w), C.byref(h), C.byref(cal), C.byref(iid), _p(K), _p(R), _p(Cc), name, 1024) != 0:
+            raise IndexError(idx)
+        return dict(width=w.value, height=h.value, calibrated=bool(cal.value), id=iid.value, K=K, R=R, C=Cc, name=name.value.decode())
+
+    def image_bgr(self, idx):
+        h, w = self.sizes[idx]
+        out = np.empty((h, w, 3), np.uint8)
+        if self.L.hcmvs_host_get_image_bgr(self.h, idx, _p(out)) != 0:
+            return None
+        return out
+
+    def sparse(self):
+        n, m = C.c_uint64(), C.c_uint64()
+        self.L.hcmvs_host_get_sparse(self.h, C.byref(n), C.byref(m), None, None, None, None)
+        xyz = np.empty((n.value, 3), np.float32); off = np.empty(n.value + 1, np.int32)
+        ids = np.empty(m.value, np.uint32); wts = np.empty(m.value, np.float32)
+        self.L.hcmvs_host_get_sparse(self.h, None, None, _p(xyz), _p(off), _p(ids), _p(wts))
+        return xyz, off, ids, wts
+
     def save_ply(self, path):
         if self.L.hcmvs_host_cloud_save_ply(self.h, path.encode()) != 0:
             raise RuntimeError("PointCloud::Save failed")
@@ -140,6 +186,17 @@ class HostScene:
             self.close()
         except Exception:
             pass
+
+
+def load_image(path):
+    """The project loader's image decoder (BMP / PNG / binary PNM -> BGR u8)."""
+    w, h = C.c_int(), C.c_int()
+    if lib().hcmvs_host_load_image(str(path).encode(), C.byref(w), C.byref(h), None) != 0:
+        raise RuntimeError(f"cannot read the header of {path}")
+    out = np.empty((h.value, w.value, 3), np.uint8)
+    if lib().hcmvs_host_load_image(str(path).encode(), C.byref(w), C.byref(h), _p(out)) != 0:
+        raise RuntimeError(f"cannot decode {path}")
+    return out
 
 
 def scale_image(gray, scale, K=None):

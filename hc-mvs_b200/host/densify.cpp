@@ -261,6 +261,7 @@ bool DepthMapsData::SelectViews(uint32_t idxImage) {
 	// SceneDensify.cpp:307-327
 	DepthData& dd = arrDepthData[idxImage];
 	dd.points.clear(); dd.neighbors.clear(); dd.valid = false;
+	if (!scene.images[idxImage].calibrated) return false; // !imageData.IsValid(), SceneDensify.cpp:3655
 	if (!scene.SelectNeighborViews(idxImage, dd.points, P.nMinViews, P.nMinViewsTrustPoint > 1 ? P.nMinViewsTrustPoint : 2, Deg2Rad(VS.fOptimAngle)))
 		return false;
 	dd.neighbors = scene.images[idxImage].neighbors;

@@ -35,11 +35,16 @@ struct Image {
 	std::vector<float> gray;     // Image::toGray(BGR2GRAY, normalised), Common/Types.inl:2352-2402
 	std::vector<ViewScore> neighbors; // all scored neighbours, best first (Image::neighbors)
 	float avgDepth = 0;
+	uint32_t ID = 0xFFFFFFFFu;   // global image ID of the project file (NO_ID: the index)
+	bool calibrated = true;      // Image::IsValid(): poseID != NO_ID (libs/MVS/Image.h)
 };
 
 struct SparsePoints { // the part of MVS::PointCloud the densifier reads
 	std::vector<float> xyz;                      // 3 per point
 	std::vector<std::vector<uint32_t>> views;    // sorted view ids per point
+	std::vector<std::vector<float>> weights;     // per-view confidences (empty when the project has none, Scene.cpp:180-181)
+	std::vector<float> normals;                  // optional, 3 per point
+	std::vector<uint8_t> colors;                 // optional, 3 per point (B,G,R)
 	size_t size() const { return views.size(); }
 };
 
@@ -70,7 +75,11 @@ struct Scene {
 	std::vector<Image> images;
 	SparsePoints pointcloud;
 	PointCloud densecloud;
-	unsigned nCalibratedImages() const { return (unsigned)images.size(); }
+	unsigned nCalibratedImages() const { unsigned n = 0; for (const Image& im: images) n += im.calibrated; return n; }
+	// MVSI project files (mvsi.h): Scene::LoadInterface / SaveInterface, libs/MVS/Scene.cpp:62-286. bDense: export the fused
+	// cloud as the project's vertices (what DensifyPointCloud's scene_dense.mvs holds) instead of the sparse points.
+	bool LoadInterface(const std::string& fileName, bool bLoadImages = true, std::string* err = nullptr);
+	bool SaveInterface(const std::string& fileName, int version = -1, bool bDense = false) const;
 	// Scene::SelectNeighborViews / FilterNeighborViews, libs/MVS/Scene.cpp:545-678
 	bool SelectNeighborViews(uint32_t ID, std::vector<uint32_t>& points, unsigned nMinViews, unsigned nMinPointViews, float fOptimAngle);
 	static bool FilterNeighborViews(std::vector<ViewScore>& neighbors, float fMinArea, float fMinScale, float fMaxScale, float fMinAngle, float fMaxAngle, unsigned nMaxViews);

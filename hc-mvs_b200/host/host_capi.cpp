@@ -1,6 +1,7 @@
 // C handle API over densify.h — see include/hcmvs_host.h.
 #include "hcmvs_host.h"
 #include "densify.h"
+#include "mvsi.h"
 #include <cstring>
 #include <algorithm>
 
@@ -141,6 +142,66 @@ int hcmvs_host_read_dmap(const char* file, uint32_t* ids, double K[9], double R[
 	if (depth) memcpy(depth, d.data(), d.size()*4);
 	if (normal && !n.empty()) memcpy(normal, n.data(), n.size()*4);
 	if (conf && !c.empty()) memcpy(conf, c.data(), c.size()*4);
+	return 0;
+}
+
+// ---- MVSI project files (mvsi.h)
+int hcmvs_host_scene_load_mvs(hcmvs_host_scene* s, const char* file, int load_images) {
+	if (!s || !file) return -1;
+	s->dd.clear();
+	return s->scene.LoadInterface(file, load_images != 0, &s->err) ? 0 : -1;
+}
+int hcmvs_host_scene_save_mvs(hcmvs_host_scene* s, const char* file, int version, int dense) {
+	if (!s || !file) return -1;
+	if (!s->scene.SaveInterface(file, version, dense != 0)) { s->err = std::string("cannot write '")+file+"'"; return -1; }
+	return 0;
+}
+int hcmvs_host_num_images(hcmvs_host_scene* s) { return s ? (int)s->scene.images.size() : -1; }
+int hcmvs_host_get_image_info(hcmvs_host_scene* s, int idx, int* w, int* h, int* calibrated, uint32_t* id, double K[9], double R[9], double C[3], char* name, int name_cap) {
+	if (!s || idx < 0 || idx >= (int)s->scene.images.size()) return -1;
+	const Image& im = s->scene.images[idx];
+	if (w) *w = im.width;
+	if (h) *h = im.height;
+	if (calibrated) *calibrated = im.calibrated;
+	if (id) *id = im.ID;
+	if (K) memcpy(K, im.camera.K, 72);
+	if (R) memcpy(R, im.camera.R, 72);
+	if (C) memcpy(C, im.camera.C, 24);
+	if (name && name_cap > 0) { strncpy(name, im.name.c_str(), (size_t)name_cap-1); name[name_cap-1] = 0; }
+	return 0;
+}
+int hcmvs_host_get_image_bgr(hcmvs_host_scene* s, int idx, uint8_t* bgr) {
+	if (!s || idx < 0 || idx >= (int)s->scene.images.size() || !bgr) return -1;
+	const Image& im = s->scene.images[idx];
+	if (im.bgr.empty()) return -1;
+	memcpy(bgr, im.bgr.data(), im.bgr.size());
+	return 0;
+}
+int hcmvs_host_get_sparse(hcmvs_host_scene* s, uint64_t* n_points, uint64_t* n_view_refs, float* xyz, int32_t* offsets, uint32_t* view_ids, float* weights) {
+	if (!s) return -1;
+	const SparsePoints& pc = s->scene.pointcloud;
+	uint64_t refs = 0;
+	for (size_t i=0; i<pc.size(); ++i) {
+		if (offsets) offsets[i] = (int32_t)refs;
+		for (size_t k=0; k<pc.views[i].size(); ++k) {
+			if (view_ids) view_ids[refs+k] = pc.views[i][k];
+			if (weights) weights[refs+k] = pc.weights.empty() ? 0.f : pc.weights[i][k];
+		}
+		refs += pc.views[i].size();
+	}
+	if (offsets) offsets[pc.size()] = (int32_t)refs;
+	if (xyz && !pc.xyz.empty()) memcpy(xyz, pc.xyz.data(), pc.xyz.size()*4);
+	if (n_points) *n_points = pc.size();
+	if (n_view_refs) *n_view_refs = refs;
+	return 0;
+}
+int hcmvs_host_load_image(const char* file, int* w, int* h, uint8_t* bgr) {
+	if (!file || !w || !h) return -1;
+	if (!bgr) return ReadImageSize(file, *w, *h) ? 0 : -1;
+	std::vector<uint8_t> px; int iw, ih;
+	if (!LoadImageBGR(file, iw, ih, px)) return -1;
+	if (iw != *w || ih != *h) return -2;
+	memcpy(bgr, px.data(), px.size());
 	return 0;
 }
 

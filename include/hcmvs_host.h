@@ -41,6 +41,20 @@ int hcmvs_host_write_dmap(const char* file, const char* image_name, const uint32
 int hcmvs_host_read_dmap_header(const char* file, int* w, int* h, int* n_ids, int* has_normal, int* has_conf);
 int hcmvs_host_read_dmap(const char* file, uint32_t* ids, double K[9], double R[9], double C[3], float* dminmax, float* depth, float* normal, float* conf);
 
+/* MVSI project files ("scene.mvs": MVS::Interface, libs/MVS/Interface.h:165-619) — Scene::LoadInterface / SaveInterface
+ * (libs/MVS/Scene.cpp:62-286). load_images: also decode the image files the project names (BMP / PNG / binary PNM), relative to
+ * the project's folder. dense: write the fused cloud as the project's vertices (DensifyPointCloud's scene_dense.mvs) instead of
+ * the sparse points. version < 0: MVSI_PROJECT_VER (5). */
+int hcmvs_host_scene_load_mvs(hcmvs_host_scene* s, const char* file, int load_images);
+int hcmvs_host_scene_save_mvs(hcmvs_host_scene* s, const char* file, int version, int dense);
+int hcmvs_host_num_images(hcmvs_host_scene* s);
+int hcmvs_host_get_image_info(hcmvs_host_scene* s, int idx, int* w, int* h, int* calibrated, uint32_t* id, double K[9], double R[9], double C[3], char* name, int name_cap);
+int hcmvs_host_get_image_bgr(hcmvs_host_scene* s, int idx, uint8_t* bgr);
+/* sparse cloud as CSR; call with NULL arrays first to learn the sizes */
+int hcmvs_host_get_sparse(hcmvs_host_scene* s, uint64_t* n_points, uint64_t* n_view_refs, float* xyz, int32_t* offsets, uint32_t* view_ids, float* weights);
+/* image decoder used by the project loader; bgr == NULL: only the size */
+int hcmvs_host_load_image(const char* file, int* w, int* h, uint8_t* bgr);
+
 #ifdef __cplusplus
 }
 #endif

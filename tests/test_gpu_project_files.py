@@ -1,0 +1,62 @@
+"""The drop-in path with FILES on both sides (SURVEY §8b inputs/outputs): an MVSI project + image files on disk ->
+Scene::LoadInterface -> DenseReconstruction on the GPU -> depthNNNN.dmap, scene_dense.ply, scene_dense.mvs — compared with the
+in-memory path on the same scene."""
+import os
+
+import numpy as np
+import pytest
+
+import common
+
+pytestmark = pytest.mark.gpu
+
+
+def test_project_on_disk_end_to_end(tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    from hcmvs_b200 import api, host
+    syn, osc, gt, imgs, ok = common.make_scene(1, 0.5)
+    hs0 = host.HostScene.from_synth(syn, imgs)                     # images named 00000.png ...
+    for i, im in enumerate(imgs):
+        assert cv2.imwrite(str(tmp_path / f"{i:05d}.png"), im)
+    hs0.save_mvs(tmp_path / "scene.mvs")
+    hs = host.HostScene.load_mvs(tmp_path / "scene.mvs")           # decodes the PNGs through the product's own reader
+    assert hs.num_images() == syn.n_views
+    for i in range(syn.n_views):
+        assert np.array_equal(hs.image_bgr(i), imgs[i])
+    clouds, depths = [], []
+    for scene, dmap_dir in ((hs0, None), (hs, str(tmp_path))):
+        ctx = api.Context(0, **common.BENCH_PARAMS)
+        try:
+            st = scene.dense_reconstruction(ctx, seed=7, run_filter=True, dmap_dir=dmap_dir)
+            clouds.append(scene.cloud()); depths.append(ctx.get_depthmap(3)[0])
+            assert st["n_points"] == len(clouds[-1]["xyz"]) > 50_000
+        finally:
+            ctx.close()
+    # cameras of the loaded project differ from the in-memory ones by <= 1 ulp in K (normalise / scale-back of the project format):
+    # the two runs agree to that level
+    n0, n1 = len(clouds[0]["xyz"]), len(clouds[1]["xyz"])
+    assert abs(n0 - n1) <= 0.002 * n0
+    assert common.agreement(depths[0], depths[1], th=1e-4) >= 0.999
+    # outputs: raw depth-data files written BEFORE the filter (ExportDepthDataRaw), the PLY and the dense project
+    for i in range(syn.n_views):
+        if not ok[i]:
+            continue
+        back = host.read_dmap(str(tmp_path / f"depth{i:04d}.dmap"))
+        assert back["depth"].shape == imgs[i].shape[:2] and back["normal"] is not None and back["conf"] is not None
+        assert back["ids"][0] == i and (back["depth"] > 0).mean() > 0.5
+        valid = back["depth"] > 0
+        assert np.mean(np.abs(back["depth"][valid] / gt[i][0][valid] - 1) < 0.01) > 0.9
+    hs.save_ply(str(tmp_path / "scene_dense.ply"))
+    raw = open(tmp_path / "scene_dense.ply", "rb").read()
+    head, body = raw.split(b"end_header\n", 1)
+    assert b"element vertex %d\n" % n1 in head and b"property float32 nx" in head and len(body) == n1 * 27
+    hs.save_mvs(tmp_path / "scene_dense.mvs", dense=True)
+    dense = host.HostScene.load_mvs(tmp_path / "scene_dense.mvs", load_images=False)
+    xyz, off, ids, wts = dense.sparse()
+    assert len(xyz) == n1 and np.array_equal(xyz, clouds[1]["xyz"]) and np.array_equal(np.diff(off), clouds[1]["n_views"])
+    assert np.array_equal(wts, clouds[1]["weights"])
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "mvsi_ref_tool")
+    if os.path.exists(tool):  # the reference's own loader accepts what the GPU path wrote
+        import subprocess
+        assert subprocess.run([tool, "to-flat", str(tmp_path / "scene_dense.mvs"), str(tmp_path / "dense.flat")], capture_output=True, text=True, check=True).stdout.strip() == "5"
+    hs0.close(); hs.close(); dense.close()
