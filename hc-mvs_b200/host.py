@@ -44,6 +44,8 @@ def lib():
         L.hcmvs_host_scene_load_mvs.argtypes = [vp, C.c_char_p, i32]
         L.hcmvs_host_scene_save_mvs.argtypes = [vp, C.c_char_p, i32, i32]
         L.hcmvs_host_num_images.argtypes = [vp]
+        L.hcmvs_host_scene_reload_images.argtypes = [vp, C.c_uint, C.c_uint, C.c_uint]
+        L.hcmvs_host_resize_area_bgr.argtypes = [vp, i32, i32, i32, i32, vp]
         L.hcmvs_host_get_image_info.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_uint32), vp, vp, vp, C.c_char_p, i32]
         L.hcmvs_host_get_image_bgr.argtypes = [vp, i32, vp]
         L.hcmvs_host_get_sparse.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), vp, vp, vp, vp]
@@ -146,6 +148,12 @@ class HostScene:
         if self.L.hcmvs_host_scene_save_mvs(self.h, str(path).encode(), version, int(dense)) != 0:
             raise RuntimeError("SaveInterface: " + self.L.hcmvs_host_last_error(self.h).decode())
 
+    def reload_images(self, resolution_level, min_resolution=640, max_resolution=3200):
+        """--resolution-level of DensifyPointCloud: shrink the images (INTER_AREA) and update the cameras."""
+        if self.L.hcmvs_host_scene_reload_images(self.h, resolution_level, min_resolution, max_resolution) != 0:
+            raise RuntimeError("ReloadImages: " + self.L.hcmvs_host_last_error(self.h).decode())
+        self.sizes = [(im["height"], im["width"]) for im in (self.image_info(i) for i in range(self.num_images()))]
+
     def num_images(self):
         return self.L.hcmvs_host_num_images(self.h)
 
@@ -196,6 +204,15 @@ def load_image(path):
     out = np.empty((h.value, w.value, 3), np.uint8)
     if lib().hcmvs_host_load_image(str(path).encode(), C.byref(w), C.byref(h), _p(out)) != 0:
         raise RuntimeError(f"cannot decode {path}")
+    return out
+
+
+def resize_area_bgr(bgr, dsize):
+    """cv::resize(bgr, dsize, interpolation=INTER_AREA) as Image::ResizeImage applies it (shrinking, 8-bit BGR); dsize = (w, h)."""
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    out = np.empty((dsize[1], dsize[0], 3), np.uint8)
+    if lib().hcmvs_host_resize_area_bgr(_p(bgr), bgr.shape[1], bgr.shape[0], dsize[0], dsize[1], _p(out)) != 0:
+        raise ValueError("resize_area_bgr: only shrinking is supported")
     return out
 
 

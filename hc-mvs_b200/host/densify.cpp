@@ -155,6 +155,113 @@ bool ScaleImage(const std::vector<float>& src, int sw, int sh, float scale, std:
 	return true;
 }
 
+// cv::resize(src, dst, Size(dw, dh), 0, 0, INTER_AREA) on an 8-bit 3-channel image, shrinking (Image::ResizeImage, Image.cpp:139-160).
+// OpenCV imgproc/src/resize.cpp: integer scale factors take resizeAreaFast_ (int block sums; the 2x2 case rounds (sum+2)>>2 in
+// ResizeAreaFastVec, any other factor saturate_cast<uchar>(sum*(1.f/area)) = round-half-even), everything else resizeArea_ with the
+// DecimateAlpha tables, f32 accumulation and a round-half-even store. Cross-checked bit for bit with cv2 in the CPU tests.
+bool ResizeAreaBGR(const uint8_t* src, int sw, int sh, int dw, int dh, uint8_t* dst) {
+	if (!src || !dst || sw < 1 || sh < 1 || dw < 1 || dh < 1 || dw > sw || dh > sh) return false;
+	const int cn = 3;
+	const double scale_x = (double)sw/dw, scale_y = (double)sh/dh;
+	const int iscale_x = RoundHalfEven(scale_x), iscale_y = RoundHalfEven(scale_y);
+	auto sat = [](float v) { const int r = (int)std::nearbyintf(v); return (uint8_t)(r < 0 ? 0 : r > 255 ? 255 : r); };
+	if (std::abs(scale_x-iscale_x) < 2.220446049250313e-16 && std::abs(scale_y-iscale_y) < 2.220446049250313e-16) {
+		const int area = iscale_x*iscale_y;
+		const float scale = 1.f/(float)area;
+		const int dwidth1 = sw/iscale_x; // destination pixels whose whole block lies inside the source
+		const bool fast2 = iscale_x == 2 && iscale_y == 2;
+		for (int dy=0; dy<dh; ++dy) {
+			uint8_t* D = dst+(size_t)dy*dw*cn;
+			const int sy0 = dy*iscale_y;
+			const int w = sy0+iscale_y <= sh ? dwidth1 : 0;
+			if (sy0 >= sh) { memset(D, 0, (size_t)dw*cn); continue; }
+			for (int dx=0; dx<dw; ++dx) for (int c=0; c<cn; ++c) {
+				const int sx0 = dx*iscale_x;
+				if (dx < w) {
+					int sum = 0;
+					for (int y=0; y<iscale_y; ++y) for (int x=0; x<iscale_x; ++x) sum += src[((size_t)(sy0+y)*sw+sx0+x)*cn+c];
+					D[dx*cn+c] = fast2 ? (uint8_t)((sum+2)>>2) : sat((float)sum*scale);
+				} else { // partial block at the border: mean of the pixels that exist
+					int sum = 0, count = 0;
+					for (int y=0; y<iscale_y && sy0+y<sh; ++y) for (int x=0; x<iscale_x && sx0+x<sw; ++x) { sum += src[((size_t)(sy0+y)*sw+sx0+x)*cn+c]; ++count; }
+					D[dx*cn+c] = count ? sat((float)sum/count) : 0;
+				}
+			}
+		}
+		return true;
+	}
+	std::vector<DecimateAlpha> xtab, ytab;
+	AreaTab(sw, dw, scale_x, xtab); AreaTab(sh, dh, scale_y, ytab);
+	const int dwn = dw*cn;
+	std::vector<float> buf(dwn), sum(dwn, 0.f);
+	int prev_dy = ytab.empty() ? 0 : ytab[0].di;
+	for (size_t j=0; j<ytab.size(); ++j) { // ResizeArea_Invoker<uchar, float>
+		const float beta = ytab[j].alpha; const int dy = ytab[j].di, sy = ytab[j].si;
+		const uint8_t* S = src+(size_t)sy*sw*cn;
+		std::fill(buf.begin(), buf.end(), 0.f);
+		for (const DecimateAlpha& t: xtab) {
+			const float a = t.alpha; const uint8_t* sp = S+(size_t)t.si*cn; float* bp = &buf[(size_t)t.di*cn];
+			bp[0] += sp[0]*a; bp[1] += sp[1]*a; bp[2] += sp[2]*a;
+		}
+		if (dy != prev_dy) {
+			uint8_t* D = dst+(size_t)prev_dy*dwn;
+			for (int dx=0; dx<dwn; ++dx) { D[dx] = sat(sum[dx]); sum[dx] = beta*buf[dx]; }
+			prev_dy = dy;
+		} else for (int dx=0; dx<dwn; ++dx) sum[dx] += beta*buf[dx];
+	}
+	if (!ytab.empty()) { uint8_t* D = dst+(size_t)prev_dy*dwn; for (int dx=0; dx<dwn; ++dx) D[dx] = sat(sum[dx]); }
+	return true;
+}
+
+// TImage::computeMaxResolution, Common/Types.inl:2442-2460
+unsigned ComputeMaxResolution(unsigned width, unsigned height, unsigned& level, unsigned minImageSize, unsigned maxImageSize) {
+	const unsigned imageSize = std::max(width, height);
+	if (level == 0) return std::min(imageSize, maxImageSize);
+	unsigned size = imageSize>>level;
+	if (size < minImageSize) {
+		level = 0;
+		while ((imageSize>>(level+1)) >= minImageSize) ++level;
+		size = imageSize>>level;
+	}
+	return std::min(size, maxImageSize);
+}
+
+bool Scene::ReloadImages(unsigned nResolutionLevel, unsigned nMinResolution, unsigned nMaxResolution, std::string* err) {
+	// Scene::ComputeDepthMaps, SceneDensify.cpp:3617-3631: RecomputeMaxResolution + ReloadImage + UpdateCamera per valid image
+	for (Image& im: images) {
+		if (!im.calibrated) continue;
+		unsigned level = nResolutionLevel; // the reference passes OPTDENSE::nResolutionLevel by reference: a lowered level sticks
+		const unsigned nMax = ComputeMaxResolution((unsigned)im.width, (unsigned)im.height, level, nMinResolution, nMaxResolution);
+		nResolutionLevel = level;
+		// Image::ResizeImage, Image.cpp:139-160 (integer arithmetic on the unsigned sizes)
+		unsigned w = (unsigned)im.width, h = (unsigned)im.height;
+		if (nMax == 0 || std::max(w, h) <= nMax) continue;
+		if (w > h) { h = h*nMax/w; w = nMax; } else { w = w*nMax/h; h = nMax; }
+		if (w < 1 || h < 1) { if (err) *err = "image '"+im.name+"' vanishes at this resolution level"; return false; }
+		if (!im.bgr.empty()) {
+			std::vector<uint8_t> scaled((size_t)w*h*3);
+			if (!ResizeAreaBGR(im.bgr.data(), im.width, im.height, (int)w, (int)h, scaled.data())) { if (err) *err = "cannot resize '"+im.name+"'"; return false; }
+			im.bgr.swap(scaled);
+			im.gray.resize((size_t)w*h);
+			ToGray(im.bgr.data(), (int)w, (int)h, im.gray.data());
+		} else if (!im.gray.empty()) { if (err) *err = "image '"+im.name+"' has gray pixels only: reload needs the colour image"; return false; }
+		// Image::UpdateCamera: K of the new resolution from the normalised intrinsics (Image.cpp:194-213, Camera.h:167-180)
+		if (im.hasKnorm) {
+			const float fScale = (float)std::max(w, h);
+			im.camera.K[0] = im.Knorm[0]*fScale; im.camera.K[4] = im.Knorm[1]*fScale;
+			if (im.Knorm[2] == 0 && im.Knorm[3] == 0) { im.camera.K[2] = 0.5*(w-1); im.camera.K[5] = 0.5*(h-1); }
+			else { im.camera.K[2] = im.Knorm[2]*fScale; im.camera.K[5] = im.Knorm[3]*fScale; }
+		} else {
+			double Kn[9]; ScaleK(im.camera.K, im.width, im.height, (int)w, (int)h, Kn);
+			memcpy(im.camera.K, Kn, sizeof(Kn));
+		}
+		im.width = (int)w; im.height = (int)h;
+		im.camera.ComposeP();
+		im.neighbors.clear();
+	}
+	return true;
+}
+
 void ScaleK(const double K[9], int w, int h, int newW, int newH, double Kout[9]) {
 	const double s = (double)(float)std::max(newW, newH)/(double)(float)std::max(w, h);
 	for (int i=0; i<9; ++i) Kout[i] = K[i];

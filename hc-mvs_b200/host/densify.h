@@ -37,6 +37,8 @@ struct Image {
 	float avgDepth = 0;
 	uint32_t ID = 0xFFFFFFFFu;   // global image ID of the project file (NO_ID: the index)
 	bool calibrated = true;      // Image::IsValid(): poseID != NO_ID (libs/MVS/Image.h)
+	double Knorm[4] = {0, 0, 0, 0}; // fx, fy, cx, cy normalised by max(width, height) as the project stores them (Platform::Camera::K)
+	bool hasKnorm = false;          // set by LoadInterface; lets a resolution change rebuild K exactly as Image::UpdateCamera does
 };
 
 struct SparsePoints { // the part of MVS::PointCloud the densifier reads
@@ -80,6 +82,9 @@ struct Scene {
 	// cloud as the project's vertices (what DensifyPointCloud's scene_dense.mvs holds) instead of the sparse points.
 	bool LoadInterface(const std::string& fileName, bool bLoadImages = true, std::string* err = nullptr);
 	bool SaveInterface(const std::string& fileName, int version = -1, bool bDense = false) const;
+	// --resolution-level / --min-resolution / --max-resolution (Scene::ComputeDepthMaps, SceneDensify.cpp:3617-3631): every calibrated
+	// image is shrunk to max(w,h) >> level (Image::ResizeImage: cv::resize INTER_AREA on the 8-bit colour image) and its camera updated
+	bool ReloadImages(unsigned nResolutionLevel, unsigned nMinResolution = 640, unsigned nMaxResolution = 3200, std::string* err = nullptr);
 	// Scene::SelectNeighborViews / FilterNeighborViews, libs/MVS/Scene.cpp:545-678
 	bool SelectNeighborViews(uint32_t ID, std::vector<uint32_t>& points, unsigned nMinViews, unsigned nMinPointViews, float fOptimAngle);
 	static bool FilterNeighborViews(std::vector<ViewScore>& neighbors, float fMinArea, float fMinScale, float fMaxScale, float fMinAngle, float fMaxAngle, unsigned nMaxViews);
@@ -99,6 +104,10 @@ struct ViewSelectionParams { // OPTDENSE fields SelectViews reads, DepthMap.cpp:
 };
 
 void ToGray(const uint8_t* bgr, int w, int h, float* gray);
+// cv::resize(.., Size(dw, dh), 0, 0, INTER_AREA) on an 8-bit BGR image, shrinking only (Image::ResizeImage, Image.cpp:139-160)
+bool ResizeAreaBGR(const uint8_t* src, int sw, int sh, int dw, int dh, uint8_t* dst);
+// TImage::computeMaxResolution, Common/Types.inl:2442-2460
+unsigned ComputeMaxResolution(unsigned width, unsigned height, unsigned& level, unsigned minImageSize, unsigned maxImageSize);
 // DepthData::ViewData::ScaleImage (DepthMap.h:232-238): cv::resize(image, scaled, Size(), scale, scale, scale > 1 ? INTER_CUBIC : INTER_AREA)
 // on the f32 gray image, restated from OpenCV's scalar code paths (imgproc/src/resize.cpp; cross-checked with cv2 in the CPU tests).
 // Returns false (and leaves dst alone) when |scale-1| < 0.15, like the reference.

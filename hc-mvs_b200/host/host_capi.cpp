@@ -156,6 +156,12 @@ int hcmvs_host_scene_save_mvs(hcmvs_host_scene* s, const char* file, int version
 	if (!s->scene.SaveInterface(file, version, dense != 0)) { s->err = std::string("cannot write '")+file+"'"; return -1; }
 	return 0;
 }
+int hcmvs_host_scene_reload_images(hcmvs_host_scene* s, unsigned resolution_level, unsigned min_resolution, unsigned max_resolution) {
+	if (!s) return -1;
+	s->dd.clear();
+	return s->scene.ReloadImages(resolution_level, min_resolution, max_resolution, &s->err) ? 0 : -1;
+}
+int hcmvs_host_resize_area_bgr(const uint8_t* src, int sw, int sh, int dw, int dh, uint8_t* dst) { return ResizeAreaBGR(src, sw, sh, dw, dh, dst) ? 0 : -1; }
 int hcmvs_host_num_images(hcmvs_host_scene* s) { return s ? (int)s->scene.images.size() : -1; }
 int hcmvs_host_get_image_info(hcmvs_host_scene* s, int idx, int* w, int* h, int* calibrated, uint32_t* id, double K[9], double R[9], double C[3], char* name, int name_cap) {
 	if (!s || idx < 0 || idx >= (int)s->scene.images.size()) return -1;

@@ -144,7 +144,7 @@ bool SaveMVSI(const std::string& fileName, const MvsiData& obj, uint32_t version
 }
 
 // ------------------------------------------------------------------------------------------------ cameras
-bool ComposeImageCamera(const MvsiData& obj, uint32_t idxImage, uint32_t w, uint32_t h, double K[9], double R[9], double C[3]) {
+bool ComposeImageCamera(const MvsiData& obj, uint32_t idxImage, uint32_t w, uint32_t h, double K[9], double R[9], double C[3], double Knorm[4]) {
 	if (idxImage >= obj.images.size() || !w || !h) return false;
 	const MvsiImage& im = obj.images[idxImage];
 	if (im.poseID == 0xFFFFFFFFu || im.platformID >= obj.platforms.size()) return false;
@@ -158,6 +158,7 @@ bool ComposeImageCamera(const MvsiData& obj, uint32_t idxImage, uint32_t w, uint
 		const double scale = 1.0/(double)(float)std::max(cam.width, cam.height); // REAL(1)/GetNormalizationScale() (a float, Camera.h:105-108)
 		Kn[0] *= scale; Kn[4] *= scale; Kn[2] *= scale; Kn[5] *= scale;
 	}
+	if (Knorm) { Knorm[0] = Kn[0]; Knorm[1] = Kn[4]; Knorm[2] = Kn[2]; Knorm[3] = Kn[5]; }
 	// Platform::GetCamera, Platform.cpp:44-54: R = camera.R*pose.R; C = pose.R^T*camera.C + pose.C (cv::Matx products, k ascending)
 	for (int i=0; i<3; ++i) for (int j=0; j<3; ++j) {
 		double s = 0; for (int k=0; k<3; ++k) s += cam.R[i*3+k]*pose.R[k*3+j];
@@ -365,8 +366,9 @@ bool Scene::LoadInterface(const std::string& fileName, bool bLoadImages, std::st
 			ToGray(im.bgr.data(), w, h, im.gray.data());
 		}
 		im.width = w; im.height = h;
-		if (!ComposeImageCamera(obj, (uint32_t)i, (uint32_t)w, (uint32_t)h, im.camera.K, im.camera.R, im.camera.C)) return fail("bad camera of image '"+src.name+"'");
+		if (!ComposeImageCamera(obj, (uint32_t)i, (uint32_t)w, (uint32_t)h, im.camera.K, im.camera.R, im.camera.C, im.Knorm)) return fail("bad camera of image '"+src.name+"'");
 		im.camera.ComposeP();
+		im.hasKnorm = true;
 		im.calibrated = true;
 		++nCalibrated;
 	}

@@ -51,7 +51,7 @@ bool SaveMVSI(const std::string& fileName, const MvsiData& obj, uint32_t version
 
 // absolute, un-normalised camera of an image at resolution w x h, exactly as Scene::LoadInterface + Image::UpdateCamera build it
 // (K normalisation Scene.cpp:80-88, pose composition Platform.cpp:44-54, CameraIntern::GetK Camera.h:167-180)
-bool ComposeImageCamera(const MvsiData& obj, uint32_t idxImage, uint32_t w, uint32_t h, double K[9], double R[9], double C[3]);
+bool ComposeImageCamera(const MvsiData& obj, uint32_t idxImage, uint32_t w, uint32_t h, double K[9], double R[9], double C[3], double Knorm[4] = nullptr);
 
 // 8-bit image files -> BGR. BMP (24/32-bit BI_RGB), PNG (8-bit gray / RGB / RGBA / palette, non-interlaced; zlib) and binary
 // PPM/PGM. JPG/TIFF/DDS/TGA/SCI (libs/IO) are out of scope: a clear error, never a silent fallback.

@@ -47,6 +47,12 @@ int hcmvs_host_read_dmap(const char* file, uint32_t* ids, double K[9], double R[
  * the sparse points. version < 0: MVSI_PROJECT_VER (5). */
 int hcmvs_host_scene_load_mvs(hcmvs_host_scene* s, const char* file, int load_images);
 int hcmvs_host_scene_save_mvs(hcmvs_host_scene* s, const char* file, int version, int dense);
+/* --resolution-level / --min-resolution / --max-resolution of DensifyPointCloud (Scene::ComputeDepthMaps, SceneDensify.cpp:3617-3631):
+ * shrink every calibrated image to max(w,h) >> level (Image::ResizeImage, cv::resize INTER_AREA on the 8-bit colour image) and update
+ * its camera (Image::UpdateCamera). */
+int hcmvs_host_scene_reload_images(hcmvs_host_scene* s, unsigned resolution_level, unsigned min_resolution, unsigned max_resolution);
+/* the resize itself: cv::resize(src, dst, Size(dw, dh), 0, 0, INTER_AREA), 8-bit BGR, dw <= sw and dh <= sh */
+int hcmvs_host_resize_area_bgr(const uint8_t* src, int sw, int sh, int dw, int dh, uint8_t* dst);
 int hcmvs_host_num_images(hcmvs_host_scene* s);
 int hcmvs_host_get_image_info(hcmvs_host_scene* s, int idx, int* w, int* h, int* calibrated, uint32_t* id, double K[9], double R[9], double C[3], char* name, int name_cap);
 int hcmvs_host_get_image_bgr(hcmvs_host_scene* s, int idx, uint8_t* bgr);

@@ -236,3 +236,52 @@ def test_image_decoders_reject_what_they_cannot_read(built, tmp_path):
         host.load_image(tmp_path / "x.jpg")
     with pytest.raises(RuntimeError):
         host.HostScene.load_mvs(tmp_path / "missing.mvs")
+
+
+def test_resize_area_bgr_matches_opencv(built):
+    """Image::ResizeImage = cv::resize(INTER_AREA) on the 8-bit colour image: the host restatement is bit-equal to cv2 for the
+    2x2 fast path ((sum+2)>>2), other integer factors (round-half-even of sum/area) and the general DecimateAlpha path."""
+    cv2 = pytest.importorskip("cv2")
+    from hcmvs_b200 import host
+    rng = np.random.default_rng(0)
+    for sw, sh, dw, dh in [(320, 240, 160, 120), (320, 240, 80, 60), (321, 241, 160, 120), (200, 140, 67, 47), (384, 216, 48, 27),
+                           (33, 17, 16, 8), (320, 240, 213, 160), (64, 48, 64, 48)]:
+        for img in (rng.integers(0, 256, (sh, sw, 3)).astype(np.uint8), cv2.GaussianBlur(rng.integers(0, 256, (sh, sw, 3)).astype(np.uint8), (0, 0), 2.0)):
+            assert np.array_equal(host.resize_area_bgr(img, (dw, dh)), cv2.resize(img, (dw, dh), interpolation=cv2.INTER_AREA)), (sw, sh, dw, dh)
+    with pytest.raises(ValueError):
+        host.resize_area_bgr(np.zeros((10, 10, 3), np.uint8), (20, 20))
+
+
+@needs_ref
+def test_resolution_level_reload(built, tmp_path):
+    """--resolution-level: Scene::ComputeDepthMaps reloads every image at max(w,h) >> level (computeMaxResolution, ResizeImage) and
+    rebuilds its camera from the normalised intrinsics (UpdateCamera)."""
+    cv2 = pytest.importorskip("cv2")
+    from hcmvs_b200 import host
+    rng = np.random.default_rng(5)
+    w, h = 322, 241                      # odd sizes: the integer size arithmetic and the general area path
+    sc = make_scene(rng, n_img=3, image_size=(w, h))
+    sc["images"] = sc["images"][:-1]
+    (tmp_path / "images").mkdir()
+    imgs = []
+    for im in sc["images"]:
+        px = cv2.GaussianBlur(rng.integers(0, 256, (h, w, 3)).astype(np.uint8), (0, 0), 1.0)
+        imgs.append(px)
+        assert cv2.imwrite(str(tmp_path / im["name"].decode()), px)
+    (tmp_path / "flat.bin").write_bytes(pack_flat(sc))
+    tool("from-flat", tmp_path / "flat.bin", tmp_path / "scene.mvs", 5)
+    for level, min_res, want_max in ((1, 100, 161), (2, 50, 80), (3, 100, 161), (0, 100, 322)):
+        # level 3: 322 >> 3 = 40 < min 100 -> the level is lowered until the size is >= min: 322 >> 1 = 161
+        hs = host.HostScene.load_mvs(tmp_path / "scene.mvs")
+        hs.reload_images(level, min_res, 3200)
+        for i, im in enumerate(sc["images"]):
+            info = hs.image_info(i)
+            nh = h * want_max // w if want_max < w else h
+            assert (info["width"], info["height"]) == (want_max, nh)
+            want_px = imgs[i] if want_max == w else cv2.resize(imgs[i], (want_max, nh), interpolation=cv2.INTER_AREA)
+            assert np.array_equal(hs.image_bgr(i), want_px)
+            cam = sc["platforms"][0]["cameras"][im["camera"]]
+            Kn = cam["K"] * (1.0 / float(np.float32(max(w, h))))             # Scene.cpp:80-88
+            Kw = Kn * float(np.float32(max(want_max, nh)))                   # Camera.h:167-180
+            assert np.array_equal(info["K"][[0, 2, 4, 5]], Kw.ravel()[[0, 2, 4, 5]])
+        hs.close()
