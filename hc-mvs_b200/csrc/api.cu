@@ -359,6 +359,57 @@ extern "C" int hcmvs_init_depthmap(hcmvs_ctx* ctx, uint32_t ref, const float* de
 	return FinishUpload(ctx, v);
 }
 
+extern "C" int hcmvs_init_depthmap_triangles(hcmvs_ctx* ctx, uint32_t ref, const double* vertices, int n_vertices, const uint32_t* tris, int n_tris, float dMin, float dMax) {
+	// InitDepthMap -> TriangulatePoints2DepthMap (SceneDensify.cpp:514-525, DepthMap.cpp:1879-1936); the caller applied dMin*0.9 / dMax*1.1
+	View* v = GetView(ctx, ref, true); if (!v) return HCMVS_ERR_ARG;
+	if (!vertices || !tris || n_vertices < 3 || n_tris < 1 || !(dMin > 0.f) || !(dMin < dMax)) { hcmvs_set_error("bad triangulation (%d vertices, %d triangles) or depth range [%g,%g)", n_vertices, n_tris, dMin, dMax); return HCMVS_ERR_ARG; }
+	cudaSetDevice(ctx->device);
+	const size_t n = (size_t)v->w*v->h;
+	// chunk list: the 32x8-pixel tiles of every triangle's bounding box (same fixed-point snapping as the kernel), clipped to the image
+	std::vector<int3> chunks;
+	for (int t=0; t<n_tris; ++t) {
+		long long X[3], Y[3];
+		for (int k=0; k<3; ++k) {
+			const uint32_t vi = tris[(size_t)t*3+k];
+			if (vi >= (uint32_t)n_vertices) { hcmvs_set_error("triangle %d refers to vertex %u of %d", t, vi, n_vertices); return HCMVS_ERR_ARG; }
+			const float fx = (float)vertices[(size_t)vi*3], fy = (float)vertices[(size_t)vi*3+1];
+			if (!(std::fabs(fx) < 1e7f) || !(std::fabs(fy) < 1e7f)) { hcmvs_set_error("vertex %u is not finite", vi); return HCMVS_ERR_ARG; }
+			X[k] = (long long)std::floor(16.f*fx+0.5f); Y[k] = (long long)std::floor(16.f*fy+0.5f);
+		}
+		const int minx = std::max((int)((std::min(X[0], std::min(X[1], X[2]))+0xF)>>4), 0), maxx = std::min((int)((std::max(X[0], std::max(X[1], X[2]))+0xF)>>4), v->w);
+		const int miny = std::max((int)((std::min(Y[0], std::min(Y[1], Y[2]))+0xF)>>4), 0), maxy = std::min((int)((std::max(Y[0], std::max(Y[1], Y[2]))+0xF)>>4), v->h);
+		for (int y=miny; y<maxy; y+=8) for (int x=minx; x<maxx; x+=32) chunks.push_back(make_int3(t, x, y));
+	}
+	cudaStream_t cs = ctx->copyStream;
+	if (v->dn_d) { cudaEvent_t done; CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming)); CK(cudaEventRecord(done, ctx->stream)); CK(cudaStreamWaitEvent(cs, done, 0)); CK(cudaEventDestroy(done)); }
+	if (!v->dn_d) CK(cudaMalloc(&v->dn_d, n*sizeof(float4)));
+	if (!v->conf_d) CK(cudaMalloc(&v->conf_d, n*4));
+	const size_t bV = ((size_t)n_vertices*24+255)&~(size_t)255, bT = ((size_t)n_tris*12+255)&~(size_t)255, bC = (chunks.size()*sizeof(int3)+255)&~(size_t)255, need = bV+bT+bC+n*4;
+	if (ctx->uploadBytes < need) {
+		CK(cudaStreamSynchronize(cs));
+		cudaFree(ctx->upload_d); ctx->upload_d = nullptr; ctx->uploadBytes = 0;
+		CK(cudaMalloc(&ctx->upload_d, need)); ctx->uploadBytes = need;
+	}
+	char* base = (char*)ctx->upload_d;
+	CK(cudaMemcpyAsync(base, vertices, (size_t)n_vertices*24, cudaMemcpyHostToDevice, cs));
+	CK(cudaMemcpyAsync(base+bV, tris, (size_t)n_tris*12, cudaMemcpyHostToDevice, cs));
+	if (!chunks.empty()) CK(cudaMemcpyAsync(base+bV+bT, chunks.data(), chunks.size()*sizeof(int3), cudaMemcpyHostToDevice, cs));
+	// pixels no triangle covers (or whose depth comes out <= 0) are uninitialised memory in the reference when bAddCorners is set
+	// (DepthMap.cpp:1895-1898); here they are 0 = "unknown", which PASS A replaces by a random hypothesis
+	CK(cudaMemsetAsync(v->dn_d, 0, n*sizeof(float4), cs));
+	CK(cudaMemsetAsync(v->conf_d, 0, n*4, cs));
+	CK(cudaMemsetAsync(base+bV+bT+bC, 0xFF, n*4, cs));
+	CK(hcmvs_launch_raster_triangles((const double*)base, (const uint32_t*)(base+bV), (const int3*)(base+bV+bT), (int)chunks.size(), v->K, v->dn_d, (int*)(base+bV+bT+bC), v->w, v->h, cs)); ctx->nLaunches += 2;
+	v->dMin = dMin; v->dMax = dMax; v->hasMaps = true;
+	if (!v->gra_d) CK(cudaMalloc(&v->gra_d, n));
+	if (!v->graValid) {
+		if (v->bgr_d) { CK(hcmvs_launch_gramap(v->bgr_d, v->gra_d, v->w, v->h, cs)); ++ctx->nLaunches; }
+		else CK(cudaMemsetAsync(v->gra_d, 0, n, cs));
+		v->graValid = true;
+	}
+	return FinishUpload(ctx, v);
+}
+
 extern "C" int hcmvs_set_depthmap(hcmvs_ctx* ctx, uint32_t view, const float* depth, const float* normal, const float* conf, float dMin, float dMax) {
 	View* v = GetView(ctx, view, true); if (!v) return HCMVS_ERR_ARG;
 	if (!depth) { hcmvs_set_error("null depth"); return HCMVS_ERR_ARG; }

@@ -80,4 +80,6 @@ cudaError_t hcmvs_launch_gramap(const uint8_t* bgr, uint8_t* gra, int w, int h, 
 cudaError_t hcmvs_launch_pack(const float* depth, const float* normal, float4* dn, size_t n, cudaStream_t st);
 cudaError_t hcmvs_launch_resize_area_up(const float* depth, const float* normal, int sw, int sh, float4* dst, int dw, int dh, cudaStream_t st);
 cudaError_t hcmvs_launch_minmax_w(const float4* dn, size_t n, float* minmax_d, cudaStream_t st);
+// init_tri.cu
+cudaError_t hcmvs_launch_raster_triangles(const double* vtx_d, const uint32_t* tris_d, const int3* chunks_d, int nChunks, const double K[9], float4* dn, int* owner_d, int w, int h, cudaStream_t st);
 cudaError_t hcmvs_launch_unpack(const float4* dn, float* depth, float* normal, size_t n, cudaStream_t st);

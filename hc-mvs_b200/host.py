@@ -44,6 +44,8 @@ def lib():
         L.hcmvs_host_scene_load_mvs.argtypes = [vp, C.c_char_p, i32]
         L.hcmvs_host_scene_save_mvs.argtypes = [vp, C.c_char_p, i32, i32]
         L.hcmvs_host_num_images.argtypes = [vp]
+        L.hcmvs_host_delaunay.argtypes = [vp, i32, vp, i32]
+        L.hcmvs_host_triangulate_init.argtypes = [vp, i32, i32, vp, i32, vp, i32, C.POINTER(i32), C.POINTER(i32), vp]
         L.hcmvs_host_scene_reload_images.argtypes = [vp, C.c_uint, C.c_uint, C.c_uint]
         L.hcmvs_host_resize_area_bgr.argtypes = [vp, i32, i32, i32, i32, vp]
         L.hcmvs_host_get_image_info.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_uint32), vp, vp, vp, C.c_char_p, i32]
@@ -106,6 +108,15 @@ class HostScene:
         if self.L.hcmvs_host_init_depth(self.h, idx, _p(d), _p(mm)) != 0:
             raise RuntimeError("view not selected")
         return d, float(mm[0]), float(mm[1])
+
+    def triangulate_init(self, idx, add_corners=True):
+        """TriangulatePointsDelaunay of a selected view -> (vertices (n,3) f64, tris (m,3) u32, dMin, dMax) (raw bounds)."""
+        nv, nt = C.c_int(), C.c_int()
+        if self.L.hcmvs_host_triangulate_init(self.h, idx, int(add_corners), None, 0, None, 0, C.byref(nv), C.byref(nt), None) != 0:
+            raise RuntimeError("triangulate_init failed")
+        v = np.empty((nv.value, 3), np.float64); t = np.empty((nt.value, 3), np.uint32); mm = np.zeros(2, np.float32)
+        self.L.hcmvs_host_triangulate_init(self.h, idx, int(add_corners), _p(v), nv.value, _p(t), nt.value, None, None, _p(mm))
+        return v, t, float(mm[0]), float(mm[1])
 
     def gray(self, idx):
         h, w = self.sizes[idx]
@@ -205,6 +216,17 @@ def load_image(path):
     if lib().hcmvs_host_load_image(str(path).encode(), C.byref(w), C.byref(h), _p(out)) != 0:
         raise RuntimeError(f"cannot decode {path}")
     return out
+
+
+def delaunay(xy):
+    """Delaunay triangulation of (n, 2) f64 points -> (m, 3) u32 faces (counter-clockwise, smallest index first, sorted)."""
+    xy = np.ascontiguousarray(xy, np.float64)
+    m = lib().hcmvs_host_delaunay(_p(xy), len(xy), None, 0)
+    if m < 0:
+        raise ValueError("degenerate point set")
+    t = np.empty((m, 3), np.uint32)
+    lib().hcmvs_host_delaunay(_p(xy), len(xy), _p(t), m)
+    return t
 
 
 def resize_area_bgr(bgr, dsize):

@@ -40,7 +40,7 @@ static inline void ProjectPointP(const Camera& cam, const float* X, float& u, fl
 	const float qx = (float)(p[0]*X[0] + p[1]*X[1] + p[2]*X[2] + p[3]);
 	const float qy = (float)(p[4]*X[0] + p[5]*X[1] + p[6]*X[2] + p[7]);
 	const float qz = (float)(p[8]*X[0] + p[9]*X[1] + p[10]*X[2] + p[11]);
-	const float invZ = qz == 0.f ? FLT_MAX : 1.f/qz; // INVERT, Common/Types.h:1216-1219
+	const float invZ = qz == 0.f ? 1000000.f : 1.f/qz; // INVERT -> INVZERO(float) = FINV_ZERO, Common/Types.h:573, 1213-1219
 	u = qx*invZ; v = qy*invZ;
 }
 
@@ -450,6 +450,14 @@ void SparseInitDepth(const Scene& scene, uint32_t idxImage, const std::vector<ui
 
 bool DepthMapsData::InitDepthMap(uint32_t idxImage) {
 	DepthData& dd = arrDepthData[idxImage];
+	if (P.nMinViewsTrustPoint >= 2) {
+		// DepthMapsData::InitDepthMap, SceneDensify.cpp:514-525 (initTriangulate; bAddCorners is the reference's default)
+		std::vector<double> vertices; std::vector<uint32_t> tris;
+		if (!TriangulateInit(scene, idxImage, dd.points, true, vertices, tris, dd.dMin, dd.dMax)) { lastError = "cannot triangulate the sparse points of the view"; return false; }
+		dd.dMin *= 0.9f; dd.dMax *= 1.1f;
+		if (hcmvs_init_depthmap_triangles(ctx, idxImage, vertices.data(), (int)(vertices.size()/3), tris.data(), (int)(tris.size()/3), dd.dMin, dd.dMax) != HCMVS_OK) return Fail("hcmvs_init_depthmap_triangles");
+		return true;
+	}
 	std::vector<float> depth;
 	SparseInitDepth(scene, idxImage, dd.points, depth, dd.dMin, dd.dMax);
 	if (hcmvs_init_depthmap(ctx, idxImage, depth.data(), nullptr, dd.dMin, dd.dMax) != HCMVS_OK) return Fail("hcmvs_init_depthmap");
@@ -593,7 +601,8 @@ bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, co
 	// writes image i's state) and splat the sparse points into the initial depth map (:783-808), in image order, while this
 	// thread uploads the images and then feeds the GPU: view i is estimated as soon as ITS selection is done, so the host work
 	// of the later views hides behind the kernels of the earlier ones. All hcmvs_* calls stay on this thread.
-	struct Prepared { std::vector<float> depth; float dMin = 0, dMax = 0; };
+	struct Prepared { std::vector<float> depth; std::vector<double> vertices; std::vector<uint32_t> tris; float dMin = 0, dMax = 0; bool ok = true; };
+	const bool triangulate = P.nMinViewsTrustPoint >= 2; // the reference's default initialisation (SceneDensify.cpp:781-812)
 	std::vector<Prepared> prep(nImages);
 	std::vector<std::atomic<int>> state(nImages); // 0 pending, 1 selected + initial depth ready, -1 rejected
 	for (auto& s: state) s.store(0);
@@ -607,7 +616,10 @@ bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, co
 		while ((i = next.fetch_add(1)) < nImages) {
 			while (i >= consumed.load(std::memory_order_acquire)+lookahead) std::this_thread::yield();
 			const bool ok = data.SelectViews(i);
-			if (ok) SparseInitDepth(scene, i, data.arrDepthData[i].points, prep[i].depth, prep[i].dMin, prep[i].dMax);
+			if (ok && triangulate) {
+				prep[i].ok = TriangulateInit(scene, i, data.arrDepthData[i].points, true, prep[i].vertices, prep[i].tris, prep[i].dMin, prep[i].dMax);
+				prep[i].dMin *= 0.9f; prep[i].dMax *= 1.1f;
+			} else if (ok) SparseInitDepth(scene, i, data.arrDepthData[i].points, prep[i].depth, prep[i].dMin, prep[i].dMax);
 			tSelectEnd.store(Now());
 			state[i].store(ok ? 1 : -1, std::memory_order_release);
 		}
@@ -625,12 +637,19 @@ bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, co
 			if (!data.InitViews(i, P.nNumViews)) { if (!data.lastError.empty()) return fail(data.lastError); dd.valid = false; }
 			else {
 				dd.dMin = prep[i].dMin; dd.dMax = prep[i].dMax;
-				if (hcmvs_init_depthmap(ctx, i, prep[i].depth.data(), nullptr, dd.dMin, dd.dMax) != HCMVS_OK) return fail(std::string("hcmvs_init_depthmap: ")+hcmvs_last_error());
-				st.h2dBytes += (uint64_t)scene.images[i].width*scene.images[i].height*4;
+				if (triangulate) {
+					if (!prep[i].ok) return fail("cannot triangulate the sparse points of a view");
+					if (hcmvs_init_depthmap_triangles(ctx, i, prep[i].vertices.data(), (int)(prep[i].vertices.size()/3), prep[i].tris.data(), (int)(prep[i].tris.size()/3), dd.dMin, dd.dMax) != HCMVS_OK)
+						return fail(std::string("hcmvs_init_depthmap_triangles: ")+hcmvs_last_error());
+					st.h2dBytes += (uint64_t)prep[i].vertices.size()*8+(uint64_t)prep[i].tris.size()*4;
+				} else {
+					if (hcmvs_init_depthmap(ctx, i, prep[i].depth.data(), nullptr, dd.dMin, dd.dMax) != HCMVS_OK) return fail(std::string("hcmvs_init_depthmap: ")+hcmvs_last_error());
+					st.h2dBytes += (uint64_t)scene.images[i].width*scene.images[i].height*4;
+				}
 				if (hcmvs_estimate_depthmap(ctx, i, 0, seed) != HCMVS_OK) return fail(std::string("hcmvs_estimate_depthmap: ")+hcmvs_last_error());
 			}
 		}
-		std::vector<float>().swap(prep[i].depth);
+		std::vector<float>().swap(prep[i].depth); std::vector<double>().swap(prep[i].vertices); std::vector<uint32_t>().swap(prep[i].tris);
 		consumed.store(i+1, std::memory_order_release);
 	}
 	for (uint32_t i=0; i<nImages; ++i) {

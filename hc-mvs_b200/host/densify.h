@@ -118,12 +118,23 @@ void ScaleK(const double K[9], int w, int h, int newW, int newH, double Kout[9])
 // sparse-point initialisation of a depth map (SceneDensify.cpp:783-808)
 void SparseInitDepth(const Scene& scene, uint32_t idxImage, const std::vector<uint32_t>& points, std::vector<float>& depth, float& dMin, float& dMax);
 
+// Delaunay triangulation of 2-D points (xy: 2 per point) — what CGAL::Delaunay_triangulation_2 gives the reference (DepthMap.cpp:1785-1808);
+// tris: 3 indices per finite face, counter-clockwise, smallest index first, sorted; adjacency (optional): face across the edge
+// opposite each vertex slot, -1 on the hull. Duplicate points are skipped like CGAL's insert().
+bool DelaunayTriangulate(const std::vector<double>& xy, std::vector<uint32_t>& tris, std::vector<int>* adjacency = nullptr);
+// TriangulatePointsDelaunay (DepthMap.cpp:1797-1876): vertices = (x, y, depth) of the view's sparse points (+ the 4 image corners with
+// their interpolated depths when bAddCorners), tris as above, raw depth bounds of the points
+bool TriangulateInit(const Scene& scene, uint32_t idxImage, const std::vector<uint32_t>& points, bool bAddCorners,
+	std::vector<double>& vertices, std::vector<uint32_t>& tris, float& dMin, float& dMax);
+
 class DepthMapsData {
 public:
 	DepthMapsData(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& params, const ViewSelectionParams& vs = ViewSelectionParams());
 	bool SelectViews(uint32_t idxImage);                                   // SceneDensify.cpp:307-327
 	bool InitViews(uint32_t idxImage, uint32_t numNeighbors);              // SceneDensify.cpp:336-397
-	bool InitDepthMap(uint32_t idxImage);                                  // SceneDensify.cpp:772-808 (sparse-point splat branch)
+	// SceneDensify.cpp:772-812: nMinViewsTrustPoint < 2 -> sparse points splatted on the host; else (the reference's default) the
+	// triangulated sparse cloud (InitDepthMap :514-525 -> TriangulatePoints2DepthMap), triangulated here and rasterised on the device
+	bool InitDepthMap(uint32_t idxImage);
 	bool EstimateDepthMap(int it_external, uint32_t idxImage, uint64_t seed); // SceneDensify.cpp:758-1072
 	bool FilterDepthMap(uint32_t idxImage, const std::vector<uint32_t>& idxNeighbors, bool bAdjust); // SceneDensify.cpp:3006-3259
 	bool FuseDepthMaps(PointCloud& pointcloud, bool bEstimateColor, bool bEstimateNormal);           // SceneDensify.cpp:3265-3495

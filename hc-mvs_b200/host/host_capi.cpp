@@ -145,6 +145,27 @@ int hcmvs_host_read_dmap(const char* file, uint32_t* ids, double K[9], double R[
 	return 0;
 }
 
+// ---- triangulated initialisation (triangulate.cpp)
+int hcmvs_host_delaunay(const double* xy, int n, uint32_t* tris, int cap_tris) {
+	if (!xy || n < 3) return -1;
+	std::vector<double> pts(xy, xy+(size_t)n*2); std::vector<uint32_t> t;
+	if (!DelaunayTriangulate(pts, t)) return -1;
+	const int m = (int)(t.size()/3);
+	if (tris) memcpy(tris, t.data(), (size_t)std::min(m, cap_tris)*12);
+	return m;
+}
+int hcmvs_host_triangulate_init(hcmvs_host_scene* s, int idx, int add_corners, double* vertices, int cap_vertices, uint32_t* tris, int cap_tris, int* n_vertices, int* n_tris, float* dminmax) {
+	if (!s || idx < 0 || idx >= (int)s->dd.size() || !s->dd[idx].valid) return -1;
+	std::vector<double> v; std::vector<uint32_t> t; float a, b;
+	if (!TriangulateInit(s->scene, (uint32_t)idx, s->dd[idx].points, add_corners != 0, v, t, a, b)) return -1;
+	if (n_vertices) *n_vertices = (int)(v.size()/3);
+	if (n_tris) *n_tris = (int)(t.size()/3);
+	if (dminmax) { dminmax[0] = a; dminmax[1] = b; }
+	if (vertices) memcpy(vertices, v.data(), std::min(v.size(), (size_t)cap_vertices*3)*8);
+	if (tris) memcpy(tris, t.data(), std::min(t.size(), (size_t)cap_tris*3)*4);
+	return 0;
+}
+
 // ---- MVSI project files (mvsi.h)
 int hcmvs_host_scene_load_mvs(hcmvs_host_scene* s, const char* file, int load_images) {
 	if (!s || !file) return -1;

@@ -91,6 +91,12 @@ int hcmvs_set_neighbors(hcmvs_ctx* ctx, uint32_t ref, const uint32_t* ids, const
 /* it_external==0 initialisation of EstimateDepthMap (SceneDensify.cpp:772-819): caller-provided rough depth
  * (0 = unknown), optional normals, depth range; builds the gradient map (InitGraMap, :581-595) on device. */
 int hcmvs_init_depthmap(hcmvs_ctx* ctx, uint32_t ref, const float* depth0, const float* normal0, float dMin, float dMax);
+/* The reference's default initialisation (nMinViewsTrustPoint >= 2): DepthMapsData::InitDepthMap -> TriangulatePoints2DepthMap
+ * (SceneDensify.cpp:514-525, DepthMap.cpp:1879-1936). The caller triangulates the projected sparse points on the host as the reference
+ * does (vertices: n_vertices x (x, y, depth) f64 in pixels; tris: n_tris x 3 indices, counter-clockwise like CGAL faces, drawn in this
+ * order); the device rasterises every triangle with the reference's 28.4 fixed-point rasteriser and gives each covered pixel the depth
+ * of its viewing ray on the triangle's plane and the plane's normal. Also builds the gradient map like hcmvs_init_depthmap. */
+int hcmvs_init_depthmap_triangles(hcmvs_ctx* ctx, uint32_t ref, const double* vertices, int n_vertices, const uint32_t* tris, int n_tris, float dMin, float dMax);
 /* Load finished maps (DepthData::Load / IncRef, DepthMap.cpp:231-302) — used before filter/fuse-only runs. */
 int hcmvs_set_depthmap(hcmvs_ctx* ctx, uint32_t view, const float* depth, const float* normal, const float* conf, float dMin, float dMax);
 int hcmvs_get_depthmap(hcmvs_ctx* ctx, uint32_t view, float* depth, float* normal, float* conf, float* dMin, float* dMax);

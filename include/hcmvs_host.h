@@ -41,6 +41,14 @@ int hcmvs_host_write_dmap(const char* file, const char* image_name, const uint32
 int hcmvs_host_read_dmap_header(const char* file, int* w, int* h, int* n_ids, int* has_normal, int* has_conf);
 int hcmvs_host_read_dmap(const char* file, uint32_t* ids, double K[9], double R[9], double C[3], float* dminmax, float* depth, float* normal, float* conf);
 
+/* Triangulated depth-map initialisation, host half (MVS::TriangulatePointsDelaunay, DepthMap.cpp:1797-1876).
+ * hcmvs_host_delaunay: Delaunay triangulation of n 2-D points (what CGAL::Delaunay_triangulation_2 computes for the reference);
+ * returns the number of faces, writes up to cap_tris index triples (counter-clockwise, smallest index first, sorted).
+ * hcmvs_host_triangulate_init: vertices (x, y, depth) + faces for a view selected with hcmvs_host_select_views; call with NULL arrays
+ * first to learn the sizes; dminmax = raw depth bounds of the points (InitDepthMap then widens them by 0.9 / 1.1). */
+int hcmvs_host_delaunay(const double* xy, int n, uint32_t* tris, int cap_tris);
+int hcmvs_host_triangulate_init(hcmvs_host_scene* s, int idx, int add_corners, double* vertices, int cap_vertices, uint32_t* tris, int cap_tris, int* n_vertices, int* n_tris, float* dminmax);
+
 /* MVSI project files ("scene.mvs": MVS::Interface, libs/MVS/Interface.h:165-619) — Scene::LoadInterface / SaveInterface
  * (libs/MVS/Scene.cpp:62-286). load_images: also decode the image files the project names (BMP / PNG / binary PNM), relative to
  * the project's folder. dense: write the fused cloud as the project's vertices (DensifyPointCloud's scene_dense.mvs) instead of

@@ -19,7 +19,10 @@ static inline float FD2R(float d) { return d*(FPI_/180.f); }              // Com
 template<typename T> static inline T SQUARE(T a) { return a*a; }
 template<typename T> static inline bool ISINSIDE(T v, T l0, T l1) { return l0 <= v && v < l1; } // Types.h:1180
 template<typename T> static inline T CLAMPT(T v, T a, T b) { return std::min(std::max(v, a), b); }
-template<typename T> static inline T INVERT(T x) { return x == T(0) ? std::numeric_limits<T>::max() : T(1)/x; } // Types.h:1216-1219
+// INVERT / INVZERO, Types.h:1213-1219: the float and double overloads of INVZERO win over the template -> 1/0 is FINV_ZERO = 1e6f (Types.h:573)
+// for float and INV_ZERO = 1e14 (:555) for double, not numeric_limits::max()
+static inline float INVERT(float x) { return x == 0.f ? 1000000.f : 1.f/x; }
+static inline double INVERT(double x) { return x == 0.0 ? 1e+14 : 1.0/x; }
 static inline int FLOOR2INT(double x) { return int(std::floor(x)); }      // Types.h:909-922 (non-fast variant is the live one)
 static inline int CEIL2INT(double x) { return int(std::ceil(x)); }
 static inline int ROUND2INT(float x) { return int(std::floor(x+.5f)); }   // Types.h:937-943
