@@ -4,6 +4,7 @@
 #include "mvsi.h"
 #include <cstring>
 #include <algorithm>
+#include <exception>
 
 using namespace hcmvs_host;
 
@@ -170,7 +171,8 @@ int hcmvs_host_triangulate_init(hcmvs_host_scene* s, int idx, int add_corners, d
 int hcmvs_host_scene_load_mvs(hcmvs_host_scene* s, const char* file, int load_images) {
 	if (!s || !file) return -1;
 	s->dd.clear();
-	return s->scene.LoadInterface(file, load_images != 0, &s->err) ? 0 : -1;
+	try { return s->scene.LoadInterface(file, load_images != 0, &s->err) ? 0 : -1; }
+	catch (const std::exception& e) { s->err = std::string("LoadInterface: ")+e.what(); return -1; } // no exception crosses the C boundary
 }
 int hcmvs_host_scene_save_mvs(hcmvs_host_scene* s, const char* file, int version, int dense) {
 	if (!s || !file) return -1;
@@ -226,7 +228,7 @@ int hcmvs_host_load_image(const char* file, int* w, int* h, uint8_t* bgr) {
 	if (!file || !w || !h) return -1;
 	if (!bgr) return ReadImageSize(file, *w, *h) ? 0 : -1;
 	std::vector<uint8_t> px; int iw, ih;
-	if (!LoadImageBGR(file, iw, ih, px)) return -1;
+	try { if (!LoadImageBGR(file, iw, ih, px)) return -1; } catch (const std::exception&) { return -1; }
 	if (iw != *w || ih != *h) return -2;
 	memcpy(bgr, px.data(), px.size());
 	return 0;

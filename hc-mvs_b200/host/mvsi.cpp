@@ -23,7 +23,7 @@ struct Reader {
 		const uint64_t n = u64();
 		if (!ok) return 0;
 		const long pos = ftell(f); fseek(f, 0, SEEK_END); const long end = ftell(f); fseek(f, pos, SEEK_SET);
-		if (n*elemBytes > (uint64_t)(end-pos)) { ok = false; return 0; }
+		if (end < pos || n > (uint64_t)(end-pos)/elemBytes) { ok = false; return 0; } // division: n*elemBytes may overflow
 		return (size_t)n;
 	}
 };
@@ -212,6 +212,7 @@ bool DecodePNG(const std::vector<uint8_t>& file, int& w, int& h, std::vector<uin
 		pos += 12+(size_t)len;
 	}
 	if (!gotHdr || w <= 0 || h <= 0) { err = "PNG without IHDR"; return false; }
+	if (w > 65535 || h > 65535) { err = "PNG larger than 65535 pixels a side"; return false; }
 	if (depth != 8 || interlace != 0) { err = "only 8-bit non-interlaced PNG is supported"; return false; }
 	int ch;
 	switch (ctype) { case 0: ch = 1; break; case 2: ch = 3; break; case 3: ch = 1; break; case 4: ch = 2; break; case 6: ch = 4; break; default: err = "bad PNG colour type"; return false; }
@@ -260,6 +261,8 @@ bool DecodeBMP(const std::vector<uint8_t>& file, int& w, int& h, std::vector<uin
 	const uint32_t comp = le32(&file[30]);
 	if ((bpp != 24 && bpp != 32 && bpp != 8) || (comp != 0 && !(comp == 3 && bpp == 32)) || bw <= 0 || bh == 0) { err = "only uncompressed 8/24/32-bit BMP is supported"; return false; }
 	w = bw; h = bh < 0 ? -bh : bh;
+	if (w > 65535 || h > 65535) { err = "BMP larger than 65535 pixels a side"; return false; }
+	if (bpp == 8 && (size_t)14+le32(&file[14])+1024 > file.size()) { err = "truncated BMP palette"; return false; }
 	const size_t rowBytes = (((size_t)w*bpp+31)/32)*4;
 	if ((size_t)off+rowBytes*(size_t)h > file.size()) { err = "truncated BMP pixels"; return false; }
 	const uint8_t* pal = bpp == 8 ? &file[14+le32(&file[14])] : nullptr;
@@ -289,7 +292,7 @@ bool ParsePNMHeader(const std::vector<uint8_t>& file, int& kind, int& w, int& h,
 	}
 	if (nv != 3) return false;
 	w = vals[0]; h = vals[1]; maxv = vals[2]; dataPos = p+1; // one whitespace byte after maxval
-	return w > 0 && h > 0;
+	return w > 0 && h > 0 && w <= 65535 && h <= 65535;
 }
 } // namespace
 

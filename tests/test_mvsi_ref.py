@@ -285,3 +285,41 @@ def test_resolution_level_reload(built, tmp_path):
             Kw = Kn * float(np.float32(max(want_max, nh)))                   # Camera.h:167-180
             assert np.array_equal(info["K"][[0, 2, 4, 5]], Kw.ravel()[[0, 2, 4, 5]])
         hs.close()
+
+
+def test_corrupt_project_and_image_files_fail_cleanly(built, tmp_path):
+    """Truncated / corrupted inputs return an error (the reference's bool-return convention) — no crash, no runaway allocation."""
+    cv2 = pytest.importorskip("cv2")
+    from hcmvs_b200 import host
+    rng = np.random.default_rng(9)
+    img = rng.integers(0, 256, (24, 32, 3)).astype(np.uint8)
+    hs = host.HostScene()
+    K = np.array([30.0, 0, 16, 0, 30, 12, 0, 0, 1])
+    for i in range(3):
+        hs.add_image(K, np.eye(3).ravel(), np.array([i * 0.1, 0, 0]), img, name=str(tmp_path / f"{i}.png"))
+        assert cv2.imwrite(str(tmp_path / f"{i}.png"), img)
+    hs.set_sparse(rng.standard_normal((20, 3)).astype(np.float32), np.arange(0, 42, 2, dtype=np.int32), np.tile([0, 1], 20).astype(np.uint32))
+    good = tmp_path / "good.mvs"
+    hs.save_mvs(good)
+    raw = good.read_bytes()
+    assert host.HostScene.load_mvs(good).num_images() == 3
+    for cut in (0, 3, 8, 13, 40, len(raw) // 2, len(raw) - 1):
+        bad = tmp_path / "bad.mvs"
+        bad.write_bytes(raw[:cut])
+        with pytest.raises(RuntimeError):
+            host.HostScene.load_mvs(bad)
+    huge = bytearray(raw); huge[12:20] = (2 ** 62).to_bytes(8, "little")       # platform count far beyond the file size
+    (tmp_path / "huge.mvs").write_bytes(bytes(huge))
+    with pytest.raises(RuntimeError):
+        host.HostScene.load_mvs(tmp_path / "huge.mvs")
+    (tmp_path / "v9.mvs").write_bytes(raw[:4] + (9).to_bytes(4, "little") + raw[8:])  # version newer than MVSI_PROJECT_VER
+    with pytest.raises(RuntimeError):
+        host.HostScene.load_mvs(tmp_path / "v9.mvs")
+    png = (tmp_path / "0.png").read_bytes()
+    for name, data in (("trunc.png", png[: len(png) // 2]), ("flip.png", png[:60] + bytes([png[60] ^ 0xFF]) + png[61:]), ("tiny.bmp", b"BM" + bytes(20))):
+        (tmp_path / name).write_bytes(data)
+        try:
+            out = host.load_image(tmp_path / name)                             # a flipped byte may still inflate: then the size must hold
+            assert out.shape == img.shape
+        except RuntimeError:
+            pass
