@@ -370,6 +370,46 @@ __global__ void k_fused_support(const float4* __restrict__ dn, const uint32_t* _
 	if (normal) { normal[i*3] = e.x; normal[i*3+1] = e.y; normal[i*3+2] = e.z; }
 }
 
+// MVS::EstimatePointColors (libs/MVS/DepthMap.cpp:2125-2161): the colour of a fused point is sampled in the view — among those that
+// see it and hold an image — whose camera is nearest along its optical axis; TImage<Pixel8U>::sample (Common/Types.inl:2248-2258) with
+// TPixel<uint8_t>'s operators (Common/Types.h:1930-1936): every product and every sum of the bilinear kernel is truncated to uint8.
+__device__ __forceinline__ uint8_t pix_mul(uint8_t c, float v) { return (uint8_t)(int)__fmul_rn(v, (float)c); }
+__global__ void __launch_bounds__(256) k_point_colors(const FuseView* __restrict__ views, int nViews, const float* __restrict__ points,
+	const uint32_t* __restrict__ offs, const uint32_t* __restrict__ vids, uint8_t* __restrict__ colors, size_t n)
+{
+	const size_t i = (size_t)blockIdx.x*blockDim.x+threadIdx.x;
+	if (i >= n) return;
+	const float3 X = make_float3(points[i*3], points[i*3+1], points[i*3+2]);
+	double best = (double)3.402823466e38f; int bestView = -1;
+	for (uint32_t k=offs[i]; k<offs[i+1]; ++k) {
+		const uint32_t id = vids[k];
+		if (id >= (uint32_t)nViews || !views[id].bgr) continue; // imageData.image.empty()
+		const double* P = views[id].cam.P;
+		const double dist = dadd(dadd(dadd(dmul(P[8], (double)X.x), dmul(P[9], (double)X.y)), dmul(P[10], (double)X.z)), P[11]); // Camera::PointDepth
+		if (best > dist) { best = dist; bestView = (int)id; }
+	}
+	uint8_t c0 = 255, c1 = 255, c2 = 255; // Pixel8U::WHITE
+	if (bestView >= 0) {
+		const FuseView& V = views[bestView];
+		const float3 q = cam_ProjectP3f(V.cam, X);
+		const float invZ = q.z == 0.f ? 1000000.f : __fdiv_rn(1.f, q.z); // INVERT
+		const float px = __fmul_rn(q.x, invZ), py = __fmul_rn(q.y, invZ);
+		if (px >= 1.f && py >= 1.f && px <= (float)(V.w-2) && py <= (float)(V.h-2)) { // isInsideWithBorder<float,1>
+			const int lx = (int)px, ly = (int)py;
+			const float x = __fsub_rn(px, (float)lx), x1 = __fsub_rn(1.f, x), y = __fsub_rn(py, (float)ly), y1 = __fsub_rn(1.f, y);
+			const uint8_t* r0 = V.bgr+((size_t)ly*V.w+lx)*3; const uint8_t* r1 = r0+(size_t)V.w*3;
+			uint8_t out[3];
+			#pragma unroll
+			for (int c=0; c<3; ++c) {
+				const uint8_t top = (uint8_t)(pix_mul(r0[c], x1)+pix_mul(r0[3+c], x)), bot = (uint8_t)(pix_mul(r1[c], x1)+pix_mul(r1[3+c], x));
+				out[c] = (uint8_t)(pix_mul(top, y1)+pix_mul(bot, y));
+			}
+			c0 = out[0]; c1 = out[1]; c2 = out[2];
+		}
+	}
+	colors[i*3] = c0; colors[i*3+1] = c1; colors[i*3+2] = c2;
+}
+
 __global__ void k_fill_u32(uint32_t* p, uint32_t v, size_t n) { const size_t i = (size_t)blockIdx.x*blockDim.x+threadIdx.x; if (i < n) p[i] = v; }
 
 } // namespace hcmvs
@@ -604,6 +644,46 @@ extern "C" int hcmvs_get_fused_support(hcmvs_ctx* ctx, uint32_t view, float* dep
 	k_fused_support<<<(unsigned)((n+255)/256), 256, 0, ctx->stream>>>(v.dn_d, v.claim_d, tmp, tmp+n, n); ++ctx->nLaunches;
 	if (depth_fuse) CK(cudaMemcpyAsync(depth_fuse, tmp, n*4, cudaMemcpyDeviceToHost, ctx->stream));
 	if (normal_fuse) CK(cudaMemcpyAsync(normal_fuse, tmp+n, n*12, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_estimate_point_colors(hcmvs_ctx* ctx, uint64_t n_points, const float* points, const uint32_t* view_offsets, const uint32_t* views, uint8_t* colors) {
+	if (!ctx) { hcmvs_set_error("null context"); return HCMVS_ERR_ARG; }
+	cudaSetDevice(ctx->device);
+	const size_t V = ctx->views.size();
+	std::vector<FuseView> hv(V);
+	for (size_t i=0; i<V; ++i) {
+		View& v = ctx->views[i];
+		FuseView& fv = hv[i]; memset(&fv, 0, sizeof(fv));
+		if (!v.set) continue;
+		{ int r = hcmvs_wait_image(ctx, v); if (r) return r; }
+		fv.bgr = v.bgr_d; fv.w = v.w; fv.h = v.h;
+		hcmvs_fill_cam(v, fv.cam);
+	}
+	const bool resident = points == nullptr; // act on the fused cloud that lives on the device
+	FuseState* f = ctx->fuse;
+	if (resident && (!f || !f->nPoints)) { hcmvs_set_error("no fused cloud on the device (call hcmvs_fuse_depthmaps) and no points given"); return HCMVS_ERR_STATE; }
+	if (!resident && (!view_offsets || !views || !colors)) { hcmvs_set_error("null argument"); return HCMVS_ERR_ARG; }
+	const size_t n = resident ? f->nPoints : (size_t)n_points;
+	if (!n) return HCMVS_OK;
+	const size_t m = resident ? f->nViewRefs : (size_t)view_offsets[n];
+	auto al = [](size_t b) { return (b+255)&~(size_t)255; };
+	const size_t bViews = al(V*sizeof(FuseView)), bPts = resident ? 0 : al(n*12), bOff = resident ? 0 : al((n+1)*4), bIds = resident ? 0 : al(m*4), bCol = resident ? 0 : al(n*3);
+	char* base; { int r = hcmvs_scratch(ctx, bViews+bPts+bOff+bIds+bCol, (void**)&base); if (r) return r; }
+	CK(cudaMemcpyAsync(base, hv.data(), V*sizeof(FuseView), cudaMemcpyHostToDevice, ctx->stream));
+	const float* pts_d = f ? f->points : nullptr; const uint32_t* off_d = f ? f->viewOffsets : nullptr; const uint32_t* ids_d = f ? f->oviews : nullptr; uint8_t* col_d = f ? f->colors : nullptr;
+	if (!resident) {
+		CK(cudaMemcpyAsync(base+bViews, points, n*12, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaMemcpyAsync(base+bViews+bPts, view_offsets, (n+1)*4, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaMemcpyAsync(base+bViews+bPts+bOff, views, m*4, cudaMemcpyHostToDevice, ctx->stream));
+		pts_d = (const float*)(base+bViews); off_d = (const uint32_t*)(base+bViews+bPts); ids_d = (const uint32_t*)(base+bViews+bPts+bOff); col_d = (uint8_t*)(base+bViews+bPts+bOff+bIds);
+	}
+	k_point_colors<<<(unsigned)((n+255)/256), 256, 0, ctx->stream>>>((const FuseView*)base, (int)V, pts_d, off_d, ids_d, col_d, n); ++ctx->nLaunches;
+	CK(cudaGetLastError());
+	if (resident) f->hasColor = true;
+	if (colors) CK(cudaMemcpyAsync(colors, col_d, n*3, cudaMemcpyDeviceToHost, ctx->stream));
+	for (View& v: ctx->views) if (v.set) { int r = hcmvs_mark_image_use(ctx, v); if (r) return r; }
 	CK(cudaStreamSynchronize(ctx->stream));
 	return HCMVS_OK;
 }

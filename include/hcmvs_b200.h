@@ -164,6 +164,11 @@ int hcmvs_download_fused_pinned(hcmvs_ctx* ctx, hcmvs_pointcloud* out);
  * depthMap_fuse / normalMap_fuse = the estimate where the pixel became part of a fused point, 0 elsewhere (:2228-2260) — the input
  * of GapInterpolation. After hcmvs_fuse_depthmaps this returns those two maps for `view` (H*W and H*W*3 floats; either may be NULL). */
 int hcmvs_get_fused_support(hcmvs_ctx* ctx, uint32_t view, float* depth_fuse, float* normal_fuse);
+/* MVS::EstimatePointColors (DepthMap.cpp:2125-2161; `--estimate-colors 1`, SceneDensify.cpp:3568-3569): per point the colour sampled in
+ * the nearest view (Camera::PointDepth) among those that see it and hold a colour image; white when none or when it projects into the
+ * 1-pixel border. points == NULL: recolour the fused cloud resident on the device (then `colors` may be NULL too); otherwise n_points
+ * host points with their CSR view lists -> colors (3 bytes per point, B G R like the images). */
+int hcmvs_estimate_point_colors(hcmvs_ctx* ctx, uint64_t n_points, const float* points, const uint32_t* view_offsets, const uint32_t* views, uint8_t* colors);
 int hcmvs_get_fused_device(hcmvs_ctx* ctx, uint64_t* n_points, uint64_t* n_view_refs, void** points_d, void** normals_d, void** colors_d,
                            void** view_offsets_d, void** views_d, void** weights_d);
 

@@ -101,3 +101,44 @@ def test_fuse_is_idempotent_on_reloaded_maps(loaded):
     b = ctx.fuse_depthmaps(True, True)
     for k in ("xyz", "views", "weights", "colors", "normals"):
         assert np.array_equal(a[k], b[k])
+
+
+def test_estimate_point_colors_matches_oracle():
+    """MVS::EstimatePointColors (--estimate-colors 1): nearest-view selection and the uint8-truncating bilinear sample, bit for bit."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import point_colors as PC
+    from test_triangulate_init import _compose_p
+    syn, osc, gt, imgs, ok = common.make_scene(1, 0.25)
+    ctx = common.make_context(syn, osc, imgs, ok)
+    try:
+        rng = np.random.default_rng(11)
+        n = 3000
+        xy = rng.uniform(-2.2, 2.2, (n, 2))
+        pts = np.stack([xy[:, 0], xy[:, 1], 0.05 * xy[:, 0] + 0.03 * xy[:, 1] + rng.normal(0, 0.01, n)], 1).astype(np.float32)   # around the C1 plane, some outside every image
+        counts = rng.integers(0, 5, n)
+        off = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint32)
+        views = np.concatenate([rng.choice(syn.n_views, c, replace=False) for c in counts] + [np.zeros(0, np.int64)]).astype(np.uint32)
+        got = ctx.estimate_point_colors(pts, off, views)
+        P_list = [_compose_p(syn.K[v], syn.R[v], syn.Cc[v]) for v in range(syn.n_views)]
+        want = PC.estimate_point_colors(P_list, imgs, pts, off, views)
+        assert np.array_equal(got, want)
+        white = (got == 255).all(axis=1)
+        assert 0.02 < white.mean() < 0.9 and (counts[~white] > 0).all()
+        # the device-resident fused cloud: recolouring must reproduce the same function of its own points / view lists
+        for i in range(syn.n_views):
+            if ok[i]:
+                osc.init_depth_sparse(i)
+                d0, _, _, lo, hi = osc.get_depthmap(i)
+                ctx.init_depthmap(i, d0, None, lo, hi); ctx.estimate_depthmap(i, 0, seed=2)
+        cloud = ctx.fuse_depthmaps(color=False, normal=True)
+        recol = ctx.estimate_point_colors()
+        off2 = np.concatenate([[0], np.cumsum(cloud["n_views"])]).astype(np.uint32)
+        sel = rng.choice(len(cloud["xyz"]), 2000, replace=False)
+        sub_off = np.concatenate([[0], np.cumsum(cloud["n_views"][sel])]).astype(np.uint32)
+        sub_views = np.concatenate([cloud["views"][off2[k]:off2[k + 1]] for k in sel]).astype(np.uint32)
+        want2 = PC.estimate_point_colors(P_list, imgs, cloud["xyz"][sel], sub_off, sub_views)
+        got2 = recol[sel]
+        assert np.array_equal(got2, want2)
+    finally:
+        ctx.close()
