@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sampler", type=int, default=0)
+    ap.add_argument("--e2e-dmap-dir", default="", help="also time the end-to-end call WITH the raw depthNNNN.dmap files written to this directory (streamed behind the GPU)")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "torch"],
                     help="N>1 map exchange: 'nccl' = hcmvs_exchange_maps (in-place NCCL broadcasts inside the C ABI), 'torch' = torch.distributed all-gather through staging slots")
     return ap.parse_args()
@@ -402,11 +403,27 @@ def run_b200(args):
             torch.cuda.synchronize()
             ts.append(time.time() - t0)
             hs2.close()
+        with_dmaps = None
+        if args.e2e_dmap_dir:
+            os.makedirs(args.e2e_dmap_dir, exist_ok=True)
+            td = []
+            for _ in range(2):
+                hs2 = host.HostScene.from_synth(syn, imgs)
+                torch.cuda.synchronize()
+                t0 = time.time()
+                sd = hs2.dense_reconstruction(ctx2, seed=1, run_filter=True, dmap_dir=args.e2e_dmap_dir)
+                torch.cuda.synchronize()
+                td.append(time.time() - t0)
+                hs2.close()
+            with_dmaps = {"seconds_per_scene": float(td[-1]), "d2h_bytes_per_step": sd["d2h_bytes"], "dir": args.e2e_dmap_dir,
+                          "note": "maps read back through the page-locked download slots and written by a host thread while later views are estimated"}
         ctx2.close()
         e2e = {"value": pix_iters_step / float(np.mean(ts)) / 1e6, "unit": "Mpix*iter/s", "h2d_bytes_per_step": st["h2d_bytes"],
                "d2h_bytes_per_step": st["d2h_bytes"], "seconds_per_scene": float(np.mean(ts)), "points": st["n_points"],
                "seconds": {k: round(float(st[k]), 4) for k in ("sec_select", "sec_upload", "sec_estimate", "sec_filter", "sec_fuse")},
                "api": "hcmvs_host.DenseReconstruction (select views, upload, estimate, filter, fuse, download cloud)"}
+        if with_dmaps:
+            e2e["with_dmaps"] = with_dmaps
     elif world > 1:
         e2e = {"value": None, "unit": "Mpix*iter/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "note": "measured at N=1 only"}
 

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libhcmvs_b200.so")
 
 EXPORTS = [
     "hcmvs_default_params", "hcmvs_last_error", "hcmvs_create", "hcmvs_destroy", "hcmvs_set_params", "hcmvs_sync",
-    "hcmvs_set_view", "hcmvs_set_neighbors", "hcmvs_set_neighbor_image", "hcmvs_init_depthmap", "hcmvs_init_depthmap_triangles", "hcmvs_set_depthmap", "hcmvs_get_depthmap",
+    "hcmvs_set_view", "hcmvs_set_neighbors", "hcmvs_set_neighbor_image", "hcmvs_init_depthmap", "hcmvs_init_depthmap_triangles", "hcmvs_download_depthmap_begin", "hcmvs_download_depthmap_wait", "hcmvs_set_depthmap", "hcmvs_get_depthmap",
     "hcmvs_set_prior", "hcmvs_set_coarse_estimate", "hcmvs_get_coarse_estimate", "hcmvs_snapshot_maps", "hcmvs_get_gradient_map", "hcmvs_score_depthmap", "hcmvs_estimate_depthmap", "hcmvs_end_depthmap", "hcmvs_score_hypotheses",
     "hcmvs_filter_depthmap", "hcmvs_commit_filtered", "hcmvs_set_fuse_priority", "hcmvs_fuse_depthmaps",
     "hcmvs_free_pointcloud", "hcmvs_get_fused_device", "hcmvs_get_fused_support", "hcmvs_estimate_point_colors", "hcmvs_download_fused", "hcmvs_download_fused_pinned", "hcmvs_get_depthmap_device", "hcmvs_set_depth_range", "hcmvs_alloc_depthmap",
@@ -83,6 +83,9 @@ def load():
     L.hcmvs_set_neighbors.argtypes = [vp, u32, vp, vp, i32, i32]
     L.hcmvs_set_neighbor_image.argtypes = [vp, u32, i32, i32, i32, vp, vp]
     L.hcmvs_init_depthmap.argtypes = [vp, u32, vp, vp, f32, f32]
+    fp = C.POINTER(C.c_float)
+    L.hcmvs_download_depthmap_begin.argtypes = [vp, u32, C.c_int]
+    L.hcmvs_download_depthmap_wait.argtypes = [vp, C.c_int, C.POINTER(fp), C.POINTER(fp), C.POINTER(fp), fp, fp]
     L.hcmvs_init_depthmap_triangles.argtypes = [vp, u32, vp, C.c_int, vp, C.c_int, f32, f32]
     L.hcmvs_set_depthmap.argtypes = [vp, u32, vp, vp, vp, f32, f32]
     L.hcmvs_get_depthmap.argtypes = [vp, u32, vp, vp, vp, C.POINTER(f32), C.POINTER(f32)]
@@ -199,6 +202,19 @@ class Context:
         """TriangulatePoints2DepthMap on the device: vertices (n, 3) f64 (x, y, depth), tris (m, 3) u32 counter-clockwise."""
         vertices = np.ascontiguousarray(vertices, np.float64); tris = np.ascontiguousarray(tris, np.uint32)
         self._ck(self.L.hcmvs_init_depthmap_triangles(self.h, ref, _p(vertices), len(vertices), _p(tris), len(tris), dmin, dmax))
+
+    def download_begin(self, view, slot):
+        """Queue the asynchronous read-back of a view's maps into page-locked slot `slot` (returns at once)."""
+        self._ck(self.L.hcmvs_download_depthmap_begin(self.h, view, slot))
+        self._dl = getattr(self, "_dl", {}); self._dl[slot] = self.sizes[view]
+
+    def download_wait(self, slot):
+        """Block until the slot's copy has landed -> (depth, normal, conf, dMin, dMax) as copies of the page-locked buffers."""
+        fp = C.POINTER(C.c_float)
+        d, n, c = fp(), fp(), fp(); lo, hi = C.c_float(), C.c_float()
+        self._ck(self.L.hcmvs_download_depthmap_wait(self.h, slot, C.byref(d), C.byref(n), C.byref(c), C.byref(lo), C.byref(hi)))
+        h, w = self._dl[slot]
+        return (np.ctypeslib.as_array(d, (h, w)).copy(), np.ctypeslib.as_array(n, (h, w, 3)).copy(), np.ctypeslib.as_array(c, (h, w)).copy(), lo.value, hi.value)
 
     def set_depthmap(self, view, depth, normal, conf, dmin, dmax):
         depth = np.ascontiguousarray(depth, np.float32)

@@ -92,6 +92,8 @@ extern "C" void hcmvs_destroy(hcmvs_ctx* ctx) {
 	for (auto& te: ctx->timed) { cudaEventDestroy(te.a); cudaEventDestroy(te.b); }
 	for (cudaEvent_t ev: ctx->eventPool) cudaEventDestroy(ev);
 	cudaFree(ctx->scratch_d); cudaFree(ctx->counters_d); cudaFree(ctx->upload_d); cudaFree(ctx->spread_d);
+	if (ctx->dlStream) { cudaStreamSynchronize(ctx->dlStream); cudaStreamDestroy(ctx->dlStream); }
+	for (DownloadSlot& d: ctx->dl) { if (d.host) cudaFreeHost(d.host); cudaFree(d.dev); if (d.unpacked) cudaEventDestroy(d.unpacked); if (d.landed) cudaEventDestroy(d.landed); }
 	if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
 	hcmvs_fuse_release(ctx);
 	hcmvs_comm_release(ctx);
@@ -442,6 +444,46 @@ extern "C" int hcmvs_get_depthmap(hcmvs_ctx* ctx, uint32_t view, float* depth, f
 	CK(cudaStreamSynchronize(ctx->stream));
 	if (dMin) *dMin = v->dMin;
 	if (dMax) *dMax = v->dMax;
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_download_depthmap_begin(hcmvs_ctx* ctx, uint32_t view, int slot) {
+	View* v = GetView(ctx, view, true); if (!v) return HCMVS_ERR_ARG;
+	if (slot < 0 || slot >= HCMVS_DOWNLOAD_SLOTS) { hcmvs_set_error("download slot %d out of range", slot); return HCMVS_ERR_ARG; }
+	if (!v->hasMaps) { hcmvs_set_error("view %u has no depth map", view); return HCMVS_ERR_STATE; }
+	cudaSetDevice(ctx->device);
+	DownloadSlot& d = ctx->dl[slot];
+	const size_t n = (size_t)v->w*v->h;
+	if (d.pending) CK(cudaEventSynchronize(d.landed)); // the caller re-used a slot it never waited for
+	if (!ctx->dlStream) CK(cudaStreamCreateWithFlags(&ctx->dlStream, cudaStreamNonBlocking));
+	if (!d.unpacked) { CK(cudaEventCreateWithFlags(&d.unpacked, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&d.landed, cudaEventDisableTiming)); }
+	if (d.hostBytes < n*20) { if (d.host) cudaFreeHost(d.host); d.host = nullptr; d.hostBytes = 0; CK(cudaHostAlloc(&d.host, n*20, cudaHostAllocDefault)); d.hostBytes = n*20; }
+	if (d.devBytes < n*20) { cudaFree(d.dev); d.dev = nullptr; d.devBytes = 0; CK(cudaMalloc(&d.dev, n*20)); d.devBytes = n*20; }
+	// unpack + a private copy of the confidences on the COMPUTE stream (device to device, a few microseconds): ordered after the view's
+	// estimation and before anything queued later can touch the maps; the PCIe transfer itself rides the download stream
+	CK(hcmvs_launch_unpack(v->dn_d, d.dev, d.dev+n, n, ctx->stream)); ++ctx->nLaunches;
+	CK(cudaMemcpyAsync(d.dev+n*4, v->conf_d, n*4, cudaMemcpyDeviceToDevice, ctx->stream));
+	CK(cudaEventRecord(d.unpacked, ctx->stream));
+	CK(cudaStreamWaitEvent(ctx->dlStream, d.unpacked, 0));
+	CK(cudaMemcpyAsync(d.host, d.dev, n*20, cudaMemcpyDeviceToHost, ctx->dlStream));
+	CK(cudaEventRecord(d.landed, ctx->dlStream));
+	d.n = n; d.dMin = v->dMin; d.dMax = v->dMax; d.pending = true;
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_download_depthmap_wait(hcmvs_ctx* ctx, int slot, const float** depth, const float** normal, const float** conf, float* dMin, float* dMax) {
+	if (!ctx || slot < 0 || slot >= HCMVS_DOWNLOAD_SLOTS) { hcmvs_set_error("download slot %d out of range", slot); return HCMVS_ERR_ARG; }
+	DownloadSlot& d = ctx->dl[slot];
+	if (!d.pending) { hcmvs_set_error("download slot %d holds nothing", slot); return HCMVS_ERR_STATE; }
+	cudaSetDevice(ctx->device);
+	CK(cudaEventSynchronize(d.landed));
+	const float* h = (const float*)d.host;
+	if (depth) *depth = h;
+	if (normal) *normal = h+d.n;
+	if (conf) *conf = h+d.n*4;
+	if (dMin) *dMin = d.dMin;
+	if (dMax) *dMax = d.dMax;
+	d.pending = false;
 	return HCMVS_OK;
 }
 

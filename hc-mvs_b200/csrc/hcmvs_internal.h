@@ -39,6 +39,14 @@ struct View { // one scene image + its DepthData (libs/MVS/DepthMap.h:214-347)
 
 struct TimedSpan { int stage; cudaEvent_t a, b; };
 
+// one slot of the asynchronous map read-back (hcmvs_download_depthmap_begin / _wait)
+struct DownloadSlot {
+	void* host = nullptr; size_t hostBytes = 0;   // page-locked: depth | normal | conf
+	float* dev = nullptr; size_t devBytes = 0;    // unpacked depth | normal staging (the maps are stored packed)
+	cudaEvent_t unpacked = nullptr, landed = nullptr;
+	size_t n = 0; float dMin = 0.f, dMax = 0.f; bool pending = false;
+};
+
 struct FuseState; // fuse.cu
 
 struct hcmvs_ctx {
@@ -57,6 +65,7 @@ struct hcmvs_ctx {
 	FuseState* fuse = nullptr;
 	SpreadConst* spread_d = nullptr; // viewspread constants of the view being estimated
 	void* comm = nullptr; int rank = 0, world = 1; // NCCL communicator of hcmvs_comm_init (exchange.cu)
+	DownloadSlot dl[HCMVS_DOWNLOAD_SLOTS]; cudaStream_t dlStream = nullptr; // device->host stream of the map read-back
 	cudaStream_t commStream = nullptr; cudaEvent_t commDone = nullptr, commReady = nullptr; bool commPending = false; // asynchronous exchanges
 };
 

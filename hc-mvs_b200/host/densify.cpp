@@ -1,12 +1,16 @@
 // Host-side mirror of DepthMapsData / Scene::DenseReconstruction over the C ABI — see densify.h.
 #include "densify.h"
 #include <algorithm>
+#include <memory>
 #include <chrono>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <thread>
 
 namespace hcmvs_host {
@@ -587,6 +591,54 @@ bool PointCloud::Save(const std::string& fileName) const {
 }
 
 // ------------------------------------------------------------------------------------------------ driver
+namespace {
+// Raw depth-data files written behind the GPU: the maps of a view are read back into one of the context's page-locked slots
+// (hcmvs_download_depthmap_begin, queued right behind the view's last estimation) while the next views are estimated, and a writer
+// thread turns every landed slot into depthNNNN.dmap (ExportDepthDataRaw). The reference writes each map from the thread that
+// estimated it (EVT_SAVEDEPTHMAP, SceneDensify.cpp:3960-3999), which is the same overlap on a CPU.
+struct DmapWriter {
+	hcmvs_ctx* ctx; const Scene& scene; const std::vector<DepthData>& dd; std::string dir;
+	std::thread th; std::mutex m; std::condition_variable cv;
+	std::deque<std::pair<int, uint32_t>> work; std::vector<int> freeSlots;
+	bool closing = false; std::string err; uint64_t bytes = 0;
+	DmapWriter(hcmvs_ctx* c, const Scene& s, const std::vector<DepthData>& d, const std::string& dr) : ctx(c), scene(s), dd(d), dir(dr) {
+		for (int k=0; k<HCMVS_DOWNLOAD_SLOTS; ++k) freeSlots.push_back(k);
+		th = std::thread([this]() { Run(); });
+	}
+	~DmapWriter() { Finish(); }
+	bool Submit(uint32_t view) { // main thread: take a free slot (waits for the writer when all are in flight) and queue the read-back
+		int slot;
+		{ std::unique_lock<std::mutex> lk(m); cv.wait(lk, [this]() { return !freeSlots.empty() || !err.empty(); }); if (!err.empty()) return false; slot = freeSlots.back(); freeSlots.pop_back(); }
+		if (hcmvs_download_depthmap_begin(ctx, view, slot) != HCMVS_OK) { std::lock_guard<std::mutex> lk(m); err = std::string("hcmvs_download_depthmap_begin: ")+hcmvs_last_error(); return false; }
+		{ std::lock_guard<std::mutex> lk(m); work.emplace_back(slot, view); }
+		cv.notify_all();
+		return true;
+	}
+	void Run() {
+		for (;;) {
+			std::pair<int, uint32_t> job;
+			{ std::unique_lock<std::mutex> lk(m); cv.wait(lk, [this]() { return !work.empty() || closing; }); if (work.empty()) return; job = work.front(); work.pop_front(); }
+			const float *d = nullptr, *n = nullptr, *c = nullptr; float lo = 0, hi = 0;
+			std::string e;
+			if (hcmvs_download_depthmap_wait(ctx, job.first, &d, &n, &c, &lo, &hi) != HCMVS_OK) e = std::string("hcmvs_download_depthmap_wait: ")+hcmvs_last_error();
+			else {
+				const Image& im = scene.images[job.second];
+				char name[64]; snprintf(name, sizeof(name), "/depth%04u.dmap", job.second);
+				if (!ExportDepthDataRaw(dir+name, im.name, dd[job.second].images, im.width, im.height, im.camera.K, im.camera.R, im.camera.C, lo, hi, im.width, im.height, d, n, c))
+					e = "cannot write "+dir+name;
+				else bytes += (uint64_t)im.width*im.height*20;
+			}
+			{ std::lock_guard<std::mutex> lk(m); freeSlots.push_back(job.first); if (!e.empty() && err.empty()) err = e; }
+			cv.notify_all();
+		}
+	}
+	bool Finish() {
+		if (th.joinable()) { { std::lock_guard<std::mutex> lk(m); closing = true; } cv.notify_all(); th.join(); }
+		return err.empty();
+	}
+};
+} // namespace
+
 bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, const ViewSelectionParams& VS, uint64_t seed, bool runFilter,
 	const std::string& dmapDir, DenseReconstructionStats* stats, std::string* err)
 {
@@ -627,6 +679,9 @@ bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, co
 	struct Joiner { std::vector<std::thread>& p; std::atomic<uint32_t>& c; ~Joiner() { c.store(0x7fffffffu); for (std::thread& th: p) if (th.joinable()) th.join(); } } joiner{pool, consumed};
 	// images are uploaded on first use by InitViews (copy stream), so the uploads of later views overlap the kernels of earlier ones
 	double t1 = Now();
+	std::unique_ptr<DmapWriter> writer;
+	if (!dmapDir.empty()) writer.reset(new DmapWriter(ctx, scene, data.arrDepthData, dmapDir));
+	const bool singleOuter = P.nEstimationIters_external <= 1; // the maps are final (and saved, :3984) after the LAST outer iteration
 	std::vector<uint32_t> valid;
 	for (uint32_t i=0; i<nImages; ++i) {
 		int s;
@@ -647,6 +702,7 @@ bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, co
 					st.h2dBytes += (uint64_t)scene.images[i].width*scene.images[i].height*4;
 				}
 				if (hcmvs_estimate_depthmap(ctx, i, 0, seed) != HCMVS_OK) return fail(std::string("hcmvs_estimate_depthmap: ")+hcmvs_last_error());
+				if (writer && singleOuter && !writer->Submit(i)) return fail(writer->err);
 			}
 		}
 		std::vector<float>().swap(prep[i].depth); std::vector<double>().swap(prep[i].vertices); std::vector<uint32_t>().swap(prep[i].tris);
@@ -665,16 +721,12 @@ bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, co
 		for (uint32_t i: valid) {
 			if (!data.arrDepthData[i].valid) continue;
 			if (!data.EstimateDepthMap((int)it, i, seed)) return fail(data.lastError);
+			if (writer && it+1 == P.nEstimationIters_external && !writer->Submit(i)) return fail(writer->err);
 		}
 	}
 	if (hcmvs_sync(ctx) != HCMVS_OK) return fail(hcmvs_last_error());
 	double t3 = Now(); st.secEstimate = t3-t1;
-	if (!dmapDir.empty())
-		for (uint32_t i: valid) if (data.arrDepthData[i].valid) {
-			char name[64]; snprintf(name, sizeof(name), "/depth%04u.dmap", i);
-			if (!data.SaveDepthMapRaw(i, dmapDir+name)) return fail("cannot write "+dmapDir+name);
-			st.d2hBytes += (uint64_t)scene.images[i].width*scene.images[i].height*20;
-		}
+	// (the last read-backs / .dmap files finish behind the filter and fusion kernels; the writer is joined before returning)
 	if (runFilter) {
 		// Scene::DenseReconstructionFilter, SceneDensify.cpp:4093-4185: neighbours = those with a depth map, at most 8
 		for (uint32_t i: valid) {
@@ -692,6 +744,7 @@ bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, co
 	if (!data.FuseDepthMaps(scene.densecloud, true, true)) return fail(data.lastError);
 	st.d2hBytes += (uint64_t)scene.densecloud.size()*(12+12+3+4)+(uint64_t)scene.densecloud.views.size()*8;
 	st.secFuse = Now()-t4;
+	if (writer) { if (!writer->Finish()) return fail(writer->err); st.d2hBytes += writer->bytes; }
 	if (stats) *stats = st;
 	return true;
 }

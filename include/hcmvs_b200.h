@@ -100,6 +100,15 @@ int hcmvs_init_depthmap_triangles(hcmvs_ctx* ctx, uint32_t ref, const double* ve
 /* Load finished maps (DepthData::Load / IncRef, DepthMap.cpp:231-302) — used before filter/fuse-only runs. */
 int hcmvs_set_depthmap(hcmvs_ctx* ctx, uint32_t view, const float* depth, const float* normal, const float* conf, float dMin, float dMax);
 int hcmvs_get_depthmap(hcmvs_ctx* ctx, uint32_t view, float* depth, float* normal, float* conf, float* dMin, float* dMax);
+/* Asynchronous read-back of a view's maps into page-locked memory owned by the context — what a .dmap writer should be fed from
+ * (SaveDepthMap / ExportDepthDataRaw after the last outer iteration, SceneDensify.cpp:3984-3989, DepthMap.cpp:2781-2846).
+ * _begin queues, behind the work already queued for the view, an unpack on the compute stream and a device->host copy on a stream of its
+ * own into slot `slot` (0 .. HCMVS_DOWNLOAD_SLOTS-1), and returns at once: later kernels overlap the copy. _wait blocks until that copy
+ * has landed and returns pointers to depth (H*W), normal (H*W*3) and conf (H*W) inside the slot, valid until the slot is used again.
+ * _wait touches nothing but its slot and may be called from another thread than the one driving the context (a writer thread). */
+#define HCMVS_DOWNLOAD_SLOTS 4
+int hcmvs_download_depthmap_begin(hcmvs_ctx* ctx, uint32_t view, int slot);
+int hcmvs_download_depthmap_wait(hcmvs_ctx* ctx, int slot, const float** depth, const float** normal, const float** conf, float* dMin, float* dMax);
 /* DepthData::graMap (u8, H*W) built by hcmvs_init_depthmap (InitGraMap, SceneDensify.cpp:581-595). */
 int hcmvs_get_gradient_map(hcmvs_ctx* ctx, uint32_t view, uint8_t* gra);
 /* Optional plane prior (DepthData::depthMapPrior, DepthMap.cpp:941-955); NULL clears it. */

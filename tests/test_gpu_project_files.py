@@ -30,6 +30,9 @@ def test_project_on_disk_end_to_end(tmp_path):
             st = scene.dense_reconstruction(ctx, seed=7, run_filter=True, dmap_dir=dmap_dir)
             clouds.append(scene.cloud()); depths.append(ctx.get_depthmap(3)[0])
             assert st["n_points"] == len(clouds[-1]["xyz"]) > 50_000
+            if dmap_dir:  # the fused cloud lives in the context's page-locked arena: write the outputs while the context is alive
+                scene.save_ply(str(tmp_path / "scene_dense.ply"))
+                scene.save_mvs(tmp_path / "scene_dense.mvs", dense=True)
         finally:
             ctx.close()
     # cameras of the loaded project differ from the in-memory ones by <= 1 ulp in K (normalise / scale-back of the project format):
@@ -46,11 +49,9 @@ def test_project_on_disk_end_to_end(tmp_path):
         assert back["ids"][0] == i and (back["depth"] > 0).mean() > 0.5
         valid = back["depth"] > 0
         assert np.mean(np.abs(back["depth"][valid] / gt[i][0][valid] - 1) < 0.01) > 0.9
-    hs.save_ply(str(tmp_path / "scene_dense.ply"))
     raw = open(tmp_path / "scene_dense.ply", "rb").read()
     head, body = raw.split(b"end_header\n", 1)
     assert b"element vertex %d\n" % n1 in head and b"property float32 nx" in head and len(body) == n1 * 27
-    hs.save_mvs(tmp_path / "scene_dense.mvs", dense=True)
     dense = host.HostScene.load_mvs(tmp_path / "scene_dense.mvs", load_images=False)
     xyz, off, ids, wts = dense.sparse()
     assert len(xyz) == n1 and np.array_equal(xyz, clouds[1]["xyz"]) and np.array_equal(np.diff(off), clouds[1]["n_views"])
@@ -60,3 +61,37 @@ def test_project_on_disk_end_to_end(tmp_path):
         import subprocess
         assert subprocess.run([tool, "to-flat", str(tmp_path / "scene_dense.mvs"), str(tmp_path / "dense.flat")], capture_output=True, text=True, check=True).stdout.strip() == "5"
     hs0.close(); hs.close(); dense.close()
+
+
+def test_async_download_slots_match_synchronous_readback():
+    """hcmvs_download_depthmap_begin / _wait (page-locked slots, copy on its own stream) return exactly what hcmvs_get_depthmap does,
+    also when later work has already overwritten the view's maps, and misuse is an error, not a crash."""
+    from hcmvs_b200 import api
+    syn, osc, gt, imgs, ok = common.make_scene(1, 0.25)
+    ctx = common.make_context(syn, osc, imgs, ok)
+    try:
+        want = {}
+        for k, ref in enumerate((0, 2, 5, 7, 8)):
+            osc.init_depth_sparse(ref)
+            d0, _, _, lo, hi = osc.get_depthmap(ref)
+            ctx.init_depthmap(ref, d0, None, lo, hi)
+            ctx.estimate_depthmap(ref, 0, seed=9)
+            if k < 4:
+                ctx.download_begin(ref, k)                                   # queued behind the estimation, returns at once
+            want[ref] = None
+        ctx.set_depthmap(0, np.zeros_like(d0), None, None, lo, hi)           # overwrite view 0 AFTER its read-back was queued
+        for k, ref in enumerate((0, 2, 5, 7)):
+            got = ctx.download_wait(k)
+            if ref != 0:
+                ref_d, ref_n, ref_c, rlo, rhi = ctx.get_depthmap(ref)
+                assert np.array_equal(got[0], ref_d) and np.array_equal(got[1], ref_n) and np.array_equal(got[2], ref_c) and (got[3], got[4]) == (rlo, rhi)
+            else:
+                assert (got[0] > 0).mean() > 0.5                              # the estimate, not the zeros written later
+        ctx.download_begin(8, 0)                                              # a slot is reusable once waited for
+        assert np.array_equal(ctx.download_wait(0)[0], ctx.get_depthmap(8)[0])
+        with pytest.raises(api.HcmvsError):
+            ctx.download_wait(1)                                              # nothing pending
+        with pytest.raises(api.HcmvsError):
+            ctx.download_begin(0, 99)
+    finally:
+        ctx.close()
