@@ -40,11 +40,15 @@ struct FuseArgs {
 	int nNb; int nb[HCMVS_MAX_FUSE_VIEWS];
 	unsigned nMinViewsFuse;
 	float depthTh, normalError;
-	uint8_t* state;   // per ref pixel: 0 not a seed / removed, 1 undecided, 2 emitted
+	// Seeds (valid, unclaimed pixels of the reference view) are COMPACTED in raster order before anything else: slot s <-> pixel
+	// seeds[s]. Only ~1 pixel in 6 of a C2 view is a seed and they are scattered, so per-pixel kernels ran with 5 of 32 lanes active
+	// (ncu: thread_inst_executed_per_inst_executed 5.3); every per-seed array below is indexed by slot.
+	const uint32_t* seeds; const uint2* nSeedsPtr; // nSeedsPtr->x = number of seeds (device resident: no host round trip)
+	uint8_t* state;   // per seed slot: 0 removed, 1 undecided, 2 emitted, 3 emitted but still waiting for contested probes
 	uint32_t* mask;   // merged neighbours (bit k = nb[k]) of emitted seeds
 	int* counters;    // [0] undecided seeds, [1] rounds, [2] seeds
 	int* trace;       // optional: undecided seeds after each round (debug)
-	uint32_t* probes; size_t probeStride; // [neighbour][pixel] probe cache
+	uint32_t* probes; size_t probeStride; // [neighbour][slot] probe cache
 };
 
 struct Probe { int q; float z; };
@@ -78,74 +82,108 @@ __device__ __forceinline__ float dot3f(const float3 a, const float3 b) { return 
 // their probes. The geometry of a probe is static: the seed's 3-D point, the pixel it hits in each neighbour view, and — while
 // that pixel is alive (depth != 0, not claimed) — whether it would merge, be invalidated, or be left alone. Only liveness
 // changes during the fusion of this view, so the f64 projections are done once and the rounds below are integer work.
-__global__ void __launch_bounds__(256) k_fuse_probe(const FuseArgs a) {
+// raster-ordered compaction of the seeds: per-chunk counts (k_seed_count) -> exclusive scan (k_fuse_scan) -> scatter (k_seed_scatter)
+#define FUSE_CHUNK 1024 // pixels (or seed slots) per block
+__device__ __forceinline__ bool is_seed(const FuseView& R, int p) { return R.dn[p].w != 0.f && R.claim[p] != CLAIM_TAKEN; } // SceneDensify.cpp:3347-3354
+__global__ void __launch_bounds__(256) k_seed_count(const FuseArgs a, uint2* __restrict__ blockSums) {
+	__shared__ unsigned sP[8];
 	const FuseView& R = a.views[a.ref];
 	const int nPix = R.w*R.h;
-	const int p = blockIdx.x*blockDim.x+threadIdx.x;
-	int mySeeds = 0;
-	if (p < nPix) {
-		const float4 e = R.dn[p];
-		const bool seed = e.w != 0.f && R.claim[p] != CLAIM_TAKEN;
-		a.state[p] = seed ? 1 : 0;
-		mySeeds = seed;
-		if (seed) {
-		const int x = p%R.w, y = p/R.w;
-		const float3 point = seed_point(R, x, y, e.w);
-		const float3 normal = cam_NormalC2W(R.cam, make_float3(e.x, e.y, e.z));
-		// neighbours in chunks of 4: the projections first, then the 4 independent gathers in flight together (the kernel is
-		// bound by gather latency, not bandwidth), then the classification
-		for (int k0=0; k0<a.nNb; k0+=4) {
-			Probe pr[4]; float4 eB[4]; uint32_t cB[4];
-			#pragma unroll
-			for (int j=0; j<4; ++j) {
-				pr[j].q = -1; pr[j].z = 0.f;
-				if (k0+j < a.nNb) { const FuseView& B = a.views[a.nb[k0+j]]; if (B.hasMaps) pr[j] = probe_view(B, point); }
-			}
-			#pragma unroll
-			for (int j=0; j<4; ++j) {
-				eB[j] = make_float4(0.f, 0.f, 0.f, 0.f); cB[j] = CLAIM_TAKEN;
-				if (pr[j].q >= 0) { const FuseView& B = a.views[a.nb[k0+j]]; eB[j] = B.dn[pr[j].q]; cB[j] = B.claim[pr[j].q]; }
-			}
-			#pragma unroll
-			for (int j=0; j<4; ++j) {
-				if (k0+j >= a.nNb) break;
-				uint32_t code = PROBE_DEAD;
-				if (pr[j].q >= 0 && eB[j].w != 0.f && cB[j] != CLAIM_TAKEN) {
-					uint32_t cls = PROBE_NONE;
-					bool merge = false;
-					if (depth_similar(pr[j].z, eB[j].w, a.depthTh)) {
-						const float3 normalB = cam_NormalC2W(a.views[a.nb[k0+j]].cam, make_float3(eB[j].x, eB[j].y, eB[j].z));
-						merge = dot3f(normal, normalB) > a.normalError;
-					}
-					if (merge) cls = PROBE_MERGE; else if (pr[j].z < eB[j].w) cls = PROBE_INVAL;
-					code = (uint32_t)pr[j].q | (cls<<30);
-				}
-				a.probes[(size_t)(k0+j)*a.probeStride+p] = code;
-			}
+	unsigned n = 0;
+	const int base = blockIdx.x*FUSE_CHUNK;
+	for (int i=threadIdx.x; i<FUSE_CHUNK; i+=256) { const int p = base+i; if (p < nPix && is_seed(R, p)) ++n; }
+	for (int s=16; s>0; s>>=1) n += __shfl_xor_sync(0xffffffffu, n, s);
+	if ((threadIdx.x&31) == 0) sP[threadIdx.x>>5] = n;
+	__syncthreads();
+	if (threadIdx.x == 0) { unsigned t = 0; for (int i=0; i<8; ++i) t += sP[i]; blockSums[blockIdx.x] = make_uint2(t, 0); }
+}
+__global__ void __launch_bounds__(256) k_seed_scatter(const FuseArgs a, const uint2* __restrict__ blockSums, int nBlocks, uint32_t* __restrict__ seeds) {
+	// each thread owns 4 consecutive pixels so that the slots keep raster order
+	__shared__ unsigned sP[256];
+	const FuseView& R = a.views[a.ref];
+	const int nPix = R.w*R.h;
+	const int p0 = blockIdx.x*FUSE_CHUNK+threadIdx.x*4;
+	bool f[4]; unsigned n = 0;
+	for (int i=0; i<4; ++i) { f[i] = p0+i < nPix && is_seed(R, p0+i); n += f[i]; }
+	sP[threadIdx.x] = n;
+	__syncthreads();
+	for (int off=1; off<256; off<<=1) {
+		unsigned t = 0;
+		if (threadIdx.x >= off) t = sP[threadIdx.x-off];
+		__syncthreads();
+		sP[threadIdx.x] += t;
+		__syncthreads();
+	}
+	unsigned slot = blockSums[blockIdx.x].x+(sP[threadIdx.x]-n);
+	for (int i=0; i<4; ++i) if (f[i]) seeds[slot++] = (uint32_t)(p0+i);
+	if (blockIdx.x == 0 && threadIdx.x == 0) { const int tot = (int)blockSums[nBlocks].x; a.counters[0] = tot; a.counters[2] = tot; }
+}
+
+// ---- phase 0 (own kernel, one thread per SEED): classify the probes. The geometry of a probe is static: the seed's 3-D point, the
+// pixel it hits in each neighbour view, and — while that pixel is alive (depth != 0, not claimed) — whether it would merge, be
+// invalidated, or be left alone. Only liveness changes during the fusion of this view, so the f64 projections are done once and the
+// rounds below are integer work.
+__global__ void __launch_bounds__(256) k_fuse_probe(const FuseArgs a) {
+	const FuseView& R = a.views[a.ref];
+	const int s = blockIdx.x*blockDim.x+threadIdx.x;
+	if (s >= (int)a.nSeedsPtr->x) return;
+	const int p = (int)a.seeds[s];
+	const float4 e = R.dn[p];
+	a.state[s] = 1;
+	const int x = p%R.w, y = p/R.w;
+	const float3 point = seed_point(R, x, y, e.w);
+	const float3 normal = cam_NormalC2W(R.cam, make_float3(e.x, e.y, e.z));
+	// neighbours in chunks of 4: the projections first, then the 4 independent gathers in flight together (the kernel is
+	// bound by gather latency, not bandwidth), then the classification
+	for (int k0=0; k0<a.nNb; k0+=4) {
+		Probe pr[4]; float4 eB[4]; uint32_t cB[4];
+		#pragma unroll
+		for (int j=0; j<4; ++j) {
+			pr[j].q = -1; pr[j].z = 0.f;
+			if (k0+j < a.nNb) { const FuseView& B = a.views[a.nb[k0+j]]; if (B.hasMaps) pr[j] = probe_view(B, point); }
 		}
+		#pragma unroll
+		for (int j=0; j<4; ++j) {
+			eB[j] = make_float4(0.f, 0.f, 0.f, 0.f); cB[j] = CLAIM_TAKEN;
+			if (pr[j].q >= 0) { const FuseView& B = a.views[a.nb[k0+j]]; eB[j] = B.dn[pr[j].q]; cB[j] = B.claim[pr[j].q]; }
+		}
+		#pragma unroll
+		for (int j=0; j<4; ++j) {
+			if (k0+j >= a.nNb) break;
+			uint32_t code = PROBE_DEAD;
+			if (pr[j].q >= 0 && eB[j].w != 0.f && cB[j] != CLAIM_TAKEN) {
+				uint32_t cls = PROBE_NONE;
+				bool merge = false;
+				if (depth_similar(pr[j].z, eB[j].w, a.depthTh)) {
+					const float3 normalB = cam_NormalC2W(a.views[a.nb[k0+j]].cam, make_float3(eB[j].x, eB[j].y, eB[j].z));
+					merge = dot3f(normal, normalB) > a.normalError;
+				}
+				if (merge) cls = PROBE_MERGE; else if (pr[j].z < eB[j].w) cls = PROBE_INVAL;
+				code = (uint32_t)pr[j].q | (cls<<30);
+			}
+			a.probes[(size_t)(k0+j)*a.probeStride+s] = code;
 		}
 	}
-	mySeeds = cg::reduce(cg::tiled_partition<32>(cg::this_thread_block()), mySeeds, cg::plus<int>());
-	if ((threadIdx.x&31) == 0 && mySeeds) { atomicAdd(&a.counters[0], mySeeds); atomicAdd(&a.counters[2], mySeeds); }
 }
 
 // ---- the reserve / resolve rounds (cooperative: grid.sync between the phases)
 __global__ void __launch_bounds__(256) k_fuse_view(const FuseArgs a) {
 	cg::grid_group grid = cg::this_grid();
 	const FuseView& R = a.views[a.ref];
-	const int nPix = R.w*R.h;
+	const int nSeeds = (int)a.nSeedsPtr->x;
 	const int tid = blockIdx.x*blockDim.x+threadIdx.x, nThreads = gridDim.x*blockDim.x;
 	int undecided = *(volatile int*)&a.counters[0];
 	int round = 0;
 	while (undecided > 0) {
 		// ---- phase 1: every unfinished seed reserves each live neighbour pixel it has not dealt with yet
-		for (int p=tid; p<nPix; p+=nThreads) {
-			const uint8_t st = a.state[p];
+		for (int s=tid; s<nSeeds; s+=nThreads) {
+			const uint8_t st = a.state[s];
 			if (st != 1 && st != 3) continue;
+			const int p = (int)a.seeds[s]; // the raster index orders the reservations
 			for (int k0=0; k0<a.nNb; k0+=4) { // 4 independent probe -> pixel gathers in flight
 				uint32_t code[4], cl[4]; float dz[4];
 				#pragma unroll
-				for (int j=0; j<4; ++j) code[j] = k0+j < a.nNb ? a.probes[(size_t)(k0+j)*a.probeStride+p] : PROBE_DEAD;
+				for (int j=0; j<4; ++j) code[j] = k0+j < a.nNb ? a.probes[(size_t)(k0+j)*a.probeStride+s] : PROBE_DEAD;
 				#pragma unroll
 				for (int j=0; j<4; ++j) {
 					dz[j] = 0.f; cl[j] = CLAIM_TAKEN;
@@ -171,16 +209,17 @@ __global__ void __launch_bounds__(256) k_fuse_view(const FuseArgs a) {
 		//    will NOT be emitted: it releases everything;
 		//  * otherwise it waits for the lower seeds it conflicts with (the lowest unfinished seed never waits).
 		int nDone = 0;
-		for (int p=tid; p<nPix; p+=nThreads) {
-			const uint8_t st = a.state[p];
+		for (int s=tid; s<nSeeds; s+=nThreads) {
+			const uint8_t st = a.state[s];
 			if (st != 1 && st != 3) continue;
-			uint32_t merged = st == 3 ? a.mask[p] : 0u;
+			const int p = (int)a.seeds[s];
+			uint32_t merged = st == 3 ? a.mask[s] : 0u;
 			uint32_t heldMerge = 0, heldInval = 0;
 			unsigned nContested = 0, nContestedMerge = 0;
 			for (int k0=0; k0<a.nNb; k0+=4) {
 				uint32_t code[4], cl[4]; float dz[4];
 				#pragma unroll
-				for (int j=0; j<4; ++j) code[j] = k0+j < a.nNb ? a.probes[(size_t)(k0+j)*a.probeStride+p] : PROBE_DEAD;
+				for (int j=0; j<4; ++j) code[j] = k0+j < a.nNb ? a.probes[(size_t)(k0+j)*a.probeStride+s] : PROBE_DEAD;
 				#pragma unroll
 				for (int j=0; j<4; ++j) {
 					dz[j] = 0.f; cl[j] = CLAIM_TAKEN;
@@ -194,7 +233,7 @@ __global__ void __launch_bounds__(256) k_fuse_view(const FuseArgs a) {
 				for (int j=0; j<4; ++j) {
 					if (code[j] == PROBE_DEAD || (code[j]>>30) == PROBE_NONE) continue;
 					const int k = k0+j;
-					if (cl[j] == CLAIM_TAKEN || dz[j] == 0.f) { a.probes[(size_t)k*a.probeStride+p] = PROBE_DEAD; continue; }
+					if (cl[j] == CLAIM_TAKEN || dz[j] == 0.f) { a.probes[(size_t)k*a.probeStride+s] = PROBE_DEAD; continue; }
 					if (cl[j] == (uint32_t)p) { if ((code[j]>>30) == PROBE_MERGE) heldMerge |= 1u<<k; else heldInval |= 1u<<k; }
 					else { ++nContested; nContestedMerge += (code[j]>>30) == PROBE_MERGE; }
 				}
@@ -205,24 +244,24 @@ __global__ void __launch_bounds__(256) k_fuse_view(const FuseArgs a) {
 					const uint32_t bit = 1u<<k;
 					if (!((heldMerge|heldInval) & bit)) continue;
 					const FuseView& B = a.views[a.nb[k]];
-					const size_t pi = (size_t)k*a.probeStride+p;
+					const size_t pi = (size_t)k*a.probeStride+s;
 					const uint32_t q = a.probes[pi] & 0x3FFFFFFFu;
 					if (heldMerge & bit) B.claim[q] = CLAIM_TAKEN; // merged probes keep their pixel index for k_fuse_emit
 					else { B.dn[q].w = 0.f; __threadfence(); B.claim[q] = CLAIM_FREE; a.probes[pi] = PROBE_DEAD; } // :3447-3449
 				}
 				merged |= heldMerge;
 				// a merged probe must not be looked at again: park it as PROBE_NONE (pixel index kept)
-				for (int k=0; k<a.nNb; ++k) if (heldMerge & (1u<<k)) { const size_t pi = (size_t)k*a.probeStride+p; a.probes[pi] = (a.probes[pi] & 0x3FFFFFFFu) | (PROBE_NONE<<30); }
-				a.mask[p] = merged;
-				if (nContested == 0) { R.claim[p] = CLAIM_TAKEN; a.state[p] = 2; ++nDone; }
-				else a.state[p] = 3;
+				for (int k=0; k<a.nNb; ++k) if (heldMerge & (1u<<k)) { const size_t pi = (size_t)k*a.probeStride+s; a.probes[pi] = (a.probes[pi] & 0x3FFFFFFFu) | (PROBE_NONE<<30); }
+				a.mask[s] = merged;
+				if (nContested == 0) { R.claim[p] = CLAIM_TAKEN; a.state[s] = 2; ++nDone; }
+				else a.state[s] = 3;
 			} else if (nViews+nContestedMerge < a.nMinViewsFuse) {
 				for (int k=0; k<a.nNb; ++k) {
 					if (!((heldMerge|heldInval) & (1u<<k))) continue;
 					const FuseView& B = a.views[a.nb[k]];
-					B.claim[a.probes[(size_t)k*a.probeStride+p] & 0x3FFFFFFFu] = CLAIM_FREE;
+					B.claim[a.probes[(size_t)k*a.probeStride+s] & 0x3FFFFFFFu] = CLAIM_FREE;
 				}
-				a.state[p] = 0; ++nDone;
+				a.state[s] = 0; ++nDone;
 			}
 		}
 		nDone = cg::reduce(cg::tiled_partition<32>(cg::this_thread_block()), nDone, cg::plus<int>());
@@ -235,9 +274,9 @@ __global__ void __launch_bounds__(256) k_fuse_view(const FuseArgs a) {
 	if (tid == 0) a.counters[1] = round;
 }
 
-// ------------------------------------------------------------------ raster-ordered compaction of the emitted seeds
-#define FUSE_CHUNK 1024 // pixels per block
-__global__ void __launch_bounds__(256) k_fuse_count(const uint8_t* __restrict__ state, const uint32_t* __restrict__ mask, int nPix, uint2* __restrict__ blockSums) {
+// ------------------------------------------------------------------ raster-ordered compaction of the emitted seeds (slot order == raster order)
+__global__ void __launch_bounds__(256) k_fuse_count(const uint8_t* __restrict__ state, const uint32_t* __restrict__ mask, const uint2* __restrict__ nSeedsPtr, uint2* __restrict__ blockSums) {
+	const int nPix = (int)nSeedsPtr->x; // number of seed slots
 	__shared__ unsigned sP[8], sV[8];
 	unsigned nP = 0, nV = 0;
 	const int base = blockIdx.x*FUSE_CHUNK;
@@ -290,10 +329,10 @@ __global__ void __launch_bounds__(256) k_fuse_emit(const FuseArgs a, const uint2
 	// each thread owns 4 consecutive pixels of the chunk so that the output keeps raster order
 	__shared__ unsigned sP[256], sV[256];
 	const FuseView& R = a.views[a.ref];
-	const int nPix = R.w*R.h;
-	const int p0 = blockIdx.x*FUSE_CHUNK+threadIdx.x*4;
+	const int nSeeds = (int)a.nSeedsPtr->x;
+	const int s0 = blockIdx.x*FUSE_CHUNK+threadIdx.x*4;
 	unsigned nP = 0, nV = 0;
-	for (int i=0; i<4; ++i) { const int p = p0+i; if (p < nPix && a.state[p] == 2) { ++nP; nV += 1+__popc(a.mask[p]); } }
+	for (int i=0; i<4; ++i) { const int s = s0+i; if (s < nSeeds && a.state[s] == 2) { ++nP; nV += 1+__popc(a.mask[s]); } }
 	sP[threadIdx.x] = nP; sV[threadIdx.x] = nV;
 	__syncthreads();
 	for (int off=1; off<256; off<<=1) {
@@ -307,14 +346,15 @@ __global__ void __launch_bounds__(256) k_fuse_emit(const FuseArgs a, const uint2
 	unsigned long long ip = out.basePoint+bs.x+(sP[threadIdx.x]-nP);
 	unsigned long long iv = out.baseView+bs.y+(sV[threadIdx.x]-nV);
 	for (int i=0; i<4; ++i) {
-		const int p = p0+i;
-		if (p >= nPix || a.state[p] != 2) continue;
+		const int s = s0+i;
+		if (s >= nSeeds || a.state[s] != 2) continue;
+		const int p = (int)a.seeds[s];
 		const int x = p%R.w, y = p/R.w;
 		const float4 e = R.dn[p];
 		const float depth = e.w;
 		const float3 point = seed_point(R, x, y, depth);
 		const float3 normal = cam_NormalC2W(R.cam, make_float3(e.x, e.y, e.z));
-		const uint32_t merged = a.mask[p];
+		const uint32_t merged = a.mask[s];
 		// SceneDensify.cpp:3359-3379
 		uint32_t vid[HCMVS_MAX_FUSE_VIEWS+1]; float vw[HCMVS_MAX_FUSE_VIEWS+1]; int nv = 1;
 		vid[0] = (uint32_t)a.ref; vw[0] = conf2weight(R.conf[p], depth);
@@ -326,7 +366,7 @@ __global__ void __launch_bounds__(256) k_fuse_emit(const FuseArgs a, const uint2
 		for (int k=0; k<a.nNb; ++k) {
 			if (!(merged & (1u<<k))) continue;
 			const FuseView& B = a.views[a.nb[k]];
-			Probe pr; pr.q = (int)(a.probes[(size_t)k*a.probeStride+p] & 0x3FFFFFFFu); pr.z = 0.f;
+			Probe pr; pr.q = (int)(a.probes[(size_t)k*a.probeStride+s] & 0x3FFFFFFFu); pr.z = 0.f;
 			const int xB = pr.q%B.w, yB = pr.q/B.w;
 			const float4 eB = B.dn[pr.q];
 			const float depthB = eB.w;
@@ -421,6 +461,7 @@ struct FuseState {
 	FuseView* views_d = nullptr; size_t nViews = 0;
 	uint8_t* state_d = nullptr; uint32_t* mask_d = nullptr; size_t pixCap = 0;
 	uint2* blockSums_d = nullptr; size_t blockCap = 0;
+	uint32_t* seeds_d = nullptr; uint2* seedSums_d = nullptr; // compacted seed pixels of the view being fused + their per-chunk offsets
 	int* counters_d = nullptr; int* trace_d = nullptr;
 	uint32_t* probes_d = nullptr; size_t probeCap = 0;
 	// growing output
@@ -435,7 +476,7 @@ void hcmvs_fuse_release(hcmvs_ctx* ctx) {
 	FuseState* f = ctx->fuse; if (!f) return;
 	cudaFree(f->trace_d); cudaFree(f->probes_d);
 	if (f->pinned) cudaFreeHost(f->pinned);
-	cudaFree(f->views_d); cudaFree(f->state_d); cudaFree(f->mask_d); cudaFree(f->blockSums_d); cudaFree(f->counters_d);
+	cudaFree(f->views_d); cudaFree(f->state_d); cudaFree(f->mask_d); cudaFree(f->blockSums_d); cudaFree(f->counters_d); cudaFree(f->seeds_d); cudaFree(f->seedSums_d);
 	cudaFree(f->points); cudaFree(f->normals); cudaFree(f->colors); cudaFree(f->viewOffsets); cudaFree(f->oviews); cudaFree(f->weights);
 	delete f; ctx->fuse = nullptr;
 }
@@ -490,11 +531,14 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 	CK(cudaMemcpyAsync(f->views_d, hv.data(), V*sizeof(FuseView), cudaMemcpyHostToDevice, ctx->stream));
 	if (f->pixCap < maxPix) {
 		CK(cudaStreamSynchronize(ctx->stream));
-		cudaFree(f->state_d); cudaFree(f->mask_d);
-		CK(cudaMalloc(&f->state_d, maxPix)); CK(cudaMalloc(&f->mask_d, maxPix*4)); f->pixCap = maxPix;
+		cudaFree(f->state_d); cudaFree(f->mask_d); cudaFree(f->seeds_d);
+		CK(cudaMalloc(&f->state_d, maxPix)); CK(cudaMalloc(&f->mask_d, maxPix*4)); CK(cudaMalloc(&f->seeds_d, maxPix*4)); f->pixCap = maxPix;
 	}
 	const size_t maxBlocks = (maxPix+FUSE_CHUNK-1)/FUSE_CHUNK;
-	if (f->blockCap < maxBlocks+1) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(f->blockSums_d); CK(cudaMalloc(&f->blockSums_d, (maxBlocks+1)*sizeof(uint2))); f->blockCap = maxBlocks+1; }
+	if (f->blockCap < maxBlocks+1) {
+		CK(cudaStreamSynchronize(ctx->stream)); cudaFree(f->blockSums_d); cudaFree(f->seedSums_d);
+		CK(cudaMalloc(&f->blockSums_d, (maxBlocks+1)*sizeof(uint2))); CK(cudaMalloc(&f->seedSums_d, (maxBlocks+1)*sizeof(uint2))); f->blockCap = maxBlocks+1;
+	}
 	if (!f->counters_d) CK(cudaMalloc(&f->counters_d, 4*sizeof(int)));
 	if (!f->trace_d) CK(cudaMalloc(&f->trace_d, 256*sizeof(int)));
 	size_t maxNb = 1; for (const Conn& c: conns) maxNb = std::max(maxNb, ctx->views[c.idx].nbIds.size());
@@ -526,12 +570,18 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 		a.state = f->state_d; a.mask = f->mask_d; a.counters = f->counters_d; a.trace = debug ? f->trace_d : nullptr;
 		a.probes = f->probes_d; a.probeStride = maxPix;
 		const int nPix = v.w*v.h;
+		const int nBlocks = (nPix+FUSE_CHUNK-1)/FUSE_CHUNK;
+		a.seeds = f->seeds_d; a.nSeedsPtr = f->seedSums_d+nBlocks;
 		CK(cudaMemsetAsync(f->counters_d, 0, 4*sizeof(int), ctx->stream));
+		// seeds of this view, compacted in raster order; their number stays on the device (grids are sized for the worst case, idle
+		// blocks exit at once)
+		k_seed_count<<<nBlocks, 256, 0, ctx->stream>>>(a, f->seedSums_d); ++ctx->nLaunches;
+		k_fuse_scan<<<1, 1024, 0, ctx->stream>>>(f->seedSums_d, nBlocks); ++ctx->nLaunches;
+		k_seed_scatter<<<nBlocks, 256, 0, ctx->stream>>>(a, f->seedSums_d, nBlocks, f->seeds_d); ++ctx->nLaunches;
 		k_fuse_probe<<<(nPix+255)/256, 256, 0, ctx->stream>>>(a); ++ctx->nLaunches;
 		void* args[] = {(void*)&a};
 		CK(cudaLaunchCooperativeKernel((void*)k_fuse_view, dim3(f->coopBlocks), dim3(256), args, 0, ctx->stream)); ++ctx->nLaunches;
-		const int nBlocks = (nPix+FUSE_CHUNK-1)/FUSE_CHUNK;
-		k_fuse_count<<<nBlocks, 256, 0, ctx->stream>>>(f->state_d, f->mask_d, nPix, f->blockSums_d); ++ctx->nLaunches;
+		k_fuse_count<<<nBlocks, 256, 0, ctx->stream>>>(f->state_d, f->mask_d, a.nSeedsPtr, f->blockSums_d); ++ctx->nLaunches;
 		k_fuse_scan<<<1, 1024, 0, ctx->stream>>>(f->blockSums_d, nBlocks); ++ctx->nLaunches;
 		uint2 tot; int cnt[4];
 		CK(cudaMemcpyAsync(&tot, f->blockSums_d+nBlocks, sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
