@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sampler", type=int, default=0)
     ap.add_argument("--e2e-dmap-dir", default="", help="also time the end-to-end call WITH the raw depthNNNN.dmap files written to this directory (streamed behind the GPU)")
+    ap.add_argument("--no-split-rows", action="store_true", help="N>1: do not split the views of the incomplete last round into row bands")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "torch"],
                     help="N>1 map exchange: 'nccl' = hcmvs_exchange_maps (in-place NCCL broadcasts inside the C ABI), 'torch' = torch.distributed all-gather through staging slots")
     return ap.parse_args()
@@ -263,20 +264,22 @@ def run_b200(args):
     init = {i: hs.init_depth(i) for i in valid}
     # views are dealt round-robin in fusion (connection) order — SURVEY §8(e)
     from hcmvs_b200 import shard
-    plan = shard.make_plan(valid, nall, world)
+    use_lib_nccl = world > 1 and args.exchange == "nccl"
+    plan = shard.make_plan(valid, nall, world, split_rows=use_lib_nccl and not args.no_split_rows)
     order, mine = plan.order, plan.views_of(rank)
+    mine_whole, split_views = plan.whole_views_of(rank), plan.split_views()
     inner = (W - 14) * (H - 14)
     pix_iters_step = inner * int(P.nEstimationIters) * len(valid)
 
     lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
     filtered_views = {v for v in valid if min(8, len(nbs[v]["ids"])) >= 2}
-    use_lib_nccl = world > 1 and args.exchange == "nccl"
     if use_lib_nccl:
         # the library's own NCCL communicator: rank 0 creates the id, torch.distributed only carries its 128 bytes
         ids = [api.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         ctx.comm_init(ids[0], rank, world)
         owner_rounds = plan.round_owner_arrays(V)
+        owner_split = plan.split_owner_array(V)
         owner_filtered = plan.owner_array(V, only=filtered_views)
     elif world > 1:
         # exchange buffers (one slot per view, replicated on every rank)
@@ -297,7 +300,7 @@ def run_b200(args):
 
     def upload_initial():
         # H2D of the rough depth maps: done before the clock starts (`value` = inputs resident in HBM)
-        for v in mine:
+        for v in sorted(set(mine) | set(split_views)):  # every rank estimates a band of the row-split views
             ctx.init_depthmap(v, init[v][0], None, init[v][1], init[v][2])
         ctx.sync()
 
@@ -306,9 +309,15 @@ def run_b200(args):
             # round s: every rank estimates its s-th view, then those views are broadcast in place (one NCCL group) on the
             # communication stream while round s+1 is being estimated
             for s_, own in enumerate(owner_rounds):
-                if s_ < len(mine):
-                    ctx.estimate_depthmap(mine[s_], 0, 1)
+                if s_ < len(mine_whole):
+                    ctx.estimate_depthmap(mine_whole[s_], 0, 1)
                 ctx.exchange_maps(own, 0, overlap=True)
+            # the views of the incomplete last round: every rank estimates its band of rows, the bands are broadcast in place
+            for v in split_views:
+                r0, r1 = plan.rows_of(rank, H)
+                ctx.estimate_depthmap_rows(v, r0, r1, 0, 1)
+            if split_views:
+                ctx.exchange_maps(owner_split, 0, overlap=True)
             ctx.exchange_wait()
         else:
             for v in mine:
@@ -439,7 +448,7 @@ def run_b200(args):
             "metric": "PatchMatch Mpix*iter/s", "value": value, "unit": "Mpix*iter/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.config], "scale": args.scale, "views": V, "image": [W, H], "neighbours": 5,
-                       "patchmatch_iters": int(P.nEstimationIters), "stages": "estimate(A+B+C) + filter + fuse", "parallelism": f"view-sharded x{world}" + (f", map exchange: {args.exchange}" if world > 1 else ""),
+                       "patchmatch_iters": int(P.nEstimationIters), "stages": "estimate(A+B+C) + filter + fuse", "parallelism": f"view-sharded x{world}" + (f", map exchange: {args.exchange}" if world > 1 else "") + (f", {len(split_views)} view(s) row-split over all ranks" if split_views else ""),
                        "l2": "inputs per view (5 neighbour images + maps, ~77 MB) re-read per launch; 49-view working set 2.3 GB > 126 MB L2"},
             "scene_seconds": sec_step, "fused_points": npoints, "fuse_rounds": int(tm["n_fuse_rounds"]), "stage_ms_per_step_rank0": stages,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,

@@ -597,7 +597,7 @@ static int BuildRefConst(hcmvs_ctx* ctx, View* v, uint32_t ref, int it_external,
 	const hcmvs_params& P = ctx->P;
 	if (v->nMatch < 1) { hcmvs_set_error("view %u has no matching neighbours (call hcmvs_set_neighbors)", ref); return HCMVS_ERR_STATE; }
 	std::memset(&rc, 0, sizeof(rc));
-	rc.w = v->w; rc.h = v->h;
+	rc.w = v->w; rc.h = v->h; rc.y0 = 0; rc.y1 = v->h;
 	rc.fx = v->K[0]; rc.fy = v->K[4]; rc.cx = v->K[2]; rc.cy = v->K[5];
 	Inv33(v->K, rc.Hr);
 	rc.img0 = v->img_d; rc.pitch0 = v->w; rc.gra = v->gra_d; rc.prior = v->prior_d;
@@ -668,7 +668,14 @@ extern "C" int hcmvs_end_depthmap(hcmvs_ctx* ctx, uint32_t ref) {
 	return HCMVS_OK;
 }
 
-extern "C" int hcmvs_estimate_depthmap(hcmvs_ctx* ctx, uint32_t ref, int it_external, uint64_t seed) {
+static int EstimateRows(hcmvs_ctx* ctx, uint32_t ref, int it_external, uint64_t seed, int rowBegin, int rowEnd);
+extern "C" int hcmvs_estimate_depthmap(hcmvs_ctx* ctx, uint32_t ref, int it_external, uint64_t seed) { return EstimateRows(ctx, ref, it_external, seed, 0, -1); }
+extern "C" int hcmvs_estimate_depthmap_rows(hcmvs_ctx* ctx, uint32_t ref, int it_external, uint64_t seed, int row_begin, int row_end) {
+	if (row_begin < 0 || row_end <= row_begin) { hcmvs_set_error("bad row range [%d, %d)", row_begin, row_end); return HCMVS_ERR_ARG; }
+	return EstimateRows(ctx, ref, it_external, seed, row_begin, row_end);
+}
+
+static int EstimateRows(hcmvs_ctx* ctx, uint32_t ref, int it_external, uint64_t seed, int rowBegin, int rowEnd) {
 	View* v = GetView(ctx, ref, true); if (!v) return HCMVS_ERR_ARG;
 	int r = RequireMaps(v, ref); if (r) return r;
 	if (it_external < 0) { hcmvs_set_error("negative outer iteration"); return HCMVS_ERR_ARG; }
@@ -686,6 +693,16 @@ extern "C" int hcmvs_estimate_depthmap(hcmvs_ctx* ctx, uint32_t ref, int it_exte
 	const size_t n = (size_t)v->w*v->h;
 	RefConst rc; r = BuildRefConst(ctx, v, ref, it_external, seed, rc); if (r) return r;
 	const bool tex = P.sampler != 1;
+	if (rowEnd >= 0) {
+		// A band of a row-split view (multi-GPU load balance): a pixel of half-sweep k only depends on pixels at most `reach` rows away
+		// in half-sweep k-1 (propagation sources / smoothness neighbours), so computing the band plus a halo of 2*iterations*reach rows
+		// reproduces the rows [rowBegin, rowEnd) of the full-image estimate bit for bit (counter RNG per pixel) without any exchange
+		// inside the estimation; halo rows hold by-products that the owner of those rows overwrites in the exchange.
+		if (rowEnd > v->h) { hcmvs_set_error("row range [%d, %d) outside the %d rows of view %u", rowBegin, rowEnd, v->h, ref); return HCMVS_ERR_ARG; }
+		const int reach = it_external == 0 ? std::max(P.rb_far_reach, 1) : std::max(P.propagatehalfwin, 5);
+		const int halo = 2*(int)P.nEstimationIters*reach+4;
+		rc.y0 = std::max(0, rowBegin-halo); rc.y1 = std::min(v->h, rowEnd+halo);
+	}
 	rc.coarse = v->coarse_d;
 	if (P.viewspread && it_external >= 1) {
 		// viewspread (DepthMap.cpp:1504-1608) reads the matching neighbours' maps of the previous outer iteration

@@ -93,6 +93,13 @@ extern "C" int hcmvs_exchange_maps(hcmvs_ctx* ctx, const int32_t* owner, uint32_
 	cudaSetDevice(ctx->device);
 	// every rank walks the same list in the same order: the broadcasts pair up by position
 	for (uint32_t i=0; i<n_views; ++i) {
+		if (owner[i] == HCMVS_OWNER_SPLIT_ROWS) {
+			// a view estimated in row bands by every rank (hcmvs_estimate_depthmap_rows): each rank contributes its band in place
+			View& v = ctx->views[i];
+			if (what != HCMVS_EXCHANGE_ESTIMATED) { hcmvs_set_error("row-split ownership only applies to the estimated maps (view %u)", i); return HCMVS_ERR_ARG; }
+			if (!v.set || !v.hasMaps || !v.dn_d || !v.conf_d) { hcmvs_set_error("rank %d holds no maps of the row-split view %u", ctx->rank, i); return HCMVS_ERR_STATE; }
+			continue;
+		}
 		if (owner[i] < 0) continue;
 		if (owner[i] >= ctx->world) { hcmvs_set_error("view %u is owned by rank %d of %d", i, owner[i], ctx->world); return HCMVS_ERR_ARG; }
 		View& v = ctx->views[i];
@@ -120,6 +127,16 @@ extern "C" int hcmvs_exchange_maps(hcmvs_ctx* ctx, const int32_t* owner, uint32_
 	} else hcmvs_time_begin(ctx, ST_EXCHANGE);
 	NK(g_nccl.GroupStart());
 	for (uint32_t i=0; i<n_views; ++i) {
+		if (owner[i] == HCMVS_OWNER_SPLIT_ROWS) {
+			View& v = ctx->views[i];
+			for (int r=0; r<ctx->world; ++r) {
+				const size_t row0 = (size_t)r*v.h/ctx->world, row1 = (size_t)(r+1)*v.h/ctx->world, cnt = (row1-row0)*v.w;
+				if (!cnt) continue;
+				NK(g_nccl.Broadcast(v.dn_d+row0*v.w, v.dn_d+row0*v.w, cnt*4, ncclFloat, r, (ncclComm_t)ctx->comm, st));
+				NK(g_nccl.Broadcast(v.conf_d+row0*v.w, v.conf_d+row0*v.w, cnt, ncclFloat, r, (ncclComm_t)ctx->comm, st));
+			}
+			continue;
+		}
 		if (owner[i] < 0) continue;
 		View& v = ctx->views[i];
 		const size_t n = (size_t)v.w*v.h;

@@ -38,6 +38,7 @@ struct NbViewConst {
 // everything one reference view's scoring kernels need; passed by value as a __grid_constant__
 struct RefConst {
 	int w, h;
+	int y0, y1;                  // rows [y0, y1) this launch estimates (the whole image, or one rank's band + halo of a row-split view)
 	double fx, fy, cx, cy;       // K0
 	double Hr[9];                // K0^-1
 	const float* img0; int pitch0;

@@ -10,11 +10,36 @@ from dataclasses import dataclass
 from typing import Dict, List
 
 
+OWNER_SPLIT_ROWS = -2         # HCMVS_OWNER_SPLIT_ROWS (include/hcmvs_b200.h)
+
+
 @dataclass
 class ShardPlan:
     order: List[int]          # views in connection order
     world: int
     slots: int                # exchange slots per rank
+    split_rows: bool = False  # the views left over after the full rounds are estimated in row bands by ALL ranks
+
+    def whole_rounds(self) -> int:
+        return len(self.order) // self.world if self.split_rows else self.slots
+
+    def split_views(self) -> List[int]:
+        """Views of the last, incomplete round: with split_rows every rank estimates the band rows_of(rank, H) of each of them."""
+        return self.order[self.whole_rounds() * self.world:] if self.split_rows else []
+
+    def rows_of(self, rank: int, height: int):
+        return rank * height // self.world, (rank + 1) * height // self.world
+
+    def whole_views_of(self, rank: int) -> List[int]:
+        n = self.whole_rounds() * self.world
+        return [v for k, v in enumerate(self.order[:n]) if k % self.world == rank]
+
+    def split_owner_array(self, n_views: int):
+        import numpy as np
+        o = np.full(n_views, -1, np.int32)
+        for v in self.split_views():
+            o[v] = OWNER_SPLIT_ROWS
+        return o
 
     def owner(self, k: int) -> int:
         return k % self.world
@@ -39,7 +64,7 @@ class ShardPlan:
         """One owner list per estimation round s (the s-th view of every rank): the exchange of round s overlaps round s+1."""
         import numpy as np
         out = []
-        for s in range(self.slots):
+        for s in range(self.whole_rounds()):
             o = np.full(n_views, -1, np.int32)
             for k in range(s*self.world, min((s+1)*self.world, len(self.order))):
                 o[self.order[k]] = k % self.world
@@ -51,10 +76,13 @@ class ShardPlan:
         return {v: (k % self.world, k // self.world) for k, v in enumerate(self.order)}
 
 
-def make_plan(valid_views, n_scored_neighbors, world):
+def make_plan(valid_views, n_scored_neighbors, world, split_rows=False):
+    """split_rows: 49 views on 8 ranks are 6 full rounds + 1 view; instead of one rank estimating a 7th view while seven wait, every
+    rank estimates one eighth of its rows (+ the halo its dependencies reach, hcmvs_estimate_depthmap_rows) and the bands are
+    exchanged in place. Filtering of those views stays with owner(k) = k % world."""
     order = sorted(valid_views, key=lambda i: (-n_scored_neighbors[i], i))
     slots = (len(order) + world - 1) // world if order else 0
-    return ShardPlan(order=order, world=world, slots=slots)
+    return ShardPlan(order=order, world=world, slots=slots, split_rows=bool(split_rows and world > 1 and len(order) % world))
 
 
 def exchange_maps(plan, rank, send_dn, send_cf, recv_dn, recv_cf, export_fn, import_fn, sync_fn, dist, post_sync=None):

@@ -120,6 +120,11 @@ int hcmvs_score_depthmap(hcmvs_ctx* ctx, uint32_t ref, int it_external, uint64_t
  * sweeps (EstimateDepthMapTmp / DepthEstimator::ProcessPixel, DepthMap.cpp:1050-1501) and, on the last outer
  * iteration, EndDepthMapTmp (SceneDensify.cpp:688-744). */
 int hcmvs_estimate_depthmap(hcmvs_ctx* ctx, uint32_t ref, int it_external, uint64_t seed);
+/* The same for the rows [row_begin, row_end) of the view only: a band plus the halo its dependencies reach (2 x iterations x the
+ * propagation reach) is estimated, which reproduces those rows of the full-image result bit for bit. Used to split a view between
+ * GPUs (every rank a band, no exchange inside the estimation); rows outside the band hold by-products afterwards. Same preconditions
+ * as hcmvs_estimate_depthmap: the initial maps of the whole view must be present. */
+int hcmvs_estimate_depthmap_rows(hcmvs_ctx* ctx, uint32_t ref, int it_external, uint64_t seed, int row_begin, int row_end);
 /* DepthMapsData::EndDepthMapTmp (PASS C) alone — SceneDensify.cpp:688-744 */
 int hcmvs_end_depthmap(hcmvs_ctx* ctx, uint32_t ref);
 /* Parity hook: DepthEstimator::ScorePixel (DepthMap.cpp:987-1046) for caller-fixed per-pixel hypotheses.
@@ -193,6 +198,8 @@ int hcmvs_get_fused_device(hcmvs_ctx* ctx, uint64_t* n_points, uint64_t* n_view_
 #define HCMVS_COMM_ID_BYTES 128
 #define HCMVS_EXCHANGE_ESTIMATED 0
 #define HCMVS_EXCHANGE_FILTERED 1
+#define HCMVS_OWNER_SPLIT_ROWS (-2)  /* owner[i]: view i was estimated in `world` row bands (hcmvs_estimate_depthmap_rows), band r =
+                                        rows [r*H/world, (r+1)*H/world) on rank r; HCMVS_EXCHANGE_ESTIMATED broadcasts every band from its rank */
 #define HCMVS_EXCHANGE_ASYNC 0x100   /* OR into `what`: run the broadcasts on a communication stream, behind the work queued so far and
                                         overlapping the work queued afterwards (the next view's sweeps); hcmvs_exchange_wait joins */
 int hcmvs_comm_unique_id(void* id128);

@@ -146,3 +146,27 @@ def test_window_sampler_is_bit_identical(full):
     share = t["n_window_walks"] * 32.0 / max(t["n_view_scores"], 1)
     print(f"\nwindow sampler: {100 * share:.1f} % of the (hypothesis, view) walks served from shared memory")
     assert share > 0.05
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_row_bands_reproduce_the_full_estimate(full, world):
+    """hcmvs_estimate_depthmap_rows (a view split between GPUs): every band, estimated on its own with the halo its dependencies reach,
+    equals the same rows of the full-image estimate bit for bit — depth, normal and confidence."""
+    syn, osc, gt, imgs, ok, ctx = full
+    ref = 4
+    want = _estimate(ctx, osc, ref, seed=31)
+    osc.init_depth_sparse(ref)
+    d0, _, _, lo, hi = osc.get_depthmap(ref)
+    H = d0.shape[0]
+    got = [np.zeros_like(x) for x in want[:3]]
+    for r in range(world):
+        r0, r1 = r * H // world, (r + 1) * H // world
+        ctx.init_depthmap(ref, d0, None, lo, hi)                 # what "another rank" starts from
+        ctx.estimate_depthmap_rows(ref, r0, r1, 0, 31)
+        band = ctx.get_depthmap(ref)
+        for g, b in zip(got, band[:3]):
+            g[r0:r1] = b[r0:r1]
+    for g, w in zip(got, want[:3]):
+        assert np.array_equal(g, w)
+    with pytest.raises(Exception):
+        ctx.estimate_depthmap_rows(ref, 10, 5)

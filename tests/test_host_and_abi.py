@@ -113,6 +113,24 @@ def test_shard_plan_covers_every_view_once():
         assert len({loc[v] for v in valid}) == len(valid) and all(s < plan.slots for _, s in loc.values())
 
 
+def test_shard_plan_row_split_of_the_incomplete_round():
+    """49 views on 8 ranks: 6 whole rounds + 1 view that every rank estimates a band of; bands tile the rows exactly."""
+    from hcmvs_b200 import shard
+    valid = list(range(49)); nall = {v: 12 - v % 5 for v in valid}
+    for world in (2, 4, 8):
+        plan = shard.make_plan(valid, nall, world, split_rows=True)
+        assert plan.whole_rounds() == 49 // world and len(plan.split_views()) == 49 % world
+        whole = [v for r in range(world) for v in plan.whole_views_of(r)]
+        assert sorted(whole + plan.split_views()) == valid and len({len(plan.whole_views_of(r)) for r in range(world)}) == 1
+        rows = [plan.rows_of(r, 1201) for r in range(world)]
+        assert rows[0][0] == 0 and rows[-1][1] == 1201 and all(rows[i][1] == rows[i + 1][0] for i in range(world - 1))
+        o = plan.split_owner_array(49)
+        assert (o == shard.OWNER_SPLIT_ROWS).sum() == len(plan.split_views()) and len(plan.round_owner_arrays(49)) == plan.whole_rounds()
+        assert all((a >= 0).sum() == world for a in plan.round_owner_arrays(49))
+    assert not shard.make_plan(list(range(48)), {v: 1 for v in range(48)}, 8, split_rows=True).split_views()   # nothing left over
+    assert not shard.make_plan(valid, nall, 1, split_rows=True).split_views()
+
+
 def test_scale_image_matches_opencv(built):
     """ViewData::ScaleImage (DepthMap.h:232-238) = cv::resize INTER_AREA (shrinking) / INTER_CUBIC (enlarging) on the f32 gray image.
     The host restatement follows OpenCV's scalar code: bit-equal to cv2 for the general area decimation; the vectorised kernels cv2
