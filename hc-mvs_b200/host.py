@@ -44,6 +44,8 @@ def lib():
         L.hcmvs_host_scene_load_mvs.argtypes = [vp, C.c_char_p, i32]
         L.hcmvs_host_scene_save_mvs.argtypes = [vp, C.c_char_p, i32, i32]
         L.hcmvs_host_num_images.argtypes = [vp]
+        L.hcmvs_host_pointcloud_filter.argtypes = [vp, vp, i32]
+        L.hcmvs_host_pointcloud_filter.restype = C.c_long
         L.hcmvs_host_delaunay.argtypes = [vp, i32, vp, i32]
         L.hcmvs_host_triangulate_init.argtypes = [vp, i32, i32, vp, i32, vp, i32, C.POINTER(i32), C.POINTER(i32), vp]
         L.hcmvs_host_scene_reload_images.argtypes = [vp, C.c_uint, C.c_uint, C.c_uint]
@@ -190,6 +192,13 @@ class HostScene:
         ids = np.empty(m.value, np.uint32); wts = np.empty(m.value, np.float32)
         self.L.hcmvs_host_get_sparse(self.h, None, None, _p(xyz), _p(off), _p(ids), _p(wts))
         return xyz, off, ids, wts
+
+    def pointcloud_filter(self, ctx, th_remove):
+        """Scene::PointCloudFilter on the dense cloud; returns the number of removed points."""
+        r = self.L.hcmvs_host_pointcloud_filter(self.h, ctx.h, th_remove)
+        if r < 0:
+            raise RuntimeError(self.L.hcmvs_host_last_error(self.h).decode())
+        return r
 
     def save_ply(self, path):
         if self.L.hcmvs_host_cloud_save_ply(self.h, path.encode()) != 0:

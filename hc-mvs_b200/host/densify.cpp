@@ -590,6 +590,41 @@ bool PointCloud::Save(const std::string& fileName) const {
 	return ok;
 }
 
+// ------------------------------------------------------------------------------------------------ point-cloud filter
+long Scene::PointCloudFilter(hcmvs_ctx* ctx, int thRemove, std::string* err) {
+	PointCloud& pc = densecloud;
+	const size_t n = pc.size();
+	if (!n) return 0;
+	std::vector<int32_t> vis(n);
+	if (hcmvs_pointcloud_filter(ctx, n, pc.points.data(), pc.viewOffsets.data(), pc.views.data(), vis.data(), nullptr) != HCMVS_OK) { if (err) *err = std::string("hcmvs_pointcloud_filter: ")+hcmvs_last_error(); return -1; }
+	// RFOREACH(idxPoint) if (visibility[idxPoint] <= thRemove) pointcloud.RemovePoint(idxPoint) — :4310-4314 with PointCloud::RemovePoint
+	// (PointCloud.cpp:54-69) = cList::RemoveAt: the LAST element takes the removed one's place
+	std::vector<uint32_t> order(n);
+	for (size_t i=0; i<n; ++i) order[i] = (uint32_t)i;
+	size_t size = n;
+	for (size_t i=n; i-- > 0;) if (vis[i] <= thRemove) { if (i+1 != size) order[i] = order[size-1]; --size; }
+	const long removed = (long)(n-size);
+	if (!removed) return 0;
+	const bool hasN = !pc.normals.empty(), hasC = !pc.colors.empty(), hasW = !pc.weights.empty();
+	std::vector<float> P(size*3), N(hasN ? size*3 : 0), W; std::vector<uint8_t> C(hasC ? size*3 : 0); std::vector<uint32_t> off(size+1), ids;
+	off[0] = 0;
+	for (size_t k=0; k<size; ++k) { const uint32_t i = order[k]; off[k+1] = off[k]+(pc.viewOffsets[i+1]-pc.viewOffsets[i]); }
+	ids.resize(off[size]); if (hasW) W.resize(off[size]);
+	for (size_t k=0; k<size; ++k) {
+		const uint32_t i = order[k];
+		memcpy(&P[k*3], &pc.points[i*3], 12);
+		if (hasN) memcpy(&N[k*3], &pc.normals[i*3], 12);
+		if (hasC) memcpy(&C[k*3], &pc.colors[i*3], 3);
+		const uint32_t a = pc.viewOffsets[i], cnt = pc.viewOffsets[i+1]-a;
+		memcpy(&ids[off[k]], &pc.views[a], (size_t)cnt*4);
+		if (hasW) memcpy(&W[off[k]], &pc.weights[a], (size_t)cnt*4);
+	}
+	auto put = [](auto& arr, const auto& v) { arr.resize(v.size()); if (!v.empty()) memcpy(arr.data(), v.data(), v.size()*sizeof(v[0])); };
+	put(pc.points, P); put(pc.viewOffsets, off); put(pc.views, ids);
+	if (hasN) put(pc.normals, N); if (hasC) put(pc.colors, C); if (hasW) put(pc.weights, W);
+	return removed;
+}
+
 // ------------------------------------------------------------------------------------------------ driver
 namespace {
 // Raw depth-data files written behind the GPU: the maps of a view are read back into one of the context's page-locked slots

@@ -84,6 +84,10 @@ struct Scene {
 	bool SaveInterface(const std::string& fileName, int version = -1, bool bDense = false) const;
 	// --resolution-level / --min-resolution / --max-resolution (Scene::ComputeDepthMaps, SceneDensify.cpp:3617-3631): every calibrated
 	// image is shrunk to max(w,h) >> level (Image::ResizeImage: cv::resize INTER_AREA on the 8-bit colour image) and its camera updated
+	// Scene::PointCloudFilter (SceneDensify.cpp:4189-4320): visibility votes on the device (hcmvs_pointcloud_filter), then the points with
+	// visibility <= thRemove are removed in the reference's order (RFOREACH + cList::RemoveAt, which moves the last point into the hole).
+	// The context must hold the views' cameras (it does after DenseReconstruction). Returns the number of removed points, -1 on error.
+	long PointCloudFilter(hcmvs_ctx* ctx, int thRemove, std::string* err = nullptr);
 	bool ReloadImages(unsigned nResolutionLevel, unsigned nMinResolution = 640, unsigned nMaxResolution = 3200, std::string* err = nullptr);
 	// Scene::SelectNeighborViews / FilterNeighborViews, libs/MVS/Scene.cpp:545-678
 	bool SelectNeighborViews(uint32_t ID, std::vector<uint32_t>& points, unsigned nMinViews, unsigned nMinPointViews, float fOptimAngle);

@@ -121,6 +121,10 @@ int hcmvs_host_cloud_get(hcmvs_host_scene* s, float* xyz, float* normals, uint8_
 	if (weights) memcpy(weights, pc.weights.data(), pc.weights.size()*4);
 	return 0;
 }
+long hcmvs_host_pointcloud_filter(hcmvs_host_scene* s, hcmvs_ctx* ctx, int th_remove) {
+	if (!s || !ctx) return -1;
+	return s->scene.PointCloudFilter(ctx, th_remove, &s->err);
+}
 int hcmvs_host_cloud_save_ply(hcmvs_host_scene* s, const char* file) { return (s && file && s->scene.densecloud.Save(file)) ? 0 : -1; }
 
 int hcmvs_host_write_dmap(const char* file, const char* image_name, const uint32_t* ids, int n_ids, int image_w, int image_h,

@@ -183,6 +183,11 @@ int hcmvs_get_fused_support(hcmvs_ctx* ctx, uint32_t view, float* depth_fuse, fl
  * 1-pixel border. points == NULL: recolour the fused cloud resident on the device (then `colors` may be NULL too); otherwise n_points
  * host points with their CSR view lists -> colors (3 bytes per point, B G R like the images). */
 int hcmvs_estimate_point_colors(hcmvs_ctx* ctx, uint64_t n_points, const float* points, const uint32_t* view_offsets, const uint32_t* views, uint8_t* colors);
+/* Scene::PointCloudFilter (SceneDensify.cpp:4189-4320; DensifyPointCloud --filter-point-cloud < 0): the visibility vote of every
+ * (point, view) viewing cone over the whole cloud. visibility[i] is the reference's signed count; the caller removes the points with
+ * visibility <= thRemove (hcmvs_host::Scene::PointCloudFilter does, in the reference's order). points == NULL: the fused cloud
+ * resident on the device. stats3 (optional): [0] cones tested against every point (fallback), [1] unused, [2] candidate tests. */
+int hcmvs_pointcloud_filter(hcmvs_ctx* ctx, uint64_t n_points, const float* points, const uint32_t* view_offsets, const uint32_t* views, int32_t* visibility, uint64_t* stats3);
 int hcmvs_get_fused_device(hcmvs_ctx* ctx, uint64_t* n_points, uint64_t* n_view_refs, void** points_d, void** normals_d, void** colors_d,
                            void** view_offsets_d, void** views_d, void** weights_d);
 

@@ -34,6 +34,9 @@ int hcmvs_host_dense_reconstruction(hcmvs_host_scene* s, hcmvs_ctx* ctx, const h
 int hcmvs_host_cloud_size(hcmvs_host_scene* s, uint64_t* n_points, uint64_t* n_view_refs);
 int hcmvs_host_cloud_get(hcmvs_host_scene* s, float* xyz, float* normals, uint8_t* colors, uint32_t* view_offsets, uint32_t* views, float* weights);
 int hcmvs_host_cloud_save_ply(hcmvs_host_scene* s, const char* file);
+/* Scene::PointCloudFilter(thRemove) (SceneDensify.cpp:4189-4320) on the scene's dense cloud: device votes, removal in the reference's
+ * order. Returns the number of removed points, -1 on error. */
+long hcmvs_host_pointcloud_filter(hcmvs_host_scene* s, hcmvs_ctx* ctx, int th_remove);
 /* raw "DR" depth-data files (MVS::ExportDepthDataRaw / ImportDepthDataRaw, DepthMap.cpp:2781-2925) */
 int hcmvs_host_write_dmap(const char* file, const char* image_name, const uint32_t* ids, int n_ids, int image_w, int image_h,
                           const double K[9], const double R[9], const double C[3], float dmin, float dmax, int w, int h,

@@ -1,0 +1,13 @@
+import sys, time; sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+import numpy as np, torch
+from hcmvs_b200 import api, host
+from hcmvs_b200.synth import SynthScene
+syn = SynthScene(2, 1.0, 0)
+imgs = [syn.render(i, want_depth=False, want_normal=False)[0] for i in range(syn.n_views)]
+ctx = api.Context(0, nNumViews=5, nEstimationIters=3, nEstimationIters_external=1, nMinViewsTrustPoint=1, adapthalfwin=5)
+hs = host.HostScene.from_synth(syn, imgs)
+st = hs.dense_reconstruction(ctx, seed=1, run_filter=True)
+torch.cuda.synchronize(); t0 = time.time()
+vis, stats = ctx.pointcloud_filter()
+torch.cuda.synchronize(); dt = time.time()-t0
+print(f"C2 PointCloudFilter votes: {len(vis)} points, {dt:.2f} s, {int(stats[2])/1e9:.1f} G candidate tests, fallback cones {int(stats[0])}, <= -1: {(vis<=-1).sum()}, > 0: {(vis>0).sum()}")

@@ -142,3 +142,49 @@ def test_estimate_point_colors_matches_oracle():
         assert np.array_equal(got2, want2)
     finally:
         ctx.close()
+
+
+def test_pointcloud_filter_votes_match_oracle():
+    """Scene::PointCloudFilter: the binned GPU vote == the brute-force numpy restatement, integer for integer — on a synthetic cloud with
+    a second, occluded / occluding layer (so that votes exist), points listed for views they do not project into (fallback path),
+    and on a real fused cloud."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import cloud_filter as CF
+    syn, osc, gt, imgs, ok = common.make_scene(1, 0.25)
+    ctx = common.make_context(syn, osc, imgs, ok)
+    cams = {v: dict(C=np.asarray(syn.Cc[v], np.float64), K=np.asarray(syn.K[v], np.float64).ravel(), width=imgs[v].shape[1]) for v in range(syn.n_views)}
+    try:
+        rng = np.random.default_rng(21)
+        n = 5000
+        xy = rng.uniform(-0.8, 0.8, (n, 2))
+        z = 0.05 * xy[:, 0] + 0.03 * xy[:, 1]
+        layer = rng.uniform(size=n)
+        z = np.where(layer < 0.15, z + rng.uniform(0.2, 1.5, n), np.where(layer < 0.3, z - rng.uniform(0.2, 1.5, n), z + rng.normal(0, 0.002, n)))
+        pts = np.stack([xy[:, 0], xy[:, 1], z], 1).astype(np.float32)
+        pts[:20] *= 40                                                 # far outside every image: listed views they do not project into
+        counts = rng.integers(1, 5, n)
+        off = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint32)
+        views = np.concatenate([np.sort(rng.choice(syn.n_views, c, replace=False)) for c in counts]).astype(np.uint32)
+        got, stats = ctx.pointcloud_filter(pts, off, views)
+        want = CF.visibility(cams, pts, off, views)
+        assert np.array_equal(got, want)
+        assert (got > 0).sum() > 5 and (got < 0).sum() > 20 and stats[0] >= 20 and stats[2] > 0
+        # the fused cloud resident on the device
+        for i in range(syn.n_views):
+            if ok[i]:
+                osc.init_depth_sparse(i)
+                d0, _, _, lo, hi = osc.get_depthmap(i)
+                ctx.init_depthmap(i, d0, None, lo, hi); ctx.estimate_depthmap(i, 0, seed=4)
+        cloud = ctx.fuse_depthmaps(color=False, normal=False)
+        vis, stats = ctx.pointcloud_filter()
+        m = len(cloud["xyz"])
+        assert len(vis) == m
+        sel = np.sort(rng.choice(m, 1500, replace=False))             # the oracle is O(n^2): check against a brute-force vote restricted to sources in sel
+        off2 = np.concatenate([[0], np.cumsum(cloud["n_views"])]).astype(np.uint32)
+        sub = cloud["xyz"][:4000]; sub_off = off2[:4001]; sub_views = cloud["views"][:off2[4000]]
+        got_sub, _ = ctx.pointcloud_filter(sub, sub_off, sub_views)
+        assert np.array_equal(got_sub, CF.visibility(cams, sub, sub_off, sub_views))
+        print(f"\npoint-cloud filter: {m} points, {int(stats[2])} candidate tests ({stats[2] / max(off2[-1], 1):.0f} per cone), {(vis <= -1).sum()} points at or below -1")
+    finally:
+        ctx.close()

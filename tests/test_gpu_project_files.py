@@ -95,3 +95,35 @@ def test_async_download_slots_match_synchronous_readback():
             ctx.download_begin(0, 99)
     finally:
         ctx.close()
+
+
+def test_host_pointcloud_filter_removal_order():
+    """Scene::PointCloudFilter through the host mirror: device votes, then RFOREACH + RemovePoint (the LAST point moves into the hole,
+    PointCloud.cpp:54-69 / cList::RemoveAt) — the surviving cloud, in order, equals a Python simulation on the same votes."""
+    from hcmvs_b200 import api, host
+    syn, osc, gt, imgs, ok = common.make_scene(1, 0.25)
+    ctx = api.Context(0, **common.BENCH_PARAMS)
+    hs = host.HostScene.from_synth(syn, imgs)
+    try:
+        hs.dense_reconstruction(ctx, seed=3, run_filter=True)
+        before = hs.cloud()
+        vis, _ = ctx.pointcloud_filter()                     # the same cloud, resident on the device
+        th = -1                                               # DensifyPointCloud --filter-point-cloud -1
+        order = list(range(len(vis)))
+        size = len(order)
+        for i in range(len(vis) - 1, -1, -1):
+            if vis[i] <= th:
+                if i + 1 != size:
+                    order[i] = order[size - 1]
+                size -= 1
+        order = np.asarray(order[:size])
+        removed = hs.pointcloud_filter(ctx, th)
+        after = hs.cloud()
+        assert removed == len(vis) - size and 0 < removed < len(vis) // 4
+        assert np.array_equal(after["xyz"], before["xyz"][order]) and np.array_equal(after["n_views"], before["n_views"][order])
+        assert np.array_equal(after["colors"], before["colors"][order]) and np.array_equal(after["normals"], before["normals"][order])
+        off = np.concatenate([[0], np.cumsum(before["n_views"])])
+        want_views = np.concatenate([before["views"][off[i]:off[i + 1]] for i in order])
+        assert np.array_equal(after["views"], want_views)
+    finally:
+        hs.close(); ctx.close()
