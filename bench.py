@@ -396,6 +396,22 @@ def run_b200(args):
                             "note": "texture write-back 32 B/clk/SM, 16 B per bilinear sample (ncu l1tex__tex_writeback_active 79.6 %)"}
     stages = {k: tm[k] / args.steps for k in ("ms_prep", "ms_score", "ms_sweeps", "ms_end", "ms_filter", "ms_fuse", "ms_exchange")}
     launches = tm["n_launches"]
+    # ---- the HBM-bound stages against the measured copy bandwidth (SURVEY §8d's algorithmic bytes; rank 0's share)
+    hbm_peak = peaks.get("hbm_gbs")
+    stage_rooflines = {}
+    if tm["ms_filter"] > 0:
+        gbs = tm["filter_bytes"] / (tm["ms_filter"] / 1e3) / 1e9  # filter_bytes and ms_filter both accumulate over the timed steps
+        stage_rooflines["filter"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak if hbm_peak else None,
+                                     "bytes": "(24 n + 16) B per reference pixel, n = neighbour maps (8)"}
+    if tm["ms_fuse"] > 0 and npoints:
+        # per seed 27 B (depth, conf, normal, colour, claim) + 8 B per probe; per merged view 23 B; ~40 B per emitted point (last fusion)
+        merged = max(int(tm.get("fuse_view_refs", 0)) - npoints, 0)
+        fb = tm["fuse_seeds"] * 27.0 + tm["fuse_probes"] * 8.0 + merged * 23.0 + npoints * 40.0
+        gbs = fb / (tm["ms_fuse"] / args.steps / 1e3) / 1e9
+        stage_rooflines["fuse"] = {"bound": "hbm (gather latency)", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak if hbm_peak else None,
+                                   "seeds": int(tm["fuse_seeds"]), "probes": int(tm["fuse_probes"]),
+                                   "bytes": "27 B per seed + 8 B per probe + 40 B per point (merged views' 23 B not counted)"}
+    roofline["stages"] = stage_rooflines
 
     # ---- e2e: the host-facing DenseReconstruction call with HOST buffers (uploads + downloads inside the timed region)
     e2e = None

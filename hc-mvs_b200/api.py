@@ -52,6 +52,7 @@ class Timers(C.Structure):
         ("ms_filter", C.c_double), ("ms_fuse", C.c_double),
         ("n_hypotheses", C.c_uint64), ("n_pixel_iters", C.c_uint64), ("n_view_scores", C.c_uint64), ("n_smooth_terms", C.c_uint64),
         ("n_launches", C.c_uint32), ("n_fuse_rounds", C.c_uint64), ("n_window_walks", C.c_uint64), ("ms_exchange", C.c_double),
+        ("filter_bytes", C.c_uint64), ("fuse_seeds", C.c_uint64), ("fuse_probes", C.c_uint64),
     ]
 
 

@@ -150,6 +150,7 @@ extern "C" int hcmvs_get_timers(hcmvs_ctx* ctx, hcmvs_timers* t) {
 	t->ms_prep = ctx->stageMs[ST_PREP]; t->ms_filter = ctx->stageMs[ST_FILTER]; t->ms_fuse = ctx->stageMs[ST_FUSE]; t->ms_exchange = ctx->stageMs[ST_EXCHANGE];
 	t->n_hypotheses = c[0]; t->n_view_scores = c[1]; t->n_pixel_iters = c[2]; t->n_smooth_terms = c[3]; t->n_window_walks = c[4];
 	t->n_launches = ctx->nLaunches; t->n_fuse_rounds = ctx->fuseRounds;
+	t->filter_bytes = ctx->filterBytes; t->fuse_seeds = ctx->fuseSeeds; t->fuse_probes = ctx->fuseProbes;
 	return HCMVS_OK;
 }
 extern "C" int hcmvs_reset_timers(hcmvs_ctx* ctx) {
@@ -157,7 +158,7 @@ extern "C" int hcmvs_reset_timers(hcmvs_ctx* ctx) {
 	cudaSetDevice(ctx->device);
 	DrainTimers(ctx);
 	for (double& m: ctx->stageMs) m = 0;
-	ctx->nLaunches = 0;
+	ctx->nLaunches = 0; ctx->filterBytes = 0;
 	CK(cudaMemset(ctx->counters_d, 0, 8*sizeof(unsigned long long)));
 	return HCMVS_OK;
 }

@@ -195,6 +195,7 @@ extern "C" int hcmvs_filter_depthmap(hcmvs_ctx* ctx, uint32_t ref, const uint32_
 	k_filter_vote<<<g, b, 0, ctx->stream>>>(fc_d, proj, v.dn_d, v.conf_d, bAdjust, v.fdepth_d, v.fconf_d); ++ctx->nLaunches;
 	CK(cudaGetLastError());
 	hcmvs_time_end(ctx);
+	ctx->filterBytes += (uint64_t)(24*n+16)*(uint64_t)v.w*v.h; // n x (8 read + 8 written + 8 read back) + 8 in + 8 out per reference pixel
 	v.hasFiltered = true;
 	if (out_depth) CK(cudaMemcpyAsync(out_depth, v.fdepth_d, plane*4, cudaMemcpyDeviceToHost, ctx->stream));
 	if (out_conf) CK(cudaMemcpyAsync(out_conf, v.fconf_d, plane*4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -558,7 +558,7 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 	const float normalError = std::cos((P.fNormalDiffThreshold*P.normalweight)*(FPI/180.f));
 	size_t nPoints = 0, nViewRefs = 0;
 	hcmvs_time_begin(ctx, ST_FUSE);
-	uint64_t totalRounds = 0;
+	uint64_t totalRounds = 0, totalSeeds = 0, totalProbes = 0;
 	for (const Conn& conn: conns) {
 		View& v = ctx->views[conn.idx];
 		FuseArgs a; memset(&a, 0, sizeof(a));
@@ -587,7 +587,7 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 		CK(cudaMemcpyAsync(&tot, f->blockSums_d+nBlocks, sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
 		CK(cudaMemcpyAsync(cnt, f->counters_d, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
 		CK(cudaStreamSynchronize(ctx->stream));
-		totalRounds += (uint64_t)cnt[1];
+		totalRounds += (uint64_t)cnt[1]; totalSeeds += (uint64_t)cnt[2]; totalProbes += (uint64_t)cnt[2]*(uint64_t)a.nNb;
 		if (debug) {
 			int tr[256]; cudaMemcpy(tr, f->trace_d, sizeof(tr), cudaMemcpyDeviceToHost);
 			fprintf(stderr, "[fuse] view %u: %d seeds, %d rounds, %u points, %u view refs; undecided after round:", conn.idx, cnt[2], cnt[1], tot.x, tot.y);
@@ -619,7 +619,7 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 	}
 	hcmvs_time_end(ctx);
 	for (View& v: ctx->views) if (v.set && v.hasMaps) { int r = hcmvs_mark_image_use(ctx, v); if (r) return r; } // colours were read
-	ctx->fuseRounds = totalRounds;
+	ctx->fuseRounds = totalRounds; ctx->fuseSeeds = totalSeeds; ctx->fuseProbes = totalProbes;
 	f->nPoints = nPoints; f->nViewRefs = nViewRefs; f->hasColor = estimate_color != 0; f->hasNormal = estimate_normal != 0;
 	if (nPoints) { // close the CSR offsets on the device
 		const uint32_t last = (uint32_t)nViewRefs;

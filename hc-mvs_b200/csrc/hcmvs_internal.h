@@ -61,7 +61,7 @@ struct hcmvs_ctx {
 	std::vector<TimedSpan> timed; std::vector<cudaEvent_t> eventPool;
 	double stageMs[ST_COUNT] = {0, 0, 0, 0, 0, 0, 0};
 	uint32_t nLaunches = 0;
-	uint64_t fuseRounds = 0;
+	uint64_t fuseRounds = 0, fuseSeeds = 0, fuseProbes = 0, filterBytes = 0;
 	FuseState* fuse = nullptr;
 	SpreadConst* spread_d = nullptr; // viewspread constants of the view being estimated
 	void* comm = nullptr; int rank = 0, world = 1; // NCCL communicator of hcmvs_comm_init (exchange.cu)

@@ -69,6 +69,10 @@ typedef struct hcmvs_timers {
 	uint64_t n_fuse_rounds;    /* reserve/commit rounds of the last hcmvs_fuse_depthmaps */
 	uint64_t n_window_walks;   /* sampler 2: warp-level (hypothesis, view) patch walks served from the shared-memory windows */
 	double ms_exchange;        /* hcmvs_exchange_maps (NCCL) */
+	/* work of the HBM-bound stages, for their rooflines */
+	uint64_t filter_bytes;     /* sum over hcmvs_filter_depthmap calls of (24 n + 16) B x reference pixels, n = neighbour maps */
+	uint64_t fuse_seeds;       /* seed pixels scanned by the last hcmvs_fuse_depthmaps */
+	uint64_t fuse_probes;      /* (seed, neighbour view) probes of the last hcmvs_fuse_depthmaps */
 } hcmvs_timers;
 
 void hcmvs_default_params(hcmvs_params* p);              /* OPTDENSE defaults, DepthMap.cpp:69-143 */
