@@ -443,12 +443,31 @@ def run_b200(args):
             with_dmaps = {"seconds_per_scene": float(td[-1]), "d2h_bytes_per_step": sd["d2h_bytes"], "dir": args.e2e_dmap_dir,
                           "note": "maps read back through the page-locked download slots and written by a host thread while later views are estimated"}
         ctx2.close()
+        # the same call with the reference's DEFAULT initialisation (nMinViewsTrustPoint = 2: the sparse points are triangulated on the
+        # host and rasterised on the device) — reported next to the splat start that both arms of this bench time
+        default_init = None
+        try:
+            p3 = dict(params); p3["nMinViewsTrustPoint"] = 2
+            ctx3 = api.Context(local, **p3)
+            host.HostScene.from_synth(syn, imgs).dense_reconstruction(ctx3, seed=1, run_filter=True)
+            hs3 = host.HostScene.from_synth(syn, imgs)
+            torch.cuda.synchronize()
+            t0 = time.time()
+            s3 = hs3.dense_reconstruction(ctx3, seed=1, run_filter=True)
+            torch.cuda.synchronize()
+            t3 = time.time() - t0
+            hs3.close(); ctx3.close()
+            default_init = {"value": pix_iters_step / t3 / 1e6, "seconds_per_scene": t3, "points": s3["n_points"], "h2d_bytes_per_step": s3["h2d_bytes"],
+                            "note": "nMinViewsTrustPoint = 2 (InitDepthMap / TriangulatePoints2DepthMap): host Delaunay + device rasteriser"}
+        except Exception as e:  # informational only
+            default_init = {"value": None, "note": f"failed: {e}"}
         e2e = {"value": pix_iters_step / float(np.mean(ts)) / 1e6, "unit": "Mpix*iter/s", "h2d_bytes_per_step": st["h2d_bytes"],
                "d2h_bytes_per_step": st["d2h_bytes"], "seconds_per_scene": float(np.mean(ts)), "points": st["n_points"],
                "seconds": {k: round(float(st[k]), 4) for k in ("sec_select", "sec_upload", "sec_estimate", "sec_filter", "sec_fuse")},
                "api": "hcmvs_host.DenseReconstruction (select views, upload, estimate, filter, fuse, download cloud)"}
         if with_dmaps:
             e2e["with_dmaps"] = with_dmaps
+        e2e["default_init"] = default_init
     elif world > 1:
         e2e = {"value": None, "unit": "Mpix*iter/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "note": "measured at N=1 only"}
 
