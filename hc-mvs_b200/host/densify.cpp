@@ -577,13 +577,21 @@ bool PointCloud::Save(const std::string& fileName) const {
 	fprintf(f, "property float32 x\nproperty float32 y\nproperty float32 z\nproperty uint8 red\nproperty uint8 green\nproperty uint8 blue\n");
 	if (hasN) fprintf(f, "property float32 nx\nproperty float32 ny\nproperty float32 nz\n");
 	fprintf(f, "end_header\n");
-	std::vector<uint8_t> rec(hasN ? 27 : 15);
-	for (size_t i=0; i<n; ++i) {
-		memcpy(&rec[0], &points[i*3], 12);
-		if (!colors.empty()) { rec[12] = colors[i*3+2]; rec[13] = colors[i*3+1]; rec[14] = colors[i*3]; } // stored b,g,r
-		else rec[12] = rec[13] = rec[14] = 255; // Color::WHITE
-		if (hasN) memcpy(&rec[15], &normals[i*3], 12);
-		fwrite(rec.data(), 1, rec.size(), f);
+	// records are assembled a chunk at a time and written with one fwrite per chunk (a 19.6 M-point C2 cloud is 530 MB: one call per
+	// 27-byte record would make the writer, not the GPU, the slowest stage of the run)
+	const size_t recBytes = hasN ? 27 : 15, chunk = (size_t)1<<18;
+	std::vector<uint8_t> buf(recBytes*std::min(chunk, n));
+	const bool hasC = !colors.empty();
+	for (size_t i0=0; i0<n; i0+=chunk) {
+		const size_t m = std::min(chunk, n-i0);
+		uint8_t* rec = buf.data();
+		for (size_t i=i0; i<i0+m; ++i, rec+=recBytes) {
+			memcpy(rec, &points[i*3], 12);
+			if (hasC) { rec[12] = colors[i*3+2]; rec[13] = colors[i*3+1]; rec[14] = colors[i*3]; } // stored b,g,r
+			else rec[12] = rec[13] = rec[14] = 255; // Color::WHITE
+			if (hasN) memcpy(rec+15, &normals[i*3], 12);
+		}
+		fwrite(buf.data(), recBytes, m, f);
 	}
 	const bool ok = ferror(f) == 0;
 	fclose(f);
