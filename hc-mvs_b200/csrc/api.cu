@@ -92,7 +92,7 @@ extern "C" void hcmvs_destroy(hcmvs_ctx* ctx) {
 	for (auto& te: ctx->timed) { cudaEventDestroy(te.a); cudaEventDestroy(te.b); }
 	for (cudaEvent_t ev: ctx->eventPool) cudaEventDestroy(ev);
 	cudaFree(ctx->scratch_d); cudaFree(ctx->counters_d); cudaFree(ctx->upload_d); cudaFree(ctx->spread_d);
-	if (ctx->dlStream) { cudaStreamSynchronize(ctx->dlStream); cudaStreamDestroy(ctx->dlStream); }
+	if (ctx->dlStream) { cudaStreamSynchronize(ctx->dlStream); cudaStreamDestroy(ctx->dlStream); ctx->dlStream = nullptr; }
 	for (DownloadSlot& d: ctx->dl) { if (d.host) cudaFreeHost(d.host); cudaFree(d.dev); if (d.unpacked) cudaEventDestroy(d.unpacked); if (d.landed) cudaEventDestroy(d.landed); }
 	if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
 	hcmvs_fuse_release(ctx);

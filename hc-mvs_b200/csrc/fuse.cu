@@ -469,16 +469,31 @@ struct FuseState {
 	uint32_t* oviews = nullptr; float* weights = nullptr; size_t capViews = 0;
 	int coopBlocks = 0;
 	void* pinned = nullptr; size_t pinnedBytes = 0; // page-locked host arena of hcmvs_download_fused_pinned (grow-only)
+	// The arena is laid out for CAPACITIES (arenaPoints points, arenaViews view references), so that the ranges a view's emit kernel
+	// has just written can be copied out at their final place while the next views are still being fused (download stream); a cloud
+	// that outgrows the capacities falls back to one copy at the end and a larger arena for the next scene.
+	size_t arenaPoints = 0, arenaViews = 0; bool arenaColor = false, arenaNormal = false;
+	bool streamed = false; size_t streamedPoints = 0, streamedViews = 0; cudaEvent_t emitted = nullptr;
 	size_t nPoints = 0, nViewRefs = 0; bool hasColor = false, hasNormal = false; // last fused cloud (device resident)
 };
 
 void hcmvs_fuse_release(hcmvs_ctx* ctx) {
 	FuseState* f = ctx->fuse; if (!f) return;
 	cudaFree(f->trace_d); cudaFree(f->probes_d);
+	if (ctx->dlStream) cudaStreamSynchronize(ctx->dlStream);
 	if (f->pinned) cudaFreeHost(f->pinned);
+	if (f->emitted) cudaEventDestroy(f->emitted);
 	cudaFree(f->views_d); cudaFree(f->state_d); cudaFree(f->mask_d); cudaFree(f->blockSums_d); cudaFree(f->counters_d); cudaFree(f->seeds_d); cudaFree(f->seedSums_d);
 	cudaFree(f->points); cudaFree(f->normals); cudaFree(f->colors); cudaFree(f->viewOffsets); cudaFree(f->oviews); cudaFree(f->weights);
 	delete f; ctx->fuse = nullptr;
+}
+
+struct ArenaLayout { size_t oPts, oNrm, oCol, oOff, oViews, oW, total; };
+static ArenaLayout LayoutFor(size_t capPoints, size_t capViews, bool hasNormal, bool hasColor) {
+	auto al = [](size_t b) { return (b+255)&~(size_t)255; };
+	ArenaLayout L; L.oPts = 0; L.oNrm = L.oPts+al(capPoints*12); L.oCol = L.oNrm+al(hasNormal ? capPoints*12 : 0); L.oOff = L.oCol+al(hasColor ? capPoints*3 : 0);
+	L.oViews = L.oOff+al((capPoints+1)*4); L.oW = L.oViews+al(capViews*4); L.total = L.oW+al(capViews*4);
+	return L;
 }
 
 template<typename T>
@@ -487,6 +502,7 @@ static int Grow(hcmvs_ctx* ctx, T*& ptr, size_t used, size_t newCap, size_t elem
 	CK(cudaMalloc(&np, newCap*elemsPer*sizeof(T)));
 	if (ptr && used) CK(cudaMemcpyAsync(np, ptr, used*elemsPer*sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
+	if (ctx->dlStream) CK(cudaStreamSynchronize(ctx->dlStream)); // streamed copies may still read the old buffer
 	cudaFree(ptr); ptr = np;
 	return HCMVS_OK;
 }
@@ -557,6 +573,14 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 	const float FPI = (float)3.14159265358979323846;
 	const float normalError = std::cos((P.fNormalDiffThreshold*P.normalweight)*(FPI/180.f));
 	size_t nPoints = 0, nViewRefs = 0;
+	// stream the cloud out while it is being built when the caller keeps it on the device (out == NULL, the hcmvs_download_fused_pinned
+	// path) and an arena laid out for this kind of cloud exists from an earlier scene
+	f->streamed = !out && f->pinned && f->arenaPoints && f->arenaColor == (estimate_color != 0) && f->arenaNormal == (estimate_normal != 0);
+	f->streamedPoints = f->streamedViews = 0;
+	if (f->streamed) {
+		if (!ctx->dlStream) CK(cudaStreamCreateWithFlags(&ctx->dlStream, cudaStreamNonBlocking));
+		if (!f->emitted) CK(cudaEventCreateWithFlags(&f->emitted, cudaEventDisableTiming));
+	}
 	hcmvs_time_begin(ctx, ST_FUSE);
 	uint64_t totalRounds = 0, totalSeeds = 0, totalProbes = 0;
 	for (const Conn& conn: conns) {
@@ -615,6 +639,20 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 		fo.basePoint = nPoints; fo.baseView = nViewRefs; fo.estimateColor = estimate_color; fo.estimateNormal = estimate_normal;
 		k_fuse_emit<<<nBlocks, 256, 0, ctx->stream>>>(a, f->blockSums_d, fo); ++ctx->nLaunches;
 		CK(cudaGetLastError());
+		if (f->streamed && nPoints+tot.x <= f->arenaPoints && nViewRefs+tot.y <= f->arenaViews) {
+			// what this view emitted is final: copy it to its place in the arena behind the emit kernel, on the download stream
+			const ArenaLayout L = LayoutFor(f->arenaPoints, f->arenaViews, f->arenaNormal, f->arenaColor);
+			char* base = (char*)f->pinned;
+			CK(cudaEventRecord(f->emitted, ctx->stream));
+			CK(cudaStreamWaitEvent(ctx->dlStream, f->emitted, 0));
+			CK(cudaMemcpyAsync(base+L.oPts+nPoints*12, f->points+nPoints*3, (size_t)tot.x*12, cudaMemcpyDeviceToHost, ctx->dlStream));
+			if (estimate_normal) CK(cudaMemcpyAsync(base+L.oNrm+nPoints*12, f->normals+nPoints*3, (size_t)tot.x*12, cudaMemcpyDeviceToHost, ctx->dlStream));
+			if (estimate_color) CK(cudaMemcpyAsync(base+L.oCol+nPoints*3, f->colors+nPoints*3, (size_t)tot.x*3, cudaMemcpyDeviceToHost, ctx->dlStream));
+			CK(cudaMemcpyAsync(base+L.oOff+nPoints*4, f->viewOffsets+nPoints, (size_t)tot.x*4, cudaMemcpyDeviceToHost, ctx->dlStream));
+			CK(cudaMemcpyAsync(base+L.oViews+nViewRefs*4, f->oviews+nViewRefs, (size_t)tot.y*4, cudaMemcpyDeviceToHost, ctx->dlStream));
+			CK(cudaMemcpyAsync(base+L.oW+nViewRefs*4, f->weights+nViewRefs, (size_t)tot.y*4, cudaMemcpyDeviceToHost, ctx->dlStream));
+			f->streamedPoints = nPoints+tot.x; f->streamedViews = nViewRefs+tot.y;
+		} else f->streamed = false; // outgrew the arena (or not streaming): hcmvs_download_fused_pinned copies everything at the end
 		nPoints += tot.x; nViewRefs += tot.y;
 	}
 	hcmvs_time_end(ctx);
@@ -666,21 +704,31 @@ extern "C" int hcmvs_download_fused_pinned(hcmvs_ctx* ctx, hcmvs_pointcloud* out
 	memset(out, 0, sizeof(*out));
 	const size_t n = f->nPoints, m = f->nViewRefs;
 	if (!n) return HCMVS_OK;
-	auto al = [](size_t b) { return (b+255)&~(size_t)255; };
-	const size_t oPts = 0, oNrm = oPts+al(n*12), oCol = oNrm+al(f->hasNormal ? n*12 : 0), oOff = oCol+al(f->hasColor ? n*3 : 0),
-		oViews = oOff+al((n+1)*4), oW = oViews+al(m*4), total = oW+al(m*4);
-	if (f->pinnedBytes < total) {
+	const bool fits = f->pinned && n <= f->arenaPoints && m <= f->arenaViews && f->arenaColor == f->hasColor && f->arenaNormal == f->hasNormal;
+	if (!fits) {
+		if (ctx->dlStream) CK(cudaStreamSynchronize(ctx->dlStream));
 		if (f->pinned) cudaFreeHost(f->pinned);
-		f->pinned = nullptr; f->pinnedBytes = 0;
-		const size_t cap = total+total/8; // head-room: the next scene of the same size does not re-pin
-		CK(cudaHostAlloc(&f->pinned, cap, cudaHostAllocDefault));
-		f->pinnedBytes = cap;
+		f->pinned = nullptr; f->pinnedBytes = 0; f->streamed = false;
+		// head-room: the next scene of the same size streams into this arena while it is fused
+		f->arenaPoints = n+n/8; f->arenaViews = m+m/8; f->arenaColor = f->hasColor; f->arenaNormal = f->hasNormal;
+		const ArenaLayout L = LayoutFor(f->arenaPoints, f->arenaViews, f->arenaNormal, f->arenaColor);
+		CK(cudaHostAlloc(&f->pinned, L.total, cudaHostAllocDefault));
+		f->pinnedBytes = L.total;
 	}
+	const ArenaLayout L = LayoutFor(f->arenaPoints, f->arenaViews, f->arenaNormal, f->arenaColor);
 	char* base = (char*)f->pinned;
 	out->n_points = n;
-	out->points = (float*)(base+oPts); out->view_offsets = (uint32_t*)(base+oOff); out->views = (uint32_t*)(base+oViews); out->weights = (float*)(base+oW);
-	if (f->hasNormal) out->normals = (float*)(base+oNrm);
-	if (f->hasColor) out->colors = (uint8_t*)(base+oCol);
+	out->points = (float*)(base+L.oPts); out->view_offsets = (uint32_t*)(base+L.oOff); out->views = (uint32_t*)(base+L.oViews); out->weights = (float*)(base+L.oW);
+	if (f->hasNormal) out->normals = (float*)(base+L.oNrm);
+	if (f->hasColor) out->colors = (uint8_t*)(base+L.oCol);
+	if (f->streamed && f->streamedPoints == n && f->streamedViews == m) {
+		// everything but the closing CSR offset already crossed PCIe behind the emit kernels
+		CK(cudaMemcpyAsync(out->view_offsets+n, f->viewOffsets+n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->dlStream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		return HCMVS_OK;
+	}
+	if (ctx->dlStream) CK(cudaStreamSynchronize(ctx->dlStream));
 	return hcmvs_download_fused(ctx, out->points, out->normals, out->colors, out->view_offsets, out->views, out->weights);
 }
 
