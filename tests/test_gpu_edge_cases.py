@@ -135,3 +135,55 @@ def test_error_convention(small):
     # the context is still usable after every refused call
     d, n = common.perturbed_hypotheses(gt[0][0], gt[0][1], syn.K[0], seed=1)
     assert np.isfinite(ctx.score_hypotheses(0, d, n, 0)).all()
+
+
+def test_triangulated_init_edge_cases(small):
+    """hcmvs_init_depthmap_triangles: a minimal mesh (3 points + nothing else), triangles partly or wholly outside the image, slivers
+    thinner than the 1/16-pixel grid, and malformed input -> the numpy oracle's maps, or a clean error."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import triangulate_init as T
+    syn, osc, gt, imgs, ok, ctx = small
+    ref = 1
+    h, w = imgs[ref].shape[:2]
+    K = np.asarray(syn.K[ref], np.float64).ravel()
+    cases = {
+        "one triangle": (np.array([[10.2, 8.7, 5.0], [100.9, 20.1, 5.5], [40.3, 90.6, 6.0]]), np.array([[0, 1, 2]])),
+        "clockwise (draws nothing)": (np.array([[10.2, 8.7, 5.0], [100.9, 20.1, 5.5], [40.3, 90.6, 6.0]]), np.array([[0, 2, 1]])),
+        "partly outside": (np.array([[-50.0, -30.0, 5.0], [w + 40.0, 10.0, 6.0], [w / 2, h + 70.0, 5.5], [w / 2, h / 2, 5.2]]), np.array([[0, 1, 3], [1, 2, 3], [2, 0, 3]])),
+        "sliver + overlap (last face wins)": (np.array([[20.0, 20.0, 5.0], [120.0, 20.01, 5.0], [70.0, 20.02, 5.0], [20.0, 100.0, 6.0], [120.0, 100.0, 6.0], [70.0, 10.0, 4.0]]),
+                                              np.array([[0, 1, 2], [0, 1, 3], [1, 4, 3], [0, 5, 1], [0, 1, 4]])),
+        "behind the camera (z <= 0 is skipped)": (np.array([[10.0, 10.0, -5.0], [150.0, 10.0, -5.0], [80.0, 110.0, -5.0]]), np.array([[0, 1, 2]])),
+    }
+    for name, (v, t) in cases.items():
+        ctx.init_depthmap_triangles(ref, v, t, 1.0, 100.0)
+        d, n = ctx.get_depthmap(ref)[:2]
+        od, on = T.rasterize(v, t.astype(np.int64), K, w, h)
+        assert np.array_equal(d, od) and np.array_equal(n, on), name
+    assert (ctx.get_depthmap(ref)[0] == 0).all()                                 # the last case drew nothing
+    v, t = cases["one triangle"]
+    for bad_v, bad_t, lo, hi in ((v, np.array([[0, 1, 7]]), 1.0, 2.0), (v[:2], t, 1.0, 2.0), (v, t, 2.0, 1.0), (np.where(v > 90, np.inf, v), t, 1.0, 2.0)):
+        with pytest.raises(api.HcmvsError):
+            ctx.init_depthmap_triangles(ref, bad_v, bad_t, lo, hi)
+
+
+def test_row_band_of_a_small_image_and_bad_ranges(small):
+    """hcmvs_estimate_depthmap_rows where the halo is larger than the image (the band becomes the whole view) and invalid ranges."""
+    syn, osc, gt, imgs, ok, ctx = small
+    ref = 3
+    osc.init_depth_sparse(ref)
+    d0, _, _, lo, hi = osc.get_depthmap(ref)
+    ctx.init_depthmap(ref, d0, None, lo, hi); ctx.estimate_depthmap(ref, 0, 13)
+    want = ctx.get_depthmap(ref)
+    h = d0.shape[0]
+    got = [np.zeros_like(x) for x in want[:3]]
+    for r0, r1 in ((0, 17), (17, h - 40), (h - 40, h)):
+        ctx.init_depthmap(ref, d0, None, lo, hi); ctx.estimate_depthmap_rows(ref, r0, r1, 0, 13)
+        band = ctx.get_depthmap(ref)
+        for g, b in zip(got, band[:3]):
+            g[r0:r1] = b[r0:r1]
+    for g, x in zip(got, want[:3]):
+        assert np.array_equal(g, x)
+    for r0, r1 in ((5, 5), (-1, 10), (0, h + 1)):
+        with pytest.raises(api.HcmvsError):
+            ctx.estimate_depthmap_rows(ref, r0, r1, 0, 13)
