@@ -83,7 +83,10 @@ __device__ __forceinline__ float dot3f(const float3 a, const float3 b) { return 
 // that pixel is alive (depth != 0, not claimed) — whether it would merge, be invalidated, or be left alone. Only liveness
 // changes during the fusion of this view, so the f64 projections are done once and the rounds below are integer work.
 // raster-ordered compaction of the seeds: per-chunk counts (k_seed_count) -> exclusive scan (k_fuse_scan) -> scatter (k_seed_scatter)
-#define FUSE_CHUNK 1024 // pixels (or seed slots) per block
+#ifndef FUSE_CHUNK
+#define FUSE_CHUNK 256 // pixels (or seed slots) per block of the count / scatter / emit kernels (256 threads)
+#endif
+#define FUSE_ITEMS (FUSE_CHUNK/256) // consecutive pixels / slots per thread: keeps the raster order inside a block
 __device__ __forceinline__ bool is_seed(const FuseView& R, int p) { return R.dn[p].w != 0.f && R.claim[p] != CLAIM_TAKEN; } // SceneDensify.cpp:3347-3354
 __global__ void __launch_bounds__(256) k_seed_count(const FuseArgs a, uint2* __restrict__ blockSums) {
 	__shared__ unsigned sP[8];
@@ -98,13 +101,13 @@ __global__ void __launch_bounds__(256) k_seed_count(const FuseArgs a, uint2* __r
 	if (threadIdx.x == 0) { unsigned t = 0; for (int i=0; i<8; ++i) t += sP[i]; blockSums[blockIdx.x] = make_uint2(t, 0); }
 }
 __global__ void __launch_bounds__(256) k_seed_scatter(const FuseArgs a, const uint2* __restrict__ blockSums, int nBlocks, uint32_t* __restrict__ seeds) {
-	// each thread owns 4 consecutive pixels so that the slots keep raster order
+	// each thread owns FUSE_ITEMS consecutive pixels so that the slots keep raster order
 	__shared__ unsigned sP[256];
 	const FuseView& R = a.views[a.ref];
 	const int nPix = R.w*R.h;
-	const int p0 = blockIdx.x*FUSE_CHUNK+threadIdx.x*4;
-	bool f[4]; unsigned n = 0;
-	for (int i=0; i<4; ++i) { f[i] = p0+i < nPix && is_seed(R, p0+i); n += f[i]; }
+	const int p0 = blockIdx.x*FUSE_CHUNK+threadIdx.x*FUSE_ITEMS;
+	bool f[FUSE_ITEMS]; unsigned n = 0;
+	for (int i=0; i<FUSE_ITEMS; ++i) { f[i] = p0+i < nPix && is_seed(R, p0+i); n += f[i]; }
 	sP[threadIdx.x] = n;
 	__syncthreads();
 	for (int off=1; off<256; off<<=1) {
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(256) k_seed_scatter(const FuseArgs a, const ui
 		__syncthreads();
 	}
 	unsigned slot = blockSums[blockIdx.x].x+(sP[threadIdx.x]-n);
-	for (int i=0; i<4; ++i) if (f[i]) seeds[slot++] = (uint32_t)(p0+i);
+	for (int i=0; i<FUSE_ITEMS; ++i) if (f[i]) seeds[slot++] = (uint32_t)(p0+i);
 	if (blockIdx.x == 0 && threadIdx.x == 0) { const int tot = (int)blockSums[nBlocks].x; a.counters[0] = tot; a.counters[2] = tot; }
 }
 
@@ -326,13 +329,13 @@ struct FuseOut {
 };
 
 __global__ void __launch_bounds__(256) k_fuse_emit(const FuseArgs a, const uint2* __restrict__ blockSums, const FuseOut out) {
-	// each thread owns 4 consecutive pixels of the chunk so that the output keeps raster order
+	// each thread owns FUSE_ITEMS consecutive slots of the chunk so that the output keeps raster order
 	__shared__ unsigned sP[256], sV[256];
 	const FuseView& R = a.views[a.ref];
 	const int nSeeds = (int)a.nSeedsPtr->x;
-	const int s0 = blockIdx.x*FUSE_CHUNK+threadIdx.x*4;
+	const int s0 = blockIdx.x*FUSE_CHUNK+threadIdx.x*FUSE_ITEMS;
 	unsigned nP = 0, nV = 0;
-	for (int i=0; i<4; ++i) { const int s = s0+i; if (s < nSeeds && a.state[s] == 2) { ++nP; nV += 1+__popc(a.mask[s]); } }
+	for (int i=0; i<FUSE_ITEMS; ++i) { const int s = s0+i; if (s < nSeeds && a.state[s] == 2) { ++nP; nV += 1+__popc(a.mask[s]); } }
 	sP[threadIdx.x] = nP; sV[threadIdx.x] = nV;
 	__syncthreads();
 	for (int off=1; off<256; off<<=1) {
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__(256) k_fuse_emit(const FuseArgs a, const uint2
 	const uint2 bs = blockSums[blockIdx.x];
 	unsigned long long ip = out.basePoint+bs.x+(sP[threadIdx.x]-nP);
 	unsigned long long iv = out.baseView+bs.y+(sV[threadIdx.x]-nV);
-	for (int i=0; i<4; ++i) {
+	for (int i=0; i<FUSE_ITEMS; ++i) {
 		const int s = s0+i;
 		if (s >= nSeeds || a.state[s] != 2) continue;
 		const int p = (int)a.seeds[s];
