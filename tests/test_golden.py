@@ -127,3 +127,43 @@ def test_gpu_reproduces_extended_golden():
         assert common.agreement(GX["vs_redblack_depth"], ctx.get_depthmap(ref)[0]) >= 0.99
     finally:
         ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ default init / cloud post-processing
+TRI = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c1_quarter_triinit.npz")
+
+
+def test_host_triangulation_reproduces_golden(built):
+    """TriangulatePointsDelaunay in the product host code == the committed oracle fixture (generated with scipy's Qhull): faces and
+    projected vertices exactly, corner depths to f32 rounding. Needs neither scipy nor a GPU."""
+    import common
+    from hcmvs_b200 import api, host
+    g = np.load(TRI)
+    syn, osc, gt, imgs, ok = common.make_scene(1, 0.25)
+    hs = host.HostScene.from_synth(syn, imgs)
+    for ref in (0, 7):
+        assert hs.select_views(api.default_params(), ref) > 0
+        v, t, lo, hi = hs.triangulate_init(ref)
+        assert np.array_equal(t, g[f"v{ref}_faces"]) and np.array_equal(v[:-4], g[f"v{ref}_vertices"][:-4])
+        assert np.allclose(v[-4:], g[f"v{ref}_vertices"][-4:], rtol=2e-6, atol=0) and np.array_equal(np.array([lo, hi], np.float32), g[f"v{ref}_range"])
+    hs.close()
+
+
+@pytest.mark.gpu
+def test_gpu_default_init_and_cloud_postprocessing_reproduce_golden():
+    """Device rasteriser, EstimatePointColors and PointCloudFilter votes against the committed oracle outputs, bit for bit."""
+    import common
+    g = np.load(TRI)
+    syn, osc, gt, imgs, ok = common.make_scene(1, 0.25)
+    ctx = common.make_context(syn, osc, imgs, ok)
+    try:
+        for ref in (0, 7):
+            lo, hi = g[f"v{ref}_range"]
+            ctx.init_depthmap_triangles(ref, g[f"v{ref}_vertices"], g[f"v{ref}_faces"], float(lo) * 0.9, float(hi) * 1.1)
+            d, n = ctx.get_depthmap(ref)[:2]
+            assert np.array_equal(d, g[f"v{ref}_depth"]) and np.array_equal(n, g[f"v{ref}_normal"])
+        pts, off, views = g["cloud_points"], g["cloud_offsets"], g["cloud_views"]
+        assert np.array_equal(ctx.estimate_point_colors(pts, off, views), g["cloud_colors"])
+        assert np.array_equal(ctx.pointcloud_filter(pts, off, views)[0], g["cloud_visibility"])
+    finally:
+        ctx.close()
