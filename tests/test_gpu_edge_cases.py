@@ -187,3 +187,31 @@ def test_row_band_of_a_small_image_and_bad_ranges(small):
     for r0, r1 in ((5, 5), (-1, 10), (0, h + 1)):
         with pytest.raises(api.HcmvsError):
             ctx.estimate_depthmap_rows(ref, r0, r1, 0, 13)
+
+
+def test_row_bands_in_a_later_outer_iteration():
+    """it_external = 1 ('+'-shaped candidate set, reach 5, EndDepthMapTmp at the end): bands + halo still reproduce the full estimate."""
+    syn, osc, gt, imgs, ok = common.make_scene(1, 0.25)
+    ctx = common.make_context(syn, osc, imgs, ok, nEstimationIters_external=2, propagatehalfwin=5, propagatestep=4)
+    try:
+        ref = 6
+        osc.init_depth_sparse(ref)
+        d0, _, _, lo, hi = osc.get_depthmap(ref)
+        ctx.init_depthmap(ref, d0, None, lo, hi)
+        ctx.estimate_depthmap(ref, 0, 21)
+        first = ctx.get_depthmap(ref)                                 # state after outer iteration 0 (no PASS C yet)
+        ctx.estimate_depthmap(ref, 1, 21)
+        want = ctx.get_depthmap(ref)
+        h = d0.shape[0]
+        got = [np.zeros_like(x) for x in want[:3]]
+        for r0, r1 in ((0, h // 3), (h // 3, 2 * h // 3), (2 * h // 3, h)):
+            ctx.set_depthmap(ref, first[0], first[1], first[2], first[3], first[4])
+            ctx.estimate_depthmap_rows(ref, r0, r1, 1, 21)
+            band = ctx.get_depthmap(ref)
+            for g, b in zip(got, band[:3]):
+                g[r0:r1] = b[r0:r1]
+        for g, x in zip(got, want[:3]):
+            assert np.array_equal(g, x)
+        assert (want[0] > 0).mean() > 0.5
+    finally:
+        ctx.close()
