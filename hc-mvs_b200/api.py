@@ -106,6 +106,7 @@ def load():
     L.hcmvs_fuse_depthmaps.argtypes = [vp, i32, i32, C.POINTER(PointCloudC)]
     L.hcmvs_free_pointcloud.argtypes = [C.POINTER(PointCloudC)]
     L.hcmvs_get_fused_support.argtypes = [vp, u32, vp, vp]
+    L.hcmvs_download_fused_pinned.argtypes = [vp, C.POINTER(PointCloudC)]
     L.hcmvs_estimate_point_colors.argtypes = [vp, C.c_uint64, vp, vp, vp, vp]
     L.hcmvs_pointcloud_filter.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, vp]
     L.hcmvs_get_fused_device.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)] + [C.POINTER(vp)] * 6
@@ -327,6 +328,14 @@ class Context:
         vis = np.zeros(len(points), np.int32)
         self._ck(self.L.hcmvs_pointcloud_filter(self.h, len(points), _p(points), _p(view_offsets), _p(views), _p(vis), _p(stats)))
         return vis, stats
+
+    def download_fused_pinned(self):
+        """Copy the device-resident fused cloud into the context's page-locked arena; returns (n_points, bytes that crossed PCIe)."""
+        pc = PointCloudC()
+        self._ck(self.L.hcmvs_download_fused_pinned(self.h, C.byref(pc)))
+        n = int(pc.n_points)
+        m = int(pc.view_offsets[n]) if n else 0
+        return n, n * (12 + (12 if pc.normals else 0) + (3 if pc.colors else 0) + 4) + 4 + m * 8
 
     def fuse_depthmaps_device(self, color=True, normal=True):
         """FuseDepthMaps leaving the cloud in HBM; returns (n_points, n_view_refs)."""
