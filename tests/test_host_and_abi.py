@@ -39,6 +39,18 @@ def test_every_declared_symbol_is_exported(built):
     assert archs == {"sm_100a"}, archs
 
 
+def test_headers_are_plain_c_and_link_from_c(built, tmp_path):
+    """The drop-in boundary is a C ABI: every header under include/ compiles as strict C99 and a C program links and calls it."""
+    src = tmp_path / "abi_check.c"
+    src.write_text('#include "hcmvs_b200.h"\n#include "hcmvs_host.h"\n#include "hcmvs_synth.h"\n'
+                   'int main(void) { hcmvs_params p; hcmvs_default_params(&p); return (p.nNumViews == 5 && p.nMinViewsTrustPoint == 2 && hcmvs_sync(0) < 0) ? 0 : 1; }\n')
+    inc, libdir = os.path.join(ROOT, "include"), os.path.join(ROOT, "hc-mvs_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I" + inc, str(src)], check=True)
+    exe = tmp_path / "abi_check"
+    subprocess.run(["gcc", "-std=c99", "-I" + inc, str(src), "-L" + libdir, "-lhcmvs_b200", "-Wl,-rpath," + libdir, "-o", str(exe)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
+
+
 def test_no_cpu_fallback_and_error_convention(built):
     """Without a CUDA device creation fails with a message (bool-return convention -> status codes); defaults mirror OPTDENSE."""
     import torch
