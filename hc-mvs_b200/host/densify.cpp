@@ -704,12 +704,14 @@ bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, co
 	std::atomic<uint32_t> next{0}, consumed{0};
 	std::atomic<double> tSelectEnd{t0};
 	const uint32_t lookahead = 24; // bounds the host memory held by prepared depth maps
-	const unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), nImages));
+	// one core stays with this thread: it feeds the GPU, and a worker that spins on it would let the launch queue run dry
+	const unsigned hc = std::thread::hardware_concurrency();
+	const unsigned nt = std::max(1u, std::min(hc > 1 ? hc-1 : 1u, nImages));
 	std::vector<std::thread> pool;
 	for (unsigned t=0; t<nt; ++t) pool.emplace_back([&]() {
 		uint32_t i;
 		while ((i = next.fetch_add(1)) < nImages) {
-			while (i >= consumed.load(std::memory_order_acquire)+lookahead) std::this_thread::yield();
+			while (i >= consumed.load(std::memory_order_acquire)+lookahead) std::this_thread::sleep_for(std::chrono::microseconds(200)); // throttled: sleep, do not spin
 			const bool ok = data.SelectViews(i);
 			if (ok && triangulate) {
 				prep[i].ok = TriangulateInit(scene, i, data.arrDepthData[i].points, true, prep[i].vertices, prep[i].tris, prep[i].dMin, prep[i].dMax);
