@@ -16,7 +16,7 @@ EXPORTS = [
     "hcmvs_set_view", "hcmvs_set_neighbors", "hcmvs_set_neighbor_image", "hcmvs_init_depthmap", "hcmvs_init_depthmap_triangles", "hcmvs_download_depthmap_begin", "hcmvs_download_depthmap_wait", "hcmvs_set_depthmap", "hcmvs_get_depthmap",
     "hcmvs_set_prior", "hcmvs_set_coarse_estimate", "hcmvs_get_coarse_estimate", "hcmvs_snapshot_maps", "hcmvs_get_gradient_map", "hcmvs_score_depthmap", "hcmvs_estimate_depthmap", "hcmvs_estimate_depthmap_rows", "hcmvs_end_depthmap", "hcmvs_score_hypotheses",
     "hcmvs_filter_depthmap", "hcmvs_commit_filtered", "hcmvs_set_fuse_priority", "hcmvs_fuse_depthmaps",
-    "hcmvs_free_pointcloud", "hcmvs_get_fused_device", "hcmvs_get_fused_support", "hcmvs_estimate_point_colors", "hcmvs_pointcloud_filter", "hcmvs_download_fused", "hcmvs_download_fused_pinned", "hcmvs_get_depthmap_device", "hcmvs_set_depth_range", "hcmvs_alloc_depthmap",
+    "hcmvs_free_pointcloud", "hcmvs_get_fused_device", "hcmvs_get_fused_support", "hcmvs_estimate_point_colors", "hcmvs_estimate_point_normals", "hcmvs_pointcloud_filter", "hcmvs_download_fused", "hcmvs_download_fused_pinned", "hcmvs_get_depthmap_device", "hcmvs_set_depth_range", "hcmvs_alloc_depthmap",
     "hcmvs_comm_unique_id", "hcmvs_comm_init", "hcmvs_exchange_maps", "hcmvs_exchange_wait", "hcmvs_export_maps_d", "hcmvs_import_maps_d", "hcmvs_get_timers", "hcmvs_reset_timers", "hcmvs_stream",
 ]
 
@@ -109,6 +109,7 @@ def load():
     L.hcmvs_download_fused_pinned.argtypes = [vp, C.POINTER(PointCloudC)]
     L.hcmvs_estimate_point_colors.argtypes = [vp, C.c_uint64, vp, vp, vp, vp]
     L.hcmvs_pointcloud_filter.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, vp]
+    L.hcmvs_estimate_point_normals.argtypes = [vp, C.c_uint64, vp, vp, vp, C.c_int, vp]
     L.hcmvs_get_fused_device.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)] + [C.POINTER(vp)] * 6
     L.hcmvs_get_depthmap_device.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(vp), C.POINTER(f32), C.POINTER(f32)]
     L.hcmvs_set_depth_range.argtypes = [vp, u32, f32, f32]
@@ -313,6 +314,19 @@ class Context:
         points = np.ascontiguousarray(points, np.float32); view_offsets = np.ascontiguousarray(view_offsets, np.uint32); views = np.ascontiguousarray(views, np.uint32)
         out = np.zeros((len(points), 3), np.uint8)
         self._ck(self.L.hcmvs_estimate_point_colors(self.h, len(points), _p(points), _p(view_offsets), _p(views), _p(out)))
+        return out
+
+    def estimate_point_normals(self, points=None, view_offsets=None, views=None, num_neighbors=16):
+        """MVS::EstimatePointNormals (k-NN PCA, oriented to the first view) for host points or the resident fused cloud."""
+        if points is None:
+            n = C.c_uint64()
+            self._ck(self.L.hcmvs_get_fused_device(self.h, C.byref(n), None, None, None, None, None, None, None))
+            out = np.zeros((int(n.value), 3), np.float32)
+            self._ck(self.L.hcmvs_estimate_point_normals(self.h, 0, None, None, None, num_neighbors, _p(out)))
+            return out
+        points = np.ascontiguousarray(points, np.float32); view_offsets = np.ascontiguousarray(view_offsets, np.uint32); views = np.ascontiguousarray(views, np.uint32)
+        out = np.zeros((len(points), 3), np.float32)
+        self._ck(self.L.hcmvs_estimate_point_normals(self.h, len(points), _p(points), _p(view_offsets), _p(views), num_neighbors, _p(out)))
         return out
 
     def pointcloud_filter(self, points=None, view_offsets=None, views=None):

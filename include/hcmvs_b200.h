@@ -187,6 +187,12 @@ int hcmvs_get_fused_support(hcmvs_ctx* ctx, uint32_t view, float* depth_fuse, fl
  * 1-pixel border. points == NULL: recolour the fused cloud resident on the device (then `colors` may be NULL too); otherwise n_points
  * host points with their CSR view lists -> colors (3 bytes per point, B G R like the images). */
 int hcmvs_estimate_point_colors(hcmvs_ctx* ctx, uint64_t n_points, const float* points, const uint32_t* view_offsets, const uint32_t* views, uint8_t* colors);
+/* MVS::EstimatePointNormals (DepthMap.cpp:2221-2269; `--estimate-normals 1`, SceneDensify.cpp:3570-3571): per point the least-variance
+ * direction of its num_neighbors (reference default 16) nearest neighbours plus itself — what CGAL::pca_estimate_normals computes —
+ * flipped to face the first view that sees the point. points == NULL: the fused cloud resident on the device (its normal buffer is
+ * overwritten; `normals` may be NULL); otherwise host points with CSR view lists -> normals (3 floats per point). The neighbour search
+ * is bounded (about 25 mean point spacings): an isolated outlier with fewer neighbours inside gets the fit of those it has, or 0. */
+int hcmvs_estimate_point_normals(hcmvs_ctx* ctx, uint64_t n_points, const float* points, const uint32_t* view_offsets, const uint32_t* views, int num_neighbors, float* normals);
 /* Scene::PointCloudFilter (SceneDensify.cpp:4189-4320; DensifyPointCloud --filter-point-cloud < 0): the visibility vote of every
  * (point, view) viewing cone over the whole cloud. visibility[i] is the reference's signed count; the caller removes the points with
  * visibility <= thRemove (hcmvs_host::Scene::PointCloudFilter does, in the reference's order). points == NULL: the fused cloud

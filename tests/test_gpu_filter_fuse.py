@@ -188,3 +188,40 @@ def test_pointcloud_filter_votes_match_oracle():
         print(f"\npoint-cloud filter: {m} points, {int(stats[2])} candidate tests ({stats[2] / max(off2[-1], 1):.0f} per cone), {(vis <= -1).sum()} points at or below -1")
     finally:
         ctx.close()
+
+
+def test_estimate_point_normals_matches_oracle():
+    """MVS::EstimatePointNormals: grid k-NN + Jacobi PCA on the device vs cKDTree + eigh. The normal is a function of the neighbour
+    set; wherever that set is unambiguous and the least-variance direction is well separated the two agree to 1e-3 degree."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import point_normals as PN
+    syn, osc, gt, imgs, ok = common.make_scene(1, 0.25)
+    ctx = common.make_context(syn, osc, imgs, ok)
+    try:
+        rng = np.random.default_rng(33)
+        clouds = []
+        xy = rng.uniform(-1.5, 1.5, (20000, 2))                                                      # a noisy slanted plane (the C1 surface)
+        clouds.append(np.stack([xy[:, 0], xy[:, 1], 0.05 * xy[:, 0] + 0.03 * xy[:, 1] + rng.normal(0, 0.003, len(xy))], 1))
+        clouds.append(rng.normal(0, 1, (6000, 3)) * [3.0, 1.0, 0.2])                                 # a volumetric blob: uneven density, no surface
+        clouds.append(np.concatenate([clouds[0][:300] * 50, rng.uniform(-1, 1, (12, 3)) * 1e-3]))   # far apart sparse points + a tiny cluster
+        cams = np.asarray(syn.Cc, np.float64).reshape(-1, 3)
+        for ci, pts in enumerate(clouds):
+            pts = pts.astype(np.float32)
+            n = len(pts)
+            counts = rng.integers(1, 4, n)
+            off = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint32)
+            views = rng.integers(0, syn.n_views, int(off[-1])).astype(np.uint32)
+            for k in (16, 5):
+                got = ctx.estimate_point_normals(pts, off, views, num_neighbors=k)
+                want, gap = PN.estimate_point_normals(pts, off, views, cams, num_neighbors=k)
+                assert np.allclose(np.linalg.norm(got, axis=1), 1, atol=1e-5)
+                ang = np.degrees(np.arccos(np.clip((got * want).sum(axis=1), -1, 1)))
+                well = gap > 1e-3
+                assert well.mean() > 0.9 and np.mean(ang[well] < 1e-3 * 57.3 + 0.02) > 0.999, (ci, k, float(np.mean(ang[well] < 0.08)), float(ang[well].max()))
+                first = views[off[:-1].astype(np.int64)]
+                assert np.all((got * (cams[first].astype(np.float32) - pts)).sum(axis=1) >= -1e-6)    # faces its first view
+        with pytest.raises(Exception):
+            ctx.estimate_point_normals(clouds[0].astype(np.float32), off, views, num_neighbors=64)
+    finally:
+        ctx.close()
