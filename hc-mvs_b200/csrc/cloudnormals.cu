@@ -179,6 +179,7 @@ extern "C" int hcmvs_estimate_point_normals(hcmvs_ctx* ctx, uint64_t n_points, c
 		if (hcmvs_get_fused_device(ctx, &n, &m, &p, &nn, nullptr, &o, &w, nullptr) != HCMVS_OK || !n) { hcmvs_set_error("no fused cloud on the device (call hcmvs_fuse_depthmaps) and no points given"); return HCMVS_ERR_STATE; }
 		if (!nn) { hcmvs_set_error("the resident cloud was fused without normals: fuse with estimate_normal = 1 (the buffer is reused) or pass host points"); return HCMVS_ERR_STATE; }
 		pts_d = (const float*)p; offs_d = (const uint32_t*)o; ids_d = (const uint32_t*)w; nrm_d = (float*)nn;
+		hcmvs_fuse_invalidate_stream(ctx); // the normals streamed to the page-locked arena during the fusion are about to be replaced
 	} else {
 		if (!view_offsets || !views || !normals) { hcmvs_set_error("null argument"); return HCMVS_ERR_ARG; }
 		if (!n) return HCMVS_OK;

@@ -480,6 +480,9 @@ struct FuseState {
 	size_t nPoints = 0, nViewRefs = 0; bool hasColor = false, hasNormal = false; // last fused cloud (device resident)
 };
 
+// the resident cloud was modified in place (recoloured / normals re-estimated): what was streamed to the arena is stale
+void hcmvs_fuse_invalidate_stream(hcmvs_ctx* ctx) { if (ctx && ctx->fuse) ctx->fuse->streamed = false; }
+
 void hcmvs_fuse_release(hcmvs_ctx* ctx) {
 	FuseState* f = ctx->fuse; if (!f) return;
 	cudaFree(f->trace_d); cudaFree(f->probes_d);
@@ -782,7 +785,7 @@ extern "C" int hcmvs_estimate_point_colors(hcmvs_ctx* ctx, uint64_t n_points, co
 	}
 	k_point_colors<<<(unsigned)((n+255)/256), 256, 0, ctx->stream>>>((const FuseView*)base, (int)V, pts_d, off_d, ids_d, col_d, n); ++ctx->nLaunches;
 	CK(cudaGetLastError());
-	if (resident) f->hasColor = true;
+	if (resident) { f->hasColor = true; f->streamed = false; } // the arena copy (if any) no longer matches
 	if (colors) CK(cudaMemcpyAsync(colors, col_d, n*3, cudaMemcpyDeviceToHost, ctx->stream));
 	for (View& v: ctx->views) if (v.set) { int r = hcmvs_mark_image_use(ctx, v); if (r) return r; }
 	CK(cudaStreamSynchronize(ctx->stream));

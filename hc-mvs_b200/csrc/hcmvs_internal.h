@@ -74,6 +74,7 @@ int  hcmvs_scratch(hcmvs_ctx* ctx, size_t bytes, void** out);
 void hcmvs_time_begin(hcmvs_ctx* ctx, int stage);
 void hcmvs_time_end(hcmvs_ctx* ctx);
 void hcmvs_fuse_release(hcmvs_ctx* ctx);
+void hcmvs_fuse_invalidate_stream(hcmvs_ctx* ctx); // the resident fused cloud was edited in place
 void hcmvs_comm_release(hcmvs_ctx* ctx);
 void hcmvs_fill_cam(const View& v, CamConst& c);
 int  hcmvs_mark_image_use(hcmvs_ctx* ctx, View& v);   // record v.lastUse on the compute stream
