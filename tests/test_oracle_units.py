@@ -200,3 +200,77 @@ def test_resize_area_up_matches_opencv():
             want = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_AREA)
             got = O.resize_area_up(src, dw, dh)
             assert np.array_equal(want, got), (sh, sw, dh, dw, cn, np.abs(want - got).max())
+
+
+# ------------------------------------------------------------------------------------------------ numpy oracles of the cloud / init steps
+def _oracle_path():
+    import os, sys
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def test_cloud_filter_oracle_closed_form():
+    """Scene::PointCloudFilter restatement on a hand-made configuration: two points on one viewing ray. The far point's cone (height
+    1.02 x 2) holds the near point, which lies in front and is not depth-similar -> the near point loses #views(far); the near point's
+    cone ends at 1.02 and never reaches the far point; a third point off the ray by 3 pixels is outside both one-pixel cones."""
+    _oracle_path()
+    import cloud_filter as CF
+    f, w = 1000.0, 1000
+    cams = {0: dict(C=np.zeros(3), K=np.array([f, 0, 500, 0, f, 500, 0, 0, 1.0]), width=w), 1: dict(C=np.array([5.0, 0, 0]), K=np.array([f, 0, 500, 0, f, 500, 0, 0, 1.0]), width=w)}
+    pts = np.array([[0, 0, 1.0], [0, 0, 2.0], [3.0 / f * 2.0, 0, 2.0]], np.float32)
+    off = np.array([0, 1, 3, 4], np.uint32)           # point 0: view 0; point 1: views 0 and 1; point 2: view 0
+    views = np.array([0, 0, 1, 0], np.uint32)
+    vis = CF.visibility(cams, pts, off, views)
+    assert vis.tolist() == [-2, 0, 0]
+    # the same ray seen the other way round: a point BEHIND the apex inside its height -> +#views(behind)
+    pts2 = np.array([[0, 0, 2.0], [0, 0, 2.03]], np.float32)   # 1.5 % apart: not depth-similar (1 %), inside 1.02 x 2 = 2.04
+    vis2 = CF.visibility(cams, pts2, np.array([0, 1, 3], np.uint32), np.array([0, 0, 1], np.uint32))
+    assert vis2.tolist() == [-2, 2]                   # cone of point 0 sees point 1 behind it (+2); cone of point 1 (view 0) sees point 0 in front (-2)
+
+
+def test_point_colors_oracle_closed_form():
+    """EstimatePointColors restatement: a point that projects exactly on a pixel centre takes that pixel (weights 1, 0: no truncation
+    loss), the nearer of two views wins, the 1-pixel border and unseen points are white; a half-way sample shows the uint8 truncation
+    of every product (TPixel<uint8_t>::operator*)."""
+    _oracle_path()
+    import point_colors as PC
+    K = np.array([[100.0, 0, 8], [0, 100.0, 6], [0, 0, 1]])
+    P_near = np.hstack([K, np.zeros((3, 1))])                                  # camera at the origin looking down +z
+    P_far = np.hstack([K, (K @ np.array([0, 0, 5.0]))[:, None]])               # the same camera moved back by 5
+    rng = np.random.default_rng(0)
+    img_a = rng.integers(0, 256, (12, 16, 3)).astype(np.uint8); img_b = rng.integers(0, 256, (12, 16, 3)).astype(np.uint8)
+    X = lambda u, v, z: [(u - 8) * z / 100.0, (v - 6) * z / 100.0, z]
+    pts = np.array([X(5, 4, 2.0), X(5, 4, 2.0), X(0.5, 4, 2.0), X(5.5, 4, 2.0), X(5, 4, 2.0)], np.float32)
+    off = np.array([0, 2, 3, 4, 5, 5], np.uint32)
+    views = np.array([1, 0, 0, 0, 0], np.uint32)                               # point 0 lists the far view first: the nearer one must still win
+    got = PC.estimate_point_colors([P_near, P_far], [img_a, img_b], pts, off, views)
+    assert got[0].tolist() == img_a[4, 5].tolist() and got[1].tolist() == img_a[4, 5].tolist()
+    assert got[2].tolist() == [255, 255, 255] and got[4].tolist() == [255, 255, 255]   # inside the 1-pixel border / seen by no view
+    half = (np.float32(0.5) * img_a[4, 5].astype(np.float32)).astype(np.uint8).astype(np.int32) + (np.float32(0.5) * img_a[4, 6].astype(np.float32)).astype(np.uint8)
+    assert got[3].tolist() == half.astype(np.uint8).tolist()                   # floor(a/2) + floor(b/2), not round((a+b)/2)
+
+
+def test_point_normals_and_triangulated_init_oracles_closed_form():
+    """k-NN PCA on an exact plane returns the plane's normal facing the camera; one triangle on a fronto-parallel plane rasterises to a
+    constant depth with the top-left fill rule deciding the shared edge of two triangles exactly once."""
+    _oracle_path()
+    import point_normals as PN
+    import triangulate_init as T
+    rng = np.random.default_rng(1)
+    xy = rng.uniform(-1, 1, (500, 2))
+    n_true = np.array([0.2, -0.3, 1.0]); n_true /= np.linalg.norm(n_true)
+    pts = np.stack([xy[:, 0], xy[:, 1], -(n_true[0] * xy[:, 0] + n_true[1] * xy[:, 1]) / n_true[2]], 1).astype(np.float32)
+    off = np.arange(501, dtype=np.uint32); views = np.zeros(500, np.uint32)
+    nrm, gap = PN.estimate_point_normals(pts, off, views, np.array([[0, 0, 10.0], [0, 0, -10.0]]), 16)
+    assert np.abs((nrm * n_true).sum(axis=1) - 1).max() < 1e-5 and gap.min() > 1e-2      # camera 0 is on the +n side
+    nrm2, _ = PN.estimate_point_normals(pts, off, np.ones(500, np.uint32), np.array([[0, 0, 10.0], [0, 0, -10.0]]), 16)
+    assert np.abs((nrm2 * n_true).sum(axis=1) + 1).max() < 1e-5                          # seen from below: flipped
+    K = np.array([100.0, 0, 8, 0, 100.0, 6, 0, 0, 1])
+    v = np.array([[2.0, 2.0, 4.0], [12.0, 2.0, 4.0], [2.0, 10.0, 4.0], [12.0, 10.0, 4.0]])
+    faces = T.canonical_faces(np.array([[0, 1, 2], [1, 3, 2]]), v[:, :2])
+    d, n = T.rasterize(v, faces, K, 16, 12)
+    inside = np.zeros((12, 16), bool); inside[2:10, 2:12] = True                          # pixel centres in [2, 12) x [2, 10): the fill rule keeps left / top edges
+    assert np.array_equal(d > 0, inside) and np.allclose(d[inside], 4.0, rtol=1e-6) and np.allclose(np.abs(n[inside]), [0, 0, 1], atol=1e-6)
+    d1, _ = T.rasterize(v, faces[:1], K, 16, 12); d2, _ = T.rasterize(v, faces[1:], K, 16, 12)
+    assert not np.any((d1 > 0) & (d2 > 0)) and np.array_equal((d1 > 0) | (d2 > 0), inside)  # the diagonal's pixels belong to exactly one face
