@@ -46,6 +46,9 @@ def lib():
         L.hcmvs_host_num_images.argtypes = [vp]
         L.hcmvs_host_pointcloud_filter.argtypes = [vp, vp, i32]
         L.hcmvs_host_pointcloud_filter.restype = C.c_long
+        L.hcmvs_host_cloud_remove_by_visibility.argtypes = [vp, vp, i32]
+        L.hcmvs_host_cloud_remove_by_visibility.restype = C.c_long
+        L.hcmvs_host_cloud_set.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, vp, vp]
         L.hcmvs_host_delaunay.argtypes = [vp, i32, vp, i32]
         L.hcmvs_host_triangulate_init.argtypes = [vp, i32, i32, vp, i32, vp, i32, C.POINTER(i32), C.POINTER(i32), vp]
         L.hcmvs_host_scene_reload_images.argtypes = [vp, C.c_uint, C.c_uint, C.c_uint]
@@ -199,6 +202,15 @@ class HostScene:
         if r < 0:
             raise RuntimeError(self.L.hcmvs_host_last_error(self.h).decode())
         return r
+
+    def set_cloud(self, xyz, view_offsets, views, normals=None, colors=None, weights=None):
+        a = lambda x, t: None if x is None else np.ascontiguousarray(x, t)
+        xyz, view_offsets, views = a(xyz, np.float32), a(view_offsets, np.uint32), a(views, np.uint32)
+        if self.L.hcmvs_host_cloud_set(self.h, len(xyz), _p(xyz), _p(a(normals, np.float32)), _p(a(colors, np.uint8)), _p(view_offsets), _p(views), _p(a(weights, np.float32))) != 0:
+            raise ValueError("bad cloud")
+
+    def remove_by_visibility(self, visibility, th_remove):
+        return self.L.hcmvs_host_cloud_remove_by_visibility(self.h, _p(np.ascontiguousarray(visibility, np.int32)), th_remove)
 
     def save_ply(self, path):
         if self.L.hcmvs_host_cloud_save_ply(self.h, path.encode()) != 0:

@@ -605,8 +605,13 @@ long Scene::PointCloudFilter(hcmvs_ctx* ctx, int thRemove, std::string* err) {
 	if (!n) return 0;
 	std::vector<int32_t> vis(n);
 	if (hcmvs_pointcloud_filter(ctx, n, pc.points.data(), pc.viewOffsets.data(), pc.views.data(), vis.data(), nullptr) != HCMVS_OK) { if (err) *err = std::string("hcmvs_pointcloud_filter: ")+hcmvs_last_error(); return -1; }
-	// RFOREACH(idxPoint) if (visibility[idxPoint] <= thRemove) pointcloud.RemovePoint(idxPoint) — :4310-4314 with PointCloud::RemovePoint
-	// (PointCloud.cpp:54-69) = cList::RemoveAt: the LAST element takes the removed one's place
+	return RemovePointsByVisibility(pc, vis.data(), thRemove);
+}
+
+long RemovePointsByVisibility(PointCloud& pc, const int32_t* vis, int thRemove) {
+	// RFOREACH(idxPoint) if (visibility[idxPoint] <= thRemove) pointcloud.RemovePoint(idxPoint) — SceneDensify.cpp:4310-4314 with
+	// PointCloud::RemovePoint (PointCloud.cpp:54-69) = cList::RemoveAt: the LAST element takes the removed one's place
+	const size_t n = pc.size();
 	std::vector<uint32_t> order(n);
 	for (size_t i=0; i<n; ++i) order[i] = (uint32_t)i;
 	size_t size = n;
@@ -624,8 +629,8 @@ long Scene::PointCloudFilter(hcmvs_ctx* ctx, int thRemove, std::string* err) {
 		if (hasN) memcpy(&N[k*3], &pc.normals[i*3], 12);
 		if (hasC) memcpy(&C[k*3], &pc.colors[i*3], 3);
 		const uint32_t a = pc.viewOffsets[i], cnt = pc.viewOffsets[i+1]-a;
-		memcpy(&ids[off[k]], &pc.views[a], (size_t)cnt*4);
-		if (hasW) memcpy(&W[off[k]], &pc.weights[a], (size_t)cnt*4);
+		if (cnt) memcpy(&ids[off[k]], &pc.views[a], (size_t)cnt*4);
+		if (hasW && cnt) memcpy(&W[off[k]], &pc.weights[a], (size_t)cnt*4);
 	}
 	auto put = [](auto& arr, const auto& v) { arr.resize(v.size()); if (!v.empty()) memcpy(arr.data(), v.data(), v.size()*sizeof(v[0])); };
 	put(pc.points, P); put(pc.viewOffsets, off); put(pc.views, ids);

@@ -94,6 +94,10 @@ struct Scene {
 	static bool FilterNeighborViews(std::vector<ViewScore>& neighbors, float fMinArea, float fMinScale, float fMaxScale, float fMinAngle, float fMaxAngle, unsigned nMaxViews);
 };
 
+// the removal step of Scene::PointCloudFilter (SceneDensify.cpp:4310-4314): points with visibility <= thRemove, last to first, each hole
+// filled by the then-last point (PointCloud::RemovePoint / cList::RemoveAt). Returns the number of removed points.
+long RemovePointsByVisibility(PointCloud& pc, const int32_t* visibility, int thRemove);
+
 struct DepthData { // host part of MVS::DepthData, libs/MVS/DepthMap.h:214-347
 	std::vector<uint32_t> images;     // [0] = reference, [1..] = matching views
 	std::vector<ViewScore> neighbors; // filtered, <= nMaxViews

@@ -125,6 +125,22 @@ long hcmvs_host_pointcloud_filter(hcmvs_host_scene* s, hcmvs_ctx* ctx, int th_re
 	if (!s || !ctx) return -1;
 	return s->scene.PointCloudFilter(ctx, th_remove, &s->err);
 }
+int hcmvs_host_cloud_set(hcmvs_host_scene* s, uint64_t n, const float* xyz, const float* normals, const uint8_t* colors, const uint32_t* view_offsets, const uint32_t* views, const float* weights) {
+	if (!s || (n && (!xyz || !view_offsets || !views))) return -1;
+	PointCloud& pc = s->scene.densecloud;
+	const size_t m = n ? view_offsets[n] : 0;
+	pc.points.resize(n*3); if (n) memcpy(pc.points.data(), xyz, n*12);
+	pc.viewOffsets.resize(n+1); if (n) memcpy(pc.viewOffsets.data(), view_offsets, (n+1)*4); else pc.viewOffsets.data()[0] = 0;
+	pc.views.resize(m); if (m) memcpy(pc.views.data(), views, m*4);
+	if (normals) { pc.normals.resize(n*3); if (n) memcpy(pc.normals.data(), normals, n*12); } else pc.normals.clear();
+	if (colors) { pc.colors.resize(n*3); if (n) memcpy(pc.colors.data(), colors, n*3); } else pc.colors.clear();
+	if (weights) { pc.weights.resize(m); if (m) memcpy(pc.weights.data(), weights, m*4); } else pc.weights.clear();
+	return 0;
+}
+long hcmvs_host_cloud_remove_by_visibility(hcmvs_host_scene* s, const int32_t* visibility, int th_remove) {
+	if (!s || !visibility) return -1;
+	return RemovePointsByVisibility(s->scene.densecloud, visibility, th_remove);
+}
 int hcmvs_host_cloud_save_ply(hcmvs_host_scene* s, const char* file) { return (s && file && s->scene.densecloud.Save(file)) ? 0 : -1; }
 
 int hcmvs_host_write_dmap(const char* file, const char* image_name, const uint32_t* ids, int n_ids, int image_w, int image_h,

@@ -37,6 +37,10 @@ int hcmvs_host_cloud_save_ply(hcmvs_host_scene* s, const char* file);
 /* Scene::PointCloudFilter(thRemove) (SceneDensify.cpp:4189-4320) on the scene's dense cloud: device votes, removal in the reference's
  * order. Returns the number of removed points, -1 on error. */
 long hcmvs_host_pointcloud_filter(hcmvs_host_scene* s, hcmvs_ctx* ctx, int th_remove);
+/* its removal step alone, on caller-provided votes (no device needed), and a setter for the scene's dense cloud (CSR view lists;
+ * normals / colors / weights may be NULL) */
+long hcmvs_host_cloud_remove_by_visibility(hcmvs_host_scene* s, const int32_t* visibility, int th_remove);
+int hcmvs_host_cloud_set(hcmvs_host_scene* s, uint64_t n, const float* xyz, const float* normals, const uint8_t* colors, const uint32_t* view_offsets, const uint32_t* views, const float* weights);
 /* raw "DR" depth-data files (MVS::ExportDepthDataRaw / ImportDepthDataRaw, DepthMap.cpp:2781-2925) */
 int hcmvs_host_write_dmap(const char* file, const char* image_name, const uint32_t* ids, int n_ids, int image_w, int image_h,
                           const double K[9], const double R[9], const double C[3], float dmin, float dmax, int w, int h,

@@ -162,3 +162,39 @@ def test_scale_image_matches_opencv(built):
         assert np.allclose(Ks[[0, 4, 2, 5]], K[[0, 4, 2, 5]] * s, rtol=1e-7) and Ks[8] == 1
     for sc in (1.0, 0.9, 1.14):                                       # |scale-1| < 0.15: the reference keeps the image
         assert host.scale_image(img, sc) is None
+
+
+def test_pointcloud_filter_removal_order_and_ply_writer(built, tmp_path):
+    """Scene::PointCloudFilter's removal (RFOREACH + RemovePoint: the last point moves into the hole) against a direct simulation, on
+    random votes; then PointCloud::Save: binary little-endian PLY, x y z float32, red green blue uint8 (stored B G R), nx ny nz."""
+    from hcmvs_b200 import host
+    rng = np.random.default_rng(4)
+    n = 5000
+    xyz = rng.standard_normal((n, 3)).astype(np.float32); nrm = rng.standard_normal((n, 3)).astype(np.float32); col = rng.integers(0, 256, (n, 3)).astype(np.uint8)
+    counts = rng.integers(1, 6, n); off = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint32)
+    views = rng.integers(0, 30, int(off[-1])).astype(np.uint32); wts = rng.uniform(0, 1, int(off[-1])).astype(np.float32)
+    vis = rng.integers(-3, 4, n).astype(np.int32)
+    vis[-1] = -3; vis[0] = -3                                                # the last and the first point go too
+    hs = host.HostScene()
+    hs.set_cloud(xyz, off, views, nrm, col, wts)
+    removed = hs.remove_by_visibility(vis, -1)
+    ids = list(range(n))                                                       # the reference's loop, literally
+    for i in range(n - 1, -1, -1):
+        if vis[i] <= -1:
+            last = ids.pop()
+            if i < len(ids):
+                ids[i] = last
+    ids = np.asarray(ids)
+    after = hs.cloud()
+    assert removed == n - len(ids) == int((vis <= -1).sum())
+    assert np.array_equal(after["xyz"], xyz[ids]) and np.array_equal(after["normals"], nrm[ids]) and np.array_equal(after["colors"], col[ids])
+    assert np.array_equal(after["n_views"], counts[ids])
+    assert np.array_equal(after["views"], np.concatenate([views[off[i]:off[i + 1]] for i in ids])) and np.array_equal(after["weights"], np.concatenate([wts[off[i]:off[i + 1]] for i in ids]))
+    assert hs.remove_by_visibility(np.zeros(len(ids), np.int32), -1) == 0     # nothing below the threshold: untouched
+    path = tmp_path / "cloud.ply"
+    hs.save_ply(str(path))
+    head, body = path.read_bytes().split(b"end_header\n", 1)
+    assert head.startswith(b"ply\nformat binary_little_endian 1.0\nelement vertex %d\n" % len(ids)) and head.count(b"property") == 9
+    rec = np.frombuffer(body, dtype=np.dtype([("p", "<f4", 3), ("rgb", "u1", 3), ("n", "<f4", 3)]))
+    assert len(rec) == len(ids) and np.array_equal(rec["p"], xyz[ids]) and np.array_equal(rec["rgb"], col[ids][:, ::-1]) and np.array_equal(rec["n"], nrm[ids])
+    hs.close()
