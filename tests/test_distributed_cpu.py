@@ -82,3 +82,53 @@ def test_owner_arrays_are_consistent_across_ranks():
         assert counts.max() - counts.min() <= 1                       # round-robin in connection order balances the ranks
         sub = plan.owner_array(11, only={0, 5, 9})
         assert set(np.where(sub >= 0)[0]) == {0, 5, 9} and all(sub[v] == owner[v] for v in (0, 5, 9))
+
+
+def _worker_split(rank, world, port, q):
+    """The lib-NCCL schedule of bench.py on CPU tensors: whole rounds broadcast per view from their owner, the views of the incomplete
+    last round estimated in row bands by every rank and assembled by in-place broadcasts of the bands (HCMVS_OWNER_SPLIT_ROWS)."""
+    sys.path.insert(0, ROOT)
+    from hcmvs_b200 import shard
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    h, w = 13, 5                                                      # 13 rows over 2 ranks: bands of 6 and 7 rows
+    valid = list(range(7)); nall = {v: 9 - (v % 3) for v in valid}
+    plan = shard.make_plan(valid, nall, world, split_rows=True)
+    maps = {v: torch.zeros((h, w, 4)) for v in valid}                 # every rank holds a buffer for every view
+    for v in plan.whole_views_of(rank):
+        maps[v] = torch.from_numpy(_expected(v, h, w)[0])
+    r0, r1 = plan.rows_of(rank, h)
+    for v in plan.split_views():
+        maps[v][r0:r1] = torch.from_numpy(_expected(v, h, w)[0])[r0:r1]   # only this rank's band is valid
+        maps[v][:r0] = -7.0; maps[v][r1:] = -7.0                           # halo by-products: must be overwritten by the owners
+    def exchange(owner):
+        for v in range(len(owner)):
+            if owner[v] == shard.OWNER_SPLIT_ROWS:
+                for r in range(world):
+                    a, b = plan.rows_of(r, h)
+                    band = maps[v][a:b].contiguous()
+                    dist.broadcast(band, src=r)
+                    maps[v][a:b] = band
+            elif owner[v] >= 0:
+                dist.broadcast(maps[v], src=int(owner[v]))
+    for own in plan.round_owner_arrays(len(valid)):
+        exchange(own)
+    exchange(plan.split_owner_array(len(valid)))
+    ok = all(np.array_equal(maps[v].numpy(), _expected(v, h, w)[0]) for v in valid)
+    q.put((rank, ok, len(plan.split_views()), (r0, r1)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_row_split_exchange_gloo():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_split, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), "a rank did not end up with every view's full maps"
+    assert all(r[2] == 1 for r in res) and [r[3] for r in res] == [(0, 6), (6, 13)]   # 7 views on 2 ranks: 3 whole rounds + 1 split view
