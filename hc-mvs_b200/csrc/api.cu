@@ -40,7 +40,8 @@ extern "C" void hcmvs_default_params(hcmvs_params* p) {
 // ------------------------------------------------------------------------------------------------ context
 static int CheckParams(const hcmvs_params& p) {
 	if (p.adapthalfwin < 1 || p.adapthalfwin > 7) { hcmvs_set_error("adapthalfwin must be in [1,7] (reference nTexels = 64, DepthMap.h:358)"); return HCMVS_ERR_ARG; }
-	if (p.nRandomIters > 64 || p.nEstimationIters > 60) { hcmvs_set_error("iteration counts out of range"); return HCMVS_ERR_ARG; }
+	// the refinement walks scaleRanges[] (12 entries, DepthMap.cpp:384) from index <= 2 by at most nRandomIters steps
+	if (p.nRandomIters > 9 || p.nEstimationIters > 60) { hcmvs_set_error("iteration counts out of range (nRandomIters <= 9: scaleRanges has 12 entries, DepthMap.cpp:384)"); return HCMVS_ERR_ARG; }
 	if (p.rb_far_reach < 1) { hcmvs_set_error("rb_far_reach must be >= 1"); return HCMVS_ERR_ARG; }
 	if (p.rb_prop_dirs != 2 && p.rb_prop_dirs != 4) { hcmvs_set_error("rb_prop_dirs must be 2 or 4"); return HCMVS_ERR_ARG; }
 	if (!(p.fNCCThresholdKeep > 0.f)) { hcmvs_set_error("fNCCThresholdKeep must be > 0"); return HCMVS_ERR_ARG; }
@@ -476,6 +477,8 @@ extern "C" int hcmvs_download_depthmap_wait(hcmvs_ctx* ctx, int slot, const floa
 	if (!ctx || slot < 0 || slot >= HCMVS_DOWNLOAD_SLOTS) { hcmvs_set_error("download slot %d out of range", slot); return HCMVS_ERR_ARG; }
 	DownloadSlot& d = ctx->dl[slot];
 	if (!d.pending) { hcmvs_set_error("download slot %d holds nothing", slot); return HCMVS_ERR_STATE; }
+	// THREADING CONTRACT: this is the one entry point that may run on another thread (a .dmap writer) while the owning thread keeps
+	// driving the context. It therefore touches nothing but its own slot and that slot's event — no timers, no scratch, no stream.
 	cudaSetDevice(ctx->device);
 	CK(cudaEventSynchronize(d.landed));
 	const float* h = (const float*)d.host;
@@ -526,7 +529,7 @@ extern "C" int hcmvs_set_coarse_estimate(hcmvs_ctx* ctx, uint32_t view, int wc, 
 	cudaSetDevice(ctx->device);
 	if (!depth) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(v->coarse_d); v->coarse_d = nullptr; return HCMVS_OK; }
 	if (!normal || wc < 2 || hc < 2) { hcmvs_set_error("coarse estimate needs depth and normal maps of at least 2x2"); return HCMVS_ERR_ARG; }
-	if (wc > v->w && hc > v->h) { hcmvs_set_error("coarse estimate %dx%d is larger than view %u (%dx%d): INTER_AREA decimation is not the hand-off the restore tree does", wc, hc, view, v->w, v->h); return HCMVS_ERR_UNSUPPORTED; }
+	if (wc > v->w || hc > v->h) { hcmvs_set_error("coarse estimate %dx%d is larger than view %u (%dx%d): INTER_AREA decimation is not the hand-off the restore tree does", wc, hc, view, v->w, v->h); return HCMVS_ERR_UNSUPPORTED; }
 	if (!v->hasMaps) { hcmvs_set_error("view %u has no depth map / range yet (call hcmvs_init_depthmap first)", view); return HCMVS_ERR_STATE; }
 	const size_t nc = (size_t)wc*hc, n = (size_t)v->w*v->h;
 	float* tmp; int r = hcmvs_scratch(ctx, nc*16+64, (void**)&tmp); if (r) return r;

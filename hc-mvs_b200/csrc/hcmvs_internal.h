@@ -65,6 +65,7 @@ struct hcmvs_ctx {
 	FuseState* fuse = nullptr;
 	SpreadConst* spread_d = nullptr; // viewspread constants of the view being estimated
 	void* comm = nullptr; int rank = 0, world = 1; // NCCL communicator of hcmvs_comm_init (exchange.cu)
+	void* ctlComm = nullptr; cudaStream_t ctlStream = nullptr; float* ctl_d = nullptr; size_t ctlCap = 0; // pre-exchange agreement (status + depth ranges)
 	DownloadSlot dl[HCMVS_DOWNLOAD_SLOTS]; cudaStream_t dlStream = nullptr; // device->host stream of the map read-back
 	cudaStream_t commStream = nullptr; cudaEvent_t commDone = nullptr, commReady = nullptr; bool commPending = false; // asynchronous exchanges
 };

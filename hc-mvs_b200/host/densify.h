@@ -53,6 +53,11 @@ struct SparsePoints { // the part of MVS::PointCloud the densifier reads
 // Array that either owns its storage or borrows it (the fused cloud lives in the CUDA context's page-locked arena)
 template<typename T>
 struct Array {
+	Array() = default;
+	// an owning array re-points at its own storage when copied or moved; a borrowing one keeps the borrowed pointer
+	Array(const Array& o) : p(o.p), n(o.n), own(o.own) { if (!own.empty()) p = own.data(); }
+	Array(Array&& o) noexcept : p(o.p), n(o.n), own(std::move(o.own)) { if (!own.empty()) p = own.data(); o.p = nullptr; o.n = 0; }
+	Array& operator=(Array o) noexcept { own.swap(o.own); n = o.n; p = own.empty() ? o.p : own.data(); return *this; }
 	const T* data() const { return p; }
 	T* data() { return own.empty() ? const_cast<T*>(p) : own.data(); }
 	size_t size() const { return n; }

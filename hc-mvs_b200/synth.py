@@ -22,7 +22,7 @@ class SynthCfg(C.Structure):
 
 
 def _load():
-    path = os.path.join(_HERE, "libhcmvs_host.so")
+    path = os.path.join(_HERE, "libhcmvs_synth.so")  # stand-alone: loads nothing of the CUDA product
     if not os.path.exists(path):
         raise ImportError(f"{path} missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
     lib = C.CDLL(path)

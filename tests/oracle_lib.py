@@ -166,6 +166,11 @@ class OracleScene:
         self.L.orc_get_depthmap(self.h, i, _p(d), _p(n), _p(c), _p(mm))
         return d, n, c, float(mm[0]), float(mm[1])
 
+    def set_prior(self, i, prior):
+        """DepthData::depthMapPrior (DepthMap.cpp:941-955); None removes it."""
+        prior = np.ascontiguousarray(prior, np.float32) if prior is not None else None
+        assert self.L.orc_set_prior(self.h, i, _p(prior)) == 0
+
     def set_coarse(self, i, depth, normal):
         """restore tree: coarse maps of the previous level -> resized to the view, widen [dMin,dMax) (None clears)."""
         if depth is None:

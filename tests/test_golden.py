@@ -47,8 +47,10 @@ def test_gpu_reproduces_golden():
     ctx.estimate_depthmap(ref, 0, seed=3)
     gd = ctx.get_depthmap(ref)[0]
     assert common.agreement(G["redblack_depth"], gd) >= 0.99           # same algorithm, same counter RNG
-    both = (G["raster_depth"] > 0) & (G["redblack_depth"] > 0) & (np.abs(G["raster_depth"] - G["redblack_depth"]) / np.maximum(G["raster_depth"], 1e-9) < 0.01)
-    assert common.agreement(G["raster_depth"], gd, mask=both) >= 0.98   # vs the reference's raster sweep, where that is well defined
+    # vs the reference's raster sweep, UNMASKED: the GPU is as close to it as the CPU statement of the same red-black algorithm is
+    # (160x120 view: the rim seen by fewer than two matching views is a large share of the map, see tests/test_gpu_gates.py)
+    a_raster = common.agreement(G["raster_depth"], gd)
+    assert a_raster >= common.agreement(G["raster_depth"], G["redblack_depth"]) - 0.005, a_raster
     for i in range(syn.n_views):
         d = G[f"map{i}_depth"]
         ctx.set_depthmap(i, d, gt[i][1], G[f"map{i}_conf"], float(gt[i][0][gt[i][0] > 0].min() * 0.5), float(gt[i][0].max() * 2))
@@ -166,4 +168,81 @@ def test_gpu_default_init_and_cloud_postprocessing_reproduce_golden():
         assert np.array_equal(ctx.estimate_point_colors(pts, off, views), g["cloud_colors"])
         assert np.array_equal(ctx.pointcloud_filter(pts, off, views)[0], g["cloud_visibility"])
     finally:
+        ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ third fixture: the plane-prior cost term
+import make_golden_prior  # noqa: E402
+
+GP = np.load(os.path.join(HERE, "golden", "c1_quarter_prior.npz"))
+
+
+def test_oracle_reproduces_prior_golden_and_the_closed_form():
+    """DepthMap.cpp:941-955. The oracle still reproduces the stored scores, and the stored scores obey the reference's formula: every
+    valid view score goes through the same affine map s -> s (1 - pp) + 2 (1 - exp(-D^2 / (2 sigma^2))) pp, D = |prior - d| / prior, so
+    wherever the two best views are both below thRobust before and after, the aggregated score (their mean) follows the same map."""
+    cur = make_golden_prior.build()
+    assert set(cur) == set(GP.files)
+    for k in ("prior", "hyp_depth", "hyp_normal", "score_noprior", "score_prior0", "init_depth", "init_range"):
+        assert np.array_equal(cur[k], GP[k]), k
+    assert np.abs(cur["score_prior1"] - GP["score_prior1"]).max() < 2e-6       # smoothness: libm expf / acosf last-bit drift
+    for k in ("it0_depth", "it1_depth", "it1_depth_noprior"):
+        assert common.agreement(GP[k], cur[k]) > 0.97, k
+    pp, sg = make_golden_prior.PRIOR_PARAMS["para_prior"], make_golden_prior.PRIOR_PARAMS["fsigmaPrior"]
+    s0, s1, pr, d = GP["score_noprior"].astype(np.float64), GP["score_prior0"].astype(np.float64), GP["prior"].astype(np.float64), GP["hyp_depth"].astype(np.float64)
+    inner = GP["score_noprior"] != 2.0
+    assert np.array_equal(GP["score_prior0"][inner & (pr == 0)], GP["score_noprior"][inner & (pr == 0)])   # no prior at the pixel: untouched
+    with np.errstate(divide="ignore", invalid="ignore"):
+        D = np.abs(pr - d) / pr
+    term = 2 * (1 - np.exp(-D * D / (2 * sg * sg))) * pp
+    th_robust = 1.2 * 0.55
+    # both best views valid (aggregate well below thRobust/2 + slack on either side) -> the aggregate is the mean of two mapped scores
+    clean = inner & (pr != 0) & (s0 < 0.25) & (s1 < 0.45)
+    assert clean.sum() > 2000
+    want = s0 * (1 - pp) + term
+    assert np.abs(want - s1)[clean].max() < 5e-6, np.abs(want - s1)[clean].max()
+    assert th_robust > 0.6
+
+
+@pytest.mark.gpu
+def test_gpu_prior_term_matches_oracle_and_golden():
+    """hcmvs_set_prior + the prior-weighted cost on the device: per-hypothesis scores within 1e-4 of the stored oracle scores, and the
+    authors' two-outer-iteration schedule (photo2geo 1) reproduces the oracle's red-black maps — live oracle and fixture."""
+    syn, osc, gt, imgs, ok = common.make_scene(1, 0.25)
+    ctx = common.make_context(syn, osc, imgs, ok)
+    ref = make_golden_prior.REF
+    try:
+        ctx.set_params(photo2geo=0, **make_golden_prior.PRIOR_PARAMS)
+        d, n = GP["hyp_depth"], GP["hyp_normal"]
+        assert np.abs(ctx.score_hypotheses(ref, d, n, 0) - GP["score_noprior"]).max() <= 1e-4
+        ctx.set_prior(ref, GP["prior"])
+        got0 = ctx.score_hypotheses(ref, d, n, 0)
+        assert np.abs(got0 - GP["score_prior0"]).max() <= 1e-4
+        assert np.abs(ctx.score_hypotheses(ref, d, n, 1) - GP["score_prior1"]).max() <= 1e-4
+        assert np.mean(got0 != GP["score_noprior"]) > 0.5                      # the term is really on
+        over = dict(nEstimationIters=2, nEstimationIters_external=2, propagatehalfwin=5, propagatestep=4, photo2geo=1)
+        ctx.set_params(**over)
+        lo, hi = float(GP["init_range"][0]), float(GP["init_range"][1])
+        ctx.init_depthmap(ref, GP["init_depth"], None, lo, hi)
+        ctx.estimate_depthmap(ref, 0, seed=71)
+        assert common.agreement(GP["it0_depth"], ctx.get_depthmap(ref)[0]) >= 0.99      # outer iteration 0 < photo2geo: prior ignored
+        ctx.estimate_depthmap(ref, 1, seed=71)
+        g1 = ctx.get_depthmap(ref)
+        a_fix = common.agreement(GP["it1_depth"], g1[0])
+        a_without = common.agreement(GP["it1_depth_noprior"], g1[0])
+        # live oracle with the same prior
+        osc.set_params(**over, **make_golden_prior.PRIOR_PARAMS)
+        osc.set_prior(ref, GP["prior"])
+        osc.init_depth_sparse(ref)
+        osc.estimate(ref, it_external=0, seed=71, threads=4, mode=2, far_reach=11)
+        osc.estimate(ref, it_external=1, seed=71, threads=4, mode=2, far_reach=11)
+        od = osc.get_depthmap(ref)[0]
+        osc.set_prior(ref, None)
+        osc.set_params(nEstimationIters=3, nEstimationIters_external=1, propagatehalfwin=1, propagatestep=4, photo2geo=2, para_prior=0.3, fsigmaPrior=0.2)
+        a_live = common.agreement(od, g1[0])
+        print(f"\nprior term: GPU vs stored oracle run {a_fix:.4f}, vs live oracle {a_live:.4f}; vs the run WITHOUT the prior {a_without:.4f}")
+        assert a_fix >= 0.99 and a_live >= 0.995
+        assert a_without < a_fix - 0.02                                         # and it changes the result the way it does in the oracle
+    finally:
+        ctx.set_prior(ref, None)
         ctx.close()

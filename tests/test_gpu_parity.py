@@ -112,7 +112,9 @@ def test_estimate_matches_redblack_oracle_and_reference(scene, ctx):
           f"on self-consistent pixels {a_ref:.4f}); within 1% of GT: GPU {a_gt_gpu:.4f} reference {a_gt_ref:.4f}; "
           f"hyp/pixel-iter {t['n_hypotheses'] / max(t['n_pixel_iters'], 1):.2f}")
     assert a_rb >= 0.995
-    assert a_ref >= 0.98
+    # UNMASKED against the reference's raster sweep: as close to it as a second run of the reference itself (another seed) is
+    assert a_ref_raw >= a_self - 0.015, (a_ref_raw, a_self)
+    assert a_ref >= 0.98               # (additional) on the pixels where the reference agrees with itself
     assert a_gt_gpu >= a_gt_ref - 0.01
 
 
