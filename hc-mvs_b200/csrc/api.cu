@@ -81,7 +81,7 @@ static void FreeView(View& v) {
 	if (v.ready) cudaEventDestroy(v.ready);
 	if (v.imgReady) cudaEventDestroy(v.imgReady);
 	if (v.lastUse) cudaEventDestroy(v.lastUse);
-	cudaFree(v.img_d); cudaFree(v.bgr_d); cudaFree(v.gra_d); cudaFree(v.dn_d); cudaFree(v.conf_d); cudaFree(v.prior_d); cudaFree(v.coarse_d); cudaFree(v.dnPrev_d); cudaFree(v.confPrev_d); cudaFree(v.fdepth_d); cudaFree(v.fconf_d); cudaFree(v.claim_d);
+	cudaFree(v.img_d); cudaFree(v.bgr_d); cudaFree(v.gra_d); cudaFree(v.dn_d); cudaFree(v.conf_d); cudaFree(v.prior_d); cudaFree(v.coarse_d); cudaFree(v.dnPrev_d); cudaFree(v.confPrev_d); cudaFree(v.fdepth_d); cudaFree(v.fconf_d);
 	v = View();
 }
 

@@ -6,49 +6,81 @@
 // depths it occludes. Later seeds see those claims / zeroed depths, so the result is order dependent.
 // That order is kept here by "deterministic reservations": views are still processed one after another, but
 // inside a view every undecided seed reserves (atomicMin of its raster index) each neighbour pixel it would
-// touch; a seed that holds all its reservations precedes every undecided seed it conflicts with, so it can
-// run its CPU action immediately. Seeds with disjoint footprints commit in the same round; the lowest
-// undecided seed always commits, so the loop terminates, and the outcome is bit-identical to the raster
-// scan. One cooperative launch per view (grid.sync between the reserve and commit phases), then a
-// raster-ordered scan/compaction writes the points in the CPU's order.
+// touch; a seed that holds a reservation precedes every undecided seed it conflicts with, so it can run its
+// CPU action on that pixel immediately. Seeds with disjoint footprints commit in the same round; the lowest
+// undecided seed always commits, so the loop terminates, and the outcome is bit-identical to the raster scan.
+//
+// Round 2 layout (profiles/r02_notes.md): the whole scene is fused by ONE persistent cooperative kernel
+// (k_fuse_scene; grid.sync between the stages of a view, no launch gaps, no host round trip per view), over
+// 32-byte per-pixel RECORDS {depth, claim, world normal, weight, colour} built once per scene, so that every
+// probe of a neighbour pixel is ONE aligned DRAM sector (the round-1 kernels gathered float4 + claim word +
+// conf + colour from four arrays: 2 sectors per probe, 3 more per merged view in the emit).
 #include "hcmvs_internal.h"
 #include "camera.cuh"
 #include <cooperative_groups.h>
-#include <cooperative_groups/reduce.h>
 #include <vector>
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
 #include <cstdio>
+#include <sched.h>
 
 namespace cg = cooperative_groups;
 
 namespace hcmvs {
 
 #define CLAIM_FREE 0xFFFFFFFFu
-#define CLAIM_TAKEN 0xFFFFFFFEu
+
+// one pixel of one view as the fusion reads it: 32 bytes = one DRAM sector, READ-ONLY during the fusion (what changes — liveness
+// and reservations — lives in the bitmap and the compact claim array below), derived once from the view's maps: world-space normal (Cast<float>(R^T n), SceneDensify.cpp:3358), Conf2Weight(conf, depth)
+// (:154-156, :3357), the colour packed b | g<<8 | r<<16
+struct __align__(32) FuseRec { float depth; uint32_t pad0; float nx, ny; float nz, weight; uint32_t bgr; uint32_t pad1; };
+static_assert(sizeof(FuseRec) == 32, "one sector per pixel");
 
 struct FuseView {
-	float4* dn; const float* conf; const uint8_t* bgr; uint32_t* claim;
-	int w, h; int hasMaps;
+	FuseRec* rec; float4* dn; const uint8_t* bgr;
+	uint32_t* alive;   // 1 bit per pixel: depth != 0, not merged into a point, not zeroed (SceneDensify.cpp:3347-3354, :3396-3398). All views
+	                   // together are ~12 MB: L2 resident. It IS the liveness: every transition clears the bit before the phase's barrier.
+	uint32_t* claim;   // per pixel: CLAIM_FREE or the raster index of the seed that reserved it (4 B/px: 8 pixels per sector)
+	int w, h; int hasMaps; int hasBgr;
 	CamConst cam;
 };
 
-struct FuseArgs {
-	FuseView* views;
-	int ref;
-	int nNb; int nb[HCMVS_MAX_FUSE_VIEWS];
-	unsigned nMinViewsFuse;
-	float depthTh, normalError;
-	// Seeds (valid, unclaimed pixels of the reference view) are COMPACTED in raster order before anything else: slot s <-> pixel
-	// seeds[s]. Only ~1 pixel in 6 of a C2 view is a seed and they are scattered, so per-pixel kernels ran with 5 of 32 lanes active
-	// (ncu: thread_inst_executed_per_inst_executed 5.3); every per-seed array below is indexed by slot.
-	const uint32_t* seeds; const uint2* nSeedsPtr; // nSeedsPtr->x = number of seeds (device resident: no host round trip)
-	uint8_t* state;   // per seed slot: 0 removed, 1 undecided, 2 emitted, 3 emitted but still waiting for contested probes
+// a view in fusion order with the neighbours it probes (DepthData::neighbors, all of them — not only the matching ones)
+struct FusePlanView { int view; int nNb; int nb[HCMVS_MAX_FUSE_VIEWS]; int order[HCMVS_MAX_FUSE_VIEWS+1]; }; // order: -1 (the view itself) and 0..nNb-1 sorted by view id
+
+struct FuseOut {
+	float* points; float* normals; uint8_t* colors; uint32_t* viewOffsets; uint32_t* views; float* weights;
+	unsigned long long capPoints, capRefs;
+	int estimateColor, estimateNormal;
+};
+
+// per-seed-slot state of the view being fused; two sets, so that the emit of view r-1 shares its stages with the seed scan of view r
+struct FuseSlots {
+	uint32_t* seeds;  // slot -> pixel (raster order)
+	uint8_t* state;   // 0 removed, 1 undecided, 2 emitted, 3 emitted but still waiting for contested probes
 	uint32_t* mask;   // merged neighbours (bit k = nb[k]) of emitted seeds
-	int* counters;    // [0] undecided seeds, [1] rounds, [2] seeds
-	int* trace;       // optional: undecided seeds after each round (debug)
-	uint32_t* probes; size_t probeStride; // [neighbour][slot] probe cache
+	uint32_t* probes; // [neighbour][slot] probe cache, stride probeStride
+	float4* stgPoint; float4* stgNormal; // staged fused point (xyz, packed colour) and normal of a final slot
+	float* stgW;      // [1 + neighbour][slot] staged weights (0: the seed's own), stride probeStride
+};
+
+struct FuseCtl {
+	unsigned wlCount[2]; int overflow; int pad;
+	unsigned long long cumPoints, cumRefs;   // cloud size after the views emitted so far
+	unsigned long long rounds, seeds, probes;
+};
+
+struct FuseJob {
+	FuseView* views; const FusePlanView* plan; int nPlan;
+	FuseSlots sl[2]; size_t probeStride;
+	uint32_t* wl[2];                  // undecided slots of the current / next round
+	unsigned* blkSeeds; unsigned* blkEmit; // per-block counts of the two ordered compactions (blkEmit: points, view references)
+	FuseCtl* ctl;
+	unsigned nMinViewsFuse; float depthTh, normalError;
+	FuseOut out;
+	volatile unsigned long long* progress; // host-mapped: [0] views emitted, [1+2r], [2+2r] cloud size after view r (nullable)
+	unsigned long long* trace;        // debug: 6 globaltimer stamps + 2 counters per view (HCMVS_FUSE_DEBUG)
 };
 
 struct Probe { int q; float z; };
@@ -77,337 +109,465 @@ __device__ __forceinline__ float dot3f(const float3 a, const float3 b) { return 
 #define PROBE_MERGE 1u   // depth and normal agree (SceneDensify.cpp:3400-3423): claimed if the seed survives
 #define PROBE_INVAL 2u   // occluded by the seed (:3424-3427): zeroed if the seed survives
 #define PROBE_DEAD  0xFFFFFFFFu
+#define PROBE_PIX   0x3FFFFFFFu
 
-// ---- phase 0 (own kernel, full grid): find the seeds (valid depth, not yet claimed, SceneDensify.cpp:3347-3354) and classify
-// their probes. The geometry of a probe is static: the seed's 3-D point, the pixel it hits in each neighbour view, and — while
-// that pixel is alive (depth != 0, not claimed) — whether it would merge, be invalidated, or be left alone. Only liveness
-// changes during the fusion of this view, so the f64 projections are done once and the rounds below are integer work.
-// raster-ordered compaction of the seeds: per-chunk counts (k_seed_count) -> exclusive scan (k_fuse_scan) -> scatter (k_seed_scatter)
-#ifndef FUSE_CHUNK
-#define FUSE_CHUNK 256 // pixels (or seed slots) per block of the count / scatter / emit kernels (256 threads)
+// Everything the stages of the persistent kernel exchange goes through L2 (ld.cg / st.cg): the kernel never ends between the
+// stages, so L1 lines would go stale.
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define FUSE_STAMP(i) do { if (a.trace && gtid == 0 && r < a.nPlan) a.trace[8*r+(i)] = gtimer(); } while (0)
+
+// ------------------------------------------------------------------ records: one pass over a view's maps
+__global__ void __launch_bounds__(256) k_fuse_build(const FuseView* __restrict__ views, int view, const float* __restrict__ conf, unsigned long long* __restrict__ nValid) {
+	const FuseView& V = views[view];
+	const size_t n = (size_t)V.w*V.h;
+	const size_t i = (size_t)blockIdx.x*blockDim.x+threadIdx.x;
+	unsigned valid = 0;
+	if (i < n) {
+		const float4 e = V.dn[i];
+		const float3 nw = cam_NormalC2W(V.cam, make_float3(e.x, e.y, e.z));
+		uint32_t c = 0;
+		if (V.bgr) { const uint8_t* s = V.bgr+i*3; c = (uint32_t)s[0] | ((uint32_t)s[1]<<8) | ((uint32_t)s[2]<<16); }
+		uint4* dst = reinterpret_cast<uint4*>(V.rec+i);
+		dst[0] = make_uint4(__float_as_uint(e.w), 0u, __float_as_uint(nw.x), __float_as_uint(nw.y));
+		dst[1] = make_uint4(__float_as_uint(nw.z), __float_as_uint(conf2weight(conf[i], e.w)), c, 0u);
+		valid = e.w != 0.f;
+	}
+	const unsigned word = __ballot_sync(0xffffffffu, valid);
+	if ((threadIdx.x&31) == 0 && i < n) V.alive[i>>5] = word;
+	valid = __reduce_add_sync(0xffffffffu, valid);
+	if ((threadIdx.x&31) == 0 && valid) atomicAdd(nValid, (unsigned long long)valid);
+}
+
+// ------------------------------------------------------------------ block helpers (256 threads)
+#define FUSE_NT 256
+// exclusive prefix of v over the block + block total; `sw` = 8 words of shared memory
+__device__ __forceinline__ unsigned block_scan(unsigned v, unsigned* sw, unsigned& total) {
+	const int lane = threadIdx.x&31, wid = threadIdx.x>>5;
+	unsigned inc = v;
+	#pragma unroll
+	for (int o=1; o<32; o<<=1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+	__syncthreads(); // sw may still be read by the previous call
+	if (lane == 31) sw[wid] = inc;
+	__syncthreads();
+	unsigned base = 0, tot = 0;
+	#pragma unroll
+	for (int i=0; i<FUSE_NT/32; ++i) { const unsigned t = sw[i]; if (i < wid) base += t; tot += t; }
+	total = tot;
+	return base+inc-v;
+}
+// sum over the block
+__device__ __forceinline__ unsigned long long block_sum(unsigned long long v, unsigned long long* sw) {
+	#pragma unroll
+	for (int o=16; o>0; o>>=1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	__syncthreads();
+	if ((threadIdx.x&31) == 0) sw[threadIdx.x>>5] = v;
+	__syncthreads();
+	unsigned long long t = 0;
+	#pragma unroll
+	for (int i=0; i<FUSE_NT/32; ++i) t += sw[i];
+	return t;
+}
+
+// ------------------------------------------------------------------ stages of one view
+#define FUSE_FN __forceinline__
+#ifdef FUSE_CHECK
+#define FUSE_CHK(cond, id) do { if (!(cond)) { atomicCAS(&a.ctl->overflow, 0, (id)); return; } } while (0)
+#define FUSE_CHKR(cond, id) do { if (!(cond)) { atomicCAS(&a.ctl->overflow, 0, (id)); return 0; } } while (0)
+#else
+#define FUSE_CHK(cond, id) do { } while (0)
+#define FUSE_CHKR(cond, id) do { } while (0)
 #endif
-#define FUSE_ITEMS (FUSE_CHUNK/256) // consecutive pixels / slots per thread: keeps the raster order inside a block
-__device__ __forceinline__ bool is_seed(const FuseView& R, int p) { return R.dn[p].w != 0.f && R.claim[p] != CLAIM_TAKEN; } // SceneDensify.cpp:3347-3354
-__global__ void __launch_bounds__(256) k_seed_count(const FuseArgs a, uint2* __restrict__ blockSums) {
-	__shared__ unsigned sP[8];
-	const FuseView& R = a.views[a.ref];
-	const int nPix = R.w*R.h;
-	unsigned n = 0;
-	const int base = blockIdx.x*FUSE_CHUNK;
-	for (int i=threadIdx.x; i<FUSE_CHUNK; i+=256) { const int p = base+i; if (p < nPix && is_seed(R, p)) ++n; }
-	for (int s=16; s>0; s>>=1) n += __shfl_xor_sync(0xffffffffu, n, s);
-	if ((threadIdx.x&31) == 0) sP[threadIdx.x>>5] = n;
-	__syncthreads();
-	if (threadIdx.x == 0) { unsigned t = 0; for (int i=0; i<8; ++i) t += sP[i]; blockSums[blockIdx.x] = make_uint2(t, 0); }
-}
-__global__ void __launch_bounds__(256) k_seed_scatter(const FuseArgs a, const uint2* __restrict__ blockSums, int nBlocks, uint32_t* __restrict__ seeds) {
-	// each thread owns FUSE_ITEMS consecutive pixels so that the slots keep raster order
-	__shared__ unsigned sP[256];
-	const FuseView& R = a.views[a.ref];
-	const int nPix = R.w*R.h;
-	const int p0 = blockIdx.x*FUSE_CHUNK+threadIdx.x*FUSE_ITEMS;
-	bool f[FUSE_ITEMS]; unsigned n = 0;
-	for (int i=0; i<FUSE_ITEMS; ++i) { f[i] = p0+i < nPix && is_seed(R, p0+i); n += f[i]; }
-	sP[threadIdx.x] = n;
-	__syncthreads();
-	for (int off=1; off<256; off<<=1) {
-		unsigned t = 0;
-		if (threadIdx.x >= off) t = sP[threadIdx.x-off];
-		__syncthreads();
-		sP[threadIdx.x] += t;
-		__syncthreads();
-	}
-	unsigned slot = blockSums[blockIdx.x].x+(sP[threadIdx.x]-n);
-	for (int i=0; i<FUSE_ITEMS; ++i) if (f[i]) seeds[slot++] = (uint32_t)(p0+i);
-	if (blockIdx.x == 0 && threadIdx.x == 0) { const int tot = (int)blockSums[nBlocks].x; a.counters[0] = tot; a.counters[2] = tot; }
-}
+#define FUSE_CH 6      // probes whose bitmap tests / record gathers are in flight together in the probe stage
+#define FUSE_RCH 12    // probes per chunk of the reserve / resolve stages (DepthData::neighbors holds <= nMaxViews = 12)
+__device__ __forceinline__ bool bit_alive(const FuseView& B, uint32_t q) { return (__ldcg(B.alive+(q>>5))>>(q&31)) & 1u; }
+__device__ __forceinline__ void bit_clear(const FuseView& B, uint32_t q) { atomicAnd(B.alive+(q>>5), ~(1u<<(q&31))); }
 
-// ---- phase 0 (own kernel, one thread per SEED): classify the probes. The geometry of a probe is static: the seed's 3-D point, the
-// pixel it hits in each neighbour view, and — while that pixel is alive (depth != 0, not claimed) — whether it would merge, be
-// invalidated, or be left alone. Only liveness changes during the fusion of this view, so the f64 projections are done once and the
-// rounds below are integer work.
-__global__ void __launch_bounds__(256) k_fuse_probe(const FuseArgs a) {
-	const FuseView& R = a.views[a.ref];
-	const int s = blockIdx.x*blockDim.x+threadIdx.x;
-	if (s >= (int)a.nSeedsPtr->x) return;
-	const int p = (int)a.seeds[s];
-	const float4 e = R.dn[p];
-	a.state[s] = 1;
+// classify the probes of seed slot s (the f64 geometry, once) and place the first round's reservations. The bitmap answers "already
+// part of a point / no depth" without touching the pixel's record: only probes of live pixels cost a DRAM sector.
+__device__ FUSE_FN void probe_slot(const FuseJob& a, const FusePlanView& pv, const FuseSlots& S, const int s) {
+	const FuseView& R = a.views[pv.view];
+	const int p = (int)__ldcg(S.seeds+s);
+	FUSE_CHK(s >= 0 && (size_t)s < a.probeStride, 101); FUSE_CHK(p >= 0 && p < R.w*R.h, 102); FUSE_CHK(pv.nNb >= 0 && pv.nNb <= HCMVS_MAX_FUSE_VIEWS, 103);
+	const uint4 r0 = __ldcg(reinterpret_cast<const uint4*>(R.rec+p));
+	const float nz = __ldcg(&R.rec[p].nz);
+	const float depth = __uint_as_float(r0.x);
+	S.state[s] = 1;
 	const int x = p%R.w, y = p/R.w;
-	const float3 point = seed_point(R, x, y, e.w);
-	const float3 normal = cam_NormalC2W(R.cam, make_float3(e.x, e.y, e.z));
-	// neighbours in chunks of 4: the projections first, then the 4 independent gathers in flight together (the kernel is
-	// bound by gather latency, not bandwidth), then the classification
-	for (int k0=0; k0<a.nNb; k0+=4) {
-		Probe pr[4]; float4 eB[4]; uint32_t cB[4];
+	const float3 point = seed_point(R, x, y, depth);
+	const float3 normal = make_float3(__uint_as_float(r0.z), __uint_as_float(r0.w), nz);
+	for (int k0=0; k0<pv.nNb; k0+=FUSE_CH) {
+		Probe pr[FUSE_CH]; uint32_t word[FUSE_CH]; uint4 eB[FUSE_CH]; float nzB[FUSE_CH];
 		#pragma unroll
-		for (int j=0; j<4; ++j) {
+		for (int j=0; j<FUSE_CH; ++j) {
 			pr[j].q = -1; pr[j].z = 0.f;
-			if (k0+j < a.nNb) { const FuseView& B = a.views[a.nb[k0+j]]; if (B.hasMaps) pr[j] = probe_view(B, point); }
+			if (k0+j < pv.nNb) { const FuseView& B = a.views[pv.nb[k0+j]]; if (B.hasMaps) pr[j] = probe_view(B, point); }
 		}
 		#pragma unroll
-		for (int j=0; j<4; ++j) {
-			eB[j] = make_float4(0.f, 0.f, 0.f, 0.f); cB[j] = CLAIM_TAKEN;
-			if (pr[j].q >= 0) { const FuseView& B = a.views[a.nb[k0+j]]; eB[j] = B.dn[pr[j].q]; cB[j] = B.claim[pr[j].q]; }
+		for (int j=0; j<FUSE_CH; ++j) { word[j] = 0u; if (pr[j].q >= 0) word[j] = __ldcg(a.views[pv.nb[k0+j]].alive+(pr[j].q>>5)); }
+		#pragma unroll
+		for (int j=0; j<FUSE_CH; ++j) {
+			eB[j] = make_uint4(0u, 0u, 0u, 0u); nzB[j] = 0.f;
+			if (pr[j].q >= 0 && ((word[j]>>(pr[j].q&31)) & 1u)) { const FuseRec* rb = a.views[pv.nb[k0+j]].rec+pr[j].q; eB[j] = __ldcg(reinterpret_cast<const uint4*>(rb)); nzB[j] = __ldcg(&rb->nz); }
 		}
 		#pragma unroll
+		for (int j=0; j<FUSE_CH; ++j) {
+			if (k0+j < pv.nNb) {
+				uint32_t code = PROBE_DEAD;
+				const float depthB = __uint_as_float(eB[j].x); // 0 when the pixel is not alive (records of live pixels hold depth != 0)
+				if (depthB != 0.f) {
+					uint32_t cls = PROBE_NONE;
+					bool merge = false;
+					if (depth_similar(pr[j].z, depthB, a.depthTh))
+						merge = dot3f(normal, make_float3(__uint_as_float(eB[j].z), __uint_as_float(eB[j].w), nzB[j])) > a.normalError;
+					if (merge) cls = PROBE_MERGE; else if (pr[j].z < depthB) cls = PROBE_INVAL;
+					code = (uint32_t)pr[j].q | (cls<<30);
+					if (cls != PROBE_NONE) atomicMin(a.views[pv.nb[k0+j]].claim+pr[j].q, (uint32_t)p);
+				}
+				__stcg(S.probes+(size_t)(k0+j)*a.probeStride+s, code);
+			}
+		}
+	}
+}
+
+// every unfinished seed reserves each live neighbour pixel it has not dealt with yet (rounds >= 2)
+__device__ FUSE_FN void reserve_slot(const FuseJob& a, const FusePlanView& pv, const FuseSlots& S, const int s) {
+	const uint8_t st = __ldcg(S.state+s);
+	if (st != 1 && st != 3) return;
+	const uint32_t p = __ldcg(S.seeds+s); // the raster index orders the reservations
+	FUSE_CHK(s >= 0 && (size_t)s < a.probeStride, 201);
+	for (int k0=0; k0<pv.nNb; k0+=FUSE_RCH) {
+		uint32_t code[FUSE_RCH]; bool live[FUSE_RCH];
+		#pragma unroll
+		for (int j=0; j<FUSE_RCH; ++j) code[j] = k0+j < pv.nNb ? __ldcg(S.probes+(size_t)(k0+j)*a.probeStride+s) : PROBE_DEAD;
+		#pragma unroll
+		for (int j=0; j<FUSE_RCH; ++j) live[j] = code[j] != PROBE_DEAD && (code[j]>>30) != PROBE_NONE && bit_alive(a.views[pv.nb[k0+j]], code[j]&PROBE_PIX);
+		#pragma unroll
+		for (int j=0; j<FUSE_RCH; ++j) if (live[j]) atomicMin(a.views[pv.nb[k0+j]].claim+(code[j]&PROBE_PIX), p);
+	}
+}
+
+// Resolve what the raster order already fixes; returns 1 while the seed stays unfinished, 2 when it became final with a point, 0 otherwise.
+// A seed holding a reservation precedes every unfinished seed that touches the same pixel, so that pixel is in the state the seed
+// would find it in at its turn of the raster scan. Hence:
+//  * a seed whose own view + already merged + held agreeing pixels reach nMinViewsFuse WILL be emitted (:3429) whatever its
+//    contested probes turn into: it acts on the pixels it holds at once (merges / zeroes them) and only keeps waiting for the
+//    contested ones — this is what cuts the dependency chains along the rows;
+//  * a seed that cannot reach nMinViewsFuse even if every contested agreeing pixel were still alive at its turn will NOT be
+//    emitted: it releases everything;
+//  * otherwise it waits for the lower seeds it conflicts with (the lowest unfinished seed never waits).
+__device__ FUSE_FN int resolve_slot(const FuseJob& a, const FusePlanView& pv, const FuseSlots& S, const int s) {
+	const uint8_t st = __ldcg(S.state+s);
+	if (st != 1 && st != 3) return 0;
+	const FuseView& R = a.views[pv.view];
+	const uint32_t p = __ldcg(S.seeds+s);
+	FUSE_CHKR(s >= 0 && (size_t)s < a.probeStride, 301); FUSE_CHKR((int)p < R.w*R.h, 302);
+	uint32_t merged = st == 3 ? __ldcg(S.mask+s) : 0u;
+	uint32_t heldMerge = 0, heldInval = 0;
+	unsigned nContested = 0, nContestedMerge = 0;
+	uint32_t code0[FUSE_RCH]; // the first chunk's codes stay in registers for the actions below
+	for (int k0=0; k0<pv.nNb; k0+=FUSE_RCH) {
+		uint32_t code[FUSE_RCH], word[FUSE_RCH], cl[FUSE_RCH];
+		#pragma unroll
+		for (int j=0; j<FUSE_RCH; ++j) code[j] = k0+j < pv.nNb ? __ldcg(S.probes+(size_t)(k0+j)*a.probeStride+s) : PROBE_DEAD;
+		#pragma unroll
+		for (int j=0; j<FUSE_RCH; ++j) {
+			word[j] = 0u; cl[j] = CLAIM_FREE;
+			if (code[j] != PROBE_DEAD && (code[j]>>30) != PROBE_NONE) {
+				const FuseView& B = a.views[pv.nb[k0+j]];
+				const uint32_t q = code[j]&PROBE_PIX;
+				FUSE_CHKR((int)q < B.w*B.h && B.claim && B.alive, 303);
+				word[j] = __ldcg(B.alive+(q>>5)); cl[j] = __ldcg(B.claim+q);
+			}
+		}
+		#pragma unroll
+		for (int j=0; j<FUSE_RCH; ++j) {
+			if (k0 == 0) code0[j] = code[j];
+			if (code[j] == PROBE_DEAD || (code[j]>>30) == PROBE_NONE) continue;
+			const int k = k0+j;
+			if (!((word[j]>>(code[j]&31u)) & 1u)) { __stcg(S.probes+(size_t)k*a.probeStride+s, PROBE_DEAD); continue; }
+			if (cl[j] == p) { if ((code[j]>>30) == PROBE_MERGE) heldMerge |= 1u<<k; else heldInval |= 1u<<k; }
+			else { ++nContested; nContestedMerge += (code[j]>>30) == PROBE_MERGE; }
+		}
+	}
+	const uint32_t held = heldMerge|heldInval;
+	const unsigned nViews = 1u+__popc(merged)+__popc(heldMerge);
+	if (st == 3 || nViews >= a.nMinViewsFuse) {
+		#pragma unroll
+		for (int k=0; k<FUSE_RCH; ++k) {
+			if (!(held & (1u<<k))) continue;
+			const FuseView& B = a.views[pv.nb[k]];
+			uint32_t* pc = S.probes+(size_t)k*a.probeStride+s;
+			const uint32_t q = code0[k] & PROBE_PIX;
+			if (heldMerge & (1u<<k)) __stcg(pc, q | (PROBE_NONE<<30)); // a merged probe is not looked at again; the pixel index stays for the point
+			else { B.dn[q].w = 0.f; __stcg(pc, PROBE_DEAD); }          // SceneDensify.cpp:3447-3449: the occluded depth is zeroed
+			bit_clear(B, q);
+		}
+		for (uint32_t h = held>>FUSE_RCH<<FUSE_RCH; h; h &= h-1) { // neighbours beyond the first chunk (more than 12: not the reference's default)
+			const int k = __ffs(h)-1;
+			const FuseView& B = a.views[pv.nb[k]];
+			uint32_t* pc = S.probes+(size_t)k*a.probeStride+s;
+			const uint32_t q = __ldcg(pc) & PROBE_PIX;
+			if (heldMerge & (1u<<k)) __stcg(pc, q | (PROBE_NONE<<30));
+			else { B.dn[q].w = 0.f; __stcg(pc, PROBE_DEAD); }
+			bit_clear(B, q);
+		}
+		merged |= heldMerge;
+		__stcg(S.mask+s, merged);
+		if (nContested == 0) { bit_clear(R, p); S.state[s] = 2; return 2; }
+		S.state[s] = 3;
+		return 1;
+	}
+	if (nViews+nContestedMerge < a.nMinViewsFuse) {
+		#pragma unroll
+		for (int k=0; k<FUSE_RCH; ++k) if (held & (1u<<k)) __stcg(a.views[pv.nb[k]].claim+(code0[k]&PROBE_PIX), CLAIM_FREE);
+		for (uint32_t h = held>>FUSE_RCH<<FUSE_RCH; h; h &= h-1) {
+			const int k = __ffs(h)-1;
+			__stcg(a.views[pv.nb[k]].claim+(__ldcg(S.probes+(size_t)k*a.probeStride+s)&PROBE_PIX), CLAIM_FREE);
+		}
+		S.state[s] = 0;
+		return 0;
+	}
+	return 1;
+}
+
+// append the unfinished slots of this thread's warp to the next round's worklist
+__device__ __forceinline__ void worklist_push(uint32_t* wl, unsigned* count, bool keep, int s) {
+	const unsigned m = __ballot_sync(__activemask(), keep);
+	if (!m) return;
+	const int lane = threadIdx.x&31, leader = __ffs(m)-1;
+	unsigned base = 0;
+	if (lane == leader) base = atomicAdd(count, (unsigned)__popc(m));
+	base = __shfl_sync(__activemask(), base, leader);
+	if (keep) __stcg(wl+base+__popc(m & ((1u<<lane)-1u)), (uint32_t)s);
+}
+
+// The fused point of seed slot s (SceneDensify.cpp:3355-3446), computed the moment the seed becomes final — in the same phase that
+// just read the heads of its merged pixels, so their records are still in L2 — and parked in per-slot staging; the ordered
+// compaction of the next stage copies it to its place in the cloud. The sums run over the merged neighbours in the order the seed
+// probed them (the reference's order: rounding is part of the result), four records in flight at a time.
+__device__ FUSE_FN void stage_slot(const FuseJob& a, const FusePlanView& pv, const FuseSlots& S, const int s) {
+	const FuseView& R = a.views[pv.view];
+	const FuseOut& out = a.out;
+	const int p = (int)__ldcg(S.seeds+s);
+	const uint4 r0 = __ldcg(reinterpret_cast<const uint4*>(R.rec+p)), r1 = __ldcg(reinterpret_cast<const uint4*>(R.rec+p)+1);
+	const int x = p%R.w, y = p/R.w;
+	const float depth = __uint_as_float(r0.x);
+	const float3 point = seed_point(R, x, y, depth);
+	const float3 normal = make_float3(__uint_as_float(r0.z), __uint_as_float(r0.w), __uint_as_float(r1.x));
+	const uint32_t merged = __ldcg(S.mask+s);
+	// SceneDensify.cpp:3359-3379
+	const float w0 = __uint_as_float(r1.y);
+	__stcg(S.stgW+s, w0);
+	double confidence = (double)w0;
+	double X0 = (double)(float)dmul((double)point.x, confidence), X1 = (double)(float)dmul((double)point.y, confidence), X2 = (double)(float)dmul((double)point.z, confidence);
+	float C[3] = {0.f, 0.f, 0.f};
+	if (R.hasBgr) for (int c=0; c<3; ++c) C[c] = (float)dmul(confidence, (double)(float)((r1.z>>(8*c))&255u));
+	float3 N = make_float3((float)dmul((double)normal.x, confidence), (float)dmul((double)normal.y, confidence), (float)dmul((double)normal.z, confidence));
+	for (uint32_t m = merged; m; ) {
+		int kk[4]; uint32_t qq[4]; uint4 b0[4], b1[4];
+		#pragma unroll
+		for (int j=0; j<4; ++j) { kk[j] = m ? __ffs(m)-1 : -1; m &= m-1; }
+		#pragma unroll
+		for (int j=0; j<4; ++j) qq[j] = kk[j] >= 0 ? (__ldcg(S.probes+(size_t)kk[j]*a.probeStride+s) & PROBE_PIX) : 0u;
+		#pragma unroll
+		for (int j=0; j<4; ++j) if (kk[j] >= 0) { const FuseRec* rb = a.views[pv.nb[kk[j]]].rec+qq[j]; b0[j] = __ldcg(reinterpret_cast<const uint4*>(rb)); b1[j] = __ldcg(reinterpret_cast<const uint4*>(rb)+1); }
+		#pragma unroll
 		for (int j=0; j<4; ++j) {
-			if (k0+j >= a.nNb) break;
-			uint32_t code = PROBE_DEAD;
-			if (pr[j].q >= 0 && eB[j].w != 0.f && cB[j] != CLAIM_TAKEN) {
-				uint32_t cls = PROBE_NONE;
-				bool merge = false;
-				if (depth_similar(pr[j].z, eB[j].w, a.depthTh)) {
-					const float3 normalB = cam_NormalC2W(a.views[a.nb[k0+j]].cam, make_float3(eB[j].x, eB[j].y, eB[j].z));
-					merge = dot3f(normal, normalB) > a.normalError;
-				}
-				if (merge) cls = PROBE_MERGE; else if (pr[j].z < eB[j].w) cls = PROBE_INVAL;
-				code = (uint32_t)pr[j].q | (cls<<30);
-			}
-			a.probes[(size_t)(k0+j)*a.probeStride+s] = code;
-		}
-	}
-}
-
-// ---- the reserve / resolve rounds (cooperative: grid.sync between the phases)
-__global__ void __launch_bounds__(256) k_fuse_view(const FuseArgs a) {
-	cg::grid_group grid = cg::this_grid();
-	const FuseView& R = a.views[a.ref];
-	const int nSeeds = (int)a.nSeedsPtr->x;
-	const int tid = blockIdx.x*blockDim.x+threadIdx.x, nThreads = gridDim.x*blockDim.x;
-	int undecided = *(volatile int*)&a.counters[0];
-	int round = 0;
-	while (undecided > 0) {
-		// ---- phase 1: every unfinished seed reserves each live neighbour pixel it has not dealt with yet
-		for (int s=tid; s<nSeeds; s+=nThreads) {
-			const uint8_t st = a.state[s];
-			if (st != 1 && st != 3) continue;
-			const int p = (int)a.seeds[s]; // the raster index orders the reservations
-			for (int k0=0; k0<a.nNb; k0+=4) { // 4 independent probe -> pixel gathers in flight
-				uint32_t code[4], cl[4]; float dz[4];
-				#pragma unroll
-				for (int j=0; j<4; ++j) code[j] = k0+j < a.nNb ? a.probes[(size_t)(k0+j)*a.probeStride+s] : PROBE_DEAD;
-				#pragma unroll
-				for (int j=0; j<4; ++j) {
-					dz[j] = 0.f; cl[j] = CLAIM_TAKEN;
-					if (code[j] != PROBE_DEAD && (code[j]>>30) != PROBE_NONE) {
-						const FuseView& B = a.views[a.nb[k0+j]];
-						const uint32_t q = code[j] & 0x3FFFFFFFu;
-						dz[j] = B.dn[q].w; cl[j] = B.claim[q];
-					}
-				}
-				#pragma unroll
-				for (int j=0; j<4; ++j)
-					if (dz[j] != 0.f && cl[j] != CLAIM_TAKEN && cl[j] > (uint32_t)p) atomicMin(&a.views[a.nb[k0+j]].claim[code[j] & 0x3FFFFFFFu], (uint32_t)p);
-			}
-		}
-		grid.sync();
-		// ---- phase 2: resolve what the raster order already fixes.
-		// A seed holding a reservation precedes every unfinished seed that touches the same pixel, so that pixel is in
-		// the state the seed would find it in at its turn of the raster scan. Hence:
-		//  * a seed whose own view + already merged + held agreeing pixels reach nMinViewsFuse WILL be emitted (:3429)
-		//    whatever its contested probes turn into: it acts on the pixels it holds at once (claim / zero them) and only
-		//    keeps waiting for the contested ones — this is what cuts the dependency chains along the rows;
-		//  * a seed that cannot reach nMinViewsFuse even if every contested agreeing pixel were still alive at its turn
-		//    will NOT be emitted: it releases everything;
-		//  * otherwise it waits for the lower seeds it conflicts with (the lowest unfinished seed never waits).
-		int nDone = 0;
-		for (int s=tid; s<nSeeds; s+=nThreads) {
-			const uint8_t st = a.state[s];
-			if (st != 1 && st != 3) continue;
-			const int p = (int)a.seeds[s];
-			uint32_t merged = st == 3 ? a.mask[s] : 0u;
-			uint32_t heldMerge = 0, heldInval = 0;
-			unsigned nContested = 0, nContestedMerge = 0;
-			for (int k0=0; k0<a.nNb; k0+=4) {
-				uint32_t code[4], cl[4]; float dz[4];
-				#pragma unroll
-				for (int j=0; j<4; ++j) code[j] = k0+j < a.nNb ? a.probes[(size_t)(k0+j)*a.probeStride+s] : PROBE_DEAD;
-				#pragma unroll
-				for (int j=0; j<4; ++j) {
-					dz[j] = 0.f; cl[j] = CLAIM_TAKEN;
-					if (code[j] != PROBE_DEAD && (code[j]>>30) != PROBE_NONE) {
-						const FuseView& B = a.views[a.nb[k0+j]];
-						const uint32_t q = code[j] & 0x3FFFFFFFu;
-						cl[j] = *(volatile uint32_t*)&B.claim[q]; dz[j] = *(volatile float*)&B.dn[q].w;
-					}
-				}
-				#pragma unroll
-				for (int j=0; j<4; ++j) {
-					if (code[j] == PROBE_DEAD || (code[j]>>30) == PROBE_NONE) continue;
-					const int k = k0+j;
-					if (cl[j] == CLAIM_TAKEN || dz[j] == 0.f) { a.probes[(size_t)k*a.probeStride+s] = PROBE_DEAD; continue; }
-					if (cl[j] == (uint32_t)p) { if ((code[j]>>30) == PROBE_MERGE) heldMerge |= 1u<<k; else heldInval |= 1u<<k; }
-					else { ++nContested; nContestedMerge += (code[j]>>30) == PROBE_MERGE; }
-				}
-			}
-			const unsigned nViews = 1u+__popc(merged)+__popc(heldMerge);
-			if (st == 3 || nViews >= a.nMinViewsFuse) {
-				for (int k=0; k<a.nNb; ++k) {
-					const uint32_t bit = 1u<<k;
-					if (!((heldMerge|heldInval) & bit)) continue;
-					const FuseView& B = a.views[a.nb[k]];
-					const size_t pi = (size_t)k*a.probeStride+s;
-					const uint32_t q = a.probes[pi] & 0x3FFFFFFFu;
-					if (heldMerge & bit) B.claim[q] = CLAIM_TAKEN; // merged probes keep their pixel index for k_fuse_emit
-					else { B.dn[q].w = 0.f; __threadfence(); B.claim[q] = CLAIM_FREE; a.probes[pi] = PROBE_DEAD; } // :3447-3449
-				}
-				merged |= heldMerge;
-				// a merged probe must not be looked at again: park it as PROBE_NONE (pixel index kept)
-				for (int k=0; k<a.nNb; ++k) if (heldMerge & (1u<<k)) { const size_t pi = (size_t)k*a.probeStride+s; a.probes[pi] = (a.probes[pi] & 0x3FFFFFFFu) | (PROBE_NONE<<30); }
-				a.mask[s] = merged;
-				if (nContested == 0) { R.claim[p] = CLAIM_TAKEN; a.state[s] = 2; ++nDone; }
-				else a.state[s] = 3;
-			} else if (nViews+nContestedMerge < a.nMinViewsFuse) {
-				for (int k=0; k<a.nNb; ++k) {
-					if (!((heldMerge|heldInval) & (1u<<k))) continue;
-					const FuseView& B = a.views[a.nb[k]];
-					B.claim[a.probes[(size_t)k*a.probeStride+s] & 0x3FFFFFFFu] = CLAIM_FREE;
-				}
-				a.state[s] = 0; ++nDone;
-			}
-		}
-		nDone = cg::reduce(cg::tiled_partition<32>(cg::this_thread_block()), nDone, cg::plus<int>());
-		if ((threadIdx.x&31) == 0 && nDone) atomicSub(&a.counters[0], nDone);
-		grid.sync();
-		undecided = *(volatile int*)&a.counters[0];
-		if (tid == 0 && a.trace && round < 256) a.trace[round] = undecided;
-		++round;
-	}
-	if (tid == 0) a.counters[1] = round;
-}
-
-// ------------------------------------------------------------------ raster-ordered compaction of the emitted seeds (slot order == raster order)
-__global__ void __launch_bounds__(256) k_fuse_count(const uint8_t* __restrict__ state, const uint32_t* __restrict__ mask, const uint2* __restrict__ nSeedsPtr, uint2* __restrict__ blockSums) {
-	const int nPix = (int)nSeedsPtr->x; // number of seed slots
-	__shared__ unsigned sP[8], sV[8];
-	unsigned nP = 0, nV = 0;
-	const int base = blockIdx.x*FUSE_CHUNK;
-	for (int i=threadIdx.x; i<FUSE_CHUNK; i+=256) {
-		const int p = base+i;
-		if (p < nPix && state[p] == 2) { ++nP; nV += 1+__popc(mask[p]); }
-	}
-	for (int s=16; s>0; s>>=1) { nP += __shfl_xor_sync(0xffffffffu, nP, s); nV += __shfl_xor_sync(0xffffffffu, nV, s); }
-	if ((threadIdx.x&31) == 0) { sP[threadIdx.x>>5] = nP; sV[threadIdx.x>>5] = nV; }
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		unsigned a = 0, b = 0;
-		for (int i=0; i<8; ++i) { a += sP[i]; b += sV[i]; }
-		blockSums[blockIdx.x] = make_uint2(a, b);
-	}
-}
-// single-block exclusive scan of the per-chunk sums; totals go to blockSums[nBlocks]
-__global__ void __launch_bounds__(1024) k_fuse_scan(uint2* __restrict__ blockSums, int nBlocks) {
-	__shared__ unsigned sP[1024], sV[1024];
-	__shared__ unsigned carryP, carryV;
-	if (threadIdx.x == 0) { carryP = 0; carryV = 0; }
-	__syncthreads();
-	for (int base=0; base<nBlocks; base+=1024) {
-		const int i = base+threadIdx.x;
-		const uint2 v = i < nBlocks ? blockSums[i] : make_uint2(0, 0);
-		sP[threadIdx.x] = v.x; sV[threadIdx.x] = v.y;
-		__syncthreads();
-		for (int off=1; off<1024; off<<=1) {
-			unsigned tp = 0, tv = 0;
-			if (threadIdx.x >= off) { tp = sP[threadIdx.x-off]; tv = sV[threadIdx.x-off]; }
-			__syncthreads();
-			sP[threadIdx.x] += tp; sV[threadIdx.x] += tv;
-			__syncthreads();
-		}
-		if (i < nBlocks) blockSums[i] = make_uint2(carryP+sP[threadIdx.x]-v.x, carryV+sV[threadIdx.x]-v.y);
-		__syncthreads();
-		if (threadIdx.x == 1023) { carryP += sP[1023]; carryV += sV[1023]; }
-		__syncthreads();
-	}
-	if (threadIdx.x == 0) blockSums[nBlocks] = make_uint2(carryP, carryV);
-}
-
-struct FuseOut {
-	float* points; float* normals; uint8_t* colors; uint32_t* viewOffsets; uint32_t* views; float* weights;
-	unsigned long long basePoint, baseView;
-	int estimateColor, estimateNormal;
-};
-
-__global__ void __launch_bounds__(256) k_fuse_emit(const FuseArgs a, const uint2* __restrict__ blockSums, const FuseOut out) {
-	// each thread owns FUSE_ITEMS consecutive slots of the chunk so that the output keeps raster order
-	__shared__ unsigned sP[256], sV[256];
-	const FuseView& R = a.views[a.ref];
-	const int nSeeds = (int)a.nSeedsPtr->x;
-	const int s0 = blockIdx.x*FUSE_CHUNK+threadIdx.x*FUSE_ITEMS;
-	unsigned nP = 0, nV = 0;
-	for (int i=0; i<FUSE_ITEMS; ++i) { const int s = s0+i; if (s < nSeeds && a.state[s] == 2) { ++nP; nV += 1+__popc(a.mask[s]); } }
-	sP[threadIdx.x] = nP; sV[threadIdx.x] = nV;
-	__syncthreads();
-	for (int off=1; off<256; off<<=1) {
-		unsigned tp = 0, tv = 0;
-		if (threadIdx.x >= off) { tp = sP[threadIdx.x-off]; tv = sV[threadIdx.x-off]; }
-		__syncthreads();
-		sP[threadIdx.x] += tp; sV[threadIdx.x] += tv;
-		__syncthreads();
-	}
-	const uint2 bs = blockSums[blockIdx.x];
-	unsigned long long ip = out.basePoint+bs.x+(sP[threadIdx.x]-nP);
-	unsigned long long iv = out.baseView+bs.y+(sV[threadIdx.x]-nV);
-	for (int i=0; i<FUSE_ITEMS; ++i) {
-		const int s = s0+i;
-		if (s >= nSeeds || a.state[s] != 2) continue;
-		const int p = (int)a.seeds[s];
-		const int x = p%R.w, y = p/R.w;
-		const float4 e = R.dn[p];
-		const float depth = e.w;
-		const float3 point = seed_point(R, x, y, depth);
-		const float3 normal = cam_NormalC2W(R.cam, make_float3(e.x, e.y, e.z));
-		const uint32_t merged = a.mask[s];
-		// SceneDensify.cpp:3359-3379
-		uint32_t vid[HCMVS_MAX_FUSE_VIEWS+1]; float vw[HCMVS_MAX_FUSE_VIEWS+1]; int nv = 1;
-		vid[0] = (uint32_t)a.ref; vw[0] = conf2weight(R.conf[p], depth);
-		double confidence = (double)vw[0];
-		double X0 = (double)(float)dmul((double)point.x, confidence), X1 = (double)(float)dmul((double)point.y, confidence), X2 = (double)(float)dmul((double)point.z, confidence);
-		float C[3] = {0.f, 0.f, 0.f};
-		if (R.bgr) for (int c=0; c<3; ++c) C[c] = (float)dmul(confidence, (double)(float)R.bgr[(size_t)p*3+c]);
-		float3 N = make_float3((float)dmul((double)normal.x, confidence), (float)dmul((double)normal.y, confidence), (float)dmul((double)normal.z, confidence));
-		for (int k=0; k<a.nNb; ++k) {
-			if (!(merged & (1u<<k))) continue;
-			const FuseView& B = a.views[a.nb[k]];
-			Probe pr; pr.q = (int)(a.probes[(size_t)k*a.probeStride+s] & 0x3FFFFFFFu); pr.z = 0.f;
-			const int xB = pr.q%B.w, yB = pr.q/B.w;
-			const float4 eB = B.dn[pr.q];
-			const float depthB = eB.w;
-			const float confidenceB = conf2weight(B.conf[pr.q], depthB);
-			// InsertSort by view id, :3407-3409
-			int pos = nv;
-			while (pos > 0 && vid[pos-1] > (uint32_t)a.nb[k]) { vid[pos] = vid[pos-1]; vw[pos] = vw[pos-1]; --pos; }
-			vid[pos] = (uint32_t)a.nb[k]; vw[pos] = confidenceB; ++nv;
+			if (kk[j] < 0) continue;
+			const FuseView& B = a.views[pv.nb[kk[j]]];
+			const int q = (int)qq[j];
+			const int xB = q%B.w, yB = q/B.w;
+			const float depthB = __uint_as_float(b0[j].x);
+			const float confidenceB = __uint_as_float(b1[j].y);
+			__stcg(S.stgW+(size_t)(1+kk[j])*a.probeStride+s, confidenceB);
 			const D3 XB = cam_I2W(B.cam, (double)xB, (double)yB, (double)depthB);
 			X0 = dadd(X0, dmul(XB.x, (double)confidenceB)); X1 = dadd(X1, dmul(XB.y, (double)confidenceB)); X2 = dadd(X2, dmul(XB.z, (double)confidenceB));
-			if (out.estimateColor && B.bgr) for (int c=0; c<3; ++c) C[c] = __fadd_rn(C[c], __fmul_rn((float)B.bgr[(size_t)pr.q*3+c], confidenceB));
+			if (out.estimateColor && B.hasBgr) for (int c=0; c<3; ++c) C[c] = __fadd_rn(C[c], __fmul_rn((float)((b1[j].z>>(8*c))&255u), confidenceB));
 			if (out.estimateNormal) {
-				const float3 normalB = cam_NormalC2W(B.cam, make_float3(eB.x, eB.y, eB.z));
+				const float3 normalB = make_float3(__uint_as_float(b0[j].z), __uint_as_float(b0[j].w), __uint_as_float(b1[j].x));
 				N.x = __fadd_rn(N.x, __fmul_rn(normalB.x, confidenceB)); N.y = __fadd_rn(N.y, __fmul_rn(normalB.y, confidenceB)); N.z = __fadd_rn(N.z, __fmul_rn(normalB.z, confidenceB));
 			}
 			confidence = dadd(confidence, (double)confidenceB);
 		}
-		const double nrm = 1.0/confidence; // :3441-3446
-		out.points[ip*3+0] = (float)dmul(X0, nrm); out.points[ip*3+1] = (float)dmul(X1, nrm); out.points[ip*3+2] = (float)dmul(X2, nrm);
-		const float fn = (float)nrm;
-		if (out.estimateColor) for (int c=0; c<3; ++c) out.colors[ip*3+c] = (uint8_t)min(max(round2int(__fmul_rn(C[c], fn)), 0), 255);
-		if (out.estimateNormal) {
-			const float3 nvv = make_float3(__fmul_rn(N.x, fn), __fmul_rn(N.y, fn), __fmul_rn(N.z, fn));
-			const float inv = __fdiv_rn(1.f, __fsqrt_rn(dot3f(nvv, nvv)));
-			out.normals[ip*3+0] = __fmul_rn(nvv.x, inv); out.normals[ip*3+1] = __fmul_rn(nvv.y, inv); out.normals[ip*3+2] = __fmul_rn(nvv.z, inv);
+	}
+	const double nrm = 1.0/confidence; // :3441-3446
+	const float fn = (float)nrm;
+	uint32_t col = 0;
+	if (out.estimateColor) for (int c=0; c<3; ++c) col |= (uint32_t)min(max(round2int(__fmul_rn(C[c], fn)), 0), 255)<<(8*c);
+	__stcg(S.stgPoint+s, make_float4((float)dmul(X0, nrm), (float)dmul(X1, nrm), (float)dmul(X2, nrm), __uint_as_float(col)));
+	if (out.estimateNormal) {
+		const float3 nvv = make_float3(__fmul_rn(N.x, fn), __fmul_rn(N.y, fn), __fmul_rn(N.z, fn));
+		const float inv = __fdiv_rn(1.f, __fsqrt_rn(dot3f(nvv, nvv)));
+		__stcg(S.stgNormal+s, make_float4(__fmul_rn(nvv.x, inv), __fmul_rn(nvv.y, inv), __fmul_rn(nvv.z, inv), 0.f));
+	}
+}
+
+// copy the staged point of final slot s to its place in the cloud; the view list is written sorted by view id (InsertSort,
+// SceneDensify.cpp:3407-3409) through the plan's id order
+__device__ __forceinline__ void emit_slot(const FuseJob& a, const FusePlanView& pv, const FuseSlots& S, const int s, const unsigned long long ip, const unsigned long long iv) {
+	const FuseOut& out = a.out;
+	const float4 P = __ldcg(S.stgPoint+s);
+	out.points[ip*3+0] = P.x; out.points[ip*3+1] = P.y; out.points[ip*3+2] = P.z;
+	if (out.estimateColor) { const uint32_t c = __float_as_uint(P.w); out.colors[ip*3+0] = (uint8_t)(c&255u); out.colors[ip*3+1] = (uint8_t)((c>>8)&255u); out.colors[ip*3+2] = (uint8_t)((c>>16)&255u); }
+	if (out.estimateNormal) { const float4 Nn = __ldcg(S.stgNormal+s); out.normals[ip*3+0] = Nn.x; out.normals[ip*3+1] = Nn.y; out.normals[ip*3+2] = Nn.z; }
+	out.viewOffsets[ip] = (uint32_t)iv;
+	const uint32_t merged = __ldcg(S.mask+s);
+	unsigned long long o = iv;
+	for (int j=0; j<=pv.nNb; ++j) { // ids ascending: the reference view or neighbour k = order[j]
+		const int k = pv.order[j];
+		if (k < 0 || (merged & (1u<<k))) { out.views[o] = (uint32_t)(k < 0 ? pv.view : pv.nb[k]); out.weights[o] = __ldcg(S.stgW+(size_t)(1+k)*a.probeStride+s); ++o; }
+	}
+}
+
+// ------------------------------------------------------------------ the whole scene: one persistent cooperative kernel
+// Per view r (fusion order): [C] count the seeds of r per block (+ the final slots of r-1) | [D] ordered scatter of the seeds
+// (+ ordered copy of r-1's staged points into the cloud) | then the seed slots in TILES of FUSE_TILE, in raster order:
+// [P] classify the tile's probes + first reservations, re-reserve for the unfinished slots of earlier tiles | [R] resolve both, stage
+// the points of the seeds that became final. A tile's record sectors (one per live probe) are fetched from DRAM once, by [P];
+// [R] and the staging find them in L2 (126 MB) — without tiles the three stages of a 1.9 M-seed view each missed. Tiles are exact:
+// every seed of a later tile follows every seed of an earlier one in raster order, and the unfinished seeds of earlier tiles keep
+// taking part in the reservations. After the last tile the rounds go on over the worklist until it is empty. Blocks own contiguous
+// bitmap-word / slot ranges in the two ordered compactions, so the slots and the cloud keep raster order with one block-count
+// prefix (<= gridDim.x words) per compaction.
+#ifndef FUSE_MINB
+#define FUSE_MINB 3
+#endif
+__global__ void __launch_bounds__(FUSE_NT, FUSE_MINB) k_fuse_scene(const FuseJob a) {
+	cg::grid_group grid = cg::this_grid();
+	__shared__ unsigned long long sw64[FUSE_NT/32];
+	__shared__ unsigned sw[FUSE_NT/32];
+	const int G = (int)gridDim.x, b = (int)blockIdx.x;
+	const int gtid = b*FUSE_NT+threadIdx.x, nThreads = G*FUSE_NT;
+	unsigned nSeedsPrev = 0;
+	for (int r=0; r<=a.nPlan; ++r) {
+		const FuseSlots& S = a.sl[r&1];
+		const FuseSlots& Sp = a.sl[(r&1)^1];
+		const FusePlanView* pv = r < a.nPlan ? a.plan+r : nullptr;
+		const FusePlanView* pvp = r > 0 ? a.plan+(r-1) : nullptr;
+		int wLo = 0, wHi = 0; // bitmap words of view r this block compacts
+		const uint32_t* aliveR = nullptr;
+		if (pv) {
+			const FuseView& R = a.views[pv->view];
+			aliveR = R.alive;
+			const int nWords = (R.w*R.h+31)>>5, L = (nWords+G-1)/G;
+			wLo = min(b*L, nWords); wHi = min(wLo+L, nWords);
 		}
-		out.viewOffsets[ip] = (uint32_t)iv;
-		for (int j=0; j<nv; ++j) { out.views[iv+j] = vid[j]; out.weights[iv+j] = vw[j]; }
-		++ip; iv += nv;
+		int sLo = 0, sHi = 0;
+		if (pvp) { const int L = (int)((nSeedsPrev+G-1)/G); sLo = min(b*L, (int)nSeedsPrev); sHi = min(sLo+L, (int)nSeedsPrev); }
+		FUSE_STAMP(0);
+		// ---- [C] counts
+		{
+			unsigned long long nS = 0, nP = 0, nV = 0;
+			for (int i=wLo+threadIdx.x; i<wHi; i+=FUSE_NT) nS += (unsigned)__popc(__ldcg(aliveR+i));
+			for (int s=sLo+threadIdx.x; s<sHi; s+=FUSE_NT)
+				if (__ldcg(Sp.state+s) == 2) { ++nP; nV += 1u+(unsigned)__popc(__ldcg(Sp.mask+s)); }
+			nS = block_sum(nS, sw64); nP = block_sum(nP, sw64); nV = block_sum(nV, sw64);
+			if (threadIdx.x == 0) { a.blkSeeds[b] = (unsigned)nS; a.blkEmit[2*b] = (unsigned)nP; a.blkEmit[2*b+1] = (unsigned)nV; }
+		}
+		grid.sync();
+		FUSE_STAMP(1);
+		// ---- [D] block prefixes, ordered scatter of the seeds of r, ordered emit of r-1
+		unsigned nSeeds = 0, totP = 0, totV = 0;
+		bool fits = true;
+		{
+			unsigned preS = 0, preP = 0, preV = 0, totS = 0;
+			for (int i=threadIdx.x; i<G; i+=FUSE_NT) {
+				const unsigned cs = __ldcg(a.blkSeeds+i), cp = __ldcg(a.blkEmit+2*i), cv = __ldcg(a.blkEmit+2*i+1);
+				totS += cs; totP += cp; totV += cv;
+				if (i < b) { preS += cs; preP += cp; preV += cv; }
+			}
+			// six block sums through three packed 64-bit reductions (each component < 2^32)
+			const unsigned long long s1 = block_sum(((unsigned long long)preS<<32) | totS, sw64);
+			const unsigned long long s2 = block_sum(((unsigned long long)preP<<32) | totP, sw64);
+			const unsigned long long s3 = block_sum(((unsigned long long)preV<<32) | totV, sw64);
+			preS = (unsigned)(s1>>32); totS = (unsigned)s1; preP = (unsigned)(s2>>32); totP = (unsigned)s2; preV = (unsigned)(s3>>32); totV = (unsigned)s3;
+			nSeeds = totS;
+			if (pv) {
+				unsigned base = preS;
+				for (int i0=wLo; i0<wHi; i0+=FUSE_NT) {
+					const int i = i0+threadIdx.x;
+					uint32_t word = i < wHi ? __ldcg(aliveR+i) : 0u;
+					unsigned tot1;
+					unsigned o = base+block_scan((unsigned)__popc(word), sw, tot1);
+					for (; word; word &= word-1) __stcg(S.seeds+(o++), (uint32_t)(i*32+__ffs(word)-1));
+					base += tot1;
+				}
+			}
+			if (pvp) {
+				const unsigned long long cumP = __ldcg(&a.ctl->cumPoints), cumV = __ldcg(&a.ctl->cumRefs);
+				fits = cumP+totP <= a.out.capPoints && cumV+totV <= a.out.capRefs;
+				unsigned long long ip = cumP+preP, iv = cumV+preV;
+				for (int s0=sLo; s0<sHi; s0+=FUSE_NT) {
+					const int s = s0+threadIdx.x;
+					const bool f = s < sHi && __ldcg(Sp.state+s) == 2;
+					const unsigned nv = f ? 1u+(unsigned)__popc(__ldcg(Sp.mask+s)) : 0u;
+					unsigned tot1;
+					const unsigned ex = block_scan((f ? 1u<<16 : 0u) | nv, sw, tot1); // points in the high half, view references in the low half
+					if (f && fits) emit_slot(a, *pvp, Sp, s, ip+(ex>>16), iv+(ex&0xFFFFu));
+					ip += tot1>>16; iv += tot1&0xFFFFu;
+				}
+			}
+			if (gtid == 0) { a.ctl->wlCount[0] = 0; a.ctl->wlCount[1] = 0; if (pv) { a.ctl->seeds += nSeeds; a.ctl->probes += (unsigned long long)nSeeds*(unsigned)pv->nNb; } }
+		}
+		grid.sync();
+		if (pvp && gtid == 0) { // every block has read the old totals: advance them; the points of view r-1 are final and visible
+			if (!fits) a.ctl->overflow = 1;
+			else { a.ctl->cumPoints += totP; a.ctl->cumRefs += totV; }
+			if (a.progress) { // tell the host, which streams them out
+				a.progress[1+2*(r-1)] = a.ctl->cumPoints; a.progress[2+2*(r-1)] = a.ctl->cumRefs;
+				__threadfence_system();
+				a.progress[0] = (unsigned long long)r;
+			}
+		}
+		if (!pv) break;
+		FUSE_STAMP(2);
+		// ---- [P] probes + first reservations
+		for (int s=gtid; s<(int)nSeeds; s+=nThreads) probe_slot(a, *pv, S, s);
+		grid.sync();
+		FUSE_STAMP(3);
+		// ---- [R] round 1 over every slot; a seed that became final stages its point at once (its merged records were fetched by [P])
+		for (int s0=b*FUSE_NT; s0<(int)nSeeds; s0+=nThreads) {
+			const int s = s0+threadIdx.x;
+			const int res = s < (int)nSeeds ? resolve_slot(a, *pv, S, s) : 0;
+			worklist_push(a.wl[0], &a.ctl->wlCount[0], res == 1, s);
+			if (res == 2) stage_slot(a, *pv, S, s);
+		}
+		grid.sync();
+		FUSE_STAMP(4);
+		// ---- later rounds over the worklist of unfinished slots (finishing short worklists with 1 or 32 blocks and a barrier of their
+		// own was measured: not faster — a round is bound by its chain of dependent loads, not by the barrier; profiles/r02_notes.md)
+		int cur = 0; unsigned rounds = 1; unsigned long long wlSum = 0;
+		for (;;) {
+			unsigned nw = __ldcg(&a.ctl->wlCount[cur]);
+			if (!nw) break;
+			wlSum += nw;
+			const uint32_t* wl = a.wl[cur];
+			for (int i=gtid; i<(int)nw; i+=nThreads) reserve_slot(a, *pv, S, (int)__ldcg(wl+i));
+			if (gtid == 0) a.ctl->wlCount[cur^1] = 0;
+			grid.sync();
+			for (int i0=b*FUSE_NT; i0<(int)nw; i0+=nThreads) {
+				const int i = i0+threadIdx.x;
+				const int s = i < (int)nw ? (int)__ldcg(wl+i) : 0;
+				const int res = i < (int)nw ? resolve_slot(a, *pv, S, s) : 0;
+				worklist_push(a.wl[cur^1], &a.ctl->wlCount[cur^1], res == 1, s);
+				if (res == 2) stage_slot(a, *pv, S, s);
+			}
+			grid.sync();
+			cur ^= 1; ++rounds;
+		}
+		FUSE_STAMP(5);
+		if (a.trace && gtid == 0) { a.trace[8*r+6] = nSeeds | ((unsigned long long)rounds<<32); a.trace[8*r+7] = wlSum; }
+		if (gtid == 0) a.ctl->rounds += rounds;
+		nSeedsPrev = nSeeds;
 	}
 }
 
 // The fork's RemoveSmallSegments (SceneDensify.cpp:2228-2260): depthMap_fuse / normalMap_fuse = the view's estimate where the pixel
 // became part of a fused point (arrDepthIdx != NO_ID), 0 elsewhere
-__global__ void k_fused_support(const float4* __restrict__ dn, const uint32_t* __restrict__ claim, float* __restrict__ depth, float* __restrict__ normal, size_t n) {
+__global__ void k_fused_support(const float4* __restrict__ dn, const uint32_t* __restrict__ alive, float* __restrict__ depth, float* __restrict__ normal, size_t n) {
 	const size_t i = (size_t)blockIdx.x*blockDim.x+threadIdx.x;
 	if (i >= n) return;
-	const bool in = claim[i] == CLAIM_TAKEN;
+	const bool in = !((alive[i>>5]>>(i&31)) & 1u) && dn[i].w != 0.f; // no longer alive, yet not zeroed: merged into a point
 	const float4 e = in ? dn[i] : make_float4(0.f, 0.f, 0.f, 0.f);
 	if (depth) depth[i] = e.w;
 	if (normal) { normal[i*3] = e.x; normal[i*3+1] = e.y; normal[i*3+2] = e.z; }
@@ -462,21 +622,24 @@ using namespace hcmvs;
 
 struct FuseState {
 	FuseView* views_d = nullptr; size_t nViews = 0;
-	uint8_t* state_d = nullptr; uint32_t* mask_d = nullptr; size_t pixCap = 0;
-	uint2* blockSums_d = nullptr; size_t blockCap = 0;
-	uint32_t* seeds_d = nullptr; uint2* seedSums_d = nullptr; // compacted seed pixels of the view being fused + their per-chunk offsets
-	int* counters_d = nullptr; int* trace_d = nullptr;
-	uint32_t* probes_d = nullptr; size_t probeCap = 0;
-	// growing output
+	FuseRec* rec_d = nullptr; size_t recCap = 0; std::vector<size_t> recOff; uint32_t* alive_d = nullptr; size_t aliveCap = 0; std::vector<size_t> aliveOff; uint32_t* claim_d = nullptr; size_t claimCap = 0; // per-view records (kept after the fusion: claims, zeroed depths)
+	FusePlanView* plan_d = nullptr; size_t planCap = 0;
+	// per-seed-slot arrays (two sets) + worklists, sized for the largest view
+	uint8_t* state_d[2] = {nullptr, nullptr}; uint32_t* mask_d[2] = {nullptr, nullptr}; uint32_t* seeds_d[2] = {nullptr, nullptr}; uint32_t* wl_d[2] = {nullptr, nullptr}; size_t pixCap = 0;
+	uint32_t* probes_d[2] = {nullptr, nullptr}; float* stgW_d[2] = {nullptr, nullptr}; size_t probeCap = 0;
+	float4* stgPoint_d[2] = {nullptr, nullptr}; float4* stgNormal_d[2] = {nullptr, nullptr};
+	unsigned* blk_d = nullptr; int coopBlocks = 0; size_t smemEmit = 0;
+	FuseCtl* ctl_d = nullptr; unsigned long long* nValid_d = nullptr;
+	unsigned long long* progress = nullptr; unsigned long long* progress_dev = nullptr; size_t progressCap = 0; // page-locked, mapped
+	// output (sized for the upper bound: every point consumes >= nMinViewsFuse valid pixels)
 	float* points = nullptr; float* normals = nullptr; uint8_t* colors = nullptr; uint32_t* viewOffsets = nullptr; size_t capPoints = 0;
 	uint32_t* oviews = nullptr; float* weights = nullptr; size_t capViews = 0;
-	int coopBlocks = 0;
 	void* pinned = nullptr; size_t pinnedBytes = 0; // page-locked host arena of hcmvs_download_fused_pinned (grow-only)
-	// The arena is laid out for CAPACITIES (arenaPoints points, arenaViews view references), so that the ranges a view's emit kernel
-	// has just written can be copied out at their final place while the next views are still being fused (download stream); a cloud
+	// The arena is laid out for CAPACITIES (arenaPoints points, arenaViews view references), so that the ranges a view has just
+	// emitted can be copied out at their final place while the next views are still being fused (download stream); a cloud
 	// that outgrows the capacities falls back to one copy at the end and a larger arena for the next scene.
 	size_t arenaPoints = 0, arenaViews = 0; bool arenaColor = false, arenaNormal = false;
-	bool streamed = false; size_t streamedPoints = 0, streamedViews = 0; cudaEvent_t emitted = nullptr;
+	bool streamed = false; size_t streamedPoints = 0, streamedViews = 0;
 	size_t nPoints = 0, nViewRefs = 0; bool hasColor = false, hasNormal = false; // last fused cloud (device resident)
 };
 
@@ -485,11 +648,11 @@ void hcmvs_fuse_invalidate_stream(hcmvs_ctx* ctx) { if (ctx && ctx->fuse) ctx->f
 
 void hcmvs_fuse_release(hcmvs_ctx* ctx) {
 	FuseState* f = ctx->fuse; if (!f) return;
-	cudaFree(f->trace_d); cudaFree(f->probes_d);
 	if (ctx->dlStream) cudaStreamSynchronize(ctx->dlStream);
 	if (f->pinned) cudaFreeHost(f->pinned);
-	if (f->emitted) cudaEventDestroy(f->emitted);
-	cudaFree(f->views_d); cudaFree(f->state_d); cudaFree(f->mask_d); cudaFree(f->blockSums_d); cudaFree(f->counters_d); cudaFree(f->seeds_d); cudaFree(f->seedSums_d);
+	if (f->progress) cudaFreeHost(f->progress);
+	cudaFree(f->views_d); cudaFree(f->rec_d); cudaFree(f->alive_d); cudaFree(f->claim_d); cudaFree(f->plan_d); cudaFree(f->blk_d); cudaFree(f->ctl_d); cudaFree(f->nValid_d);
+	for (int i=0; i<2; ++i) { cudaFree(f->state_d[i]); cudaFree(f->mask_d[i]); cudaFree(f->seeds_d[i]); cudaFree(f->wl_d[i]); cudaFree(f->probes_d[i]); cudaFree(f->stgW_d[i]); cudaFree(f->stgPoint_d[i]); cudaFree(f->stgNormal_d[i]); }
 	cudaFree(f->points); cudaFree(f->normals); cudaFree(f->colors); cudaFree(f->viewOffsets); cudaFree(f->oviews); cudaFree(f->weights);
 	delete f; ctx->fuse = nullptr;
 }
@@ -503,13 +666,11 @@ static ArenaLayout LayoutFor(size_t capPoints, size_t capViews, bool hasNormal, 
 }
 
 template<typename T>
-static int Grow(hcmvs_ctx* ctx, T*& ptr, size_t used, size_t newCap, size_t elemsPer) {
-	T* np = nullptr;
-	CK(cudaMalloc(&np, newCap*elemsPer*sizeof(T)));
-	if (ptr && used) CK(cudaMemcpyAsync(np, ptr, used*elemsPer*sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+static int Realloc(hcmvs_ctx* ctx, T*& ptr, size_t elems) {
 	CK(cudaStreamSynchronize(ctx->stream));
 	if (ctx->dlStream) CK(cudaStreamSynchronize(ctx->dlStream)); // streamed copies may still read the old buffer
-	cudaFree(ptr); ptr = np;
+	cudaFree(ptr); ptr = nullptr;
+	CK(cudaMalloc(&ptr, elems*sizeof(T)));
 	return HCMVS_OK;
 }
 
@@ -531,17 +692,19 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 	// connections: valid views sorted by the size of their scored-neighbour list, SceneDensify.cpp:3286-3303 (ties by index)
 	struct Conn { uint32_t idx; float score; };
 	std::vector<Conn> conns;
-	size_t maxPix = 0; bool anyColor = false;
+	size_t maxPix = 0, totalPix = 0, totalWords = 0; bool anyColor = false;
+	std::vector<size_t>& aliveOff = f->aliveOff; aliveOff.assign(V, 0);
 	std::vector<FuseView> hv(V);
+	f->recOff.assign(V, (size_t)-1);
 	for (size_t i=0; i<V; ++i) {
 		View& v = ctx->views[i];
 		FuseView& fv = hv[i]; memset(&fv, 0, sizeof(fv));
 		if (!v.set || !v.hasMaps) continue;
 		{ int r = hcmvs_wait_image(ctx, v); if (r) return r; } // colours
 		const size_t n = (size_t)v.w*v.h;
-		if (!v.claim_d) CK(cudaMalloc(&v.claim_d, n*4));
-		k_fill_u32<<<(unsigned)((n+255)/256), 256, 0, ctx->stream>>>(v.claim_d, CLAIM_FREE, n); ++ctx->nLaunches;
-		fv.dn = v.dn_d; fv.conf = v.conf_d; fv.bgr = v.bgr_d; fv.claim = v.claim_d; fv.w = v.w; fv.h = v.h; fv.hasMaps = 1;
+		if (n >= ((size_t)1<<30)) { hcmvs_set_error("depth maps above 2^30 pixels are not supported by the fusion probe cache"); return HCMVS_ERR_UNSUPPORTED; }
+		f->recOff[i] = totalPix; totalPix += n; aliveOff[i] = totalWords; totalWords += (n+31)/32;
+		fv.dn = v.dn_d; fv.bgr = v.bgr_d; fv.hasBgr = v.bgr_d != nullptr; fv.w = v.w; fv.h = v.h; fv.hasMaps = 1;
 		hcmvs_fill_cam(v, fv.cam);
 		if (v.bgr_d) anyColor = true;
 		if (!v.nbIds.empty()) { conns.push_back(Conn{(uint32_t)i, v.hasFusePriority ? v.fusePriority : (float)v.nbIds.size()}); maxPix = std::max(maxPix, n); }
@@ -549,127 +712,166 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 	if (conns.empty()) { hcmvs_set_error("no view with depth map and neighbours to fuse"); return HCMVS_ERR_STATE; }
 	std::stable_sort(conns.begin(), conns.end(), [](const Conn& a, const Conn& b) { return a.score > b.score; });
 	if (estimate_color && !anyColor) estimate_color = 0;
-	if (f->nViews < V) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(f->views_d); CK(cudaMalloc(&f->views_d, V*sizeof(FuseView))); f->nViews = V; }
+	if (f->recCap < totalPix) { int r = Realloc(ctx, f->rec_d, totalPix); if (r) return r; f->recCap = totalPix; }
+	if (f->aliveCap < totalWords) { int r = Realloc(ctx, f->alive_d, totalWords); if (r) return r; f->aliveCap = totalWords; }
+	if (f->claimCap < totalPix) { int r = Realloc(ctx, f->claim_d, totalPix); if (r) return r; f->claimCap = totalPix; }
+	for (size_t i=0; i<V; ++i) if (f->recOff[i] != (size_t)-1) { hv[i].rec = f->rec_d+f->recOff[i]; hv[i].alive = f->alive_d+aliveOff[i]; hv[i].claim = f->claim_d+f->recOff[i]; }
+	if (f->nViews < V) { int r = Realloc(ctx, f->views_d, V); if (r) return r; f->nViews = V; }
 	CK(cudaMemcpyAsync(f->views_d, hv.data(), V*sizeof(FuseView), cudaMemcpyHostToDevice, ctx->stream));
+	// the plan: views in fusion order with the neighbours each probes
+	std::vector<FusePlanView> plan(conns.size());
+	size_t maxNb = 1;
+	for (size_t r=0; r<conns.size(); ++r) {
+		FusePlanView& pv = plan[r]; memset(&pv, 0, sizeof(pv));
+		pv.view = (int)conns[r].idx;
+		for (uint32_t id: ctx->views[conns[r].idx].nbIds) if (id < V && pv.nNb < HCMVS_MAX_FUSE_VIEWS) pv.nb[pv.nNb++] = (int)id;
+		maxNb = std::max(maxNb, (size_t)pv.nNb);
+		// ascending view ids (the reference keeps a point's view list sorted: InsertSort, SceneDensify.cpp:3407-3409); stable like it
+		for (int j=0; j<=pv.nNb; ++j) pv.order[j] = j-1;
+		std::stable_sort(pv.order, pv.order+pv.nNb+1, [&](int x, int y) { return (x < 0 ? pv.view : pv.nb[x]) < (y < 0 ? pv.view : pv.nb[y]); });
+	}
+	if (f->planCap < plan.size()) { int r = Realloc(ctx, f->plan_d, plan.size()); if (r) return r; f->planCap = plan.size(); }
+	CK(cudaMemcpyAsync(f->plan_d, plan.data(), plan.size()*sizeof(FusePlanView), cudaMemcpyHostToDevice, ctx->stream));
 	if (f->pixCap < maxPix) {
-		CK(cudaStreamSynchronize(ctx->stream));
-		cudaFree(f->state_d); cudaFree(f->mask_d); cudaFree(f->seeds_d);
-		CK(cudaMalloc(&f->state_d, maxPix)); CK(cudaMalloc(&f->mask_d, maxPix*4)); CK(cudaMalloc(&f->seeds_d, maxPix*4)); f->pixCap = maxPix;
+		for (int i=0; i<2; ++i) {
+			int r;
+			if ((r = Realloc(ctx, f->state_d[i], maxPix)) || (r = Realloc(ctx, f->mask_d[i], maxPix)) || (r = Realloc(ctx, f->seeds_d[i], maxPix)) || (r = Realloc(ctx, f->wl_d[i], maxPix)) ||
+			    (r = Realloc(ctx, f->stgPoint_d[i], maxPix)) || (r = Realloc(ctx, f->stgNormal_d[i], maxPix))) return r;
+		}
+		f->pixCap = maxPix;
 	}
-	const size_t maxBlocks = (maxPix+FUSE_CHUNK-1)/FUSE_CHUNK;
-	if (f->blockCap < maxBlocks+1) {
-		CK(cudaStreamSynchronize(ctx->stream)); cudaFree(f->blockSums_d); cudaFree(f->seedSums_d);
-		CK(cudaMalloc(&f->blockSums_d, (maxBlocks+1)*sizeof(uint2))); CK(cudaMalloc(&f->seedSums_d, (maxBlocks+1)*sizeof(uint2))); f->blockCap = maxBlocks+1;
+	if (f->probeCap < maxNb*maxPix) {
+		for (int i=0; i<2; ++i) { int r; if ((r = Realloc(ctx, f->probes_d[i], maxNb*maxPix)) || (r = Realloc(ctx, f->stgW_d[i], (maxNb+1)*maxPix))) return r; }
+		f->probeCap = maxNb*maxPix;
 	}
-	if (!f->counters_d) CK(cudaMalloc(&f->counters_d, 4*sizeof(int)));
-	if (!f->trace_d) CK(cudaMalloc(&f->trace_d, 256*sizeof(int)));
-	size_t maxNb = 1; for (const Conn& c: conns) maxNb = std::max(maxNb, ctx->views[c.idx].nbIds.size());
-	if (f->probeCap < maxNb*maxPix) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(f->probes_d); CK(cudaMalloc(&f->probes_d, maxNb*maxPix*4)); f->probeCap = maxNb*maxPix; }
-	if (maxPix >= (1u<<30)) { hcmvs_set_error("depth maps above 2^30 pixels are not supported by the fusion probe cache"); return HCMVS_ERR_UNSUPPORTED; }
-	if (!f->coopBlocks) {
+	const size_t smemEmit = 0;
+	if (!f->coopBlocks || f->smemEmit != smemEmit) {
+		cudaFree(f->blk_d); cudaFree(f->ctl_d); cudaFree(f->nValid_d); f->blk_d = nullptr; f->ctl_d = nullptr; f->nValid_d = nullptr;
+		f->smemEmit = smemEmit;
 		int dev = ctx->device, coop = 0, sms = 0, perSm = 0;
 		cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
 		if (!coop) { hcmvs_set_error("device lacks cooperative launch"); return HCMVS_ERR_UNSUPPORTED; }
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_fuse_view, 256, 0));
+		if (smemEmit > 48*1024) CK(cudaFuncSetAttribute(k_fuse_scene, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemEmit));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_fuse_scene, FUSE_NT, smemEmit));
 		if (perSm < 1) { hcmvs_set_error("fuse kernel does not fit"); return HCMVS_ERR_CUDA; }
-		f->coopBlocks = sms*std::min(perSm, 8);
+		if (const char* e = getenv("HCMVS_FUSE_BLOCKS_PER_SM")) perSm = std::max(1, std::min(perSm, atoi(e)));
+		f->coopBlocks = sms*perSm;
+		CK(cudaMalloc(&f->blk_d, (size_t)f->coopBlocks*3*sizeof(unsigned)));
+		CK(cudaMalloc(&f->ctl_d, sizeof(FuseCtl)));
+		CK(cudaMalloc(&f->nValid_d, sizeof(unsigned long long)));
 	}
-	const unsigned nMinViewsFuse = std::min<unsigned>(P.nMinViewsFuse, (unsigned)std::count_if(ctx->views.begin(), ctx->views.end(), [](const View& v) { return v.set; }));
+	if (f->progressCap < 1+2*plan.size()) {
+		if (f->progress) { CK(cudaStreamSynchronize(ctx->stream)); cudaFreeHost(f->progress); f->progress = nullptr; }
+		f->progressCap = 1+2*plan.size();
+		CK(cudaHostAlloc(&f->progress, f->progressCap*sizeof(unsigned long long), cudaHostAllocMapped));
+		CK(cudaHostGetDevicePointer(&f->progress_dev, f->progress, 0));
+	}
+	const unsigned nSet = (unsigned)std::count_if(ctx->views.begin(), ctx->views.end(), [](const View& v) { return v.set; });
+	const unsigned nMinViewsFuse = std::min<unsigned>(P.nMinViewsFuse, nSet);
 	const float FPI = (float)3.14159265358979323846;
 	const float normalError = std::cos((P.fNormalDiffThreshold*P.normalweight)*(FPI/180.f));
-	size_t nPoints = 0, nViewRefs = 0;
+	hcmvs_time_begin(ctx, ST_FUSE);
+	// ---- records of every view with maps + the number of valid depths (bounds the cloud)
+	CK(cudaMemsetAsync(f->nValid_d, 0, sizeof(unsigned long long), ctx->stream));
+	CK(cudaMemsetAsync(f->ctl_d, 0, sizeof(FuseCtl), ctx->stream));
+	CK(cudaMemsetAsync(f->claim_d, 0xFF, totalPix*sizeof(uint32_t), ctx->stream)); // CLAIM_FREE
+	for (size_t i=0; i<V; ++i) {
+		if (f->recOff[i] == (size_t)-1) continue;
+		const size_t n = (size_t)hv[i].w*hv[i].h;
+		k_fuse_build<<<(unsigned)((n+255)/256), 256, 0, ctx->stream>>>(f->views_d, (int)i, ctx->views[i].conf_d, f->nValid_d); ++ctx->nLaunches;
+	}
+	unsigned long long nValid = 0;
+	CK(cudaMemcpyAsync(&nValid, f->nValid_d, sizeof(nValid), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	// a fused point consumes its seed pixel and every pixel it merges, and needs >= nMinViewsFuse of them
+	const size_t needPoints = (size_t)(nValid/std::max(nMinViewsFuse, 1u))+1, needRefs = (size_t)nValid+1;
+	if (f->capPoints < needPoints) {
+		int r;
+		if ((r = Realloc(ctx, f->points, needPoints*3)) || (r = Realloc(ctx, f->normals, needPoints*3)) || (r = Realloc(ctx, f->colors, needPoints*3)) || (r = Realloc(ctx, f->viewOffsets, needPoints+1))) return r;
+		f->capPoints = needPoints;
+	}
+	if (f->capViews < needRefs) {
+		int r;
+		if ((r = Realloc(ctx, f->oviews, needRefs)) || (r = Realloc(ctx, f->weights, needRefs))) return r;
+		f->capViews = needRefs;
+	}
 	// stream the cloud out while it is being built when the caller keeps it on the device (out == NULL, the hcmvs_download_fused_pinned
 	// path) and an arena laid out for this kind of cloud exists from an earlier scene
-	f->streamed = !out && f->pinned && f->arenaPoints && f->arenaColor == (estimate_color != 0) && f->arenaNormal == (estimate_normal != 0);
+	f->streamed = !out && f->pinned && f->arenaPoints && f->arenaColor == (estimate_color != 0) && f->arenaNormal == (estimate_normal != 0) && !getenv("HCMVS_FUSE_NO_STREAM");
 	f->streamedPoints = f->streamedViews = 0;
-	if (f->streamed) {
-		if (!ctx->dlStream) CK(cudaStreamCreateWithFlags(&ctx->dlStream, cudaStreamNonBlocking));
-		if (!f->emitted) CK(cudaEventCreateWithFlags(&f->emitted, cudaEventDisableTiming));
-	}
-	hcmvs_time_begin(ctx, ST_FUSE);
-	uint64_t totalRounds = 0, totalSeeds = 0, totalProbes = 0;
-	for (const Conn& conn: conns) {
-		View& v = ctx->views[conn.idx];
-		FuseArgs a; memset(&a, 0, sizeof(a));
-		a.views = f->views_d; a.ref = (int)conn.idx;
-		a.nNb = 0;
-		for (uint32_t id: v.nbIds) { if (id < V) a.nb[a.nNb++] = (int)id; }
-		a.nMinViewsFuse = nMinViewsFuse;
-		a.depthTh = P.fDepthDiffThreshold*P.depthweight; a.normalError = normalError;
-		a.state = f->state_d; a.mask = f->mask_d; a.counters = f->counters_d; a.trace = debug ? f->trace_d : nullptr;
-		a.probes = f->probes_d; a.probeStride = maxPix;
-		const int nPix = v.w*v.h;
-		const int nBlocks = (nPix+FUSE_CHUNK-1)/FUSE_CHUNK;
-		a.seeds = f->seeds_d; a.nSeedsPtr = f->seedSums_d+nBlocks;
-		CK(cudaMemsetAsync(f->counters_d, 0, 4*sizeof(int), ctx->stream));
-		// seeds of this view, compacted in raster order; their number stays on the device (grids are sized for the worst case, idle
-		// blocks exit at once)
-		k_seed_count<<<nBlocks, 256, 0, ctx->stream>>>(a, f->seedSums_d); ++ctx->nLaunches;
-		k_fuse_scan<<<1, 1024, 0, ctx->stream>>>(f->seedSums_d, nBlocks); ++ctx->nLaunches;
-		k_seed_scatter<<<nBlocks, 256, 0, ctx->stream>>>(a, f->seedSums_d, nBlocks, f->seeds_d); ++ctx->nLaunches;
-		k_fuse_probe<<<(nPix+255)/256, 256, 0, ctx->stream>>>(a); ++ctx->nLaunches;
-		void* args[] = {(void*)&a};
-		CK(cudaLaunchCooperativeKernel((void*)k_fuse_view, dim3(f->coopBlocks), dim3(256), args, 0, ctx->stream)); ++ctx->nLaunches;
-		k_fuse_count<<<nBlocks, 256, 0, ctx->stream>>>(f->state_d, f->mask_d, a.nSeedsPtr, f->blockSums_d); ++ctx->nLaunches;
-		k_fuse_scan<<<1, 1024, 0, ctx->stream>>>(f->blockSums_d, nBlocks); ++ctx->nLaunches;
-		uint2 tot; int cnt[4];
-		CK(cudaMemcpyAsync(&tot, f->blockSums_d+nBlocks, sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
-		CK(cudaMemcpyAsync(cnt, f->counters_d, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
-		CK(cudaStreamSynchronize(ctx->stream));
-		totalRounds += (uint64_t)cnt[1]; totalSeeds += (uint64_t)cnt[2]; totalProbes += (uint64_t)cnt[2]*(uint64_t)a.nNb;
-		if (debug) {
-			int tr[256]; cudaMemcpy(tr, f->trace_d, sizeof(tr), cudaMemcpyDeviceToHost);
-			fprintf(stderr, "[fuse] view %u: %d seeds, %d rounds, %u points, %u view refs; undecided after round:", conn.idx, cnt[2], cnt[1], tot.x, tot.y);
-			for (int k=0; k<std::min(cnt[1], 12); ++k) fprintf(stderr, " %d", tr[k]);
-			fprintf(stderr, "\n");
-		}
-		if (tot.x == 0) continue;
-		if (nPoints+tot.x > f->capPoints) {
-			const size_t nc = std::max<size_t>((nPoints+tot.x)*2, (size_t)1<<20);
-			int r;
-			if ((r = Grow(ctx, f->points, nPoints, nc, 3))) return r;
-			if ((r = Grow(ctx, f->normals, nPoints, nc, 3))) return r;
-			if ((r = Grow(ctx, f->colors, nPoints, nc, 3))) return r;
-			if ((r = Grow(ctx, f->viewOffsets, nPoints, nc+1, 1))) return r;
-			f->capPoints = nc;
-		}
-		if (nViewRefs+tot.y > f->capViews) {
-			const size_t nc = std::max<size_t>((nViewRefs+tot.y)*2, (size_t)1<<21);
-			int r;
-			if ((r = Grow(ctx, f->oviews, nViewRefs, nc, 1))) return r;
-			if ((r = Grow(ctx, f->weights, nViewRefs, nc, 1))) return r;
-			f->capViews = nc;
-		}
-		FuseOut fo; fo.points = f->points; fo.normals = f->normals; fo.colors = f->colors; fo.viewOffsets = f->viewOffsets; fo.views = f->oviews; fo.weights = f->weights;
-		fo.basePoint = nPoints; fo.baseView = nViewRefs; fo.estimateColor = estimate_color; fo.estimateNormal = estimate_normal;
-		k_fuse_emit<<<nBlocks, 256, 0, ctx->stream>>>(a, f->blockSums_d, fo); ++ctx->nLaunches;
-		CK(cudaGetLastError());
-		if (f->streamed && nPoints+tot.x <= f->arenaPoints && nViewRefs+tot.y <= f->arenaViews) {
-			// what this view emitted is final: copy it to its place in the arena behind the emit kernel, on the download stream
-			const ArenaLayout L = LayoutFor(f->arenaPoints, f->arenaViews, f->arenaNormal, f->arenaColor);
-			char* base = (char*)f->pinned;
-			CK(cudaEventRecord(f->emitted, ctx->stream));
-			CK(cudaStreamWaitEvent(ctx->dlStream, f->emitted, 0));
-			CK(cudaMemcpyAsync(base+L.oPts+nPoints*12, f->points+nPoints*3, (size_t)tot.x*12, cudaMemcpyDeviceToHost, ctx->dlStream));
-			if (estimate_normal) CK(cudaMemcpyAsync(base+L.oNrm+nPoints*12, f->normals+nPoints*3, (size_t)tot.x*12, cudaMemcpyDeviceToHost, ctx->dlStream));
-			if (estimate_color) CK(cudaMemcpyAsync(base+L.oCol+nPoints*3, f->colors+nPoints*3, (size_t)tot.x*3, cudaMemcpyDeviceToHost, ctx->dlStream));
-			CK(cudaMemcpyAsync(base+L.oOff+nPoints*4, f->viewOffsets+nPoints, (size_t)tot.x*4, cudaMemcpyDeviceToHost, ctx->dlStream));
-			CK(cudaMemcpyAsync(base+L.oViews+nViewRefs*4, f->oviews+nViewRefs, (size_t)tot.y*4, cudaMemcpyDeviceToHost, ctx->dlStream));
-			CK(cudaMemcpyAsync(base+L.oW+nViewRefs*4, f->weights+nViewRefs, (size_t)tot.y*4, cudaMemcpyDeviceToHost, ctx->dlStream));
-			f->streamedPoints = nPoints+tot.x; f->streamedViews = nViewRefs+tot.y;
-		} else f->streamed = false; // outgrew the arena (or not streaming): hcmvs_download_fused_pinned copies everything at the end
-		nPoints += tot.x; nViewRefs += tot.y;
-	}
+	if (f->streamed && !ctx->dlStream) CK(cudaStreamCreateWithFlags(&ctx->dlStream, cudaStreamNonBlocking));
+	memset(f->progress, 0, f->progressCap*sizeof(unsigned long long));
+	FuseJob a; memset(&a, 0, sizeof(a));
+	a.views = f->views_d; a.plan = f->plan_d; a.nPlan = (int)plan.size();
+	for (int i=0; i<2; ++i) { a.sl[i].seeds = f->seeds_d[i]; a.sl[i].state = f->state_d[i]; a.sl[i].mask = f->mask_d[i]; a.sl[i].probes = f->probes_d[i]; a.sl[i].stgPoint = f->stgPoint_d[i]; a.sl[i].stgNormal = f->stgNormal_d[i]; a.sl[i].stgW = f->stgW_d[i]; a.wl[i] = f->wl_d[i]; }
+	a.probeStride = maxPix;
+	a.blkSeeds = f->blk_d; a.blkEmit = f->blk_d+f->coopBlocks;
+	a.ctl = f->ctl_d;
+	a.nMinViewsFuse = nMinViewsFuse; a.depthTh = P.fDepthDiffThreshold*P.depthweight; a.normalError = normalError;
+	a.out.points = f->points; a.out.normals = f->normals; a.out.colors = f->colors; a.out.viewOffsets = f->viewOffsets; a.out.views = f->oviews; a.out.weights = f->weights;
+	a.out.capPoints = f->capPoints; a.out.capRefs = f->capViews; a.out.estimateColor = estimate_color; a.out.estimateNormal = estimate_normal;
+	a.progress = f->progress_dev;
+	unsigned long long* trace_d = nullptr;
+	if (debug) { CK(cudaMalloc(&trace_d, plan.size()*8*sizeof(unsigned long long))); CK(cudaMemsetAsync(trace_d, 0, plan.size()*8*sizeof(unsigned long long), ctx->stream)); a.trace = trace_d; }
+	void* args[] = {(void*)&a};
+	CK(cudaLaunchCooperativeKernel((void*)k_fuse_scene, dim3(f->coopBlocks), dim3(FUSE_NT), args, smemEmit, ctx->stream)); ++ctx->nLaunches;
 	hcmvs_time_end(ctx);
+	if (f->streamed) {
+		// follow the kernel: whatever a view emitted is final, so it crosses PCIe at its final place in the arena while the next views
+		// are still being fused
+		const ArenaLayout L = LayoutFor(f->arenaPoints, f->arenaViews, f->arenaNormal, f->arenaColor);
+		char* base = (char*)f->pinned;
+		volatile unsigned long long* pg = f->progress;
+		size_t done = 0, sentP = 0, sentV = 0, spins = 0;
+		while (done < plan.size()) {
+			const size_t now = (size_t)pg[0];
+			if (now == done) {
+				if ((++spins & 63) == 0) { const cudaError_t q = cudaStreamQuery(ctx->stream); if (q != cudaErrorNotReady) { if ((size_t)pg[0] == done) break; } }
+				sched_yield();
+				continue;
+			}
+			done = now;
+			const size_t nP = (size_t)pg[1+2*(done-1)], nV = (size_t)pg[2+2*(done-1)];
+			if (nP > f->arenaPoints || nV > f->arenaViews) { f->streamed = false; break; } // outgrew the arena: one copy at the end
+			if (nP > sentP) {
+				CK(cudaMemcpyAsync(base+L.oPts+sentP*12, f->points+sentP*3, (nP-sentP)*12, cudaMemcpyDeviceToHost, ctx->dlStream));
+				if (estimate_normal) CK(cudaMemcpyAsync(base+L.oNrm+sentP*12, f->normals+sentP*3, (nP-sentP)*12, cudaMemcpyDeviceToHost, ctx->dlStream));
+				if (estimate_color) CK(cudaMemcpyAsync(base+L.oCol+sentP*3, f->colors+sentP*3, (nP-sentP)*3, cudaMemcpyDeviceToHost, ctx->dlStream));
+				CK(cudaMemcpyAsync(base+L.oOff+sentP*4, f->viewOffsets+sentP, (nP-sentP)*4, cudaMemcpyDeviceToHost, ctx->dlStream));
+				CK(cudaMemcpyAsync(base+L.oViews+sentV*4, f->oviews+sentV, (nV-sentV)*4, cudaMemcpyDeviceToHost, ctx->dlStream));
+				CK(cudaMemcpyAsync(base+L.oW+sentV*4, f->weights+sentV, (nV-sentV)*4, cudaMemcpyDeviceToHost, ctx->dlStream));
+				sentP = nP; sentV = nV;
+			}
+		}
+		if (done < plan.size()) f->streamed = false;
+		f->streamedPoints = sentP; f->streamedViews = sentV;
+	}
+	FuseCtl ctl;
+	CK(cudaMemcpyAsync(&ctl, f->ctl_d, sizeof(ctl), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	if (ctl.overflow) { hcmvs_set_error("fused cloud exceeded its bound (%zu points / %zu view references) [code %d]", f->capPoints, f->capViews, ctl.overflow); return HCMVS_ERR_STATE; }
+	const size_t nPoints = (size_t)ctl.cumPoints, nViewRefs = (size_t)ctl.cumRefs;
+	if (debug && trace_d) {
+		std::vector<unsigned long long> tr(plan.size()*8);
+		cudaMemcpy(tr.data(), trace_d, tr.size()*8, cudaMemcpyDeviceToHost); cudaFree(trace_d);
+		double acc[5] = {0, 0, 0, 0, 0};
+		for (size_t r=0; r<plan.size(); ++r) for (int i=0; i<5; ++i) acc[i] += (double)(tr[8*r+i+1]-tr[8*r+i])*1e-3;
+		for (size_t r=0; r<plan.size(); r += (r < 8 ? 1 : 8))
+			fprintf(stderr, "[fuse] view #%zu (%d): count %.1f scatter+emit %.1f probe %.1f resolve-1 %.1f rounds %.1f us; %llu seeds, %llu rounds, worklist entries summed over the rounds %llu\n", r, plan[r].view,
+				(tr[8*r+1]-tr[8*r])*1e-3, (tr[8*r+2]-tr[8*r+1])*1e-3, (tr[8*r+3]-tr[8*r+2])*1e-3, (tr[8*r+4]-tr[8*r+3])*1e-3, (tr[8*r+5]-tr[8*r+4])*1e-3, tr[8*r+6]&0xFFFFFFFFull, tr[8*r+6]>>32, tr[8*r+7]);
+		fprintf(stderr, "[fuse] us per scene: count %.0f, scatter+emit %.0f, probe %.0f, resolve-1 %.0f, rounds %.0f; total %.0f\n", acc[0], acc[1], acc[2], acc[3], acc[4], (double)(tr[8*(plan.size()-1)+5]-tr[0])*1e-3);
+	}
+	if (debug) fprintf(stderr, "[fuse] %zu views, %llu seeds, %llu rounds, %zu points, %zu view refs, %d blocks\n", plan.size(), ctl.seeds, ctl.rounds, nPoints, nViewRefs, f->coopBlocks);
 	for (View& v: ctx->views) if (v.set && v.hasMaps) { int r = hcmvs_mark_image_use(ctx, v); if (r) return r; } // colours were read
-	ctx->fuseRounds = totalRounds; ctx->fuseSeeds = totalSeeds; ctx->fuseProbes = totalProbes;
+	ctx->fuseRounds = ctl.rounds; ctx->fuseSeeds = ctl.seeds; ctx->fuseProbes = ctl.probes;
 	f->nPoints = nPoints; f->nViewRefs = nViewRefs; f->hasColor = estimate_color != 0; f->hasNormal = estimate_normal != 0;
+	if (f->streamed && (f->streamedPoints != nPoints || f->streamedViews != nViewRefs)) f->streamed = false;
 	if (nPoints) { // close the CSR offsets on the device
 		const uint32_t last = (uint32_t)nViewRefs;
 		CK(cudaMemcpyAsync(f->viewOffsets+nPoints, &last, 4, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
 	}
-	CK(cudaStreamSynchronize(ctx->stream));
 	if (!out) return HCMVS_OK; // cloud stays on the device (hcmvs_get_fused_device / hcmvs_download_fused)
 	out->n_points = nPoints;
 	if (nPoints) {
@@ -741,11 +943,12 @@ extern "C" int hcmvs_download_fused_pinned(hcmvs_ctx* ctx, hcmvs_pointcloud* out
 extern "C" int hcmvs_get_fused_support(hcmvs_ctx* ctx, uint32_t view, float* depth_fuse, float* normal_fuse) {
 	if (!ctx || view >= ctx->views.size() || !ctx->views[view].set) { hcmvs_set_error("view %u not set", view); return HCMVS_ERR_ARG; }
 	View& v = ctx->views[view];
-	if (!v.hasMaps || !v.claim_d) { hcmvs_set_error("view %u took no part in a fusion yet (call hcmvs_fuse_depthmaps)", view); return HCMVS_ERR_STATE; }
+	FuseState* f = ctx->fuse;
+	if (!v.hasMaps || !f || view >= f->recOff.size() || f->recOff[view] == (size_t)-1 || !f->rec_d) { hcmvs_set_error("view %u took no part in a fusion yet (call hcmvs_fuse_depthmaps)", view); return HCMVS_ERR_STATE; }
 	cudaSetDevice(ctx->device);
 	const size_t n = (size_t)v.w*v.h;
 	float* tmp; int r = hcmvs_scratch(ctx, n*16, (void**)&tmp); if (r) return r;
-	k_fused_support<<<(unsigned)((n+255)/256), 256, 0, ctx->stream>>>(v.dn_d, v.claim_d, tmp, tmp+n, n); ++ctx->nLaunches;
+	k_fused_support<<<(unsigned)((n+255)/256), 256, 0, ctx->stream>>>(v.dn_d, f->alive_d+f->aliveOff[view], tmp, tmp+n, n); ++ctx->nLaunches;
 	if (depth_fuse) CK(cudaMemcpyAsync(depth_fuse, tmp, n*4, cudaMemcpyDeviceToHost, ctx->stream));
 	if (normal_fuse) CK(cudaMemcpyAsync(normal_fuse, tmp+n, n*12, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));

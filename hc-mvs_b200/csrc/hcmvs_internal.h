@@ -25,7 +25,6 @@ struct View { // one scene image + its DepthData (libs/MVS/DepthMap.h:214-347)
 	float4* coarse_d = nullptr;   // restore tree: nresize_normalMap / nresize_depthMap packed like dn
 	float4* dnPrev_d = nullptr; float* confPrev_d = nullptr; bool hasPrev = false; // maps of the previous outer iteration (viewspread)
 	float* fdepth_d = nullptr; float* fconf_d = nullptr; bool hasFiltered = false; // pending FilterDepthMap output
-	uint32_t* claim_d = nullptr;  // FuseDepthMaps' arrDepthIdx (claim / reservation word per pixel)
 	float dMin = 0.f, dMax = 0.f;
 	std::vector<uint32_t> nbIds;  // DepthData::neighbors (sorted by score)
 	std::vector<float> nbScores;
