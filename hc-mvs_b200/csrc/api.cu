@@ -81,7 +81,7 @@ static void FreeView(View& v) {
 	if (v.ready) cudaEventDestroy(v.ready);
 	if (v.imgReady) cudaEventDestroy(v.imgReady);
 	if (v.lastUse) cudaEventDestroy(v.lastUse);
-	cudaFree(v.img_d); cudaFree(v.bgr_d); cudaFree(v.gra_d); cudaFree(v.dn_d); cudaFree(v.conf_d); cudaFree(v.prior_d); cudaFree(v.coarse_d); cudaFree(v.dnPrev_d); cudaFree(v.confPrev_d); cudaFree(v.fdepth_d); cudaFree(v.fconf_d);
+	cudaFree(v.img_d); cudaFree(v.bgr_d); cudaFree(v.gra_d); cudaFree(v.dn_d); cudaFree(v.conf_d); cudaFree(v.depth_d); cudaFree(v.prior_d); cudaFree(v.coarse_d); cudaFree(v.dnPrev_d); cudaFree(v.confPrev_d); cudaFree(v.fdepth_d); cudaFree(v.fconf_d);
 	v = View();
 }
 
@@ -311,6 +311,7 @@ extern "C" int hcmvs_set_neighbor_image(hcmvs_ctx* ctx, uint32_t ref, int slot, 
 
 static int AllocMaps(hcmvs_ctx* ctx, View* v) {
 	const size_t n = (size_t)v->w*v->h;
+	v->depthValid = false;
 	if (!v->dn_d) { CK(cudaMalloc(&v->dn_d, n*sizeof(float4))); CK(cudaMemsetAsync(v->dn_d, 0, n*sizeof(float4), ctx->stream)); }
 	if (!v->conf_d) { CK(cudaMalloc(&v->conf_d, n*4)); CK(cudaMemsetAsync(v->conf_d, 0, n*4, ctx->stream)); }
 	return HCMVS_OK;
@@ -320,6 +321,7 @@ static int AllocMaps(hcmvs_ctx* ctx, View* v) {
 // for other views; consumers on the compute stream wait on v->ready. Returns once the host buffers may be reused.
 static int UploadMaps(hcmvs_ctx* ctx, View* v, const float* depth, const float* normal, const float* conf) {
 	const size_t n = (size_t)v->w*v->h;
+	v->depthValid = false;
 	cudaStream_t cs = ctx->copyStream;
 	// the view's buffers may still be in use by earlier compute work (re-initialisation of an estimated view)
 	if (v->dn_d) { cudaEvent_t done; CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming)); CK(cudaEventRecord(done, ctx->stream)); CK(cudaStreamWaitEvent(cs, done, 0)); CK(cudaEventDestroy(done)); }
@@ -366,6 +368,7 @@ extern "C" int hcmvs_init_depthmap(hcmvs_ctx* ctx, uint32_t ref, const float* de
 extern "C" int hcmvs_init_depthmap_triangles(hcmvs_ctx* ctx, uint32_t ref, const double* vertices, int n_vertices, const uint32_t* tris, int n_tris, float dMin, float dMax) {
 	// InitDepthMap -> TriangulatePoints2DepthMap (SceneDensify.cpp:514-525, DepthMap.cpp:1879-1936); the caller applied dMin*0.9 / dMax*1.1
 	View* v = GetView(ctx, ref, true); if (!v) return HCMVS_ERR_ARG;
+	v->depthValid = false;
 	if (!vertices || !tris || n_vertices < 3 || n_tris < 1 || !(dMin > 0.f) || !(dMin < dMax)) { hcmvs_set_error("bad triangulation (%d vertices, %d triangles) or depth range [%g,%g)", n_vertices, n_tris, dMin, dMax); return HCMVS_ERR_ARG; }
 	cudaSetDevice(ctx->device);
 	const size_t n = (size_t)v->w*v->h;
@@ -494,7 +497,7 @@ extern "C" int hcmvs_download_depthmap_wait(hcmvs_ctx* ctx, int slot, const floa
 extern "C" int hcmvs_get_depthmap_device(hcmvs_ctx* ctx, uint32_t view, void** dn_d, void** conf_d, float* dMin, float* dMax) {
 	View* v = GetView(ctx, view, true); if (!v) return HCMVS_ERR_ARG;
 	if (!v->hasMaps) { hcmvs_set_error("view %u has no depth map", view); return HCMVS_ERR_STATE; }
-	if (dn_d) *dn_d = v->dn_d;
+	if (dn_d) { *dn_d = v->dn_d; v->depthValid = false; } // the caller may write through the pointer
 	if (conf_d) *conf_d = v->conf_d;
 	if (dMin) *dMin = v->dMin;
 	if (dMax) *dMax = v->dMax;
@@ -605,7 +608,7 @@ static int BuildRefConst(hcmvs_ctx* ctx, View* v, uint32_t ref, int it_external,
 	rc.fx = v->K[0]; rc.fy = v->K[4]; rc.cx = v->K[2]; rc.cy = v->K[5];
 	Inv33(v->K, rc.Hr);
 	rc.img0 = v->img_d; rc.pitch0 = v->w; rc.gra = v->gra_d; rc.prior = v->prior_d;
-	rc.dn = v->dn_d; rc.conf = v->conf_d;
+	rc.dn = v->dn_d; rc.conf = v->conf_d; v->depthValid = false; // every user of a RefConst may write the maps
 	rc.nViews = v->nMatch;
 	{ int r = hcmvs_wait_image(ctx, *v); if (r) return r; }
 	for (int i=0; i<v->nMatch; ++i) {
@@ -665,6 +668,7 @@ extern "C" int hcmvs_score_depthmap(hcmvs_ctx* ctx, uint32_t ref, int it_externa
 extern "C" int hcmvs_end_depthmap(hcmvs_ctx* ctx, uint32_t ref) {
 	View* v = GetView(ctx, ref, true); if (!v) return HCMVS_ERR_ARG;
 	int r = RequireMaps(v, ref); if (r) return r;
+	v->depthValid = false;
 	cudaSetDevice(ctx->device);
 	hcmvs_time_begin(ctx, ST_END);
 	CK(hcmvs_launch_end(v->dn_d, v->conf_d, (size_t)v->w*v->h, ctx->P.fNCCThresholdKeep, ctx->stream)); ++ctx->nLaunches;

@@ -102,6 +102,7 @@ extern "C" int hcmvs_exchange_maps(hcmvs_ctx* ctx, const int32_t* owner, uint32_
 	what &= ~HCMVS_EXCHANGE_ASYNC;
 	if (what != HCMVS_EXCHANGE_ESTIMATED && what != HCMVS_EXCHANGE_FILTERED) { hcmvs_set_error("unknown exchange kind %d", what); return HCMVS_ERR_ARG; }
 	if (!ctx->comm) { hcmvs_set_error("no communicator (call hcmvs_comm_init)"); return HCMVS_ERR_STATE; }
+	for (View& v: ctx->views) v.depthValid = false; // received maps replace dn
 	if (n_views > ctx->views.size()) { hcmvs_set_error("owner list longer than the scene (%u > %zu views)", n_views, ctx->views.size()); return HCMVS_ERR_ARG; }
 	cudaSetDevice(ctx->device);
 	// Phase 1 — local checks and allocations. Nothing collective has been issued yet, so a failing rank must not simply return: its

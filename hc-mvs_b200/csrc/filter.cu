@@ -7,63 +7,126 @@
 //  k_filter_vote   — stage 2 (:3097-3248): per reference pixel, fuse/penalise (bAdjust) or strict agreement.
 #include "hcmvs_internal.h"
 #include "camera.cuh"
+#include <climits>
+#include <algorithm>
 
 namespace hcmvs {
 
-struct FilterConst {
+struct FilterConst { // passed by value (__grid_constant__): no upload, no host synchronisation per call
 	int nViews;                 // N
 	int wR, hR;
 	CamConst camRef;
 	CamConst cam[HCMVS_MAXV];
-	const float4* dn[HCMVS_MAXV];
+	const float* depth[HCMVS_MAXV]; // compact depth planes of the neighbours (View::depth_d)
 	const float* conf[HCMVS_MAXV];
 	int w[HCMVS_MAXV], h[HCMVS_MAXV];
+	const float* depthRef; const float* confRef;
 	unsigned nMinViews, nMinViewsAdjust;
 	float thDepthDiff, thDepthDiffStrict;
 	float dMin, dMax;
 };
 
 #define FILTER_EMPTY 0xFFFFFFFFFFFFFFFFull
+#define FS_SRC 32  // a block splats a 32x32 tile of one neighbour map (4 pixels per thread)
+#define FS_T 48    // ... through a 48x48 z-buffer in shared memory when the tile's footprint in the reference view fits
 
-__global__ void k_filter_splat(const FilterConst* __restrict__ fc, int n, unsigned long long* __restrict__ proj) {
-	const int w = fc->w[n], h = fc->h[n];
-	const int x = blockIdx.x*blockDim.x+threadIdx.x, y = blockIdx.y*blockDim.y+threadIdx.y;
-	if (x >= w || y >= h) return;
-	const unsigned src = (unsigned)(y*w+x);
-	const float depth = fc->dn[n][src].w;
-	if (depth == 0.f) return;
-	const D3 X = cam_I2W(fc->cam[n], (double)x, (double)y, (double)depth);
-	const D3 camX = cam_W2C(fc->camRef, X);
-	if (camX.z <= 0.0) return;
-	double u, v; cam_C2I(fc->camRef, camX, u, v);
-	const float z = (float)camX.z;
-	const unsigned long long key = ((unsigned long long)__float_as_uint(z)<<32) | (unsigned long long)(0xFFFFFFFFu-src);
-	const int xs[2] = {floor2int(u), ceil2int(u)}, ys[2] = {floor2int(v), ceil2int(v)};
+// All neighbour maps in ONE launch (blockIdx.z = neighbour). The 4 splats of a pixel and those of its neighbours land on the same
+// few reference pixels, so the nearest-z reduction is done in shared memory first and only the winners of the tile go to the
+// global z-buffer: ~1 global 64-bit atomicMin per touched reference pixel instead of 4 per source pixel (the round-1 kernel was
+// bound by L2 atomic throughput: 61 M atomics per C2 view). min is associative, so the result is the same key.
+__global__ void __launch_bounds__(256) k_filter_splat(const __grid_constant__ FilterConst fc, unsigned long long* __restrict__ projAll, size_t plane) {
+	__shared__ unsigned long long tile[FS_T*FS_T];
+	__shared__ int sBox[4];
+	const int n = blockIdx.z;
+	const int w = fc.w[n], h = fc.h[n];
+	const int x0 = blockIdx.x*FS_SRC, y0 = blockIdx.y*FS_SRC;
+	if (x0 >= w || y0 >= h) return; // the grid is sized for the largest neighbour
+	unsigned long long* proj = projAll+(size_t)n*plane;
+	const int tx = threadIdx.x&31, ty = threadIdx.x>>5;
+	if (threadIdx.x == 0) { sBox[0] = INT_MAX; sBox[1] = INT_MAX; sBox[2] = INT_MIN; sBox[3] = INT_MIN; }
+	int fx[4], fy[4]; unsigned flags = 0; unsigned long long key[4]; // flags: bit i valid, bit 4+i ceil(u) != floor(u), bit 8+i ceil(v) != floor(v)
+	int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
 	#pragma unroll
-	for (int a=0; a<2; ++a)
+	for (int i=0; i<4; ++i) {
+		const int x = x0+tx, y = y0+ty+8*i;
+		fx[i] = 0; fy[i] = 0; key[i] = FILTER_EMPTY;
+		if (x >= w || y >= h) continue;
+		const unsigned src = (unsigned)(y*w+x);
+		const float depth = fc.depth[n][src];
+		if (depth == 0.f) continue;
+		const D3 X = cam_I2W(fc.cam[n], (double)x, (double)y, (double)depth);
+		const D3 camX = cam_W2C(fc.camRef, X);
+		if (camX.z <= 0.0) continue;
+		double u, v; cam_C2I(fc.camRef, camX, u, v);
+		const float z = (float)camX.z;
+		key[i] = ((unsigned long long)__float_as_uint(z)<<32) | (unsigned long long)(0xFFFFFFFFu-src);
+		// FLOOR2INT / CEIL2INT of the f64 projection (Common/Types.h:909-936); far-off projections are clamped to a value outside any image
+		const double uc = fmin(fmax(u, -1e6), 1e6), vc = fmin(fmax(v, -1e6), 1e6);
+		if (!(u == u) || !(v == v)) { key[i] = FILTER_EMPTY; continue; }
+		const int ax = floor2int(uc), bx = ceil2int(uc), ay = floor2int(vc), by = ceil2int(vc);
+		fx[i] = ax; fy[i] = ay;
+		flags |= (1u<<i) | (bx != ax ? 16u<<i : 0u) | (by != ay ? 256u<<i : 0u);
+		mnx = min(mnx, ax); mny = min(mny, ay); mxx = max(mxx, bx); mxy = max(mxy, by);
+	}
+	mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
+	mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
+	__syncthreads();
+	if (tx == 0 && mnx != INT_MAX) { atomicMin(&sBox[0], mnx); atomicMin(&sBox[1], mny); atomicMax(&sBox[2], mxx); atomicMax(&sBox[3], mxy); }
+	__syncthreads();
+	const int bx0 = sBox[0], by0 = sBox[1];
+	if (bx0 == INT_MAX) return; // nothing valid in this tile
+	const int bw = sBox[2]-bx0+1, bh = sBox[3]-by0+1;
+	const int wR = fc.wR, hR = fc.hR;
+	if (bw <= FS_T && bh <= FS_T) {
+		for (int i=threadIdx.x; i<bw*bh; i+=256) tile[i] = FILTER_EMPTY;
+		__syncthreads();
 		#pragma unroll
-		for (int b=0; b<2; ++b) {
-			const int xr = xs[a], yr = ys[b];
-			if (xr < 0 || yr < 0 || xr >= fc->wR || yr >= fc->hR) continue;
-			if (a == 1 && xs[1] == xs[0]) continue; // same pixel twice when the projection is integral
-			if (b == 1 && ys[1] == ys[0]) continue;
-			atomicMin(&proj[(size_t)yr*fc->wR+xr], key);
+		for (int i=0; i<4; ++i) {
+			if (!(flags & (1u<<i))) continue;
+			const int lx = fx[i]-bx0, ly = fy[i]-by0;
+			const bool dx = flags & (16u<<i), dy = flags & (256u<<i);
+			atomicMin(&tile[ly*bw+lx], key[i]);
+			if (dx) atomicMin(&tile[ly*bw+lx+1], key[i]);
+			if (dy) atomicMin(&tile[(ly+1)*bw+lx], key[i]);
+			if (dx && dy) atomicMin(&tile[(ly+1)*bw+lx+1], key[i]);
 		}
+		__syncthreads();
+		for (int i=threadIdx.x; i<bw*bh; i+=256) {
+			const unsigned long long k = tile[i];
+			if (k == FILTER_EMPTY) continue;
+			const int xr = bx0+i%bw, yr = by0+i/bw;
+			if (xr < 0 || yr < 0 || xr >= wR || yr >= hR) continue;
+			atomicMin(&proj[(size_t)yr*wR+xr], k);
+		}
+	} else { // a footprint larger than the shared tile (strong zoom / rotation between the views): straight to the global z-buffer
+		#pragma unroll
+		for (int i=0; i<4; ++i) {
+			if (!(flags & (1u<<i))) continue;
+			const bool dx = flags & (16u<<i), dy = flags & (256u<<i);
+			for (int a=0; a<2; ++a) for (int b=0; b<2; ++b) {
+				if ((a && !dx) || (b && !dy)) continue; // same pixel twice when the projection is integral
+				const int xr = fx[i]+a, yr = fy[i]+b;
+				if (xr < 0 || yr < 0 || xr >= wR || yr >= hR) continue;
+				atomicMin(&proj[(size_t)yr*wR+xr], key[i]);
+			}
+		}
+	}
 }
 
 __device__ __forceinline__ float proj_depth(unsigned long long k) { return k == FILTER_EMPTY ? 0.f : __uint_as_float((unsigned)(k>>32)); }
 __device__ __forceinline__ unsigned proj_src(unsigned long long k) { return 0xFFFFFFFFu-(unsigned)(k & 0xFFFFFFFFull); }
 
-__global__ void k_filter_vote(const FilterConst* __restrict__ fc, const unsigned long long* __restrict__ proj,
-	const float4* __restrict__ dnRef, const float* __restrict__ confRef, int bAdjust,
+__global__ void __launch_bounds__(256) k_filter_vote(const __grid_constant__ FilterConst fcv, const unsigned long long* __restrict__ proj, int bAdjust,
 	float* __restrict__ newDepth, float* __restrict__ newConf)
 {
+	const FilterConst* fc = &fcv;
+	const float* __restrict__ confRef = fcv.confRef;
 	const int wR = fc->wR, hR = fc->hR;
 	const int j = blockIdx.x*blockDim.x+threadIdx.x, i = blockIdx.y*blockDim.y+threadIdx.y;
 	if (j >= wR || i >= hR) return;
 	const size_t o = (size_t)i*wR+j;
 	const size_t plane = (size_t)wR*hR;
-	const float depth = dnRef[o].w;
+	const float depth = fcv.depthRef[o];
 	float outD = 0.f, outC = 0.f;
 	const int N = fc->nViews;
 	if (depth != 0.f) {
@@ -152,6 +215,19 @@ void hcmvs_fill_cam(const View& v, CamConst& c) {
 	memcpy(c.K, v.K, 72); memcpy(c.R, v.R, 72); memcpy(c.C, v.C, 24); memcpy(c.P, v.P, 96);
 }
 
+// the compact depth plane of a view (what the splats and the vote read instead of the 16-byte stride of dn); rebuilt when a writer of dn
+// has run since (View::depthValid is cleared by every such entry point)
+static int EnsureDepthPlane(hcmvs_ctx* ctx, View& v) {
+	const size_t n = (size_t)v.w*v.h;
+	if (!v.depth_d) { CK(cudaMalloc(&v.depth_d, n*4)); v.depthValid = false; }
+	if (!v.depthValid) {
+		if (v.ready) CK(cudaStreamWaitEvent(ctx->stream, v.ready, 0));
+		CK(hcmvs_launch_unpack(v.dn_d, v.depth_d, nullptr, n, ctx->stream)); ++ctx->nLaunches;
+		v.depthValid = true;
+	}
+	return HCMVS_OK;
+}
+
 extern "C" int hcmvs_filter_depthmap(hcmvs_ctx* ctx, uint32_t ref, const uint32_t* nb_idx, int n, int bAdjust, float* out_depth, float* out_conf) {
 	if (!ctx || !nb_idx) { hcmvs_set_error("null argument"); return HCMVS_ERR_ARG; }
 	if (ref >= ctx->views.size() || !ctx->views[ref].set || !ctx->views[ref].hasMaps) { hcmvs_set_error("view %u has no depth map", ref); return HCMVS_ERR_STATE; }
@@ -164,42 +240,45 @@ extern "C" int hcmvs_filter_depthmap(hcmvs_ctx* ctx, uint32_t ref, const uint32_
 	FilterConst fc; memset(&fc, 0, sizeof(fc));
 	fc.nViews = n; fc.wR = v.w; fc.hR = v.h;
 	hcmvs_fill_cam(v, fc.camRef);
+	{ int r = EnsureDepthPlane(ctx, v); if (r) return r; }
+	fc.depthRef = v.depth_d; fc.confRef = v.conf_d;
+	int maxW = 0, maxH = 0;
 	for (int i=0; i<n; ++i) {
 		if (nb_idx[i] >= v.nbIds.size()) { hcmvs_set_error("neighbour index %u out of range", nb_idx[i]); return HCMVS_ERR_ARG; }
 		const uint32_t id = v.nbIds[nb_idx[i]];
 		if (id >= ctx->views.size() || !ctx->views[id].hasMaps) { hcmvs_set_error("neighbour view %u has no depth map", id); return HCMVS_ERR_STATE; }
-		const View& q = ctx->views[id];
+		View& q = ctx->views[id];
 		hcmvs_fill_cam(q, fc.cam[i]);
-		fc.dn[i] = q.dn_d; fc.conf[i] = q.conf_d; fc.w[i] = q.w; fc.h[i] = q.h;
+		{ int r = EnsureDepthPlane(ctx, q); if (r) return r; }
+		fc.depth[i] = q.depth_d; fc.conf[i] = q.conf_d; fc.w[i] = q.w; fc.h[i] = q.h;
+		maxW = std::max(maxW, q.w); maxH = std::max(maxH, q.h);
 	}
 	fc.nMinViews = nMinViews; fc.nMinViewsAdjust = nMinViewsAdjust;
 	fc.thDepthDiff = P.fDepthDiffThreshold*1.2f; fc.thDepthDiffStrict = P.fDepthDiffThreshold*0.8f;
 	fc.dMin = v.dMin; fc.dMax = v.dMax;
 	const size_t plane = (size_t)v.w*v.h;
 	const size_t bytesProj = plane*8*(size_t)n;
-	const size_t offConst = (bytesProj+255)&~(size_t)255;
-	char* buf; int r = hcmvs_scratch(ctx, offConst+sizeof(FilterConst)+256, (void**)&buf); if (r) return r;
+	char* buf; int r = hcmvs_scratch(ctx, bytesProj+256, (void**)&buf); if (r) return r;
 	unsigned long long* proj = (unsigned long long*)buf;
-	FilterConst* fc_d = (FilterConst*)(buf+offConst);
 	if (!v.fdepth_d) CK(cudaMalloc(&v.fdepth_d, plane*4));
 	if (!v.fconf_d) CK(cudaMalloc(&v.fconf_d, plane*4));
 	hcmvs_time_begin(ctx, ST_FILTER);
-	CK(cudaMemcpyAsync(fc_d, &fc, sizeof(fc), cudaMemcpyHostToDevice, ctx->stream));
 	CK(cudaMemsetAsync(proj, 0xFF, bytesProj, ctx->stream));
-	dim3 b(32, 8);
-	for (int i=0; i<n; ++i) {
-		dim3 g((fc.w[i]+31)/32, (fc.h[i]+7)/8);
-		k_filter_splat<<<g, b, 0, ctx->stream>>>(fc_d, i, proj+(size_t)i*plane); ++ctx->nLaunches;
+	if (n > 0) {
+		dim3 g((maxW+FS_SRC-1)/FS_SRC, (maxH+FS_SRC-1)/FS_SRC, n);
+		k_filter_splat<<<g, 256, 0, ctx->stream>>>(fc, proj, plane); ++ctx->nLaunches;
 	}
-	dim3 g((v.w+31)/32, (v.h+7)/8);
-	k_filter_vote<<<g, b, 0, ctx->stream>>>(fc_d, proj, v.dn_d, v.conf_d, bAdjust, v.fdepth_d, v.fconf_d); ++ctx->nLaunches;
+	dim3 b(32, 8), g((v.w+31)/32, (v.h+7)/8);
+	k_filter_vote<<<g, b, 0, ctx->stream>>>(fc, proj, bAdjust, v.fdepth_d, v.fconf_d); ++ctx->nLaunches;
 	CK(cudaGetLastError());
 	hcmvs_time_end(ctx);
 	ctx->filterBytes += (uint64_t)(24*n+16)*(uint64_t)v.w*v.h; // n x (8 read + 8 written + 8 read back) + 8 in + 8 out per reference pixel
 	v.hasFiltered = true;
-	if (out_depth) CK(cudaMemcpyAsync(out_depth, v.fdepth_d, plane*4, cudaMemcpyDeviceToHost, ctx->stream));
-	if (out_conf) CK(cudaMemcpyAsync(out_conf, v.fconf_d, plane*4, cudaMemcpyDeviceToHost, ctx->stream));
-	CK(cudaStreamSynchronize(ctx->stream)); // FilterConst lives on the host stack / scratch is reused by the next call
+	if (out_depth || out_conf) { // only a caller that wants the result on the host waits; the scratch z-buffer is reused in stream order
+		if (out_depth) CK(cudaMemcpyAsync(out_depth, v.fdepth_d, plane*4, cudaMemcpyDeviceToHost, ctx->stream));
+		if (out_conf) CK(cudaMemcpyAsync(out_conf, v.fconf_d, plane*4, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+	}
 	return HCMVS_OK;
 }
 
@@ -211,7 +290,7 @@ extern "C" int hcmvs_commit_filtered(hcmvs_ctx* ctx) {
 		if (!v.hasFiltered) continue;
 		const size_t n = (size_t)v.w*v.h;
 		k_commit_filtered<<<(unsigned)((n+255)/256), 256, 0, ctx->stream>>>(v.dn_d, v.conf_d, v.fdepth_d, v.fconf_d, n); ++ctx->nLaunches;
-		v.hasFiltered = false;
+		v.hasFiltered = false; v.depthValid = false;
 	}
 	CK(cudaGetLastError());
 	hcmvs_time_end(ctx);

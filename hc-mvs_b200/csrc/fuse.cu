@@ -700,6 +700,7 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 		View& v = ctx->views[i];
 		FuseView& fv = hv[i]; memset(&fv, 0, sizeof(fv));
 		if (!v.set || !v.hasMaps) continue;
+		v.depthValid = false; // occluded depths are zeroed in place
 		{ int r = hcmvs_wait_image(ctx, v); if (r) return r; } // colours
 		const size_t n = (size_t)v.w*v.h;
 		if (n >= ((size_t)1<<30)) { hcmvs_set_error("depth maps above 2^30 pixels are not supported by the fusion probe cache"); return HCMVS_ERR_UNSUPPORTED; }

@@ -21,6 +21,7 @@ struct View { // one scene image + its DepthData (libs/MVS/DepthMap.h:214-347)
 	bool graValid = false;        // gra_d matches the current image
 	float4* dn_d = nullptr;       // (normal.xyz, depth)
 	float* conf_d = nullptr;
+	float* depth_d = nullptr; bool depthValid = false; // compact copy of dn.w for the filter's splats (4 B/px instead of a 16 B stride); stale after any writer of dn
 	float* prior_d = nullptr;     // DepthData::depthMapPrior
 	float4* coarse_d = nullptr;   // restore tree: nresize_normalMap / nresize_depthMap packed like dn
 	float4* dnPrev_d = nullptr; float* confPrev_d = nullptr; bool hasPrev = false; // maps of the previous outer iteration (viewspread)
