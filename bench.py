@@ -26,7 +26,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {1: "C1 synthetic 10-view 640x480 textured plane", 2: "C2 synthetic DTU-shaped 49 views 1600x1200",
-             3: "C3 synthetic ETH3D-shaped 20 views 6048x4032", 4: "C4 synthetic video 300 views 1920x1080"}
+             3: "C3 synthetic ETH3D-shaped 20 views 6048x4032", 4: "C4 synthetic video 300 views 1920x1080",
+             5: "C5 fusion stress: FuseDepthMaps over 500 precomputed 1920x1080 depth/normal maps"}
+
+
+def config_dict(args, n_views, width, height):
+    """The workload description — IDENTICAL in both arms (the driver compares the two dicts)."""
+    if args.config == 5:
+        return {"workload": WORKLOADS[5], "scale": args.scale, "views": n_views, "image": [width, height], "neighbours": 12, "patchmatch_iters": 0,
+                "stages": "fuse"}
+    return {"workload": WORKLOADS[args.config], "scale": args.scale, "views": n_views, "image": [width, height], "neighbours": 5, "patchmatch_iters": 3,
+            "stages": "estimate(A+B+C) + filter + fuse"}
 
 
 def parse():
@@ -105,11 +115,13 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
-def make_scene(args):
+def make_scene(args, only=None):
+    """The seeded synthetic scene; `only`: render just these views (a rank of a multi-GPU run holds the pixels of its share)."""
     from hcmvs_b200.synth import SynthScene
     syn = SynthScene(args.config, args.scale, args.views)
-    imgs = [syn.render(i, want_depth=False, want_normal=False)[0] for i in range(syn.n_views)]
-    return syn, imgs
+    if only is None:
+        return syn, [syn.render(i, want_depth=False, want_normal=False)[0] for i in range(syn.n_views)]
+    return syn, {i: syn.render(i, want_depth=False, want_normal=False)[0] for i in only}
 
 
 def ncu_traffic_per_launch():
@@ -196,27 +208,68 @@ def cpu_oracle_sample(args, syn, imgs, seconds_budget=25.0, stages=True):
     return out
 
 
+def cpu_fusion_sample(args, views=12):
+    """C5 on the CPU: FuseDepthMaps of the oracle over a bounded window of the precomputed maps (single thread, like the reference)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    from hcmvs_b200.synth import SynthScene, c5_maps, frame_neighbors
+    syn = SynthScene(5, args.scale, views)
+    osc = O.OracleScene(nNumViews=5, nEstimationIters=3, nEstimationIters_external=1, nMinViewsTrustPoint=1, adapthalfwin=5)
+    maps = []
+    for i in range(syn.n_views):
+        bgr, d, n = syn.render(i)
+        osc.add_image(syn.K[i], syn.R[i], syn.Cc[i], bgr=bgr)
+        maps.append(c5_maps((d, n), 900 + i))
+    for i in range(syn.n_views):
+        ids = frame_neighbors(i, syn.n_views)
+        osc.set_neighbors(i, ids, min(5, len(ids)))
+        osc.set_depthmap(i, *maps[i])
+    t0 = time.time(); cloud = osc.fuse(True, True); sec = time.time() - t0
+    mpix = syn.n_views * syn.width * syn.height / 1e6
+    return {"value": mpix / sec, "unit": "Mpix/s", "cores": 1, "kind": "port", "seconds": sec,
+            "sample": f"FuseDepthMaps over {syn.n_views} of the {args.views or 500} maps ({syn.width}x{syn.height}), {len(cloud['xyz'])} points, 1 thread (the reference fuses on its main thread)"}, syn
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle port; the reference itself cannot be built here) on host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.config == 5:
+        vals, secs, base, syn = [], [], None, None
+        for s in range(args.warmup + args.steps):
+            base, syn = cpu_fusion_sample(args)
+            if s >= args.warmup:
+                vals.append(base["value"]); secs.append(base["seconds"])
+            if sum(secs) > 120:
+                break
+        value = float(np.mean(vals)) if vals else base["value"]
+        from hcmvs_b200.synth import SynthScene
+        full = SynthScene(5, args.scale, args.views)
+        print(json.dumps({"impl": "reference", "metric": "FuseDepthMaps Mpix/s (input depth pixels fused per second)", "value": value, "unit": "Mpix/s", "n_gpus": args.gpus,
+                          "steps": len(vals), "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3 if secs else None, "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f64/f32", "data": "synthetic", "config": config_dict(args, full.n_views, full.width, full.height),
+                          "cpu_baseline": {**base, "value": value},
+                          "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
     syn, imgs = make_scene(args)
     vals, secs = [], []
     base = None
     for s in range(args.warmup + args.steps):
-        base = cpu_oracle_sample(args, syn, imgs, seconds_budget=20.0 if args.steps + args.warmup <= 3 else 8.0, stages=(s == args.warmup + args.steps - 1))
+        base = cpu_oracle_sample(args, syn, imgs, seconds_budget=20.0 if args.steps + args.warmup <= 3 else 8.0)
         if s >= args.warmup:
-            vals.append(base["value"]); secs.append(base["seconds"])
+            # the metric of both arms is scene pixel-iterations over the WHOLE scene time (estimate + filter + fuse): the sample's
+            # per-view stage times extrapolated to the scene; the estimate-only figure stays in cpu_baseline.estimate_only
+            vals.append(base.get("scene_equivalent_value", base["value"])); secs.append(base["seconds"])
         if sum(secs) > 150:  # keep the whole run within a few minutes
             break
-    value = float(np.mean(vals)) if vals else base["value"]
+    value = float(np.mean(vals)) if vals else base.get("scene_equivalent_value", base["value"])
     line = {
         "impl": "reference", "metric": "PatchMatch Mpix*iter/s", "value": value, "unit": "Mpix*iter/s", "n_gpus": args.gpus,
         "steps": len(vals), "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3 if secs else None,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.config], "scale": args.scale, "views": syn.n_views, "neighbours": 5, "patchmatch_iters": 3},
-        "cpu_baseline": {"value": value, "unit": "Mpix*iter/s", "cores": base["cores"], "kind": "port", "sample": base["sample"],
+        "config": config_dict(args, syn.n_views, syn.width, syn.height),
+        "cpu_baseline": {"value": value, "unit": "Mpix*iter/s", "cores": base["cores"], "kind": "port", "sample": base["sample"], "estimate_only": base["value"],
                          **{k: base[k] for k in ("stage_seconds_per_view", "scene_seconds_extrapolated", "scene_equivalent_value") if k in base}},
         "e2e": {"value": value, "unit": "Mpix*iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -225,6 +278,144 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
+def sweep_roofline(tm, P, sms, peaks, peak_src, n_sweep_launches):
+    """Roofline of the dominant kernel (k_sweep): FP32-pipe bound, not HBM / tensor."""
+    fp32_peak = 2.0 * 128 * sms * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+    texels = (int(P.adapthalfwin) + 1) ** 2
+    flops = tm["n_view_scores"] * flops_per_view_score(texels) + tm["n_smooth_terms"] * 60.0
+    sweep_s = tm["ms_sweeps"] / 1e3
+    achieved = flops / sweep_s / 1e12 if sweep_s > 0 else 0.0
+    hbm_bytes = tm["n_pixel_iters"] * 64.0
+    roofline = {
+        "kernel": "k_sweep (red-black PatchMatch half-sweep)", "bound": "fp32",
+        "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
+        "peak_source": f"2*128 lanes*{sms} SM*sm_max_mhz ({peak_src} MEASURED_PEAKS.json clock)",
+        "avg_launch_ms": tm["ms_sweeps"] / max(n_sweep_launches, 1),
+        "algorithmic_flops_per_view_score": flops_per_view_score(texels),
+        "hbm": {"achieved": hbm_bytes / sweep_s / 1e9 if sweep_s > 0 else 0.0, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                "frac": (hbm_bytes / sweep_s / 1e9) / peaks.get("hbm_gbs", 1.0) if sweep_s > 0 else None, "bytes_per_pixel_iter": 64},
+        "traffic": ncu_traffic_per_launch(),
+        "traffic_note": "DRAM bytes of one k_sweep launch (ncu --set full, profiles/r01_ncu_k_sweep_final.txt; C2 view) vs 0.96 Mpix x 64 B = 61 MB algorithmic",
+        "sweep_mpix_iter_s": tm["n_pixel_iters"] / sweep_s / 1e6 if sweep_s > 0 else None,
+        "hyp_per_pixel_iter": tm["n_hypotheses"] / max(tm["n_pixel_iters"], 1),
+    }
+    # the unit that actually bounds k_sweep (DESIGN.md §4.1): a 4-tap texture gather costs 16 cycles of L1TEX write-back per warp
+    # => 2 bilinear samples / clk / SM; samples = view scores x texels
+    tex_peak = 2.0 * sms * peaks.get("sm_max_mhz", 1965.0) * 1e6
+    tex_rate = tm["n_view_scores"] * texels / sweep_s if sweep_s > 0 else 0.0
+    roofline["tex_wall"] = {"achieved": tex_rate / 1e9, "peak": tex_peak / 1e9, "unit": "Gsample/s", "frac": tex_rate / tex_peak if tex_peak else None,
+                            "note": "texture write-back 32 B/clk/SM, 16 B per bilinear sample (ncu l1tex__tex_writeback_active 79.4 %, profiles/r01_ncu_k_sweep_final.txt)"}
+    return roofline
+
+
+def stage_rooflines(tm, steps, npoints, hbm_peak):
+    """The HBM-bound stages against the measured copy bandwidth (SURVEY §8d's algorithmic bytes; this rank's share)."""
+    out = {}
+    if tm["ms_filter"] > 0:
+        gbs = tm["filter_bytes"] / (tm["ms_filter"] / 1e3) / 1e9  # filter_bytes and ms_filter both accumulate over the timed steps
+        out["filter"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak if hbm_peak else None,
+                         "bytes": "(24 n + 16) B per reference pixel, n = neighbour maps (8)"}
+    if tm["ms_fuse"] > 0 and npoints:
+        # per seed 27 B (depth, conf, normal, colour, claim) + 8 B per probe; per merged view 23 B; ~40 B per emitted point (last fusion)
+        merged = max(int(tm.get("fuse_view_refs", 0)) - npoints, 0)
+        fb = tm["fuse_seeds"] * 27.0 + tm["fuse_probes"] * 8.0 + merged * 23.0 + npoints * 40.0
+        gbs = fb / (tm["ms_fuse"] / steps / 1e3) / 1e9
+        out["fuse"] = {"bound": "hbm (random 32-byte sectors: latency, not bandwidth)", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak if hbm_peak else None,
+                       "seeds": int(tm["fuse_seeds"]), "probes": int(tm["fuse_probes"]),
+                       "bytes": "27 B per seed + 8 B per probe + 40 B per point (merged views' 23 B not counted)"}
+    return out
+
+
+def run_fusion_stress(args, torch, local):
+    """--config 5: FuseDepthMaps alone over precomputed maps (SURVEY §8d C5 recipe). A step = one fusion of all maps; the maps are restored
+    on the device between steps (fusion zeroes occluded depths in place). Single GPU: the fusion is sequential over views by definition."""
+    from hcmvs_b200 import api
+    from hcmvs_b200.synth import SynthScene, c5_maps, frame_neighbors
+    syn = SynthScene(5, args.scale, args.views)
+    V, H, W = syn.n_views, syn.height, syn.width
+    ctx = api.Context(local, nNumViews=5, nEstimationIters=3, nEstimationIters_external=1, nMinViewsTrustPoint=1, adapthalfwin=5)
+    h2d = 0
+    t_up = 0.0
+    for i in range(V):
+        bgr, d, n = syn.render(i)
+        m = c5_maps((d, n), 900 + i)
+        gray = np.zeros(d.shape, np.float32)  # fusion reads no gray image
+        t0 = time.time()
+        ctx.set_view(i, syn.K[i], syn.R[i], syn.Cc[i], gray, bgr)
+        ctx.set_depthmap(i, *m)
+        t_up += time.time() - t0
+        h2d += bgr.nbytes + m[0].nbytes + m[1].nbytes + m[2].nbytes
+    for i in range(V):
+        ids = frame_neighbors(i, V)
+        ctx.set_neighbors(i, ids, min(5, len(ids)))
+        ctx.set_fuse_priority(i, len(ids))
+    ctx.snapshot_maps()
+    ctx.sync()
+    lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+    for _ in range(args.warmup):
+        ctx.restore_snapshot(); ctx.fuse_depthmaps_device(True, True)
+    ctx.sync(); ctx.reset_timers()
+    clocks = ClockSampler(local); clocks.start()
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    t_dev, npoints, nrefs = 0.0, 0, 0
+    for _ in range(args.steps):
+        ctx.restore_snapshot(); ctx.sync()
+        ev0.record(lib_stream)
+        npoints, nrefs = ctx.fuse_depthmaps_device(True, True)
+        ev1.record(lib_stream)
+        torch.cuda.synchronize()
+        t_dev += ev0.elapsed_time(ev1) / 1e3
+    clk = clocks.stop()
+    tm = ctx.timers()
+    sec = t_dev / args.steps
+    mpix = V * W * H / 1e6
+    peaks, peak_src = load_peaks()
+    hbm_peak = peaks.get("hbm_gbs")
+    merged = max(nrefs - npoints, 0)
+    fb = tm["fuse_seeds"] * 27.0 + tm["fuse_probes"] * 8.0 + merged * 23.0 + npoints * 40.0
+    gbs = fb / sec / 1e9
+    roofline = {"kernel": "k_fuse_scene (persistent cooperative FuseDepthMaps) + k_fuse_build", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": gbs / hbm_peak if hbm_peak else None, "peak_source": f"{peak_src} MEASURED_PEAKS.json copy bandwidth",
+                "avg_launch_ms": sec * 1e3, "traffic": None,
+                "bytes": "SURVEY §8d: 27 B per seed + 8 B per probe + 23 B per merged view + 40 B per point",
+                "seeds": int(tm["fuse_seeds"]), "probes": int(tm["fuse_probes"]), "merged": merged, "points": npoints,
+                "note": "every probe is one random 32-byte sector; the kernel is bound by the latency chain of dependent sector reads between grid barriers, not by bandwidth (profiles/r02_notes.md)"}
+    # e2e: maps from HOST buffers (one set_depthmap per view) + fusion + cloud download
+    e2e = None
+    if not args.no_e2e:
+        maps = []
+        for i in range(min(V, 64)):  # bounded host memory: the first 64 views' maps are re-created and re-used round-robin
+            _, d, n = syn.render(i, want_bgr=False)
+            maps.append(c5_maps((d, n), 900 + i))
+        ctx.restore_snapshot(); ctx.fuse_depthmaps_device(True, True); ctx.download_fused_pinned()  # sizes the arena
+        torch.cuda.synchronize()
+        t0 = time.time()
+        up = 0
+        for i in range(V):
+            m = maps[i % len(maps)]
+            ctx.set_depthmap(i, *m); up += m[0].nbytes + m[1].nbytes + m[2].nbytes
+        ctx.fuse_depthmaps_device(True, True)
+        n_, d2h = ctx.download_fused_pinned()
+        torch.cuda.synchronize()
+        te = time.time() - t0
+        e2e = {"value": mpix / te, "unit": "Mpix/s", "h2d_bytes_per_step": int(up), "d2h_bytes_per_step": int(d2h), "seconds_per_scene": te, "points": int(n_),
+               "api": "C ABI: hcmvs_set_depthmap per view from host memory, hcmvs_fuse_depthmaps, hcmvs_download_fused_pinned",
+               "note": "views beyond the 64th re-use the maps of view i % 64 (host memory bound), so the e2e cloud differs from the device-timed one"}
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            cpu, _ = cpu_fusion_sample(args)
+        except Exception as e:
+            cpu = {"value": None, "unit": "Mpix/s", "cores": 1, "kind": "port", "sample": f"failed: {e}"}
+    print(json.dumps({
+        "metric": "FuseDepthMaps Mpix/s (input depth pixels fused per second)", "value": mpix / sec, "unit": "Mpix/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64/f32", "data": "synthetic",
+        "config": config_dict(args, V, W, H), "run": {"parallelism": "single GPU (FuseDepthMaps is sequential over views)", "l2": "20 B/px maps + 32 B/px fusion records of 500 views = 54 GB > 126 MB L2"},
+        "scene_seconds": sec, "fused_points": npoints, "fuse_rounds": int(tm["n_fuse_rounds"]), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": int(tm["n_launches"]), "clocks": clk}))
+    ctx.close()
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -236,6 +427,10 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — hcmvs_b200 has no CPU path (use --impl reference for the CPU oracle)")
     torch.cuda.set_device(local)
+    if args.config == 5:
+        if rank == 0:
+            run_fusion_stress(args, torch, local)
+        return
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -245,100 +440,67 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    syn, imgs = make_scene(args)
-    V, H, W = syn.n_views, syn.height, syn.width
     params = dict(nNumViews=5, nEstimationIters=3, nEstimationIters_external=1, nMinViewsTrustPoint=1, adapthalfwin=5, sampler=args.sampler)
     ctx = api.Context(local, **params)
     P = ctx.params
-    hs = host.HostScene.from_synth(syn, imgs)
-    # ---- host-side scene preparation (untimed for `value`): view selection, initial depth from the sparse points
-    valid = [i for i in range(V) if hs.select_views(P, i) > 0]
-    nbs = {i: hs.neighbors(i, 1) for i in valid}
-    nall = {i: len(hs.neighbors(i, 0)["ids"]) for i in valid}
-    for i in range(V):
-        ctx.set_view(i, syn.K[i], syn.R[i], syn.Cc[i], hs.gray(i), imgs[i])
-    for i in valid:
-        ctx.set_neighbors(i, nbs[i]["ids"], min(5, len(nbs[i]["ids"])), nbs[i]["score"])
-        ctx.set_fuse_priority(i, nall[i])
-    # initial depth maps (sparse splat, SceneDensify.cpp:783-808) computed once on the host
-    init = {i: hs.init_depth(i) for i in valid}
-    # views are dealt round-robin in fusion (connection) order — SURVEY §8(e)
-    from hcmvs_b200 import shard
-    use_lib_nccl = world > 1 and args.exchange == "nccl"
-    plan = shard.make_plan(valid, nall, world, split_rows=use_lib_nccl and not args.no_split_rows)
-    order, mine = plan.order, plan.views_of(rank)
-    mine_whole, split_views = plan.whole_views_of(rank), plan.split_views()
-    inner = (W - 14) * (H - 14)
-    pix_iters_step = inner * int(P.nEstimationIters) * len(valid)
-
     lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
-    filtered_views = {v for v in valid if min(8, len(nbs[v]["ids"])) >= 2}
-    if use_lib_nccl:
-        # the library's own NCCL communicator: rank 0 creates the id, torch.distributed only carries its 128 bytes
+    peaks, peak_src = load_peaks()
+    sms = torch.cuda.get_device_properties(local).multi_processor_count
+    e2e, cpu = None, None
+
+    if world == 1:
+        # ------------------------------------------------------------------ one GPU: the C ABI driven view by view
+        syn, imgs = make_scene(args)
+        V, H, W = syn.n_views, syn.height, syn.width
+        hs = host.HostScene.from_synth(syn, imgs)
+        # host-side scene preparation (untimed for `value`): view selection, initial depth from the sparse points
+        valid = [i for i in range(V) if hs.select_views(P, i) > 0]
+        nbs = {i: hs.neighbors(i, 1) for i in valid}
+        nall = {i: len(hs.neighbors(i, 0)["ids"]) for i in valid}
+        for i in range(V):
+            ctx.set_view(i, syn.K[i], syn.R[i], syn.Cc[i], hs.gray(i), imgs[i])
+        for i in valid:
+            ctx.set_neighbors(i, nbs[i]["ids"], min(5, len(nbs[i]["ids"])), nbs[i]["score"])
+            ctx.set_fuse_priority(i, nall[i])
+        init = {i: hs.init_depth(i) for i in valid}  # sparse splat, SceneDensify.cpp:783-808
+        filtered_views = [v for v in valid if min(8, len(nbs[v]["ids"])) >= 2]
+        n_est = len(valid)
+
+        def upload_initial():
+            # H2D of the rough depth maps: done before the clock starts (`value` = inputs resident in HBM)
+            for v in valid:
+                ctx.init_depthmap(v, init[v][0], None, init[v][1], init[v][2])
+            ctx.sync()
+
+        def hot_path():
+            for v in valid:
+                ctx.estimate_depthmap(v, 0, 1)
+            for v in filtered_views:  # FilterDepthMap: neighbours with maps, at most 8 (SceneDensify.cpp:4117-4130)
+                ctx.filter_depthmap(v, list(range(min(8, len(nbs[v]["ids"])))), adjust=True, download=False)
+            ctx.commit_filtered()
+            n = ctx.fuse_depthmaps_device(True, True)[0]  # the fused cloud stays in HBM; e2e below downloads it
+            ctx.sync()
+            return n
+        parallelism = "single GPU"
+    else:
+        # ------------------------------------------------------------------ N GPUs: hcmvs_host's DistributedReconstruction (C++) does everything;
+        # Python launches the ranks, carries the communicator id and holds the clock. Every rank renders / holds the pixels of ITS share
+        # of the images only (index % world == rank): the others reach its GPU over NVLink.
+        syn, imgs = make_scene(args, only=[i for i in range(_n_views(args)) if i % world == rank])
+        V, H, W = syn.n_views, syn.height, syn.width
         ids = [api.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         ctx.comm_init(ids[0], rank, world)
-        owner_rounds = plan.round_owner_arrays(V)
-        owner_split = plan.split_owner_array(V)
-        owner_filtered = plan.owner_array(V, only=filtered_views)
-    elif world > 1:
-        # exchange buffers (one slot per view, replicated on every rank)
-        send_dn = torch.zeros((plan.slots, H, W, 4), dtype=torch.float32, device=dev)
-        send_cf = torch.zeros((plan.slots, H, W), dtype=torch.float32, device=dev)
-        recv_dn = torch.zeros((world, plan.slots, H, W, 4), dtype=torch.float32, device=dev)
-        recv_cf = torch.zeros((world, plan.slots, H, W), dtype=torch.float32, device=dev)
+        hs = host.HostScene.from_synth(syn, imgs)
+        hs.dist_prepare(ctx, rank, world)   # selection (sharded), image uploads (1/world over PCIe + NVLink), neighbour lists, plan, initial maps
+        info = hs.dist_info()
+        n_est = info["n_valid"]
+        upload_initial = lambda: (hs.dist_upload_initial(), ctx.sync())
+        hot_path = lambda: hs.dist_run(seed=1, run_filter=True, download=False)["n_points"] if rank != 0 else _points_after(hs, ctx)
+        parallelism = f"view-sharded x{world} (C++ host: hcmvs_host::DistributedReconstruction), in-place NCCL broadcasts, {info['n_split']} view(s) row-split over all ranks"
 
-    def exchange():
-        """torch path: all-gather every rank's (normal, depth) and confidence maps over NCCL; import the others' maps."""
-        if world == 1:
-            return
-        shard.exchange_maps(
-            plan, rank, send_dn, send_cf, recv_dn, recv_cf,
-            export_fn=lambda v, s: ctx.export_maps_d(v, send_dn[s].data_ptr(), send_cf[s].data_ptr()),
-            import_fn=lambda v, r, s: ctx.import_maps_d(v, recv_dn[r, s].data_ptr(), recv_cf[r, s].data_ptr(), init[v][1], init[v][2]),
-            sync_fn=ctx.sync, dist=dist, post_sync=torch.cuda.synchronize)
-
-    def upload_initial():
-        # H2D of the rough depth maps: done before the clock starts (`value` = inputs resident in HBM)
-        for v in sorted(set(mine) | set(split_views)):  # every rank estimates a band of the row-split views
-            ctx.init_depthmap(v, init[v][0], None, init[v][1], init[v][2])
-        ctx.sync()
-
-    def hot_path():
-        if use_lib_nccl:
-            # round s: every rank estimates its s-th view, then those views are broadcast in place (one NCCL group) on the
-            # communication stream while round s+1 is being estimated
-            for s_, own in enumerate(owner_rounds):
-                if s_ < len(mine_whole):
-                    ctx.estimate_depthmap(mine_whole[s_], 0, 1)
-                ctx.exchange_maps(own, 0, overlap=True)
-            # the views of the incomplete last round: every rank estimates its band of rows, the bands are broadcast in place
-            for v in split_views:
-                r0, r1 = plan.rows_of(rank, H)
-                ctx.estimate_depthmap_rows(v, r0, r1, 0, 1)
-            if split_views:
-                ctx.exchange_maps(owner_split, 0, overlap=True)
-            ctx.exchange_wait()
-        else:
-            for v in mine:
-                ctx.estimate_depthmap(v, 0, 1)
-            exchange()
-        # FilterDepthMap: neighbours with maps, at most 8 (SceneDensify.cpp:4117-4130)
-        for v in mine:
-            if v in filtered_views:
-                ctx.filter_depthmap(v, list(range(min(8, len(nbs[v]["ids"])))), adjust=True, download=False)
-        if use_lib_nccl:
-            ctx.exchange_maps(owner_filtered, 1)     # the pending filter output (8 B/px); committed on every rank below
-            ctx.commit_filtered()
-        else:
-            ctx.commit_filtered()
-            exchange()
-        n = 0
-        if rank == 0:
-            n = ctx.fuse_depthmaps_device(True, True)[0]  # the fused cloud stays in HBM; e2e below downloads it
-        ctx.sync()
-        return n
-
+    inner = (W - 14) * (H - 14)
+    pix_iters_step = inner * int(P.nEstimationIters) * n_est
     for _ in range(args.warmup):
         upload_initial()
         hot_path()
@@ -364,57 +526,13 @@ def run_b200(args):
     tm = ctx.timers()
     sec_step = t_dev / args.steps
     value = pix_iters_step / sec_step / 1e6
-
-    # ---- roofline of the dominant kernel (k_sweep): FP32-pipe bound, not HBM / tensor
-    peaks, peak_src = load_peaks()
-    sms = torch.cuda.get_device_properties(local).multi_processor_count
-    fp32_peak = 2.0 * 128 * sms * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
-    texels = (int(P.adapthalfwin) + 1) ** 2
-    flops = tm["n_view_scores"] * flops_per_view_score(texels) + tm["n_smooth_terms"] * 60.0
-    sweep_s = tm["ms_sweeps"] / 1e3
-    n_sweep_launches = 2 * int(P.nEstimationIters) * len(mine) * args.steps
-    achieved = flops / sweep_s / 1e12 if sweep_s > 0 else 0.0
-    hbm_bytes = tm["n_pixel_iters"] * 64.0
-    roofline = {
-        "kernel": "k_sweep (red-black PatchMatch half-sweep)", "bound": "fp32",
-        "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
-        "peak_source": f"2*128 lanes*{sms} SM*sm_max_mhz ({peak_src} MEASURED_PEAKS.json clock)",
-        "avg_launch_ms": tm["ms_sweeps"] / max(n_sweep_launches, 1),
-        "algorithmic_flops_per_view_score": flops_per_view_score(texels),
-        "hbm": {"achieved": hbm_bytes / sweep_s / 1e9 if sweep_s > 0 else 0.0, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                "frac": (hbm_bytes / sweep_s / 1e9) / peaks.get("hbm_gbs", 1.0) if sweep_s > 0 else None, "bytes_per_pixel_iter": 64},
-        "traffic": ncu_traffic_per_launch(),
-        "traffic_note": "DRAM bytes of one k_sweep launch (ncu --set full, profiles/r01_ncu_k_sweep_final.txt) vs 0.96 Mpix x 64 B = 61 MB algorithmic",
-        "sweep_mpix_iter_s": tm["n_pixel_iters"] / sweep_s / 1e6 if sweep_s > 0 else None,
-        "hyp_per_pixel_iter": tm["n_hypotheses"] / max(tm["n_pixel_iters"], 1),
-    }
-    # the unit that actually bounds k_sweep: a 4-tap texture gather costs 16 cycles of L1TEX write-back per warp
-    # => 2 bilinear samples / clk / SM; samples = view scores x texels
-    tex_peak = 2.0 * sms * peaks.get("sm_max_mhz", 1965.0) * 1e6
-    tex_rate = tm["n_view_scores"] * texels / sweep_s if sweep_s > 0 else 0.0
-    roofline["tex_wall"] = {"achieved": tex_rate / 1e9, "peak": tex_peak / 1e9, "unit": "Gsample/s", "frac": tex_rate / tex_peak if tex_peak else None,
-                            "note": "texture write-back 32 B/clk/SM, 16 B per bilinear sample (ncu l1tex__tex_writeback_active 79.4 %, profiles/r01_ncu_k_sweep_final.txt)"}
+    n_mine = n_est if world == 1 else (info["n_mine_whole"] + info["n_split"])
+    roofline = sweep_roofline(tm, P, sms, peaks, peak_src, 2 * int(P.nEstimationIters) * n_mine * args.steps)
     stages = {k: tm[k] / args.steps for k in ("ms_prep", "ms_score", "ms_sweeps", "ms_end", "ms_filter", "ms_fuse", "ms_exchange")}
     launches = tm["n_launches"]
-    # ---- the HBM-bound stages against the measured copy bandwidth (SURVEY §8d's algorithmic bytes; rank 0's share)
-    hbm_peak = peaks.get("hbm_gbs")
-    stage_rooflines = {}
-    if tm["ms_filter"] > 0:
-        gbs = tm["filter_bytes"] / (tm["ms_filter"] / 1e3) / 1e9  # filter_bytes and ms_filter both accumulate over the timed steps
-        stage_rooflines["filter"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak if hbm_peak else None,
-                                     "bytes": "(24 n + 16) B per reference pixel, n = neighbour maps (8)"}
-    if tm["ms_fuse"] > 0 and npoints:
-        # per seed 27 B (depth, conf, normal, colour, claim) + 8 B per probe; per merged view 23 B; ~40 B per emitted point (last fusion)
-        merged = max(int(tm.get("fuse_view_refs", 0)) - npoints, 0)
-        fb = tm["fuse_seeds"] * 27.0 + tm["fuse_probes"] * 8.0 + merged * 23.0 + npoints * 40.0
-        gbs = fb / (tm["ms_fuse"] / args.steps / 1e3) / 1e9
-        stage_rooflines["fuse"] = {"bound": "hbm (gather latency)", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak if hbm_peak else None,
-                                   "seeds": int(tm["fuse_seeds"]), "probes": int(tm["fuse_probes"]),
-                                   "bytes": "27 B per seed + 8 B per probe + 40 B per point (merged views' 23 B not counted)"}
-    roofline["stages"] = stage_rooflines
+    roofline["stages"] = stage_rooflines(tm, args.steps, npoints, peaks.get("hbm_gbs"))
 
     # ---- e2e: the host-facing DenseReconstruction call with HOST buffers (uploads + downloads inside the timed region)
-    e2e = None
     if not args.no_e2e and world == 1:
         # one long-lived context (== one DepthMapsData object); every run re-uploads all images and initial maps from host memory
         ctx2 = api.Context(local, **params)
@@ -446,65 +564,60 @@ def run_b200(args):
         # the same call with the reference's DEFAULT initialisation (nMinViewsTrustPoint = 2: the sparse points are triangulated on the
         # host and rasterised on the device) — reported next to the splat start that both arms of this bench time
         default_init = None
-        try:
-            p3 = dict(params); p3["nMinViewsTrustPoint"] = 2
-            ctx3 = api.Context(local, **p3)
-            host.HostScene.from_synth(syn, imgs).dense_reconstruction(ctx3, seed=1, run_filter=True)
-            hs3 = host.HostScene.from_synth(syn, imgs)
-            torch.cuda.synchronize()
-            t0 = time.time()
-            s3 = hs3.dense_reconstruction(ctx3, seed=1, run_filter=True)
-            torch.cuda.synchronize()
-            t3 = time.time() - t0
-            hs3.close(); ctx3.close()
-            default_init = {"value": pix_iters_step / t3 / 1e6, "seconds_per_scene": t3, "points": s3["n_points"], "h2d_bytes_per_step": s3["h2d_bytes"],
-                            "note": "nMinViewsTrustPoint = 2 (InitDepthMap / TriangulatePoints2DepthMap): host Delaunay + device rasteriser"}
-        except Exception as e:  # informational only
-            default_init = {"value": None, "note": f"failed: {e}"}
+        if args.config == 2:
+            try:
+                p3 = dict(params); p3["nMinViewsTrustPoint"] = 2
+                ctx3 = api.Context(local, **p3)
+                host.HostScene.from_synth(syn, imgs).dense_reconstruction(ctx3, seed=1, run_filter=True)
+                hs3 = host.HostScene.from_synth(syn, imgs)
+                torch.cuda.synchronize()
+                t0 = time.time()
+                s3 = hs3.dense_reconstruction(ctx3, seed=1, run_filter=True)
+                torch.cuda.synchronize()
+                t3 = time.time() - t0
+                hs3.close(); ctx3.close()
+                default_init = {"value": pix_iters_step / t3 / 1e6, "seconds_per_scene": t3, "points": s3["n_points"], "h2d_bytes_per_step": s3["h2d_bytes"],
+                                "note": "nMinViewsTrustPoint = 2 (InitDepthMap / TriangulatePoints2DepthMap): host Delaunay + device rasteriser"}
+            except Exception as e:  # informational only
+                default_init = {"value": None, "note": f"failed: {e}"}
         e2e = {"value": pix_iters_step / float(np.mean(ts)) / 1e6, "unit": "Mpix*iter/s", "h2d_bytes_per_step": st["h2d_bytes"],
                "d2h_bytes_per_step": st["d2h_bytes"], "seconds_per_scene": float(np.mean(ts)), "points": st["n_points"],
                "seconds": {k: round(float(st[k]), 4) for k in ("sec_select", "sec_upload", "sec_estimate", "sec_filter", "sec_fuse")},
                "api": "hcmvs_host.DenseReconstruction (select views, upload, estimate, filter, fuse, download cloud)"}
         if with_dmaps:
             e2e["with_dmaps"] = with_dmaps
-        e2e["default_init"] = default_init
-    elif world > 1 and not args.no_e2e and use_lib_nccl:
-        # N > 1: the same sharded job driven through the C ABI with HOST buffers inside the timed region — every rank re-uploads all
-        # images (each rank holds every image) and its initial maps from page-locked host memory, rank 0 downloads the fused cloud
-        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
-        grays = [pin(hs.gray(i)) for i in range(V)]
-        bgrs = [pin(imgs[i]) for i in range(V)]
-        inits = {v: pin(init[v][0]) for v in sorted(set(mine) | set(split_views))}
-        h2d = sum(g.nbytes + b.nbytes for g, b in zip(grays, bgrs)) + sum(a.nbytes for a in inits.values())
-
+        if default_init:
+            e2e["default_init"] = default_init
+    elif not args.no_e2e:
+        # N > 1: ONE call per rank of the same C++ host function, hcmvs_host.DenseReconstructionDistributed, with HOST buffers inside the
+        # timed region: every rank selects 1/N of the views, uploads 1/N of the images over PCIe (the rest arrives over NVLink), its
+        # initial maps; rank 0 fuses and downloads the cloud. Wall clock between barriers, max over ranks.
         def e2e_step():
-            for i in range(V):
-                ctx.set_view(i, syn.K[i], syn.R[i], syn.Cc[i], grays[i], bgrs[i])
-            for v, a in inits.items():
-                ctx.init_depthmap(v, a, None, init[v][1], init[v][2])
-            n_ = hot_path()
-            return ctx.download_fused_pinned() if rank == 0 else (n_, 0)
-
-        e2e_step()  # warm-up: sizes the page-locked arena
-        ts, res = [], (0, 0)
-        for _ in range(max(1, min(args.steps, 3))):
+            hs2 = host.HostScene.from_synth(syn, imgs)
             barrier()
             t0 = time.time()
-            res = e2e_step()
+            st_ = hs2.dense_reconstruction_distributed(ctx, rank, world, seed=1, run_filter=True)
             barrier()
-            ts.append(time.time() - t0)
+            dt = time.time() - t0
+            if os.environ.get("HCMVS_DIST_DEBUG"):
+                print(f"[bench rank {rank}] e2e step {dt:.3f} s", file=sys.stderr)
+            hs2.close()
+            return dt, st_
+        e2e_step()  # warm-up: sizes the page-locked arena
+        ts, st = [], None
+        for _ in range(max(1, min(args.steps, 3))):
+            dt, st = e2e_step()
+            ts.append(dt)
         tt = torch.tensor([float(np.mean(ts))], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        hh = torch.tensor([float(h2d)], device=dev, dtype=torch.float64)
-        dist.all_reduce(hh, op=dist.ReduceOp.SUM)
-        e2e = {"value": pix_iters_step / float(tt.item()) / 1e6, "unit": "Mpix*iter/s", "h2d_bytes_per_step": int(hh.item()), "d2h_bytes_per_step": int(res[1]),
-               "seconds_per_scene": float(tt.item()), "points": int(res[0]),
-               "api": "C ABI per rank: hcmvs_set_view (all images) + hcmvs_init_depthmap from page-locked host memory, estimate / exchange / filter, "
-                      "fuse + hcmvs_download_fused_pinned on rank 0; max over ranks, all ranks' uploads summed"}
-    elif world > 1:
-        e2e = {"value": None, "unit": "Mpix*iter/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "note": "measured with --exchange nccl only"}
+        io = torch.tensor([float(st["h2d_bytes"]), float(st["d2h_bytes"]), float(st["n_points"])], device=dev, dtype=torch.float64)
+        dist.all_reduce(io, op=dist.ReduceOp.SUM)
+        e2e = {"value": pix_iters_step / float(tt.item()) / 1e6, "unit": "Mpix*iter/s", "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()),
+               "seconds_per_scene": float(tt.item()), "points": int(io[2].item()),
+               "seconds_rank0": {k: round(float(st[k]), 4) for k in ("sec_select", "sec_estimate", "sec_filter", "sec_fuse")},
+               "api": "hcmvs_host.DenseReconstructionDistributed on every rank (sharded view selection + all-gather, 1/N of the images over PCIe and the rest "
+                      "over NVLink, estimate / exchange / filter, fuse + cloud download on rank 0); wall clock between barriers, max over ranks, all ranks' bytes summed"}
 
-    cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             cpu = cpu_oracle_sample(args, syn, imgs)
@@ -515,9 +628,9 @@ def run_b200(args):
         line = {
             "metric": "PatchMatch Mpix*iter/s", "value": value, "unit": "Mpix*iter/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.config], "scale": args.scale, "views": V, "image": [W, H], "neighbours": 5,
-                       "patchmatch_iters": int(P.nEstimationIters), "stages": "estimate(A+B+C) + filter + fuse", "parallelism": f"view-sharded x{world}" + (f", map exchange: {args.exchange}" if world > 1 else "") + (f", {len(split_views)} view(s) row-split over all ranks" if split_views else ""),
-                       "l2": "inputs per view (5 neighbour images + maps, ~77 MB) re-read per launch; 49-view working set 2.3 GB > 126 MB L2"},
+            "config": config_dict(args, V, W, H),
+            "run": {"parallelism": parallelism, "valid_views": n_est,
+                    "l2": f"inputs per view (5 neighbour images + maps, ~{(6 * 4 + 40) * W * H / 1e6:.0f} MB) re-read per launch; scene working set {V * 44 * W * H / 1e9:.1f} GB > 126 MB L2"},
             "scene_seconds": sec_step, "fused_points": npoints, "fuse_rounds": int(tm["n_fuse_rounds"]), "stage_ms_per_step_rank0": stages,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         }
@@ -525,6 +638,20 @@ def run_b200(args):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def _n_views(args):
+    from hcmvs_b200.synth import SynthScene
+    s = SynthScene(args.config, args.scale, args.views)
+    n = s.n_views
+    s.close()
+    return n
+
+
+def _points_after(hs, ctx):
+    """rank 0 of a distributed run: the cloud stays in HBM; its size comes from the context."""
+    hs.dist_run(seed=1, run_filter=True, download=False)
+    return ctx.fused_counts()[0]
 
 
 def main():

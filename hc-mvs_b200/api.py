@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libhcmvs_b200.so")
 EXPORTS = [
     "hcmvs_default_params", "hcmvs_last_error", "hcmvs_create", "hcmvs_destroy", "hcmvs_set_params", "hcmvs_sync",
     "hcmvs_set_view", "hcmvs_set_neighbors", "hcmvs_set_neighbor_image", "hcmvs_init_depthmap", "hcmvs_init_depthmap_triangles", "hcmvs_download_depthmap_begin", "hcmvs_download_depthmap_wait", "hcmvs_set_depthmap", "hcmvs_get_depthmap",
-    "hcmvs_set_prior", "hcmvs_set_coarse_estimate", "hcmvs_get_coarse_estimate", "hcmvs_snapshot_maps", "hcmvs_get_gradient_map", "hcmvs_score_depthmap", "hcmvs_estimate_depthmap", "hcmvs_estimate_depthmap_rows", "hcmvs_end_depthmap", "hcmvs_score_hypotheses",
+    "hcmvs_set_prior", "hcmvs_set_coarse_estimate", "hcmvs_get_coarse_estimate", "hcmvs_snapshot_maps", "hcmvs_restore_snapshot", "hcmvs_get_gradient_map", "hcmvs_score_depthmap", "hcmvs_estimate_depthmap", "hcmvs_estimate_depthmap_rows", "hcmvs_end_depthmap", "hcmvs_score_hypotheses",
     "hcmvs_filter_depthmap", "hcmvs_commit_filtered", "hcmvs_set_fuse_priority", "hcmvs_fuse_depthmaps",
     "hcmvs_free_pointcloud", "hcmvs_get_fused_device", "hcmvs_get_fused_support", "hcmvs_estimate_point_colors", "hcmvs_estimate_point_normals", "hcmvs_pointcloud_filter", "hcmvs_download_fused", "hcmvs_download_fused_pinned", "hcmvs_get_depthmap_device", "hcmvs_set_depth_range", "hcmvs_alloc_depthmap",
     "hcmvs_comm_unique_id", "hcmvs_comm_init", "hcmvs_exchange_maps", "hcmvs_exchange_wait", "hcmvs_export_maps_d", "hcmvs_import_maps_d", "hcmvs_get_timers", "hcmvs_reset_timers", "hcmvs_stream",
@@ -95,6 +95,7 @@ def load():
     L.hcmvs_set_coarse_estimate.argtypes = [vp, u32, i32, i32, vp, vp]
     L.hcmvs_get_coarse_estimate.argtypes = [vp, u32, vp, vp]
     L.hcmvs_snapshot_maps.argtypes = [vp]
+    L.hcmvs_restore_snapshot.argtypes = [vp]
     L.hcmvs_score_depthmap.argtypes = [vp, u32, i32, C.c_uint64]
     L.hcmvs_estimate_depthmap.argtypes = [vp, u32, i32, C.c_uint64]
     L.hcmvs_estimate_depthmap_rows.argtypes = [vp, u32, i32, C.c_uint64, i32, i32]
@@ -262,6 +263,9 @@ class Context:
     def snapshot_maps(self):
         self._ck(self.L.hcmvs_snapshot_maps(self.h))
 
+    def restore_snapshot(self):
+        self._ck(self.L.hcmvs_restore_snapshot(self.h))
+
     def score_depthmap(self, ref, it_external=0, seed=1):
         self._ck(self.L.hcmvs_score_depthmap(self.h, ref, it_external, seed))
 
@@ -350,6 +354,12 @@ class Context:
         n = int(pc.n_points)
         m = int(pc.view_offsets[n]) if n else 0
         return n, n * (12 + (12 if pc.normals else 0) + (3 if pc.colors else 0) + 4) + 4 + m * 8
+
+    def fused_counts(self):
+        """(n_points, n_view_refs) of the fused cloud that lives on the device."""
+        n = C.c_uint64(); m = C.c_uint64()
+        self._ck(self.L.hcmvs_get_fused_device(self.h, C.byref(n), C.byref(m), None, None, None, None, None, None))
+        return int(n.value), int(m.value)
 
     def fuse_depthmaps_device(self, color=True, normal=True):
         """FuseDepthMaps leaving the cloud in HBM; returns (n_points, n_view_refs)."""

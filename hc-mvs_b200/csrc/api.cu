@@ -254,6 +254,27 @@ extern "C" int hcmvs_set_view(hcmvs_ctx* ctx, uint32_t view, int W, int H, const
 	return HCMVS_OK;
 }
 
+extern "C" int hcmvs_set_view_remote(hcmvs_ctx* ctx, uint32_t view, int W, int H, const double K[9], const double R[9], const double C[3], int has_bgr) {
+	if (!ctx || !K || !R || !C) { hcmvs_set_error("null argument"); return HCMVS_ERR_ARG; }
+	if (W < 2*HCMVS_HW+2 || H < 2*HCMVS_HW+2 || W > 65535 || H > 65535) { hcmvs_set_error("image size %dx%d unsupported", W, H); return HCMVS_ERR_ARG; }
+	if (K[1] != 0.0 || K[3] != 0.0 || K[6] != 0.0 || K[7] != 0.0) { hcmvs_set_error("K must be upper triangular with zero skew"); return HCMVS_ERR_UNSUPPORTED; }
+	cudaSetDevice(ctx->device);
+	View* v = GetView(ctx, view, false); if (!v) return HCMVS_ERR_ARG;
+	const bool reuse = v->set && v->w == W && v->h == H && (v->bgr_d != nullptr) == (has_bgr != 0);
+	if (v->set && !reuse) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaStreamSynchronize(ctx->copyStream)); FreeView(*v); }
+	v->w = W; v->h = H;
+	std::memcpy(v->K, K, 72); std::memcpy(v->R, R, 72); std::memcpy(v->C, C, 24);
+	ComposeP(K, R, C, v->P);
+	const size_t n = (size_t)W*H;
+	if (!reuse) {
+		{ int r = CreateGrayTexture(W, H, v->arr, v->tex); if (r) return r; }
+		CK(cudaMalloc(&v->img_d, n*4));
+		if (has_bgr) CK(cudaMalloc(&v->bgr_d, n*3));
+	} else v->graValid = false;
+	v->set = true;
+	return HCMVS_OK;
+}
+
 int hcmvs_mark_image_use(hcmvs_ctx* ctx, View& v) {
 	if (!v.lastUse) CK(cudaEventCreateWithFlags(&v.lastUse, cudaEventDisableTiming));
 	CK(cudaEventRecord(v.lastUse, ctx->stream));
@@ -575,6 +596,19 @@ extern "C" int hcmvs_snapshot_maps(hcmvs_ctx* ctx) {
 		CK(cudaMemcpyAsync(v.dnPrev_d, v.dn_d, n*sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
 		CK(cudaMemcpyAsync(v.confPrev_d, v.conf_d, n*4, cudaMemcpyDeviceToDevice, ctx->stream));
 		v.hasPrev = true;
+	}
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_restore_snapshot(hcmvs_ctx* ctx) {
+	if (!ctx) { hcmvs_set_error("null context"); return HCMVS_ERR_ARG; }
+	cudaSetDevice(ctx->device);
+	for (View& v: ctx->views) {
+		if (!v.set || !v.hasPrev || !v.dn_d) continue;
+		const size_t n = (size_t)v.w*v.h;
+		CK(cudaMemcpyAsync(v.dn_d, v.dnPrev_d, n*sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+		CK(cudaMemcpyAsync(v.conf_d, v.confPrev_d, n*4, cudaMemcpyDeviceToDevice, ctx->stream));
+		v.depthValid = false; v.hasMaps = true;
 	}
 	return HCMVS_OK;
 }

@@ -23,6 +23,7 @@ struct Nccl {
 	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
 	ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, ncclConfig_t*) = nullptr; // NCCL >= 2.18; optional
 	ncclResult_t (*GroupStart)() = nullptr;
 	ncclResult_t (*GroupEnd)() = nullptr;
@@ -39,7 +40,7 @@ int LoadNccl() {
 	#define SYM(field, name) *(void**)(&g_nccl.field) = dlsym(g_nccl.lib, name); if (!g_nccl.field) { hcmvs_set_error("NCCL symbol %s missing", name); return HCMVS_ERR_UNSUPPORTED; }
 	SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
 	SYM(Broadcast, "ncclBroadcast") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
-	SYM(AllReduce, "ncclAllReduce")
+	SYM(AllReduce, "ncclAllReduce") SYM(AllGather, "ncclAllGather")
 	#undef SYM
 	*(void**)(&g_nccl.CommSplit) = dlsym(g_nccl.lib, "ncclCommSplit");
 	g_nccl.ok = true;
@@ -100,9 +101,9 @@ extern "C" int hcmvs_exchange_maps(hcmvs_ctx* ctx, const int32_t* owner, uint32_
 	if (!ctx || !owner) { hcmvs_set_error("null argument"); return HCMVS_ERR_ARG; }
 	const bool async = (what & HCMVS_EXCHANGE_ASYNC) != 0;
 	what &= ~HCMVS_EXCHANGE_ASYNC;
-	if (what != HCMVS_EXCHANGE_ESTIMATED && what != HCMVS_EXCHANGE_FILTERED) { hcmvs_set_error("unknown exchange kind %d", what); return HCMVS_ERR_ARG; }
+	if (what != HCMVS_EXCHANGE_ESTIMATED && what != HCMVS_EXCHANGE_FILTERED && what != HCMVS_EXCHANGE_IMAGES) { hcmvs_set_error("unknown exchange kind %d", what); return HCMVS_ERR_ARG; }
 	if (!ctx->comm) { hcmvs_set_error("no communicator (call hcmvs_comm_init)"); return HCMVS_ERR_STATE; }
-	for (View& v: ctx->views) v.depthValid = false; // received maps replace dn
+	if (what == HCMVS_EXCHANGE_ESTIMATED) for (View& v: ctx->views) v.depthValid = false; // received maps replace dn
 	if (n_views > ctx->views.size()) { hcmvs_set_error("owner list longer than the scene (%u > %zu views)", n_views, ctx->views.size()); return HCMVS_ERR_ARG; }
 	cudaSetDevice(ctx->device);
 	// Phase 1 — local checks and allocations. Nothing collective has been issued yet, so a failing rank must not simply return: its
@@ -124,6 +125,10 @@ extern "C" int hcmvs_exchange_maps(hcmvs_ctx* ctx, const int32_t* owner, uint32_
 		if (!v.set) { hcmvs_set_error("view %u not set on rank %d (every rank holds every image)", i, ctx->rank); fail(HCMVS_ERR_STATE); continue; }
 		const size_t n = (size_t)v.w*v.h;
 		cudaError_t ce = cudaSuccess;
+		if (what == HCMVS_EXCHANGE_IMAGES) {
+			if (!v.img_d) { hcmvs_set_error("rank %d: view %u has no image buffers", ctx->rank, i); fail(HCMVS_ERR_STATE); }
+			continue;
+		}
 		if (owner[i] == ctx->rank) {
 			if (!v.hasMaps || !v.dn_d) { hcmvs_set_error("rank %d owns view %u but has no maps for it", ctx->rank, i); fail(HCMVS_ERR_STATE); }
 			else if (what == HCMVS_EXCHANGE_FILTERED && !v.hasFiltered) { hcmvs_set_error("rank %d owns view %u but has not filtered it", ctx->rank, i); fail(HCMVS_ERR_STATE); }
@@ -162,6 +167,8 @@ extern "C" int hcmvs_exchange_maps(hcmvs_ctx* ctx, const int32_t* owner, uint32_
 		st = ctx->commStream; ctx->commPending = true;
 	} else hcmvs_time_begin(ctx, ST_EXCHANGE);
 	// inside the group the first error is remembered and the group is ALWAYS closed: an open group would swallow every later NCCL call
+	if (what == HCMVS_EXCHANGE_IMAGES) // the images this rank uploaded (copy stream) must have landed before they are sent
+		for (uint32_t i=0; i<n_views; ++i) if (owner[i] == ctx->rank && ctx->views[i].imgReady) CK(cudaStreamWaitEvent(st, ctx->views[i].imgReady, 0));
 	ncclResult_t first = ncclSuccess; const char* firstWhat = "";
 	#define NG(call) do { if (first == ncclSuccess) { const ncclResult_t r_ = (call); if (r_ != ncclSuccess) { first = r_; firstWhat = #call; } } } while (0)
 	NK(g_nccl.GroupStart());
@@ -179,7 +186,10 @@ extern "C" int hcmvs_exchange_maps(hcmvs_ctx* ctx, const int32_t* owner, uint32_
 		if (owner[i] < 0) continue;
 		View& v = ctx->views[i];
 		const size_t n = (size_t)v.w*v.h;
-		if (what == HCMVS_EXCHANGE_ESTIMATED) {
+		if (what == HCMVS_EXCHANGE_IMAGES) {
+			NG(g_nccl.Broadcast(v.img_d, v.img_d, n, ncclFloat, owner[i], (ncclComm_t)ctx->comm, st));
+			if (v.bgr_d) NG(g_nccl.Broadcast(v.bgr_d, v.bgr_d, n*3, ncclUint8, owner[i], (ncclComm_t)ctx->comm, st));
+		} else if (what == HCMVS_EXCHANGE_ESTIMATED) {
 			NG(g_nccl.Broadcast(v.dn_d, v.dn_d, n*4, ncclFloat, owner[i], (ncclComm_t)ctx->comm, st));
 			NG(g_nccl.Broadcast(v.conf_d, v.conf_d, n, ncclFloat, owner[i], (ncclComm_t)ctx->comm, st));
 		} else {
@@ -191,11 +201,43 @@ extern "C" int hcmvs_exchange_maps(hcmvs_ctx* ctx, const int32_t* owner, uint32_
 	#undef NG
 	if (!async) hcmvs_time_end(ctx);
 	if (first != ncclSuccess) { hcmvs_set_error("%s -> %s", firstWhat, g_nccl.GetErrorString(first)); return HCMVS_ERR_CUDA; }
+	if (what == HCMVS_EXCHANGE_IMAGES) {
+		// the received gray images feed the gather textures (block-linear arrays); whoever samples them waits on imgReady
+		for (uint32_t i=0; i<n_views; ++i) {
+			if (owner[i] < 0 || owner[i] == ctx->rank) continue;
+			View& v = ctx->views[i];
+			CK(cudaMemcpy2DToArrayAsync(v.arr, 0, 0, v.img_d, (size_t)v.w*4, (size_t)v.w*4, v.h, cudaMemcpyDeviceToDevice, st));
+			v.graValid = false;
+			if (!v.imgReady) CK(cudaEventCreateWithFlags(&v.imgReady, cudaEventDisableTiming));
+			CK(cudaEventRecord(v.imgReady, st));
+		}
+		return HCMVS_OK;
+	}
 	for (uint32_t i=0; i<n_views; ++i) {
 		if (owner[i] < 0 || owner[i] == ctx->rank) continue;
 		View& v = ctx->views[i];
 		if (what == HCMVS_EXCHANGE_ESTIMATED) { v.hasMaps = true; v.dMin = ctl[2*i]; v.dMax = ctl[2*i+1]; } // the owner's depth range travels with the maps
 		else v.hasFiltered = true; // hcmvs_commit_filtered applies it on this rank too
 	}
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_comm_allgather_host(hcmvs_ctx* ctx, const void* send, void* recv, uint64_t bytes_per_rank) {
+	if (!ctx || !send || !recv || !bytes_per_rank) { hcmvs_set_error("null argument"); return HCMVS_ERR_ARG; }
+	if (!ctx->comm) { hcmvs_set_error("no communicator (call hcmvs_comm_init)"); return HCMVS_ERR_STATE; }
+	cudaSetDevice(ctx->device);
+	ncclComm_t cc = (ncclComm_t)(ctx->ctlComm ? ctx->ctlComm : ctx->comm);
+	cudaStream_t cs = ctx->ctlComm ? ctx->ctlStream : ctx->stream;
+	const size_t total = bytes_per_rank*(size_t)ctx->world;
+	char* buf = nullptr;
+	CK(cudaMalloc(&buf, total));
+	cudaError_t e = cudaMemcpyAsync(buf+bytes_per_rank*(size_t)ctx->rank, send, bytes_per_rank, cudaMemcpyHostToDevice, cs);
+	ncclResult_t nr = ncclSuccess;
+	if (e == cudaSuccess) nr = g_nccl.AllGather(buf+bytes_per_rank*(size_t)ctx->rank, buf, bytes_per_rank, ncclUint8, cc, cs);
+	if (e == cudaSuccess && nr == ncclSuccess) e = cudaMemcpyAsync(recv, buf, total, cudaMemcpyDeviceToHost, cs);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+	cudaFree(buf);
+	if (nr != ncclSuccess) { hcmvs_set_error("ncclAllGather -> %s", g_nccl.GetErrorString(nr)); return HCMVS_ERR_CUDA; }
+	if (e != cudaSuccess) { hcmvs_set_error("hcmvs_comm_allgather_host: %s", cudaGetErrorString(e)); return HCMVS_ERR_CUDA; }
 	return HCMVS_OK;
 }

@@ -35,6 +35,12 @@ def lib():
         L.hcmvs_host_scale_image.argtypes = [vp, i32, i32, C.c_float, vp, C.POINTER(i32), C.POINTER(i32), vp, vp]
         L.hcmvs_host_init_depth.argtypes = [vp, i32, vp, vp]
         L.hcmvs_host_dense_reconstruction.argtypes = [vp, vp, C.POINTER(api.Params), C.c_uint64, i32, C.c_char_p, vp]
+        L.hcmvs_host_dense_reconstruction_distributed.argtypes = [vp, vp, C.POINTER(api.Params), C.c_uint64, i32, i32, i32, vp]
+        L.hcmvs_host_dist_prepare.argtypes = [vp, vp, C.POINTER(api.Params), i32, i32]
+        L.hcmvs_host_dist_upload_initial.argtypes = [vp]
+        L.hcmvs_host_dist_info.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+        L.hcmvs_host_dist_run.argtypes = [vp, C.c_uint64, i32, i32, vp]
+        L.hcmvs_host_shard_plan.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]
         L.hcmvs_host_cloud_size.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.hcmvs_host_cloud_get.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.hcmvs_host_cloud_save_ply.argtypes = [vp, C.c_char_p]
@@ -76,16 +82,24 @@ class HostScene:
 
     @classmethod
     def from_synth(cls, syn, images=None):
+        """images: list (or dict) of BGR arrays per view; an entry that is None (or missing from the dict) adds the camera only — the
+        pixels of that image live on another rank (dense_reconstruction_distributed)."""
         s = cls()
         for i in range(syn.n_views):
-            bgr = images[i] if images is not None else syn.render(i, want_depth=False, want_normal=False)[0]
-            s.add_image(syn.K[i], syn.R[i], syn.Cc[i], bgr, name=f"{i:05d}.png")
+            if images is None:
+                bgr = syn.render(i, want_depth=False, want_normal=False)[0]
+            else:
+                bgr = images.get(i) if isinstance(images, dict) else images[i]
+            s.add_image(syn.K[i], syn.R[i], syn.Cc[i], bgr, name=f"{i:05d}.png", size=(syn.height, syn.width))
         s.set_sparse(syn.sparse_xyz, syn.sparse_off, syn.sparse_views)
         return s
 
-    def add_image(self, K, R, Cc, bgr, name=""):
-        bgr = np.ascontiguousarray(bgr, np.uint8)
-        h, w = bgr.shape[:2]
+    def add_image(self, K, R, Cc, bgr, name="", size=None):
+        if bgr is None:
+            h, w = size
+        else:
+            bgr = np.ascontiguousarray(bgr, np.uint8)
+            h, w = bgr.shape[:2]
         K = np.ascontiguousarray(K, np.float64); R = np.ascontiguousarray(R, np.float64); Cc = np.ascontiguousarray(Cc, np.float64)
         i = self.L.hcmvs_host_add_image(self.h, w, h, _p(K), _p(R), _p(Cc), _p(bgr), name.encode())
         if i < 0:
@@ -138,6 +152,41 @@ class HostScene:
             raise RuntimeError(self.L.hcmvs_host_last_error(self.h).decode())
         for i, sz in enumerate(self.sizes):
             ctx.sizes.setdefault(i, sz)
+        return dict(sec_select=st[0], sec_upload=st[1], sec_estimate=st[2], sec_filter=st[3], sec_fuse=st[4],
+                    h2d_bytes=int(st[5]), d2h_bytes=int(st[6]), n_points=int(st[7]))
+
+    def dense_reconstruction_distributed(self, ctx, rank, world, seed=1, run_filter=True):
+        """Scene::DenseReconstruction over `world` GPUs (one process per GPU; ctx joined the communicator). Collective."""
+        st = np.zeros(8)
+        r = self.L.hcmvs_host_dense_reconstruction_distributed(self.h, ctx.h, C.byref(ctx.params), seed, int(run_filter), int(rank), int(world), _p(st))
+        if r != 0:
+            raise RuntimeError(self.L.hcmvs_host_last_error(self.h).decode())
+        for i, sz in enumerate(self.sizes):
+            ctx.sizes.setdefault(i, sz)
+        return dict(sec_select=st[0], sec_upload=st[1], sec_estimate=st[2], sec_filter=st[3], sec_fuse=st[4],
+                    h2d_bytes=int(st[5]), d2h_bytes=int(st[6]), n_points=int(st[7]))
+
+    def _ckd(self, r):
+        if r != 0:
+            raise RuntimeError(self.L.hcmvs_host_last_error(self.h).decode())
+
+    def dist_prepare(self, ctx, rank, world):
+        self._ckd(self.L.hcmvs_host_dist_prepare(self.h, ctx.h, C.byref(ctx.params), int(rank), int(world)))
+        self._rank = int(rank)
+        for i, sz in enumerate(self.sizes):
+            ctx.sizes.setdefault(i, sz)
+
+    def dist_info(self):
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._ckd(self.L.hcmvs_host_dist_info(self.h, self._rank, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(n_valid=a.value, n_mine_whole=b.value, n_split=c.value, whole_rounds=d.value)
+
+    def dist_upload_initial(self):
+        self._ckd(self.L.hcmvs_host_dist_upload_initial(self.h))
+
+    def dist_run(self, seed=1, run_filter=True, download=False):
+        st = np.zeros(8)
+        self._ckd(self.L.hcmvs_host_dist_run(self.h, seed, int(run_filter), int(download), _p(st)))
         return dict(sec_select=st[0], sec_upload=st[1], sec_estimate=st[2], sec_filter=st[3], sec_fuse=st[4],
                     h2d_bytes=int(st[5]), d2h_bytes=int(st[6]), n_points=int(st[7]))
 
@@ -226,6 +275,16 @@ class HostScene:
             self.close()
         except Exception:
             pass
+
+
+def shard_plan(valid_views, n_scored, world, split_rows=True):
+    """The multi-GPU schedule of DenseReconstructionDistributed (host only): dict(order, owner_whole, owner_filter, whole_rounds, n_split)."""
+    valid = np.ascontiguousarray(valid_views, np.uint32); ns = np.ascontiguousarray(n_scored, np.uint32)
+    order = np.zeros(len(valid), np.uint32); ow = np.zeros(len(ns), np.int32); of = np.zeros(len(ns), np.int32)
+    wr, nsp = C.c_int(), C.c_int()
+    if lib().hcmvs_host_shard_plan(_p(valid), len(valid), _p(ns), len(ns), int(world), int(split_rows), _p(order), _p(ow), _p(of), C.byref(wr), C.byref(nsp)) != 0:
+        raise ValueError("bad plan arguments")
+    return dict(order=order, owner_whole=ow, owner_filter=of, whole_rounds=wr.value, n_split=nsp.value)
 
 
 def load_image(path):

@@ -421,6 +421,7 @@ bool DepthMapsData::InitViews(uint32_t idxImage, uint32_t numNeighbors) {
 		const ViewScore& nb = dd.neighbors[k-1];
 		Image& im = scene.images[nb.ID];
 		std::vector<float> scaled; int sw = 0, sh = 0;
+		if (im.gray.empty() && std::abs(nb.scale-1.f) >= 0.15f) { lastError = "a rescaled matching view needs its pixels in host memory (multi-GPU: hold that image on every rank)"; return false; }
 		if (!ScaleImage(im.gray, im.width, im.height, nb.scale, scaled, sw, sh)) continue;
 		double Ks[9]; ScaleK(im.camera.K, im.width, im.height, sw, sh, Ks);
 		if (hcmvs_set_neighbor_image(ctx, idxImage, (int)k-1, sw, sh, Ks, scaled.data()) != HCMVS_OK) return Fail("hcmvs_set_neighbor_image");

@@ -166,6 +166,49 @@ struct DenseReconstructionStats { double secSelect = 0, secUpload = 0, secEstima
 bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, const ViewSelectionParams& VS, uint64_t seed, bool runFilter,
 	const std::string& dmapDir, DenseReconstructionStats* stats, std::string* err);
 
+// The multi-GPU schedule (no reference counterpart: the reference is single-node CPU code). Views are dealt round-robin in
+// FuseDepthMaps' connection order (decreasing scored-neighbour count, ties by index — SceneDensify.cpp:3286-3303): view order[k] is
+// estimated in round k / world by rank k % world. With splitRows the views of the last, incomplete round are estimated in `world` row
+// bands by all ranks (49 views on 8 ranks: 6 whole rounds + 1 view an eighth of which every rank estimates, instead of one rank
+// estimating a 7th view while seven wait). Filtering of view order[k] always stays with rank k % world.
+struct ShardPlan {
+	std::vector<uint32_t> order; int world = 1; int wholeRounds = 0; bool splitRows = false;
+	std::vector<uint32_t> SplitViews() const;                 // views of the incomplete round (empty without splitRows)
+	std::vector<uint32_t> WholeViewsOf(int rank) const;       // views a rank estimates whole, in round order
+	std::vector<uint32_t> ViewsOf(int rank) const;            // views a rank filters
+	std::vector<int32_t> RoundOwners(int round, size_t nViews) const;  // owner list of one round for hcmvs_exchange_maps
+	std::vector<int32_t> SplitOwners(size_t nViews) const;    // HCMVS_OWNER_SPLIT_ROWS for the split views
+	std::vector<int32_t> Owners(size_t nViews, const std::vector<char>* only = nullptr) const;
+	void RowsOf(int rank, int height, int& r0, int& r1) const;
+};
+ShardPlan MakeShardPlan(const std::vector<uint32_t>& validViews, const std::vector<uint32_t>& nScoredNeighbors, int world, bool splitRows);
+// Scene::DenseReconstruction on `world` GPUs: one process per GPU calls this with its rank; ctx must have joined the communicator
+// (hcmvs_comm_init). Every rank holds every camera and the sparse cloud; image PIXELS are only needed for the images it uploads
+// (index % world == rank) — the others arrive over NVLink. Rank 0 returns with scene.densecloud, identical to the single-GPU cloud.
+// The same job in stages, for callers that time the hot path with its inputs already resident in HBM (bench.py's `value`):
+//   Prepare()        view selection (sharded + all-gathered), image uploads (1/world over PCIe, the rest over NVLink), neighbour lists,
+//                    the plan, the initial depth maps on the host
+//   UploadInitial()  H2D of the initial maps of the views this rank estimates (estimation overwrites them: once per Run)
+//   Run()            estimation rounds + exchanges, FilterDepthMap + exchange + commit, FuseDepthMaps on rank 0
+//                    (download: into scene.densecloud; else the cloud stays on the device)
+class DistributedReconstruction {
+public:
+	DistributedReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, const ViewSelectionParams& VS, int rank, int world);
+	~DistributedReconstruction();
+	DistributedReconstruction(const DistributedReconstruction&) = delete;
+	DistributedReconstruction& operator=(const DistributedReconstruction&) = delete;
+	bool Prepare(bool lazyInitialMaps = false); // lazy: Run() makes + uploads the initial maps on worker threads ahead of the estimation (one-call job)
+	bool UploadInitial();
+	bool Run(uint64_t seed, bool runFilter, bool download);
+	const std::string& Error() const;
+	const DenseReconstructionStats& Stats() const;
+	const ShardPlan& Plan() const;
+private:
+	struct Impl; Impl* impl;
+};
+bool DenseReconstructionDistributed(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, const ViewSelectionParams& VS, uint64_t seed, bool runFilter,
+	int rank, int world, DenseReconstructionStats* stats, std::string* err);
+
 bool ExportDepthDataRaw(const std::string& fileName, const std::string& imageFileName, const std::vector<uint32_t>& IDs, int imageW, int imageH,
 	const double K[9], const double R[9], const double C[3], float dMin, float dMax, int w, int h,
 	const float* depth, const float* normal, const float* conf);

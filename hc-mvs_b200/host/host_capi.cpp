@@ -12,6 +12,8 @@ struct hcmvs_host_scene {
 	Scene scene;
 	std::vector<DepthData> dd;
 	std::string err;
+	DistributedReconstruction* dist = nullptr; // hcmvs_host_dist_*
+	~hcmvs_host_scene() { delete dist; }
 };
 
 extern "C" {
@@ -21,13 +23,15 @@ void hcmvs_host_scene_destroy(hcmvs_host_scene* s) { delete s; }
 const char* hcmvs_host_last_error(hcmvs_host_scene* s) { return s ? s->err.c_str() : "null scene"; }
 
 int hcmvs_host_add_image(hcmvs_host_scene* s, int w, int h, const double K[9], const double R[9], const double C[3], const uint8_t* bgr, const char* name) {
-	if (!s || !K || !R || !C || !bgr || w <= 0 || h <= 0) return -1;
+	if (!s || !K || !R || !C || w <= 0 || h <= 0) return -1;
 	Image im; im.width = w; im.height = h;
 	memcpy(im.camera.K, K, 72); memcpy(im.camera.R, R, 72); memcpy(im.camera.C, C, 24);
 	im.camera.ComposeP();
-	im.bgr.assign(bgr, bgr+(size_t)w*h*3);
-	im.gray.resize((size_t)w*h);
-	ToGray(bgr, w, h, im.gray.data());
+	if (bgr) { // NULL: camera only — the pixels live on another rank (DenseReconstructionDistributed)
+		im.bgr.assign(bgr, bgr+(size_t)w*h*3);
+		im.gray.resize((size_t)w*h);
+		ToGray(bgr, w, h, im.gray.data());
+	}
 	if (name) im.name = name;
 	s->scene.images.push_back(std::move(im));
 	return (int)s->scene.images.size()-1;
@@ -101,6 +105,70 @@ int hcmvs_host_dense_reconstruction(hcmvs_host_scene* s, hcmvs_ctx* ctx, const h
 		stats[0] = st.secSelect; stats[1] = st.secUpload; stats[2] = st.secEstimate; stats[3] = st.secFilter; stats[4] = st.secFuse;
 		stats[5] = (double)st.h2dBytes; stats[6] = (double)st.d2hBytes; stats[7] = (double)s->scene.densecloud.size();
 	}
+	return 0;
+}
+
+int hcmvs_host_dense_reconstruction_distributed(hcmvs_host_scene* s, hcmvs_ctx* ctx, const hcmvs_params* p, uint64_t seed, int run_filter, int rank, int world, double* stats) {
+	if (!s || !ctx || !p) return -1;
+	DenseReconstructionStats st;
+	for (Image& im: s->scene.images) im.neighbors.clear();
+	if (!DenseReconstructionDistributed(s->scene, ctx, *p, ViewSelectionParams(), seed, run_filter != 0, rank, world, &st, &s->err)) return -2;
+	if (stats) {
+		stats[0] = st.secSelect; stats[1] = st.secUpload; stats[2] = st.secEstimate; stats[3] = st.secFilter; stats[4] = st.secFuse;
+		stats[5] = (double)st.h2dBytes; stats[6] = (double)st.d2hBytes; stats[7] = (double)s->scene.densecloud.size();
+	}
+	return 0;
+}
+
+int hcmvs_host_dist_prepare(hcmvs_host_scene* s, hcmvs_ctx* ctx, const hcmvs_params* p, int rank, int world) {
+	if (!s || !ctx || !p || world < 2 || rank < 0 || rank >= world) return -1;
+	delete s->dist;
+	s->dist = new DistributedReconstruction(s->scene, ctx, *p, ViewSelectionParams(), rank, world);
+	if (!s->dist->Prepare()) { s->err = s->dist->Error(); return -2; }
+	return 0;
+}
+int hcmvs_host_dist_info(hcmvs_host_scene* s, int rank, int* n_valid, int* n_mine_whole, int* n_split, int* whole_rounds) {
+	if (!s || !s->dist) return -1;
+	const ShardPlan& p = s->dist->Plan();
+	if (n_valid) *n_valid = (int)p.order.size();
+	if (n_mine_whole) *n_mine_whole = (int)p.WholeViewsOf(rank).size();
+	if (n_split) *n_split = (int)p.SplitViews().size();
+	if (whole_rounds) *whole_rounds = p.wholeRounds;
+	return 0;
+}
+int hcmvs_host_dist_upload_initial(hcmvs_host_scene* s) {
+	if (!s || !s->dist) return -1;
+	if (!s->dist->UploadInitial()) { s->err = s->dist->Error(); return -2; }
+	return 0;
+}
+int hcmvs_host_dist_run(hcmvs_host_scene* s, uint64_t seed, int run_filter, int download, double* stats) {
+	if (!s || !s->dist) return -1;
+	const bool ok = s->dist->Run(seed, run_filter != 0, download != 0);
+	if (!ok) { s->err = s->dist->Error(); return -2; }
+	if (stats) {
+		const DenseReconstructionStats& st = s->dist->Stats();
+		stats[0] = st.secSelect; stats[1] = st.secUpload; stats[2] = st.secEstimate; stats[3] = st.secFilter; stats[4] = st.secFuse;
+		stats[5] = (double)st.h2dBytes; stats[6] = (double)st.d2hBytes; stats[7] = (double)s->scene.densecloud.size();
+	}
+	return 0;
+}
+
+int hcmvs_host_shard_plan(const uint32_t* valid_views, int n_valid, const uint32_t* n_scored, int n_views, int world, int split_rows,
+	uint32_t* order, int32_t* owner_whole, int32_t* owner_filter, int* whole_rounds, int* n_split)
+{
+	if (!valid_views || !n_scored || n_valid < 0 || n_views <= 0 || world < 1) return -1;
+	std::vector<uint32_t> v(valid_views, valid_views+n_valid), ns(n_scored, n_scored+n_views);
+	for (uint32_t id: v) if (id >= (uint32_t)n_views) return -1;
+	const ShardPlan plan = MakeShardPlan(v, ns, world, split_rows != 0);
+	if (order) std::copy(plan.order.begin(), plan.order.end(), order);
+	if (owner_whole) { // rank that estimates the whole view, HCMVS_OWNER_SPLIT_ROWS for a row-split view, -1 outside the plan
+		std::fill(owner_whole, owner_whole+n_views, -1);
+		for (int r=0; r<plan.wholeRounds; ++r) { const std::vector<int32_t> o = plan.RoundOwners(r, (size_t)n_views); for (int i=0; i<n_views; ++i) if (o[i] >= 0) owner_whole[i] = o[i]; }
+		for (uint32_t id: plan.SplitViews()) owner_whole[id] = HCMVS_OWNER_SPLIT_ROWS;
+	}
+	if (owner_filter) { const std::vector<int32_t> o = plan.Owners((size_t)n_views); std::copy(o.begin(), o.end(), owner_filter); }
+	if (whole_rounds) *whole_rounds = plan.wholeRounds;
+	if (n_split) *n_split = (int)plan.SplitViews().size();
 	return 0;
 }
 

@@ -1,4 +1,9 @@
-"""View sharding and map exchange plan for N ranks (one process per GPU).
+"""View sharding plan for N ranks (one process per GPU) — a Python VIEW of the C++ plan.
+
+The schedule itself lives in the C++ host (hcmvs_host::MakeShardPlan / DistributedReconstruction, hc-mvs_b200/host/densify_dist.cpp):
+make_plan() below asks the host library for the order and the row-split decision, so the CPU tests of this module test the C++ logic.
+exchange_maps() is the torch.distributed slot exchange used by the gloo tests only (the GPU path broadcasts in place through
+hcmvs_exchange_maps).
 
 The scene shards by reference view: every rank holds all images and cameras, estimates the
 depth maps of its own views, and the ranks all-gather the (normal, depth) / confidence maps so that
@@ -80,9 +85,17 @@ def make_plan(valid_views, n_scored_neighbors, world, split_rows=False):
     """split_rows: 49 views on 8 ranks are 6 full rounds + 1 view; instead of one rank estimating a 7th view while seven wait, every
     rank estimates one eighth of its rows (+ the halo its dependencies reach, hcmvs_estimate_depthmap_rows) and the bands are
     exchanged in place. Filtering of those views stays with owner(k) = k % world."""
-    order = sorted(valid_views, key=lambda i: (-n_scored_neighbors[i], i))
+    from . import host
+    import numpy as np
+    valid = [int(v) for v in valid_views]
+    n_views = (max(valid) + 1) if valid else 1
+    ns = np.zeros(n_views, np.uint32)
+    for v in valid:
+        ns[v] = int(n_scored_neighbors[v])
+    p = host.shard_plan(valid, ns, world, split_rows=bool(split_rows))
+    order = [int(v) for v in p["order"]]
     slots = (len(order) + world - 1) // world if order else 0
-    return ShardPlan(order=order, world=world, slots=slots, split_rows=bool(split_rows and world > 1 and len(order) % world))
+    return ShardPlan(order=order, world=world, slots=slots, split_rows=p["n_split"] > 0)
 
 
 def exchange_maps(plan, rank, send_dn, send_cf, recv_dn, recv_cf, export_fn, import_fn, sync_fn, dist, post_sync=None):

@@ -101,3 +101,35 @@ class SynthScene:
             self.close()
         except Exception:
             pass
+
+
+def c5_maps(gt, seed):
+    """SURVEY §8(d) C5 recipe (fusion stress): GT depth x (1 + N(0, 0.002)), 2 % outliers U(dMin, dMax), normals rotated by U(0, 5 deg),
+    conf U(0.5, 1). gt = (depth, normal) of one view -> (depth, normal, conf, dMin, dMax)."""
+    rng = np.random.default_rng(seed)
+    d, n = gt
+    valid = d > 0
+    lo, hi = float(d[valid].min()), float(d[valid].max())
+    depth = (d * (1 + 0.002 * rng.standard_normal(d.shape))).astype(np.float32)
+    out = rng.uniform(size=d.shape) < 0.02
+    depth[out] = rng.uniform(lo, hi, int(out.sum())).astype(np.float32)
+    depth[~valid] = 0
+    ang = np.deg2rad(rng.uniform(0, 5, d.shape))
+    axis = rng.standard_normal(d.shape + (3,))
+    t = np.cross(n.astype(np.float64), axis)
+    t /= np.maximum(np.linalg.norm(t, axis=2, keepdims=True), 1e-12)
+    nn = np.cos(ang)[..., None] * n + np.sin(ang)[..., None] * t
+    nn /= np.maximum(np.linalg.norm(nn, axis=2, keepdims=True), 1e-12)
+    conf = rng.uniform(0.5, 1.0, d.shape).astype(np.float32)
+    conf[depth == 0] = 0
+    return depth, nn.astype(np.float32), conf, lo * 0.5, hi * 2.0
+
+
+def frame_neighbors(i, n_views, reach=6):
+    """<= 12 neighbours by frame distance, nearest first (C5: no sparse cloud, no view selection)."""
+    ids = []
+    for k in range(1, reach + 1):
+        for j in (i - k, i + k):
+            if 0 <= j < n_views:
+                ids.append(j)
+    return np.array(ids[:12], np.uint32)

@@ -171,6 +171,9 @@ int hcmvs_get_coarse_estimate(hcmvs_ctx* ctx, uint32_t view, float* depth, float
  * (hcmvs_params.viewspread) reads from the neighbour views. Call between outer iterations — after the map exchange when
  * the scene is sharded over GPUs — so that the result does not depend on the order or placement of the views. */
 int hcmvs_snapshot_maps(hcmvs_ctx* ctx);
+/* the opposite copy: every view's maps become the snapshot again (FuseDepthMaps zeroes occluded depths in place — a caller that fuses the
+ * same maps repeatedly restores them on the device instead of uploading them again) */
+int hcmvs_restore_snapshot(hcmvs_ctx* ctx);
 
 /* Copy the last fused cloud into caller-owned host arrays (sizes from hcmvs_get_fused_device); any pointer may be NULL. */
 int hcmvs_download_fused(hcmvs_ctx* ctx, float* points, float* normals, uint8_t* colors, uint32_t* view_offsets, uint32_t* views, float* weights);
@@ -213,6 +216,9 @@ int hcmvs_get_fused_device(hcmvs_ctx* ctx, uint64_t* n_points, uint64_t* n_view_
 #define HCMVS_COMM_ID_BYTES 128
 #define HCMVS_EXCHANGE_ESTIMATED 0
 #define HCMVS_EXCHANGE_FILTERED 1
+#define HCMVS_EXCHANGE_IMAGES 2      /* the gray + colour images: rank owner[i] uploaded view i from its host (hcmvs_set_view), the others only
+                                        allocated it (hcmvs_set_view_remote) and receive it over NVLink instead of PCIe — every rank
+                                        uploads 1/world of the scene and ends up holding all of it */
 #define HCMVS_OWNER_SPLIT_ROWS (-2)  /* owner[i]: view i was estimated in `world` row bands (hcmvs_estimate_depthmap_rows), band r =
                                         rows [r*H/world, (r+1)*H/world) on rank r; HCMVS_EXCHANGE_ESTIMATED broadcasts every band from its rank */
 #define HCMVS_EXCHANGE_ASYNC 0x100   /* OR into `what`: run the broadcasts on a communication stream, behind the work queued so far and
@@ -221,6 +227,11 @@ int hcmvs_comm_unique_id(void* id128);
 int hcmvs_comm_init(hcmvs_ctx* ctx, const void* id128, int rank, int world);
 int hcmvs_exchange_maps(hcmvs_ctx* ctx, const int32_t* owner, uint32_t n_views, int what);
 int hcmvs_exchange_wait(hcmvs_ctx* ctx);   /* the compute stream waits for every asynchronous exchange issued so far */
+/* hcmvs_set_view without pixels: camera + buffers of a view whose image another rank uploads (HCMVS_EXCHANGE_IMAGES delivers it). */
+int hcmvs_set_view_remote(hcmvs_ctx* ctx, uint32_t view, int W, int H, const double K[9], const double R[9], const double C[3], int has_bgr);
+/* All-gather of small host records (view-selection results of a sharded Scene::SelectNeighborViews pass ...): every rank contributes
+ * `bytes_per_rank` bytes, `recv` receives world x bytes_per_rank in rank order. Collective; staged through device memory. */
+int hcmvs_comm_allgather_host(hcmvs_ctx* ctx, const void* send, void* recv, uint64_t bytes_per_rank);
 
 /* Device pointers of a view's maps for GPU<->GPU exchange by the host plumbing (NCCL / P2P):
  * dn_d = float4 (nx,ny,nz,depth) per pixel, conf_d = float per pixel. */

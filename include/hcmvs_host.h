@@ -30,6 +30,22 @@ int hcmvs_host_scale_image(const float* src, int sw, int sh, float scale, float*
 /* Scene::DenseReconstruction (SceneDensify.cpp:3532-3574) through the C ABI with HOST buffers.
  * stats[8] = sec select, upload, estimate, filter, fuse, h2d bytes, d2h bytes, #points. dmap_dir may be NULL. */
 int hcmvs_host_dense_reconstruction(hcmvs_host_scene* s, hcmvs_ctx* ctx, const hcmvs_params* p, uint64_t seed, int run_filter, const char* dmap_dir, double* stats);
+/* The same on `world` GPUs of one box (no reference counterpart): one process per GPU, ctx joined to the communicator
+ * (hcmvs_comm_init). Every rank adds every image's camera; pixels are only needed for images with index % world == rank (bgr may be
+ * NULL in hcmvs_host_add_image for the others — they arrive over NVLink). Rank 0 ends up with the fused cloud. */
+int hcmvs_host_dense_reconstruction_distributed(hcmvs_host_scene* s, hcmvs_ctx* ctx, const hcmvs_params* p, uint64_t seed, int run_filter, int rank, int world, double* stats);
+/* The same job in stages (DistributedReconstruction::Prepare / UploadInitial / Run in densify.h), for callers that time the hot path with
+ * its inputs resident in HBM: prepare once per scene, upload_initial before every run (estimation overwrites the initial maps),
+ * run = estimation + exchanges + filter + fusion on rank 0 (download != 0: the cloud lands in the scene, else it stays on the device). */
+int hcmvs_host_dist_prepare(hcmvs_host_scene* s, hcmvs_ctx* ctx, const hcmvs_params* p, int rank, int world);
+int hcmvs_host_dist_info(hcmvs_host_scene* s, int rank, int* n_valid, int* n_mine_whole, int* n_split, int* whole_rounds); /* the plan prepare made */
+int hcmvs_host_dist_upload_initial(hcmvs_host_scene* s);
+int hcmvs_host_dist_run(hcmvs_host_scene* s, uint64_t seed, int run_filter, int download, double* stats);
+/* The schedule it follows, for inspection / tests (host only): order[n_valid] = views in FuseDepthMaps' connection order; per view the
+ * rank that estimates it whole (HCMVS_OWNER_SPLIT_ROWS: estimated in row bands by all ranks; -1: not in the plan) and the rank that
+ * filters it. Arrays of n_views entries; any output may be NULL. */
+int hcmvs_host_shard_plan(const uint32_t* valid_views, int n_valid, const uint32_t* n_scored, int n_views, int world, int split_rows,
+                          uint32_t* order, int32_t* owner_whole, int32_t* owner_filter, int* whole_rounds, int* n_split);
 /* fused cloud access */
 int hcmvs_host_cloud_size(hcmvs_host_scene* s, uint64_t* n_points, uint64_t* n_view_refs);
 int hcmvs_host_cloud_get(hcmvs_host_scene* s, float* xyz, float* normals, uint8_t* colors, uint32_t* view_offsets, uint32_t* views, float* weights);
