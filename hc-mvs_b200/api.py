@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libhcmvs_b200.so")
 EXPORTS = [
     "hcmvs_default_params", "hcmvs_last_error", "hcmvs_create", "hcmvs_destroy", "hcmvs_set_params", "hcmvs_sync",
     "hcmvs_set_view", "hcmvs_set_neighbors", "hcmvs_set_neighbor_image", "hcmvs_init_depthmap", "hcmvs_init_depthmap_triangles", "hcmvs_download_depthmap_begin", "hcmvs_download_depthmap_wait", "hcmvs_set_depthmap", "hcmvs_get_depthmap",
-    "hcmvs_set_prior", "hcmvs_set_coarse_estimate", "hcmvs_get_coarse_estimate", "hcmvs_snapshot_maps", "hcmvs_restore_snapshot", "hcmvs_get_gradient_map", "hcmvs_score_depthmap", "hcmvs_estimate_depthmap", "hcmvs_estimate_depthmap_rows", "hcmvs_end_depthmap", "hcmvs_score_hypotheses",
+    "hcmvs_set_prior", "hcmvs_set_coarse_estimate", "hcmvs_get_coarse_estimate", "hcmvs_snapshot_maps", "hcmvs_restore_snapshot", "hcmvs_remove_small_segments", "hcmvs_gap_interpolation", "hcmvs_set_view_remote", "hcmvs_comm_allgather_host", "hcmvs_get_gradient_map", "hcmvs_score_depthmap", "hcmvs_estimate_depthmap", "hcmvs_estimate_depthmap_rows", "hcmvs_end_depthmap", "hcmvs_score_hypotheses",
     "hcmvs_filter_depthmap", "hcmvs_commit_filtered", "hcmvs_set_fuse_priority", "hcmvs_fuse_depthmaps",
     "hcmvs_free_pointcloud", "hcmvs_get_fused_device", "hcmvs_get_fused_support", "hcmvs_estimate_point_colors", "hcmvs_estimate_point_normals", "hcmvs_pointcloud_filter", "hcmvs_download_fused", "hcmvs_download_fused_pinned", "hcmvs_get_depthmap_device", "hcmvs_set_depth_range", "hcmvs_alloc_depthmap",
     "hcmvs_comm_unique_id", "hcmvs_comm_init", "hcmvs_exchange_maps", "hcmvs_exchange_wait", "hcmvs_export_maps_d", "hcmvs_import_maps_d", "hcmvs_get_timers", "hcmvs_reset_timers", "hcmvs_stream",
@@ -96,6 +96,8 @@ def load():
     L.hcmvs_get_coarse_estimate.argtypes = [vp, u32, vp, vp]
     L.hcmvs_snapshot_maps.argtypes = [vp]
     L.hcmvs_restore_snapshot.argtypes = [vp]
+    L.hcmvs_remove_small_segments.argtypes = [vp, C.c_uint32, C.c_uint, C.POINTER(C.c_uint64)]
+    L.hcmvs_gap_interpolation.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_uint, C.POINTER(C.c_uint64)]
     L.hcmvs_score_depthmap.argtypes = [vp, u32, i32, C.c_uint64]
     L.hcmvs_estimate_depthmap.argtypes = [vp, u32, i32, C.c_uint64]
     L.hcmvs_estimate_depthmap_rows.argtypes = [vp, u32, i32, C.c_uint64, i32, i32]
@@ -262,6 +264,21 @@ class Context:
 
     def snapshot_maps(self):
         self._ck(self.L.hcmvs_snapshot_maps(self.h))
+
+    def remove_small_segments(self, view, speckle_size=100):
+        """DepthMapsData::RemoveSmallSegments (stock OpenMVS speckle filter) on the view's maps; returns the number of zeroed pixels."""
+        n = C.c_uint64()
+        self._ck(self.L.hcmvs_remove_small_segments(self.h, int(view), int(speckle_size), C.byref(n)))
+        return int(n.value)
+
+    def gap_interpolation(self, depth, normal=None, conf=None, gap_size=7):
+        """Small-gap branch of DepthMapsData::GapInterpolation on copies of the given maps -> (depth, normal, conf, n_filled)."""
+        d = np.ascontiguousarray(depth, np.float32).copy(); h, w = d.shape
+        nn = None if normal is None else np.ascontiguousarray(normal, np.float32).copy()
+        cc = None if conf is None else np.ascontiguousarray(conf, np.float32).copy()
+        n = C.c_uint64()
+        self._ck(self.L.hcmvs_gap_interpolation(self.h, w, h, _p(d), _p(nn), _p(cc), int(gap_size), C.byref(n)))
+        return d, nn, cc, int(n.value)
 
     def restore_snapshot(self):
         self._ck(self.L.hcmvs_restore_snapshot(self.h))

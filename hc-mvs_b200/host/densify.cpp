@@ -480,6 +480,20 @@ bool DepthMapsData::FilterDepthMap(uint32_t idxImage, const std::vector<uint32_t
 	return true;
 }
 
+bool DepthMapsData::RemoveSmallSegments(uint32_t idxImage, unsigned nSpeckleSize) {
+	if (hcmvs_remove_small_segments(ctx, idxImage, nSpeckleSize, nullptr) != HCMVS_OK) return Fail("hcmvs_remove_small_segments");
+	return true;
+}
+
+bool DepthMapsData::GapInterpolation(uint32_t idxImage, std::vector<float>& depthFuse, std::vector<float>& normalFuse, std::vector<float>& conf, unsigned nIpolGapSize) {
+	const Image& im = scene.images[idxImage];
+	const size_t n = (size_t)im.width*im.height;
+	if (depthFuse.size() != n || (!normalFuse.empty() && normalFuse.size() != n*3) || (!conf.empty() && conf.size() != n)) { lastError = "GapInterpolation: map sizes do not match the image"; return false; }
+	if (hcmvs_gap_interpolation(ctx, im.width, im.height, depthFuse.data(), normalFuse.empty() ? nullptr : normalFuse.data(), conf.empty() ? nullptr : conf.data(), nIpolGapSize, nullptr) != HCMVS_OK)
+		return Fail("hcmvs_gap_interpolation");
+	return true;
+}
+
 bool DepthMapsData::FuseDepthMaps(PointCloud& pc, bool bEstimateColor, bool bEstimateNormal) {
 	// fuse on the device, then ONE copy into the context's page-locked arena; the PointCloud borrows those arrays
 	// (valid until the next FuseDepthMaps on this context or hcmvs_destroy — see hcmvs_download_fused_pinned)

@@ -151,6 +151,11 @@ public:
 	bool EstimateDepthMap(int it_external, uint32_t idxImage, uint64_t seed); // SceneDensify.cpp:758-1072
 	bool FilterDepthMap(uint32_t idxImage, const std::vector<uint32_t>& idxNeighbors, bool bAdjust); // SceneDensify.cpp:3006-3259
 	bool FuseDepthMaps(PointCloud& pointcloud, bool bEstimateColor, bool bEstimateNormal);           // SceneDensify.cpp:3265-3495
+	// the stock OpenMVS post-filters of a view's maps: the speckle filter the fork keeps under `#if 0`
+	// (SceneDensify.cpp:1956-2042; nSpeckleSize = OPTDENSE default 100) and the small-gap branch of GapInterpolation (:2294-2352,
+	// :2640-2683; nIpolGapSize = 7) on caller-held fuse maps (H*W depth, H*W*3 normal or empty, H*W confidence or empty)
+	bool RemoveSmallSegments(uint32_t idxImage, unsigned nSpeckleSize = 100);
+	bool GapInterpolation(uint32_t idxImage, std::vector<float>& depthFuse, std::vector<float>& normalFuse, std::vector<float>& conf, unsigned nIpolGapSize = 7);
 	// raw "DR" depth-data file, ExportDepthDataRaw, DepthMap.cpp:2781-2846
 	bool SaveDepthMapRaw(uint32_t idxImage, const std::string& fileName);
 	bool UploadView(uint32_t idxImage);

@@ -204,6 +204,17 @@ int hcmvs_pointcloud_filter(hcmvs_ctx* ctx, uint64_t n_points, const float* poin
 int hcmvs_get_fused_device(hcmvs_ctx* ctx, uint64_t* n_points, uint64_t* n_view_refs, void** points_d, void** normals_d, void** colors_d,
                            void** view_offsets_d, void** views_d, void** weights_d);
 
+/* ---- per-view post-filters between estimation and fusion
+ * DepthMapsData::RemoveSmallSegments as OpenMVS ships it — the body the fork keeps under `#if 0`, SceneDensify.cpp:1956-2042: segments of
+ * 4-connected pixels with IsDepthSimilar depths (threshold fDepthDiffThreshold * 0.7) that hold fewer than speckle_size (OPTDENSE::nSpeckleSize,
+ * 100) pixels are zeroed in the view's maps (depth, normal, confidence). Identical to the CPU's order-dependent flood fill. */
+int hcmvs_remove_small_segments(hcmvs_ctx* ctx, uint32_t view, unsigned speckle_size, uint64_t* n_removed);
+/* The small-gap branch of DepthMapsData::GapInterpolation (SceneDensify.cpp:2294-2352, 2640-2683; OPTDENSE::nIpolGapSize = 7): runs of at
+ * most gap_size invalid pixels between two similar depths (threshold fDepthDiffThreshold * 2.5) are interpolated, rows first, then columns.
+ * Works on the caller's maps in place (the reference applies it to depthMap_fuse / normalMap_fuse — hcmvs_get_fused_support — and confMap):
+ * depth H*W, normal H*W*3 or NULL, conf H*W or NULL. The fork's large-gap branches are undefined behaviour and not built. */
+int hcmvs_gap_interpolation(hcmvs_ctx* ctx, int w, int h, float* depth, float* normal, float* conf, unsigned gap_size, uint64_t* n_filled);
+
 /* ---- multi-GPU: one process (one context) per GPU, views sharded by reference view. No reference counterpart: the
  * reference is single-node CPU code. Rank 0 creates an id (hcmvs_comm_unique_id), the host distributes its HCMVS_COMM_ID_BYTES bytes
  * by any means (file, socket, MPI, torch.distributed), every rank calls hcmvs_comm_init (collective). hcmvs_exchange_maps then

@@ -11,6 +11,8 @@ struct orc_scene {
 	PointCloud cloud;
 };
 
+#include <cmath>
+#include <algorithm>
 extern "C" {
 
 orc_scene* orc_scene_create() { return new orc_scene(); }
@@ -235,5 +237,95 @@ void orc_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { Philo
 float orc_sample(const float* img, int w, int h, float x, float y) { Image32F im; im.w = w; im.h = h; im.d.assign(img, img+(size_t)w*h); return SampleBilinear(im, x, y); }
 void orc_dir2normal(float a, float b, float* out) { Vec3f n; Dir2Normal(a, b, n); out[0] = n.x; out[1] = n.y; out[2] = n.z; }
 void orc_normal2dir(const float* n, float* out) { Normal2Dir(Vec3f{n[0], n[1], n[2]}, out[0], out[1]); }
+
+
+// The stock OpenMVS speckle filter that the fork keeps under `#if 0` (DepthMapsData::RemoveSmallSegments, SceneDensify.cpp:1956-2042),
+// restated with its loop order: seeds in COLUMN-major order, breadth-first growth through 4-neighbours that are valid and
+// IsDepthSimilar(depth_curr, depth_neighbor, th) — asymmetric (divides by the current pixel's depth), so a segment is what is REACHABLE
+// from its seed among the pixels no earlier segment took; segments of fewer than speckle_size pixels are zeroed (depth, normal, conf).
+// Returns the number of zeroed pixels that were valid. normal / conf may be NULL.
+int orc_remove_small_segments(float* depth, float* normal, float* conf, int w, int h, unsigned speckle_size, float th) {
+	std::vector<unsigned char> done((size_t)w*h, 0);
+	std::vector<int> seg((size_t)w*h);
+	int removed = 0;
+	for (int u=0; u<w; ++u) for (int v=0; v<h; ++v) {
+		if (done[(size_t)v*w+u]) continue;
+		size_t count = 1, curr = 0;
+		seg[0] = v*w+u;
+		while (curr < count) {
+			const int a = seg[curr];
+			const int ax = a%w, ay = a/w;
+			const float dc = depth[a];
+			if (dc > 0) {
+				const int nx[4] = {ax-1, ax+1, ax, ax}, ny[4] = {ay, ay, ay-1, ay+1};
+				for (int i=0; i<4; ++i) {
+					if (nx[i] < 0 || ny[i] < 0 || nx[i] >= w || ny[i] >= h) continue;
+					const int b = ny[i]*w+nx[i];
+					if (done[b]) continue;
+					const float dn = depth[b];
+					if (dn > 0 && std::fabs(dc-dn)/dc < th) { seg[count++] = b; done[b] = 1; } // IsDepthSimilar, Util.inl:657-669
+				}
+			}
+			++curr;
+			done[a] = 1;
+		}
+		if (count < speckle_size)
+			for (size_t i=0; i<count; ++i) {
+				const int a = seg[i];
+				if (depth[a] != 0) ++removed;
+				depth[a] = 0;
+				if (normal) { normal[(size_t)a*3] = normal[(size_t)a*3+1] = normal[(size_t)a*3+2] = 0; }
+				if (conf) conf[a] = 0;
+			}
+	}
+	return removed;
+}
+
+// The stock small-gap branch of DepthMapsData::GapInterpolation (SceneDensify.cpp:2294-2352 row-wise, :2640-2683 column-wise; the fork's
+// large-gap branches read uninitialised variables and are not restated — DESIGN.md §6): runs of <= gap_size invalid pixels between two
+// valid pixels whose depths are IsDepthSimilar(first, last, th) are filled with linearly interpolated depths and (through
+// Normal2Dir / Dir2Normal) normals; their confidence becomes the smaller of the two ends'. Rows first, then columns (which see the rows'
+// result). normal / conf may be NULL. Returns the number of filled pixels.
+int orc_gap_interpolation(float* depth, float* normal, float* conf, int w, int h, unsigned gap_size, float th) {
+	int filled = 0;
+	auto pass = [&](bool rows) {
+		const int outer = rows ? h : w, inner = rows ? w : h;
+		for (int o=0; o<outer; ++o) {
+			unsigned count = 0;
+			for (int i=0; i<inner; ++i) {
+				auto idx = [&](int k) { return rows ? (size_t)o*w+k : (size_t)k*w+o; };
+				const float d1 = depth[idx(i)];
+				if (d1 <= 0) { ++count; continue; }
+				if (count == 0) continue;
+				if (count <= gap_size && (unsigned)i > count) {
+					int k = i-(int)count;
+					const int first = k-1;
+					const float d0 = depth[idx(first)];
+					if (std::fabs(d0-d1)/d0 < th) {
+						const float diff = (d1-d0)/(float)(count+1);
+						float d = d0;
+						const float c = conf ? std::min(conf[idx(first)], conf[idx(i)]) : 0.f;
+						float p1x = 0, p1y = 0, dx = 0, dy = 0;
+						if (normal) {
+							float p2x, p2y;
+							Normal2Dir(Vec3f{normal[idx(first)*3], normal[idx(first)*3+1], normal[idx(first)*3+2]}, p1x, p1y);
+							Normal2Dir(Vec3f{normal[idx(i)*3], normal[idx(i)*3+1], normal[idx(i)*3+2]}, p2x, p2y);
+							dx = (p2x-p1x)/(float)(count+1); dy = (p2y-p1y)/(float)(count+1);
+						}
+						do {
+							depth[idx(k)] = (d += diff);
+							if (normal) { p1x += dx; p1y += dy; Vec3f n; Dir2Normal(p1x, p1y, n); normal[idx(k)*3] = n.x; normal[idx(k)*3+1] = n.y; normal[idx(k)*3+2] = n.z; }
+							if (conf) conf[idx(k)] = c;
+							++filled;
+						} while (++k < i);
+					}
+				}
+				count = 0;
+			}
+		}
+	};
+	pass(true); pass(false);
+	return filled;
+}
 
 } // extern "C"

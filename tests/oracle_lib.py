@@ -50,6 +50,8 @@ def lib():
         L.orc_score_hypotheses.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp]
         L.orc_end_depthmap.argtypes = [vp, C.c_int]
         L.orc_filter_depthmap.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, vp]
+        L.orc_remove_small_segments.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_uint, C.c_float]
+        L.orc_gap_interpolation.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_uint, C.c_float]
         L.orc_fuse.argtypes = [vp, C.c_int, C.c_int]
         L.orc_fuse_get.argtypes = [vp, vp, vp, vp, vp]
         L.orc_fuse_get_views.argtypes = [vp, vp, vp]

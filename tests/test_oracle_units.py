@@ -274,3 +274,33 @@ def test_point_normals_and_triangulated_init_oracles_closed_form():
     assert np.array_equal(d > 0, inside) and np.allclose(d[inside], 4.0, rtol=1e-6) and np.allclose(np.abs(n[inside]), [0, 0, 1], atol=1e-6)
     d1, _ = T.rasterize(v, faces[:1], K, 16, 12); d2, _ = T.rasterize(v, faces[1:], K, 16, 12)
     assert not np.any((d1 > 0) & (d2 > 0)) and np.array_equal((d1 > 0) | (d2 > 0), inside)  # the diagonal's pixels belong to exactly one face
+
+
+def test_speckle_filter_and_gap_interpolation_oracles_hand_cases():
+    """oracle/oracle_capi.cpp: orc_remove_small_segments / orc_gap_interpolation on cases small enough to check by hand."""
+    import ctypes as C
+    L = O.lib()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    # a 6x5 map: a 2x2 island of depth 2 inside a field of depth 1 (not similar at 1 %), one hole
+    d = np.ones((5, 6), np.float32); d[1:3, 1:3] = 2.0; d[4, 5] = 0
+    c = np.full((5, 6), 0.5, np.float32)
+    d1, c1 = d.copy(), c.copy()
+    assert L.orc_remove_small_segments(p(d1), None, p(c1), 6, 5, 5, C.c_float(0.01)) == 4      # the 4-pixel island dies at speckle size 5
+    assert (d1[1:3, 1:3] == 0).all() and (c1[1:3, 1:3] == 0).all() and (d1 == 1).sum() == 25
+    d2 = d.copy()
+    assert L.orc_remove_small_segments(p(d2), None, None, 6, 5, 4, C.c_float(0.01)) == 0      # ... and survives at 4
+    # asymmetric similarity: 1.0 -> 1.0101 passes (|diff|/1.0 = 0.0101 >= 0.0101? no) — use a pair whose two quotients straddle the threshold
+    a, b, th = np.float32(1.0), np.float32(1.0102), 0.0101
+    assert abs(a - b) / a >= th > abs(a - b) / b                                              # b -> a similar, a -> b not
+    row = np.array([[a, b]], np.float32)
+    r1 = row.copy()
+    # seeds in column-major order: pixel a first; a cannot reach b, so {a} and {b} are two 1-pixel segments
+    assert L.orc_remove_small_segments(p(r1), None, None, 2, 1, 2, C.c_float(th)) == 2
+    r2 = row[:, ::-1].copy()
+    # now b is the first seed and reaches a: one 2-pixel segment survives
+    assert L.orc_remove_small_segments(p(r2), None, None, 2, 1, 2, C.c_float(th)) == 0
+    # gap interpolation: a row 1 0 0 4 -> not similar (no fill); 1 0 0 1.03 at th 0.05 -> 1.01, 1.02
+    g = np.array([[1, 0, 0, 1.03, 0, 0, 0, 0, 0, 0, 0, 0, 1.0]], np.float32)
+    cf = np.array([[0.9, 0, 0, 0.4, 0, 0, 0, 0, 0, 0, 0, 0, 0.7]], np.float32)
+    assert L.orc_gap_interpolation(p(g), None, p(cf), 13, 1, 7, C.c_float(0.05)) == 2
+    assert np.allclose(g[0, :4], [1, 1.01, 1.02, 1.03], atol=1e-6) and np.allclose(cf[0, 1:3], 0.4) and (g[0, 4:12] == 0).all()   # the 8-pixel gap stays
