@@ -62,6 +62,10 @@ def lib():
         L.hcmvs_host_get_image_info.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_uint32), vp, vp, vp, C.c_char_p, i32]
         L.hcmvs_host_get_image_bgr.argtypes = [vp, i32, vp]
         L.hcmvs_host_get_sparse.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), vp, vp, vp, vp]
+        L.hcmvs_host_save_depthmap.argtypes = [C.c_char_p, vp, i32, i32]
+        L.hcmvs_host_save_normalmap.argtypes = [C.c_char_p, vp, i32, i32]
+        L.hcmvs_host_load_depthmap.argtypes = [C.c_char_p, vp, C.POINTER(i32), C.POINTER(i32)]
+        L.hcmvs_host_load_normalmap.argtypes = [C.c_char_p, vp, C.POINTER(i32), C.POINTER(i32)]
         L.hcmvs_host_load_image.argtypes = [C.c_char_p, C.POINTER(i32), C.POINTER(i32), vp]
         _lib = L
     return _lib
@@ -356,3 +360,34 @@ def read_dmap(path):
     conf = np.zeros((h.value, w.value), np.float32) if hc.value else None
     L.hcmvs_host_read_dmap(path.encode(), _p(ids), _p(K), _p(R), _p(Cc), _p(mm), _p(depth), _p(normal), _p(conf))
     return dict(ids=ids, K=K, R=R, C=Cc, dmin=float(mm[0]), dmax=float(mm[1]), depth=depth, normal=normal, conf=conf)
+
+
+def save_depthmap(path, depth):
+    """MVS::SaveDepthMap: depthmap/depthNNNN.dmap (zlib-compressed Boost binary archive of TImage<float>)."""
+    d = np.ascontiguousarray(depth, np.float32)
+    if lib().hcmvs_host_save_depthmap(str(path).encode(), _p(d), d.shape[1], d.shape[0]) != 0:
+        raise RuntimeError("SaveDepthMap failed")
+
+
+def save_normalmap(path, normal):
+    n = np.ascontiguousarray(normal, np.float32)
+    if lib().hcmvs_host_save_normalmap(str(path).encode(), _p(n), n.shape[1], n.shape[0]) != 0:
+        raise RuntimeError("SaveNormalMap failed")
+
+
+def load_depthmap(path):
+    w, h = C.c_int(), C.c_int()
+    if lib().hcmvs_host_load_depthmap(str(path).encode(), None, C.byref(w), C.byref(h)) != 0:
+        raise RuntimeError("LoadDepthMap failed")
+    d = np.zeros((h.value, w.value), np.float32)
+    lib().hcmvs_host_load_depthmap(str(path).encode(), _p(d), C.byref(w), C.byref(h))
+    return d
+
+
+def load_normalmap(path):
+    w, h = C.c_int(), C.c_int()
+    if lib().hcmvs_host_load_normalmap(str(path).encode(), None, C.byref(w), C.byref(h)) != 0:
+        raise RuntimeError("LoadNormalMap failed")
+    n = np.zeros((h.value, w.value, 3), np.float32)
+    lib().hcmvs_host_load_normalmap(str(path).encode(), _p(n), C.byref(w), C.byref(h))
+    return n

@@ -214,6 +214,14 @@ private:
 bool DenseReconstructionDistributed(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, const ViewSelectionParams& VS, uint64_t seed, bool runFilter,
 	int rank, int world, DenseReconstructionStats* stats, std::string* err);
 
+// depthmap/depthNNNN.dmap, normalmap/normalNNNN.dmap — the fork's hand-off between the pyramid levels of run.sh (MVS::SaveDepthMap /
+// LoadDepthMap / SaveNormalMap / LoadNormalMap, DepthMap.cpp:2368-2393): zlib-compressed Boost binary archives of TImage<float> /
+// TImage<Point3f>, written / parsed from the documented archive layout (host/boost_dmap.cpp; byte parity with Boost itself unverified)
+bool SaveDepthMap(const std::string& fileName, const float* depth, int w, int h);
+bool LoadDepthMap(const std::string& fileName, std::vector<float>& depth, int& w, int& h);
+bool SaveNormalMap(const std::string& fileName, const float* normal, int w, int h);
+bool LoadNormalMap(const std::string& fileName, std::vector<float>& normal, int& w, int& h);
+
 bool ExportDepthDataRaw(const std::string& fileName, const std::string& imageFileName, const std::vector<uint32_t>& IDs, int imageW, int imageH,
 	const double K[9], const double R[9], const double C[3], float dMin, float dMax, int w, int h,
 	const float* depth, const float* normal, const float* conf);

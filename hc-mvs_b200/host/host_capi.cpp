@@ -235,6 +235,21 @@ int hcmvs_host_read_dmap(const char* file, uint32_t* ids, double K[9], double R[
 }
 
 // ---- triangulated initialisation (triangulate.cpp)
+int hcmvs_host_save_depthmap(const char* file, const float* depth, int w, int h) { return file && SaveDepthMap(file, depth, w, h) ? 0 : -1; }
+int hcmvs_host_save_normalmap(const char* file, const float* normal, int w, int h) { return file && SaveNormalMap(file, normal, w, h) ? 0 : -1; }
+int hcmvs_host_load_depthmap(const char* file, float* depth, int* w, int* h) { // depth == NULL: only the size
+	if (!file || !w || !h) return -1;
+	std::vector<float> d; if (!LoadDepthMap(file, d, *w, *h)) return -1;
+	if (depth) memcpy(depth, d.data(), d.size()*4);
+	return 0;
+}
+int hcmvs_host_load_normalmap(const char* file, float* normal, int* w, int* h) {
+	if (!file || !w || !h) return -1;
+	std::vector<float> d; if (!LoadNormalMap(file, d, *w, *h)) return -1;
+	if (normal) memcpy(normal, d.data(), d.size()*4);
+	return 0;
+}
+
 int hcmvs_host_delaunay(const double* xy, int n, uint32_t* tris, int cap_tris) {
 	if (!xy || n < 3) return -1;
 	std::vector<double> pts(xy, xy+(size_t)n*2); std::vector<uint32_t> t;

@@ -64,6 +64,14 @@ int hcmvs_host_write_dmap(const char* file, const char* image_name, const uint32
 int hcmvs_host_read_dmap_header(const char* file, int* w, int* h, int* n_ids, int* has_normal, int* has_conf);
 int hcmvs_host_read_dmap(const char* file, uint32_t* ids, double K[9], double R[9], double C[3], float* dminmax, float* depth, float* normal, float* conf);
 
+/* The fork's depthmap/depthNNNN.dmap and normalmap/normalNNNN.dmap hand-off files between the pyramid levels of run.sh (MVS::SaveDepthMap /
+ * LoadDepthMap / SaveNormalMap / LoadNormalMap, DepthMap.cpp:2368-2393): zlib-compressed Boost binary archives, written / parsed from the
+ * documented archive layout (byte parity with a Boost build unverified). load: call with a NULL array first to learn w x h. */
+int hcmvs_host_save_depthmap(const char* file, const float* depth, int w, int h);
+int hcmvs_host_save_normalmap(const char* file, const float* normal, int w, int h);
+int hcmvs_host_load_depthmap(const char* file, float* depth, int* w, int* h);
+int hcmvs_host_load_normalmap(const char* file, float* normal, int* w, int* h);
+
 /* Triangulated depth-map initialisation, host half (MVS::TriangulatePointsDelaunay, DepthMap.cpp:1797-1876).
  * hcmvs_host_delaunay: Delaunay triangulation of n 2-D points (what CGAL::Delaunay_triangulation_2 computes for the reference);
  * returns the number of faces, writes up to cap_tris index triples (counter-clockwise, smallest index first, sorted).

@@ -198,3 +198,33 @@ def test_pointcloud_filter_removal_order_and_ply_writer(built, tmp_path):
     rec = np.frombuffer(body, dtype=np.dtype([("p", "<f4", 3), ("rgb", "u1", 3), ("n", "<f4", 3)]))
     assert len(rec) == len(ids) and np.array_equal(rec["p"], xyz[ids]) and np.array_equal(rec["rgb"], col[ids][:, ::-1]) and np.array_equal(rec["n"], nrm[ids])
     hs.close()
+
+
+def test_boost_archive_dmap_round_trip_and_documented_layout(tmp_path):
+    """depthmap/*.dmap / normalmap/*.dmap of the fork (MVS::SaveDepthMap / SaveNormalMap, DepthMap.cpp:2368-2393): round trip through the
+    host reader, and the bytes re-derived independently here from the documented Boost binary_oarchive layout (zlib + struct). Byte parity
+    with a real Boost build cannot be checked in this image (no Boost)."""
+    import struct, zlib
+    from hcmvs_b200 import host
+    rng = np.random.default_rng(3)
+    d = rng.uniform(0, 9, (7, 11)).astype(np.float32); d[2, 3] = 0
+    n = rng.standard_normal((7, 11, 3)).astype(np.float32)
+    fd, fn = tmp_path / "depth0000.dmap", tmp_path / "normal0000.dmap"
+    host.save_depthmap(fd, d); host.save_normalmap(fn, n)
+    assert np.array_equal(host.load_depthmap(fd), d) and np.array_equal(host.load_normalmap(fn), n)
+    head = struct.pack("<Q", 22) + b"serialization::archive" + struct.pack("<HBBBBi", 17, 4, 8, 4, 8, 1)
+    cls = b"\x00" + struct.pack("<I", 0)                                    # tracking_type + version_type of a class seen for the first time
+    want_d = head + cls * 3 + struct.pack("<ii", 11, 7) + d.tobytes()           # TImage : TDMatrix : cv::Mat_<float>, cols, rows, one raw block
+    want_n = head + cls * 3 + struct.pack("<ii", 11, 7) + cls * 2 + n.tobytes() # ... elements one by one; the first carries TPoint3 / cv::Point3_
+    raw_d, raw_n = fd.read_bytes(), fn.read_bytes()
+    assert raw_d[:2] == b"\x78\x01"                                          # zlib stream, best_speed
+    assert zlib.decompress(raw_d) == want_d and zlib.decompress(raw_n) == want_n
+    # a file written by another zlib level / implementation still loads; garbage and truncated files are refused
+    (tmp_path / "other.dmap").write_bytes(zlib.compress(want_d, 9))
+    assert np.array_equal(host.load_depthmap(tmp_path / "other.dmap"), d)
+    (tmp_path / "bad.dmap").write_bytes(raw_d[:len(raw_d) // 2])
+    with pytest.raises(RuntimeError):
+        host.load_depthmap(tmp_path / "bad.dmap")
+    (tmp_path / "bad2.dmap").write_bytes(zlib.compress(b"x" * 64))
+    with pytest.raises(RuntimeError):
+        host.load_depthmap(tmp_path / "bad2.dmap")
