@@ -35,8 +35,11 @@ def config_dict(args, n_views, width, height):
     if args.config == 5:
         return {"workload": WORKLOADS[5], "scale": args.scale, "views": n_views, "image": [width, height], "neighbours": 12, "patchmatch_iters": 0,
                 "stages": "fuse"}
-    return {"workload": WORKLOADS[args.config], "scale": args.scale, "views": n_views, "image": [width, height], "neighbours": 5, "patchmatch_iters": 3,
-            "stages": "estimate(A+B+C) + filter + fuse"}
+    d = {"workload": WORKLOADS[args.config], "scale": args.scale, "views": n_views, "image": [width, height], "neighbours": 5, "patchmatch_iters": 3,
+         "stages": "estimate(A+B+C) + filter + fuse"}
+    if args.adapthalfwin != 5:
+        d["adapthalfwin"] = args.adapthalfwin
+    return d
 
 
 def parse():
@@ -51,6 +54,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sampler", type=int, default=0)
+    ap.add_argument("--adapthalfwin", type=int, default=5, help="OPTDENSE::adapthalfwin: 5 = 6x6 texels per patch (BASELINE's configs, the CLI default), 7 = 8x8 (the authors' run.py)")
     ap.add_argument("--e2e-dmap-dir", default="", help="also time the end-to-end call WITH the raw depthNNNN.dmap files written to this directory (streamed behind the GPU)")
     ap.add_argument("--no-split-rows", action="store_true", help="N>1: do not split the views of the incomplete last round into row bands")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "torch"],
@@ -153,7 +157,7 @@ def cpu_oracle_sample(args, syn, imgs, seconds_budget=25.0, stages=True):
     import oracle_lib as O
     cores = os.cpu_count() or 1
     ref = syn.n_views // 2
-    osc = O.OracleScene(nNumViews=5, nEstimationIters=3, nEstimationIters_external=1, nMinViewsTrustPoint=1, adapthalfwin=5)
+    osc = O.OracleScene(nNumViews=5, nEstimationIters=3, nEstimationIters_external=1, nMinViewsTrustPoint=1, adapthalfwin=args.adapthalfwin)
     for i in range(syn.n_views):
         osc.add_image(syn.K[i], syn.R[i], syn.Cc[i], bgr=imgs[i])
     osc.set_sparse(syn.sparse_xyz, syn.sparse_off, syn.sparse_views)
@@ -440,7 +444,7 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    params = dict(nNumViews=5, nEstimationIters=3, nEstimationIters_external=1, nMinViewsTrustPoint=1, adapthalfwin=5, sampler=args.sampler)
+    params = dict(nNumViews=5, nEstimationIters=3, nEstimationIters_external=1, nMinViewsTrustPoint=1, adapthalfwin=args.adapthalfwin, sampler=args.sampler)
     ctx = api.Context(local, **params)
     P = ctx.params
     lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
