@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libhcmvs_b200.so")
 EXPORTS = [
     "hcmvs_default_params", "hcmvs_last_error", "hcmvs_create", "hcmvs_destroy", "hcmvs_set_params", "hcmvs_sync",
     "hcmvs_set_view", "hcmvs_set_neighbors", "hcmvs_set_neighbor_image", "hcmvs_init_depthmap", "hcmvs_init_depthmap_triangles", "hcmvs_download_depthmap_begin", "hcmvs_download_depthmap_wait", "hcmvs_set_depthmap", "hcmvs_get_depthmap",
-    "hcmvs_set_prior", "hcmvs_set_coarse_estimate", "hcmvs_get_coarse_estimate", "hcmvs_snapshot_maps", "hcmvs_restore_snapshot", "hcmvs_remove_small_segments", "hcmvs_gap_interpolation", "hcmvs_set_view_remote", "hcmvs_comm_allgather_host", "hcmvs_get_gradient_map", "hcmvs_score_depthmap", "hcmvs_estimate_depthmap", "hcmvs_estimate_depthmap_rows", "hcmvs_end_depthmap", "hcmvs_score_hypotheses",
+    "hcmvs_set_prior", "hcmvs_set_coarse_estimate", "hcmvs_get_coarse_estimate", "hcmvs_snapshot_maps", "hcmvs_restore_snapshot", "hcmvs_remove_small_segments", "hcmvs_gap_interpolation", "hcmvs_set_view_remote", "hcmvs_comm_allgather_host", "hcmvs_pin_host_memory", "hcmvs_unpin_host_memory", "hcmvs_get_gradient_map", "hcmvs_score_depthmap", "hcmvs_estimate_depthmap", "hcmvs_estimate_depthmap_rows", "hcmvs_end_depthmap", "hcmvs_score_hypotheses",
     "hcmvs_filter_depthmap", "hcmvs_commit_filtered", "hcmvs_set_fuse_priority", "hcmvs_fuse_depthmaps",
     "hcmvs_free_pointcloud", "hcmvs_get_fused_device", "hcmvs_get_fused_support", "hcmvs_estimate_point_colors", "hcmvs_estimate_point_normals", "hcmvs_pointcloud_filter", "hcmvs_download_fused", "hcmvs_download_fused_pinned", "hcmvs_get_depthmap_device", "hcmvs_set_depth_range", "hcmvs_alloc_depthmap",
     "hcmvs_comm_unique_id", "hcmvs_comm_init", "hcmvs_exchange_maps", "hcmvs_exchange_wait", "hcmvs_export_maps_d", "hcmvs_import_maps_d", "hcmvs_get_timers", "hcmvs_reset_timers", "hcmvs_stream",

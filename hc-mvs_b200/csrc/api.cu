@@ -107,6 +107,16 @@ extern "C" int hcmvs_set_params(hcmvs_ctx* ctx, const hcmvs_params* p) {
 	const int r = CheckParams(*p); if (r != HCMVS_OK) return r;
 	ctx->P = *p; return HCMVS_OK;
 }
+extern "C" int hcmvs_pin_host_memory(void* p, uint64_t bytes) {
+	if (!p || !bytes) { hcmvs_set_error("null argument"); return HCMVS_ERR_ARG; }
+	CK(cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault));
+	return HCMVS_OK;
+}
+extern "C" int hcmvs_unpin_host_memory(void* p) {
+	if (!p) return HCMVS_OK;
+	CK(cudaHostUnregister(p));
+	return HCMVS_OK;
+}
 extern "C" int hcmvs_sync(hcmvs_ctx* ctx) { if (!ctx) return HCMVS_ERR_ARG; cudaSetDevice(ctx->device); CK(cudaStreamSynchronize(ctx->stream)); return HCMVS_OK; }
 extern "C" void* hcmvs_stream(hcmvs_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 

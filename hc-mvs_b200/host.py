@@ -36,6 +36,7 @@ def lib():
         L.hcmvs_host_init_depth.argtypes = [vp, i32, vp, vp]
         L.hcmvs_host_dense_reconstruction.argtypes = [vp, vp, C.POINTER(api.Params), C.c_uint64, i32, C.c_char_p, vp]
         L.hcmvs_host_dense_reconstruction_distributed.argtypes = [vp, vp, C.POINTER(api.Params), C.c_uint64, i32, i32, i32, vp]
+        L.hcmvs_host_pin_images.argtypes = [vp, i32]
         L.hcmvs_host_dist_prepare.argtypes = [vp, vp, C.POINTER(api.Params), i32, i32]
         L.hcmvs_host_dist_upload_initial.argtypes = [vp]
         L.hcmvs_host_dist_info.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
@@ -173,6 +174,10 @@ class HostScene:
     def _ckd(self, r):
         if r != 0:
             raise RuntimeError(self.L.hcmvs_host_last_error(self.h).decode())
+
+    def pin_images(self, pin=True):
+        """Page-lock the images' pixel buffers (uploads at PCIe rate); returns the number of pinned buffers."""
+        return self.L.hcmvs_host_pin_images(self.h, int(pin))
 
     def dist_prepare(self, ctx, rank, world):
         self._ckd(self.L.hcmvs_host_dist_prepare(self.h, ctx.h, C.byref(ctx.params), int(rank), int(world)))

@@ -171,9 +171,10 @@ struct DenseReconstructionStats { double secSelect = 0, secUpload = 0, secEstima
 bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, const ViewSelectionParams& VS, uint64_t seed, bool runFilter,
 	const std::string& dmapDir, DenseReconstructionStats* stats, std::string* err);
 
-// The multi-GPU schedule (no reference counterpart: the reference is single-node CPU code). Views are dealt round-robin in
-// FuseDepthMaps' connection order (decreasing scored-neighbour count, ties by index — SceneDensify.cpp:3286-3303): view order[k] is
-// estimated in round k / world by rank k % world. With splitRows the views of the last, incomplete round are estimated in `world` row
+// The multi-GPU schedule (no reference counterpart: the reference is single-node CPU code). MakeShardPlan orders the views by
+// decreasing nScoredNeighbors, ties by index, and deals them round-robin: view order[k] is estimated in round k / world by rank k % world.
+// (DistributedReconstruction passes equal scores, i.e. INDEX order: the plan then needs no view selection, so estimation starts while the
+// other views are still being selected.) With splitRows the views of the last, incomplete round are estimated in `world` row
 // bands by all ranks (49 views on 8 ranks: 6 whole rounds + 1 view an eighth of which every rank estimates, instead of one rank
 // estimating a 7th view while seven wait). Filtering of view order[k] always stays with rank k % world.
 struct ShardPlan {
@@ -202,12 +203,13 @@ public:
 	~DistributedReconstruction();
 	DistributedReconstruction(const DistributedReconstruction&) = delete;
 	DistributedReconstruction& operator=(const DistributedReconstruction&) = delete;
-	bool Prepare(bool lazyInitialMaps = false); // lazy: Run() makes + uploads the initial maps on worker threads ahead of the estimation (one-call job)
+	bool Prepare(bool lazy = false); // lazy (the one-call job): only the images move here; Run() selects views + makes the initial maps on worker threads AHEAD of the estimation
 	bool UploadInitial();
 	bool Run(uint64_t seed, bool runFilter, bool download);
 	const std::string& Error() const;
 	const DenseReconstructionStats& Stats() const;
 	const ShardPlan& Plan() const;
+	size_t ValidViews() const; // views with enough neighbours (known after Prepare(false) / Run)
 private:
 	struct Impl; Impl* impl;
 };

@@ -68,149 +68,49 @@ std::vector<int32_t> ShardPlan::Owners(size_t nViews, const std::vector<char>* o
 }
 void ShardPlan::RowsOf(int rank, int height, int& r0, int& r1) const { r0 = (int)((long long)rank*height/world); r1 = (int)((long long)(rank+1)*height/world); }
 
-namespace {
-// what one rank tells the others about a view it selected
-struct SelHeader { uint32_t valid, nScored, nNeighbors, nPoints; float avgDepth; uint32_t pad[3]; };
-static_assert(sizeof(SelHeader) == 32, "record layout");
-}
 
 struct DistributedReconstruction::Impl {
 	Scene& scene; hcmvs_ctx* ctx; hcmvs_params P; ViewSelectionParams VS; int rank, world;
 	DepthMapsData data;
 	ShardPlan plan; std::vector<uint32_t> valid, mineWhole, split, mine;
 	struct Init { std::vector<float> depth; std::vector<double> vertices; std::vector<uint32_t> tris; };
-	std::vector<Init> init; // initial maps (host) of the views this rank estimates
-	std::vector<uint32_t> est; // those views in estimation order
-	bool lazyInit = false;     // Run() makes the initial maps on worker threads, ahead of the estimation
+	std::vector<Init> init;     // initial maps (host) of the views this rank estimates
+	std::vector<uint32_t> est;  // those views in estimation order: this rank's whole views by round, then the row-split views
+	std::vector<char> ok;       // per image: SelectViews succeeded (own + split views after SelectOne, all views after Gather)
+	std::vector<char> inited;   // per image: InitViews done on this rank
+	bool lazy = false;          // one-call job: selection + initial maps run on worker threads AHEAD of the estimation inside Run()
+	bool gathered = false;
 	DenseReconstructionStats st;
 	std::string err;
 	Impl(Scene& s, hcmvs_ctx* c, const hcmvs_params& p, const ViewSelectionParams& vs, int r, int w): scene(s), ctx(c), P(p), VS(vs), rank(r), world(w), data(s, c, p, vs) {}
 	bool fail(const std::string& m) { err = "rank "+std::to_string(rank)+": "+m; return false; }
 	bool lib(const char* what) { return fail(std::string(what)+": "+hcmvs_last_error()); }
+	int Owner(uint32_t i) const { return (int)(i%(uint32_t)world); } // uploads the image, selects its neighbours, estimates it (unless row-split), filters it
+	unsigned Threads(size_t work) const { const unsigned hc = std::thread::hardware_concurrency(); return (unsigned)std::max<size_t>(1, std::min<size_t>((hc > 1 ? hc-1 : 1u)/(unsigned)world+1u, work)); }
 	bool Prepare();
-	bool MakeInit(uint32_t i);
+	bool SelectOne(uint32_t i);   // SelectViews + the initial maps of a view this rank estimates (worker threads)
+	bool Gather();                // all-gather of the selection results; neighbour lists of every view on this rank
+	bool InitOne(uint32_t i);     // InitViews (neighbour lists to the device)
 	bool UploadOne(uint32_t i);
 	bool UploadInitial();
 	bool Run(uint64_t seed, bool runFilter, bool download);
 };
 
-bool DistributedReconstruction::Impl::Prepare() {
-	st = DenseReconstructionStats();
-	const uint32_t nImages = (uint32_t)scene.images.size();
-	const double t0 = NowD();
-	for (Image& im: scene.images) { im.camera.ComposeP(); im.neighbors.clear(); }
-	for (DepthData& dd: data.arrDepthData) dd = DepthData();
-	auto uploader = [&](uint32_t i) { return (int)(i%(uint32_t)world); };
-	// ---- 1. this rank's share of the view selection on worker threads, while this thread uploads this rank's share of the images
-	std::vector<char> ok(nImages, 0);
-	// colour travels with the gray image; a rank only knows it for the images it holds, and the scene is homogeneous in that respect
-	uint32_t hasColor = 0;
-	for (uint32_t i=0; i<nImages; ++i) if (uploader(i) == rank && !scene.images[i].bgr.empty()) hasColor = 1;
-	{
-		std::vector<uint32_t> all((size_t)world);
-		if (hcmvs_comm_allgather_host(ctx, &hasColor, all.data(), sizeof(uint32_t)) != HCMVS_OK) return lib("hcmvs_comm_allgather_host");
-		hasColor = *std::max_element(all.begin(), all.end());
-	}
-	{
-		std::atomic<uint32_t> next{0};
-		const unsigned hc = std::thread::hardware_concurrency();
-		const unsigned nt = std::max(1u, std::min((hc > 1 ? hc-1 : 1u)/(unsigned)world+1u, nImages));
-		std::vector<std::thread> pool;
-		for (unsigned t=0; t<nt; ++t) pool.emplace_back([&]() {
-			uint32_t i;
-			while ((i = next.fetch_add(1)) < nImages) if (uploader(i) == rank) ok[i] = data.SelectViews(i) ? 1 : 0;
-		});
-		bool upOk = true; std::string upErr;
-		for (uint32_t i=0; i<nImages && upOk; ++i) {
-			Image& im = scene.images[i];
-			if (uploader(i) == rank) {
-				if (im.gray.empty() && im.bgr.empty()) { upOk = false; upErr = "image "+std::to_string(i)+" has no pixels on the rank that uploads it"; break; }
-				if (!data.UploadView(i)) { upOk = false; upErr = data.lastError; break; }
-				st.h2dBytes += (uint64_t)im.width*im.height*(4+(im.bgr.empty() ? 0 : 3));
-			} else {
-				if (hcmvs_set_view_remote(ctx, i, im.width, im.height, im.camera.K, im.camera.R, im.camera.C, (int)hasColor) != HCMVS_OK) { upOk = false; upErr = std::string("hcmvs_set_view_remote: ")+hcmvs_last_error(); break; }
-				data.arrDepthData[i].uploaded = true;
-			}
-		}
-		for (std::thread& th: pool) th.join();
-		if (!upOk) return fail(upErr);
-	}
-	// every image to every rank over NVLink, behind the uploads (the broadcasts wait for each image's upload event)
-	{
-		std::vector<int32_t> owner(nImages);
-		for (uint32_t i=0; i<nImages; ++i) owner[i] = uploader(i);
-		if (hcmvs_exchange_maps(ctx, owner.data(), nImages, HCMVS_EXCHANGE_IMAGES) != HCMVS_OK) return lib("hcmvs_exchange_maps(images)");
-	}
-	// ---- 2. all-gather the selection results: header + neighbour list + the view's sparse points (padded to the longest list)
-	{
-		uint32_t maxPts = 0;
-		for (uint32_t i=0; i<nImages; ++i) if (uploader(i) == rank && ok[i]) maxPts = std::max(maxPts, (uint32_t)data.arrDepthData[i].points.size());
-		std::vector<uint32_t> allMax((size_t)world);
-		if (hcmvs_comm_allgather_host(ctx, &maxPts, allMax.data(), sizeof(uint32_t)) != HCMVS_OK) return lib("hcmvs_comm_allgather_host");
-		maxPts = *std::max_element(allMax.begin(), allMax.end());
-		const size_t perView = sizeof(SelHeader)+HCMVS_MAX_FUSE_VIEWS*sizeof(ViewScore)+(size_t)maxPts*4;
-		const size_t slots = (nImages+(uint32_t)world-1)/(uint32_t)world; // views a rank selects at most
-		std::vector<char> send(perView*slots, 0), recv(perView*slots*(size_t)world);
-		for (uint32_t i=0; i<nImages; ++i) {
-			if (uploader(i) != rank) continue;
-			char* rec = send.data()+perView*(size_t)(i/(uint32_t)world);
-			const DepthData& dd = data.arrDepthData[i];
-			SelHeader h; std::memset(&h, 0, sizeof(h));
-			h.valid = ok[i]; h.nScored = (uint32_t)scene.images[i].neighbors.size(); h.avgDepth = scene.images[i].avgDepth;
-			h.nNeighbors = (uint32_t)std::min<size_t>(dd.neighbors.size(), HCMVS_MAX_FUSE_VIEWS); h.nPoints = ok[i] ? (uint32_t)dd.points.size() : 0u;
-			std::memcpy(rec, &h, sizeof(h));
-			if (h.nNeighbors) std::memcpy(rec+sizeof(h), dd.neighbors.data(), h.nNeighbors*sizeof(ViewScore));
-			if (h.nPoints) std::memcpy(rec+sizeof(h)+HCMVS_MAX_FUSE_VIEWS*sizeof(ViewScore), dd.points.data(), (size_t)h.nPoints*4);
-		}
-		if (hcmvs_comm_allgather_host(ctx, send.data(), recv.data(), send.size()) != HCMVS_OK) return lib("hcmvs_comm_allgather_host");
-		for (uint32_t i=0; i<nImages; ++i) {
-			if (uploader(i) == rank) continue;
-			const char* rec = recv.data()+send.size()*(size_t)uploader(i)+perView*(size_t)(i/(uint32_t)world);
-			SelHeader h; std::memcpy(&h, rec, sizeof(h));
-			DepthData& dd = data.arrDepthData[i];
-			ok[i] = (char)h.valid; dd.valid = h.valid != 0;
-			scene.images[i].avgDepth = h.avgDepth;
-			scene.images[i].neighbors.assign(h.nScored, ViewScore()); // only its size is read from here on (FuseDepthMaps' connection order)
-			dd.neighbors.resize(h.nNeighbors); if (h.nNeighbors) std::memcpy(dd.neighbors.data(), rec+sizeof(h), h.nNeighbors*sizeof(ViewScore));
-			dd.points.resize(h.nPoints); if (h.nPoints) std::memcpy(dd.points.data(), rec+sizeof(h)+HCMVS_MAX_FUSE_VIEWS*sizeof(ViewScore), (size_t)h.nPoints*4);
-		}
-	}
-	st.secSelect = NowD()-t0;
-	// ---- 3. neighbour lists on every rank (filter and fusion read them), then the plan
-	valid.clear(); std::vector<uint32_t> nScored(nImages, 0);
-	for (uint32_t i=0; i<nImages; ++i) {
-		nScored[i] = (uint32_t)scene.images[i].neighbors.size();
-		if (!ok[i]) continue;
-		if (!data.InitViews(i, P.nNumViews)) { if (!data.lastError.empty()) return fail(data.lastError); data.arrDepthData[i].valid = false; continue; }
-		valid.push_back(i);
-	}
-	if (valid.empty()) return fail("no image has enough neighbour views");
-	const double tInit = NowD();
-	plan = MakeShardPlan(valid, nScored, world, true);
-	mineWhole = plan.WholeViewsOf(rank); split = plan.SplitViews(); mine = plan.ViewsOf(rank);
-	if (getenv("HCMVS_DIST_DEBUG")) fprintf(stderr, "[dist %d] prepare: select+upload+exchange+allgather %.3f s, InitViews %.3f s\n", rank, st.secSelect, tInit-(t0+st.secSelect));
-	// ---- the initial maps of the views this rank estimates, on the host (SceneDensify.cpp:781-812): now, on worker threads — or, for
-	// the one-call job, by Run() on workers that stay ahead of the estimation (the first view starts as soon as ITS map exists)
-	init.assign(nImages, Init());
-	est = mineWhole; est.insert(est.end(), split.begin(), split.end());
-	if (!lazyInit) {
-		std::atomic<size_t> next{0}; std::atomic<bool> bad{false};
-		const unsigned hc = std::thread::hardware_concurrency();
-		const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>((hc > 1 ? hc-1 : 1u)/(unsigned)world+1u, est.size()));
-		std::vector<std::thread> pool;
-		for (unsigned t=0; t<nt; ++t) pool.emplace_back([&]() { size_t k; while ((k = next.fetch_add(1)) < est.size()) if (!MakeInit(est[k])) bad.store(true); });
-		for (std::thread& th: pool) th.join();
-		if (bad.load()) return fail("cannot triangulate the sparse points of a view");
-	}
-	return true;
-}
-
-bool DistributedReconstruction::Impl::MakeInit(uint32_t i) {
+bool DistributedReconstruction::Impl::SelectOne(uint32_t i) {
+	ok[i] = data.SelectViews(i) ? 1 : 0;
+	if (!ok[i]) return true;
 	DepthData& dd = data.arrDepthData[i];
-	if (P.nMinViewsTrustPoint >= 2) {
+	if (P.nMinViewsTrustPoint >= 2) { // SceneDensify.cpp:781-812
 		if (!TriangulateInit(scene, i, dd.points, true, init[i].vertices, init[i].tris, dd.dMin, dd.dMax)) return false;
 		dd.dMin *= 0.9f; dd.dMax *= 1.1f;
 	} else SparseInitDepth(scene, i, dd.points, init[i].depth, dd.dMin, dd.dMax);
+	return true;
+}
+
+bool DistributedReconstruction::Impl::InitOne(uint32_t i) {
+	if (inited[i] || !ok[i]) return true;
+	inited[i] = 1;
+	if (!data.InitViews(i, P.nNumViews)) { if (!data.lastError.empty()) return fail(data.lastError); data.arrDepthData[i].valid = false; ok[i] = 0; }
 	return true;
 }
 
@@ -227,51 +127,158 @@ bool DistributedReconstruction::Impl::UploadOne(uint32_t i) {
 }
 
 bool DistributedReconstruction::Impl::UploadInitial() {
-	for (uint32_t i: est) if (!UploadOne(i)) return false;
+	for (uint32_t i: est) if (ok[i] && !UploadOne(i)) return false;
+	return true;
+}
+
+bool DistributedReconstruction::Impl::Prepare() {
+	st = DenseReconstructionStats();
+	const uint32_t nImages = (uint32_t)scene.images.size();
+	const double t0 = NowD();
+	for (Image& im: scene.images) { im.camera.ComposeP(); im.neighbors.clear(); }
+	for (DepthData& dd: data.arrDepthData) dd = DepthData();
+	ok.assign(nImages, 0); inited.assign(nImages, 0); init.assign(nImages, Init()); gathered = false;
+	// The plan needs nothing but the image count: views in INDEX order, view i whole on rank i % world in round i / world, the last
+	// nImages % world views in row bands on every rank. (FuseDepthMaps' connection order, :3286-3303, only matters to the fusion itself;
+	// dealing by index lets a rank start estimating its first view while the other views are still being selected.)
+	{
+		std::vector<uint32_t> all(nImages), zeros(nImages, 0);
+		for (uint32_t i=0; i<nImages; ++i) all[i] = i;
+		plan = MakeShardPlan(all, zeros, world, true);
+	}
+	mineWhole = plan.WholeViewsOf(rank); split = plan.SplitViews(); mine = plan.ViewsOf(rank);
+	est = mineWhole; est.insert(est.end(), split.begin(), split.end());
+	// colour travels with the gray image; a rank only knows it for the images it holds, and the scene is homogeneous in that respect
+	uint32_t hasColor = 0;
+	for (uint32_t i=0; i<nImages; ++i) if (Owner(i) == rank && !scene.images[i].bgr.empty()) hasColor = 1;
+	{
+		std::vector<uint32_t> all((size_t)world);
+		if (hcmvs_comm_allgather_host(ctx, &hasColor, all.data(), sizeof(uint32_t)) != HCMVS_OK) return lib("hcmvs_comm_allgather_host");
+		hasColor = *std::max_element(all.begin(), all.end());
+	}
+	// ---- images: this rank's share over PCIe, everything to every rank over NVLink behind it (the broadcasts wait for each upload's event)
+	std::atomic<size_t> next{0}; std::atomic<bool> bad{false};
+	std::vector<std::thread> pool;
+	if (!lazy) // staged job: select + make the initial maps of this rank's views now, while this thread moves the images
+		for (unsigned t=0; t<Threads(est.size()); ++t) pool.emplace_back([&]() { size_t k; while ((k = next.fetch_add(1)) < est.size()) if (!SelectOne(est[k])) bad.store(true); });
+	bool upOk = true; std::string upErr;
+	for (uint32_t i=0; i<nImages && upOk; ++i) {
+		Image& im = scene.images[i];
+		if (Owner(i) == rank) {
+			if (im.gray.empty() && im.bgr.empty()) { upOk = false; upErr = "image "+std::to_string(i)+" has no pixels on the rank that uploads it"; break; }
+			if (!data.UploadView(i)) { upOk = false; upErr = data.lastError; break; }
+			st.h2dBytes += (uint64_t)im.width*im.height*(4+(im.bgr.empty() ? 0 : 3));
+		} else {
+			if (hcmvs_set_view_remote(ctx, i, im.width, im.height, im.camera.K, im.camera.R, im.camera.C, (int)hasColor) != HCMVS_OK) { upOk = false; upErr = std::string("hcmvs_set_view_remote: ")+hcmvs_last_error(); break; }
+			data.arrDepthData[i].uploaded = true;
+		}
+	}
+	if (upOk) {
+		std::vector<int32_t> owner(nImages);
+		for (uint32_t i=0; i<nImages; ++i) owner[i] = Owner(i);
+		if (hcmvs_exchange_maps(ctx, owner.data(), nImages, HCMVS_EXCHANGE_IMAGES) != HCMVS_OK) { upOk = false; upErr = std::string("hcmvs_exchange_maps(images): ")+hcmvs_last_error(); }
+	}
+	for (std::thread& th: pool) th.join();
+	if (!upOk) return fail(upErr);
+	if (bad.load()) return fail("cannot triangulate the sparse points of a view");
+	if (!lazy) {
+		for (uint32_t i: est) if (!InitOne(i)) return false; // before the gather: a view whose InitViews fails is reported as not valid
+		if (!Gather()) return false;
+		st.secSelect = NowD()-t0;
+	}
+	if (getenv("HCMVS_DIST_DEBUG")) fprintf(stderr, "[dist %d] prepare (%s) %.3f s\n", rank, lazy ? "images only; selection rides the estimation" : "images + selection + gather", NowD()-t0);
+	return true;
+}
+
+namespace {
+// what one rank tells the others about a view it selected
+struct SelHeader { uint32_t valid, nScored, nNeighbors, nPoints; float avgDepth; uint32_t pad[3]; };
+static_assert(sizeof(SelHeader) == 32, "record layout");
+}
+
+bool DistributedReconstruction::Impl::Gather() {
+	// all-gather of the selection results (header + neighbour list; every rank needs them for the filter decisions, rank 0 for the fusion),
+	// then the neighbour lists of every valid view go to the device
+	if (gathered) return true;
+	const uint32_t nImages = (uint32_t)scene.images.size();
+	const size_t perView = sizeof(SelHeader)+HCMVS_MAX_FUSE_VIEWS*sizeof(ViewScore);
+	const size_t slots = (nImages+(uint32_t)world-1)/(uint32_t)world; // views a rank owns at most
+	std::vector<char> send(perView*slots, 0), recv(perView*slots*(size_t)world);
+	for (uint32_t i=0; i<nImages; ++i) {
+		if (Owner(i) != rank) continue;
+		char* rec = send.data()+perView*(size_t)(i/(uint32_t)world);
+		const DepthData& dd = data.arrDepthData[i];
+		SelHeader h; std::memset(&h, 0, sizeof(h));
+		h.valid = ok[i]; h.nScored = (uint32_t)scene.images[i].neighbors.size(); h.avgDepth = scene.images[i].avgDepth;
+		h.nNeighbors = (uint32_t)std::min<size_t>(dd.neighbors.size(), HCMVS_MAX_FUSE_VIEWS);
+		std::memcpy(rec, &h, sizeof(h));
+		if (h.nNeighbors) std::memcpy(rec+sizeof(h), dd.neighbors.data(), h.nNeighbors*sizeof(ViewScore));
+	}
+	if (hcmvs_comm_allgather_host(ctx, send.data(), recv.data(), send.size()) != HCMVS_OK) return lib("hcmvs_comm_allgather_host");
+	const std::vector<uint32_t> splitViews = plan.SplitViews();
+	for (uint32_t i=0; i<nImages; ++i) {
+		if (Owner(i) == rank) continue;
+		if (std::find(splitViews.begin(), splitViews.end(), i) != splitViews.end()) continue; // every rank selected the row-split views itself
+		const char* rec = recv.data()+send.size()*(size_t)Owner(i)+perView*(size_t)(i/(uint32_t)world);
+		SelHeader h; std::memcpy(&h, rec, sizeof(h));
+		DepthData& dd = data.arrDepthData[i];
+		ok[i] = (char)h.valid; dd.valid = h.valid != 0;
+		scene.images[i].avgDepth = h.avgDepth;
+		scene.images[i].neighbors.assign(h.nScored, ViewScore()); // only its size is read from here on (FuseDepthMaps' connection order)
+		dd.neighbors.resize(h.nNeighbors); if (h.nNeighbors) std::memcpy(dd.neighbors.data(), rec+sizeof(h), h.nNeighbors*sizeof(ViewScore));
+	}
+	valid.clear();
+	for (uint32_t i=0; i<nImages; ++i) { if (!InitOne(i)) return false; if (ok[i]) valid.push_back(i); }
+	if (valid.empty()) return fail("no image has enough neighbour views");
+	gathered = true;
 	return true;
 }
 
 bool DistributedReconstruction::Impl::Run(uint64_t seed, bool runFilter, bool download) {
 	const uint32_t nImages = (uint32_t)scene.images.size();
-	// one-call job: the initial maps are made by workers, in estimation order, while this thread feeds the GPU
-	std::vector<std::atomic<int>> ready(lazyInit ? est.size() : 0);
+	const double tRun = NowD();
+	// one-call job: selection + initial maps are made by workers, in estimation order, while this thread feeds the GPU
+	std::vector<std::atomic<int>> ready(lazy ? est.size() : 0);
 	for (auto& r: ready) r.store(0);
-	std::atomic<size_t> nextInit{0};
+	std::atomic<size_t> nextSel{0};
 	std::vector<std::thread> pool;
 	struct Joiner { std::vector<std::thread>& p; ~Joiner() { for (std::thread& th: p) if (th.joinable()) th.join(); } } joiner{pool};
-	if (lazyInit) {
-		const unsigned hc = std::thread::hardware_concurrency();
-		const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>((hc > 1 ? hc-1 : 1u)/(unsigned)world+1u, est.size()));
-		for (unsigned t=0; t<nt; ++t) pool.emplace_back([&]() { size_t k; while ((k = nextInit.fetch_add(1)) < est.size()) ready[k].store(MakeInit(est[k]) ? 1 : -1, std::memory_order_release); });
+	if (lazy) {
+		// the other views this rank OWNS but does not estimate whole (none: owners estimate their views) need no work here; the row-split
+		// views are selected by every rank
+		for (unsigned t=0; t<Threads(est.size()); ++t) pool.emplace_back([&]() { size_t k; while ((k = nextSel.fetch_add(1)) < est.size()) ready[k].store(SelectOne(est[k]) ? 1 : -1, std::memory_order_release); });
 	}
-	size_t nextEst = 0; // position in `est` (whole views in round order, then the split views)
-	auto initialMaps = [&](uint32_t i) -> bool {
-		if (!lazyInit) return true;
-		int r; while ((r = ready[nextEst].load(std::memory_order_acquire)) == 0) std::this_thread::yield();
-		if (r < 0) return fail("cannot triangulate the sparse points of a view");
-		if (est[nextEst] != i) return fail("internal: estimation order");
-		++nextEst;
-		if (!UploadOne(i)) return false;
-		std::vector<float>().swap(init[i].depth); std::vector<double>().swap(init[i].vertices); std::vector<uint32_t>().swap(init[i].tris);
+	size_t nextEst = 0; // position in `est`
+	auto prepareView = [&](uint32_t i) -> bool { // neighbour lists + initial maps of a view about to be estimated; false + empty err: the view is not valid
+		if (lazy) {
+			int r; while ((r = ready[nextEst].load(std::memory_order_acquire)) == 0) std::this_thread::yield();
+			if (r < 0) return fail("cannot triangulate the sparse points of a view");
+			if (est[nextEst] != i) return fail("internal: estimation order");
+			++nextEst;
+			if (!InitOne(i)) return false;
+			if (ok[i]) { if (!UploadOne(i)) return false; std::vector<float>().swap(init[i].depth); std::vector<double>().swap(init[i].vertices); std::vector<uint32_t>().swap(init[i].tris); }
+		}
 		return true;
 	};
 	const double t1 = NowD();
-	// ---- 4. estimation: round s = the s-th view of every rank, broadcast in place behind round s+1; then the row-split views
+	// ---- estimation: round s = the s-th view of every rank, broadcast in place behind round s+1; then the row-split views
 	for (unsigned it=0; it<std::max(1u, P.nEstimationIters_external); ++it) { // SceneDensify.cpp:3684
 		if (it > 0 && P.viewspread && hcmvs_snapshot_maps(ctx) != HCMVS_OK) return lib("hcmvs_snapshot_maps");
 		for (int s=0; s<plan.wholeRounds; ++s) {
 			if ((size_t)s < mineWhole.size()) {
 				const uint32_t i = mineWhole[(size_t)s];
-				if (it == 0 && !initialMaps(i)) return false;
-				if (hcmvs_estimate_depthmap(ctx, i, (int)it, seed) != HCMVS_OK) return lib("hcmvs_estimate_depthmap");
+				if (it == 0 && !prepareView(i)) return false;
+				if (ok[i]) { if (hcmvs_estimate_depthmap(ctx, i, (int)it, seed) != HCMVS_OK) return lib("hcmvs_estimate_depthmap"); }
+				else if (it == 0 && hcmvs_alloc_depthmap(ctx, i) != HCMVS_OK) return lib("hcmvs_alloc_depthmap"); // a view without neighbours: empty maps keep the rounds aligned
 			}
 			const std::vector<int32_t> own = plan.RoundOwners(s, nImages);
 			if (hcmvs_exchange_maps(ctx, own.data(), nImages, HCMVS_EXCHANGE_ESTIMATED|HCMVS_EXCHANGE_ASYNC) != HCMVS_OK) return lib("hcmvs_exchange_maps");
 		}
 		for (uint32_t i: split) {
-			if (it == 0 && !initialMaps(i)) return false;
+			if (it == 0 && !prepareView(i)) return false;
 			int r0, r1; plan.RowsOf(rank, scene.images[i].height, r0, r1);
-			if (hcmvs_estimate_depthmap_rows(ctx, i, (int)it, seed, r0, r1) != HCMVS_OK) return lib("hcmvs_estimate_depthmap_rows");
+			if (ok[i]) { if (hcmvs_estimate_depthmap_rows(ctx, i, (int)it, seed, r0, r1) != HCMVS_OK) return lib("hcmvs_estimate_depthmap_rows"); }
+			else if (it == 0 && hcmvs_alloc_depthmap(ctx, i) != HCMVS_OK) return lib("hcmvs_alloc_depthmap");
 		}
 		if (!split.empty()) {
 			const std::vector<int32_t> own = plan.SplitOwners(nImages);
@@ -279,15 +286,20 @@ bool DistributedReconstruction::Impl::Run(uint64_t seed, bool runFilter, bool do
 		}
 		if (hcmvs_exchange_wait(ctx) != HCMVS_OK) return lib("hcmvs_exchange_wait");
 	}
+	if (lazy) {
+		for (std::thread& th: pool) if (th.joinable()) th.join();
+		if (!Gather()) return false; // off the critical path: the GPU is still busy with the last rounds
+		st.secSelect = NowD()-tRun;
+	}
 	if (hcmvs_sync(ctx) != HCMVS_OK) return lib("hcmvs_sync"); // attribution of the stage times only: the filter kernels queue behind the estimation anyway
 	const double t3 = NowD(); st.secEstimate = t3-t1;
-	// ---- 5. FilterDepthMap on the owners (neighbours with a depth map, at most 8; SceneDensify.cpp:4093-4185), exchange, commit
+	// ---- FilterDepthMap on the owners (neighbours with a depth map, at most 8; SceneDensify.cpp:4093-4185), exchange, commit
 	if (runFilter) {
 		std::vector<char> filtered(nImages, 0);
 		auto neighboursOf = [&](uint32_t i) {
 			const DepthData& dd = data.arrDepthData[i];
 			std::vector<uint32_t> idxNb;
-			for (uint32_t k=0; k<dd.neighbors.size() && idxNb.size() < 8; ++k) if (data.arrDepthData[dd.neighbors[k].ID].valid) idxNb.push_back(k);
+			for (uint32_t k=0; k<dd.neighbors.size() && idxNb.size() < 8; ++k) if (ok[dd.neighbors[k].ID]) idxNb.push_back(k);
 			return idxNb;
 		};
 		for (uint32_t i: valid) if (neighboursOf(i).size() >= std::min(P.nMinViewsFilter, scene.nCalibratedImages()-1)) filtered[i] = 1; // the same decision on every rank
@@ -317,12 +329,13 @@ bool DistributedReconstruction::Impl::Run(uint64_t seed, bool runFilter, bool do
 DistributedReconstruction::DistributedReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, const ViewSelectionParams& VS, int rank, int world)
 	: impl(new Impl(scene, ctx, P, VS, rank, world)) {}
 DistributedReconstruction::~DistributedReconstruction() { delete impl; }
-bool DistributedReconstruction::Prepare(bool lazyInitialMaps) { impl->lazyInit = lazyInitialMaps; return impl->Prepare(); }
+bool DistributedReconstruction::Prepare(bool lazy) { impl->lazy = lazy; return impl->Prepare(); }
 bool DistributedReconstruction::UploadInitial() { return impl->UploadInitial(); }
 bool DistributedReconstruction::Run(uint64_t seed, bool runFilter, bool download) { return impl->Run(seed, runFilter, download); }
 const std::string& DistributedReconstruction::Error() const { return impl->err; }
 const DenseReconstructionStats& DistributedReconstruction::Stats() const { return impl->st; }
 const ShardPlan& DistributedReconstruction::Plan() const { return impl->plan; }
+size_t DistributedReconstruction::ValidViews() const { return impl->valid.size(); }
 
 bool DenseReconstructionDistributed(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, const ViewSelectionParams& VS, uint64_t seed, bool runFilter,
 	int rank, int world, DenseReconstructionStats* stats, std::string* err)

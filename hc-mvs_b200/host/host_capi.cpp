@@ -13,7 +13,9 @@ struct hcmvs_host_scene {
 	std::vector<DepthData> dd;
 	std::string err;
 	DistributedReconstruction* dist = nullptr; // hcmvs_host_dist_*
-	~hcmvs_host_scene() { delete dist; }
+	std::vector<void*> pinned;                 // hcmvs_host_pin_images
+	void Unpin() { for (void* p: pinned) hcmvs_unpin_host_memory(p); pinned.clear(); }
+	~hcmvs_host_scene() { delete dist; Unpin(); }
 };
 
 extern "C" {
@@ -120,6 +122,18 @@ int hcmvs_host_dense_reconstruction_distributed(hcmvs_host_scene* s, hcmvs_ctx* 
 	return 0;
 }
 
+int hcmvs_host_pin_images(hcmvs_host_scene* s, int pin) {
+	// page-lock the pixel buffers of the scene's images (gray + colour): the uploads then run at PCIe rate. The buffers must not be
+	// re-allocated while pinned (hcmvs_host_scene_reload_images: unpin first).
+	if (!s) return -1;
+	s->Unpin();
+	if (!pin) return 0;
+	for (Image& im: s->scene.images) {
+		if (!im.gray.empty() && hcmvs_pin_host_memory(im.gray.data(), im.gray.size()*4) == HCMVS_OK) s->pinned.push_back(im.gray.data());
+		if (!im.bgr.empty() && hcmvs_pin_host_memory(im.bgr.data(), im.bgr.size()) == HCMVS_OK) s->pinned.push_back(im.bgr.data());
+	}
+	return (int)s->pinned.size();
+}
 int hcmvs_host_dist_prepare(hcmvs_host_scene* s, hcmvs_ctx* ctx, const hcmvs_params* p, int rank, int world) {
 	if (!s || !ctx || !p || world < 2 || rank < 0 || rank >= world) return -1;
 	delete s->dist;
@@ -130,7 +144,7 @@ int hcmvs_host_dist_prepare(hcmvs_host_scene* s, hcmvs_ctx* ctx, const hcmvs_par
 int hcmvs_host_dist_info(hcmvs_host_scene* s, int rank, int* n_valid, int* n_mine_whole, int* n_split, int* whole_rounds) {
 	if (!s || !s->dist) return -1;
 	const ShardPlan& p = s->dist->Plan();
-	if (n_valid) *n_valid = (int)p.order.size();
+	if (n_valid) *n_valid = (int)s->dist->ValidViews();
 	if (n_mine_whole) *n_mine_whole = (int)p.WholeViewsOf(rank).size();
 	if (n_split) *n_split = (int)p.SplitViews().size();
 	if (whole_rounds) *whole_rounds = p.wholeRounds;

@@ -257,6 +257,9 @@ int hcmvs_alloc_depthmap(hcmvs_ctx* ctx, uint32_t view);
 
 int hcmvs_get_timers(hcmvs_ctx* ctx, hcmvs_timers* t);
 int hcmvs_reset_timers(hcmvs_ctx* ctx);
+/* Page-lock / release caller-owned host memory (cudaHostRegister): uploads from registered buffers run at PCIe rate and asynchronously. */
+int hcmvs_pin_host_memory(void* p, uint64_t bytes);
+int hcmvs_unpin_host_memory(void* p);
 /* CUDA stream the context launches on (cudaStream_t as void*), for event timing by the caller. */
 void* hcmvs_stream(hcmvs_ctx* ctx);
 

@@ -30,6 +30,9 @@ int hcmvs_host_scale_image(const float* src, int sw, int sh, float scale, float*
 /* Scene::DenseReconstruction (SceneDensify.cpp:3532-3574) through the C ABI with HOST buffers.
  * stats[8] = sec select, upload, estimate, filter, fuse, h2d bytes, d2h bytes, #points. dmap_dir may be NULL. */
 int hcmvs_host_dense_reconstruction(hcmvs_host_scene* s, hcmvs_ctx* ctx, const hcmvs_params* p, uint64_t seed, int run_filter, const char* dmap_dir, double* stats);
+/* Page-lock (pin != 0) or release the pixel buffers of the scene's images, so that DenseReconstruction uploads them at PCIe rate.
+ * Returns the number of pinned buffers. Unpin before anything re-allocates the images (hcmvs_host_scene_reload_images). */
+int hcmvs_host_pin_images(hcmvs_host_scene* s, int pin);
 /* The same on `world` GPUs of one box (no reference counterpart): one process per GPU, ctx joined to the communicator
  * (hcmvs_comm_init). Every rank adds every image's camera; pixels are only needed for images with index % world == rank (bgr may be
  * NULL in hcmvs_host_add_image for the others — they arrive over NVLink). Rank 0 ends up with the fused cloud. */
