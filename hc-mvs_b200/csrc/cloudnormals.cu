@@ -17,7 +17,7 @@
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { hcmvs_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return HCMVS_ERR_CUDA; } } while (0)
 #define PN_MAXK 32 // neighbours + the point itself
-#define PN_MAXR 24 // the search cube stops growing at (2*24+1)^3 cells: bounded work for isolated outliers (see k_pn_normals)
+#define PN_MAXR 24 // per grid level the search cube stops growing at (2*24+1)^3 cells; unfinished points go on at the next, 8x coarser level
 
 namespace hcmvs {
 
@@ -70,22 +70,28 @@ __device__ __forceinline__ void pn_smallest_eigvec(double a[3][3], double out[3]
 struct PnCam { float cx, cy, cz; };
 
 // one thread per point, in sorted (cell) order
+// query == nullptr: every point, in sorted (cell) order; else the listed points (a coarser level of the grid hierarchy re-visits the points
+// whose fine-level search hit the PN_MAXR cap). pending / nPending collect the points whose K1 nearest are still not proven.
 __global__ void __launch_bounds__(128) k_pn_normals(const PnGrid G, const float4* __restrict__ spos, uint32_t n, const unsigned long long* __restrict__ cellKeys,
 	const uint32_t* __restrict__ cellStart, uint32_t nCells, int K1, const uint32_t* __restrict__ offs, const uint32_t* __restrict__ views,
-	const PnCam* __restrict__ cams, uint32_t nCams, float* __restrict__ normals)
+	const PnCam* __restrict__ cams, uint32_t nCams, float* __restrict__ normals,
+	const uint32_t* __restrict__ query, uint32_t nQuery, const float* __restrict__ pts, uint32_t* __restrict__ pending, uint32_t* __restrict__ nPending)
 {
 	const uint32_t j = blockIdx.x*blockDim.x+threadIdx.x;
-	if (j >= n) return;
-	const float4 P = spos[j];
+	if (j >= (query ? nQuery : n)) return;
+	float4 P;
+	if (query) { const uint32_t i = query[j]; P = make_float4(pts[(size_t)i*3], pts[(size_t)i*3+1], pts[(size_t)i*3+2], __int_as_float((int)i)); }
+	else P = spos[j];
 	const uint32_t self = (uint32_t)__float_as_int(P.w);
 	const int cx = pn_cell(P.x, G.minx, G.invh, G.nx), cy = pn_cell(P.y, G.miny, G.invh, G.ny), cz = pn_cell(P.z, G.minz, G.invh, G.nz);
 	float bd[PN_MAXK]; uint32_t bj[PN_MAXK]; // the K1 best so far, ascending by distance (sorted positions' indices)
 	int nb = 0;
 	// An isolated outlier would otherwise grow its cube through thousands of empty shells (O(R^3) cell look-ups: minutes on a 20 M-point
-	// cloud). Beyond PN_MAXR cells (~25 mean point spacings) the search stops and the normal is fitted to what was found — 3 or more
-	// points — or left zero: the one place where this differs from CGAL's unbounded k-NN, and only for points with fewer than K
-	// neighbours inside that radius.
+	// cloud). Beyond PN_MAXR cells (~25 mean point spacings) the search stops at THIS level: the point is handed to a grid with 8x
+	// larger cells (hcmvs_estimate_point_normals loops over the levels), so the k-NN stays exact — CGAL's unbounded search — at a
+	// bounded cost per level. (What was found so far is fitted anyway: the value of a point no level could finish.)
 	const int maxR = min(max(G.nx, max(G.ny, G.nz)), PN_MAXR);
+	bool proven = false;
 	for (int R=0; R<=maxR; ++R) {
 		for (int dz=-R; dz<=R; ++dz) {
 			const int z = cz+dz; if (z < 0 || z >= G.nz) continue;
@@ -120,9 +126,11 @@ __global__ void __launch_bounds__(128) k_pn_normals(const PnGrid G, const float4
 			if (cy-R > 0) reach = fminf(reach, P.y-ly); if (cy+R < G.ny-1) reach = fminf(reach, hy-P.y);
 			if (cz-R > 0) reach = fminf(reach, P.z-lz); if (cz+R < G.nz-1) reach = fminf(reach, hz-P.z);
 			reach = fmaxf(reach, 0.f)*0.9999f; // slack for the rounding of the cell assignment
-			if (bd[K1-1] <= reach*reach) break;
+			if (bd[K1-1] <= reach*reach) { proven = true; break; }
 		}
 	}
+	// the cap stopped the search before the K1 nearest were certain (and the cube did not cover the whole grid): a coarser level goes on
+	if (!proven && maxR < max(G.nx, max(G.ny, G.nz)) && pending) pending[atomicAdd(nPending, 1u)] = self;
 	float nx = 0.f, ny = 0.f, nz = 0.f;
 	if (nb >= 3) {
 		// linear_least_squares_fitting_3 over the points: centroid, covariance, least-variance direction (f64)
@@ -219,32 +227,52 @@ extern "C" int hcmvs_estimate_point_normals(hcmvs_ctx* ctx, uint64_t n_points, c
 	h = std::max(h, std::max(ext[0], std::max(ext[1], ext[2]))/2000000.0); // 21-bit cell coordinates
 	PnGrid G; uint32_t nCells = 0;
 	int rc = HCMVS_OK;
-	for (int it=0; it<6; ++it) {
-		G.minx = mm[0]; G.miny = mm[1]; G.minz = mm[2]; G.h = (float)h; G.invh = (float)(1.0/h);
-		G.nx = (int)std::min(2097151.0, std::floor(ext[0]/h)+1); G.ny = (int)std::min(2097151.0, std::floor(ext[1]/h)+1); G.nz = (int)std::min(2097151.0, std::floor(ext[2]/h)+1);
+	auto buildGrid = [&](double hh) -> bool { // cell keys -> sort -> occupied cells (keys + counts); nCells on the host
+		G.minx = mm[0]; G.miny = mm[1]; G.minz = mm[2]; G.h = (float)hh; G.invh = (float)(1.0/hh);
+		G.nx = (int)std::min(2097151.0, std::floor(ext[0]/hh)+1); G.ny = (int)std::min(2097151.0, std::floor(ext[1]/hh)+1); G.nz = (int)std::min(2097151.0, std::floor(ext[2]/hh)+1);
 		k_pn_keys<<<(N+255)/256, 256, 0, st>>>(G, pts_d, N, keys_d, vals_d);
 		if (cub::DeviceRadixSort::SortPairs(tmp_d, tmpBytes, keys_d, keys2_d, vals_d, vals2_d, (int)N, 0, 63, st) != cudaSuccess ||
-		    cub::DeviceRunLengthEncode::Encode(tmp_d, tmpBytes, keys2_d, cellKeys_d, cellCount_d, nRuns_d, (int)N, st) != cudaSuccess) { hcmvs_set_error("cub failed"); rc = HCMVS_ERR_CUDA; break; }
+		    cub::DeviceRunLengthEncode::Encode(tmp_d, tmpBytes, keys2_d, cellKeys_d, cellCount_d, nRuns_d, (int)N, st) != cudaSuccess) { hcmvs_set_error("cub failed"); rc = HCMVS_ERR_CUDA; return false; }
 		ctx->nLaunches += 3;
-		if (cudaMemcpyAsync(&nCells, nRuns_d, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { hcmvs_set_error("point normals: %s", cudaGetErrorString(cudaGetLastError())); rc = HCMVS_ERR_CUDA; break; }
+		if (cudaMemcpyAsync(&nCells, nRuns_d, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { hcmvs_set_error("point normals: %s", cudaGetErrorString(cudaGetLastError())); rc = HCMVS_ERR_CUDA; return false; }
+		return true;
+	};
+	for (int it=0; it<6; ++it) {
+		if (!buildGrid(h)) break;
 		const double occ = (double)N/std::max<uint32_t>(nCells, 1);
 		if ((occ >= 2.0 && occ <= 8.0) || it == 5 || N <= 64) break;
 		h *= std::sqrt(4.0/occ); // occupancy of a surface grows with h^2
 	}
+	uint32_t *pendA_d = nullptr, *pendB_d = nullptr, *nPend_d = nullptr;
 	if (rc == HCMVS_OK) {
-		CK(cudaMemsetAsync(cellCount_d+nCells, 0, 4, st));
-		cub::DeviceScan::ExclusiveSum(tmp_d, tmpBytes, cellCount_d, cellStart_d, (int)nCells+1, st);
-		k_pn_sorted_pos<<<(N+255)/256, 256, 0, st>>>(vals2_d, N, pts_d, spos_d);
 		std::vector<PnCam> cams(ctx->views.size());
 		for (size_t v=0; v<cams.size(); ++v) { cams[v].cx = (float)ctx->views[v].C[0]; cams[v].cy = (float)ctx->views[v].C[1]; cams[v].cz = (float)ctx->views[v].C[2]; }
 		CK(cudaMalloc(&cams_d, std::max<size_t>(cams.size(), 1)*sizeof(PnCam)));
 		if (!cams.empty()) CK(cudaMemcpyAsync(cams_d, cams.data(), cams.size()*sizeof(PnCam), cudaMemcpyHostToDevice, st));
-		k_pn_normals<<<(N+127)/128, 128, 0, st>>>(G, spos_d, N, cellKeys_d, cellStart_d, nCells, K1, offs_d, ids_d, cams_d, (uint32_t)cams.size(), nrm_d);
-		ctx->nLaunches += 3;
-		if (cudaGetLastError() != cudaSuccess) { hcmvs_set_error("point normals launch failed"); rc = HCMVS_ERR_CUDA; }
+		CK(cudaMalloc(&pendA_d, (size_t)N*4)); CK(cudaMalloc(&pendB_d, (size_t)N*4)); CK(cudaMalloc(&nPend_d, 4));
+		// level 0: every point on the fine grid; level L: the points still pending, on a grid with 8^L times larger cells
+		uint32_t nQuery = 0; const uint32_t* query_d = nullptr;
+		for (int level=0; level<12 && rc == HCMVS_OK; ++level) {
+			if (level > 0) { h *= 8.0; if (!buildGrid(h)) break; }
+			CK(cudaMemsetAsync(cellCount_d+nCells, 0, 4, st));
+			cub::DeviceScan::ExclusiveSum(tmp_d, tmpBytes, cellCount_d, cellStart_d, (int)nCells+1, st);
+			k_pn_sorted_pos<<<(N+255)/256, 256, 0, st>>>(vals2_d, N, pts_d, spos_d);
+			CK(cudaMemsetAsync(nPend_d, 0, 4, st));
+			uint32_t* out_d = (level&1) ? pendB_d : pendA_d;
+			const uint32_t work = level == 0 ? N : nQuery;
+			k_pn_normals<<<(work+127)/128, 128, 0, st>>>(G, spos_d, N, cellKeys_d, cellStart_d, nCells, K1, offs_d, ids_d, cams_d, (uint32_t)cams.size(), nrm_d,
+				query_d, nQuery, pts_d, out_d, nPend_d);
+			ctx->nLaunches += 3;
+			if (cudaGetLastError() != cudaSuccess) { hcmvs_set_error("point normals launch failed"); rc = HCMVS_ERR_CUDA; break; }
+			uint32_t nPend = 0;
+			if (cudaMemcpyAsync(&nPend, nPend_d, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { hcmvs_set_error("point normals: %s", cudaGetErrorString(cudaGetLastError())); rc = HCMVS_ERR_CUDA; break; }
+			if (!nPend) break;
+			query_d = out_d; nQuery = nPend;
+		}
 		if (rc == HCMVS_OK && normals && cudaMemcpyAsync(normals, nrm_d, (size_t)N*12, cudaMemcpyDeviceToHost, st) != cudaSuccess) { hcmvs_set_error("cannot read the normals back"); rc = HCMVS_ERR_CUDA; }
 		if (cudaStreamSynchronize(st) != cudaSuccess && rc == HCMVS_OK) { hcmvs_set_error("point normals: %s", cudaGetErrorString(cudaGetLastError())); rc = HCMVS_ERR_CUDA; }
 	}
+	cudaFree(pendA_d); cudaFree(pendB_d); cudaFree(nPend_d);
 	cudaFree(keys_d); cudaFree(keys2_d); cudaFree(vals_d); cudaFree(vals2_d); cudaFree(cellKeys_d); cudaFree(cellCount_d); cudaFree(cellStart_d); cudaFree(nRuns_d);
 	cudaFree(spos_d); cudaFree(tmp_d); cudaFree(cams_d); cudaFree(pts_own); cudaFree(nrm_own); cudaFree(offs_own); cudaFree(ids_own);
 	return rc;

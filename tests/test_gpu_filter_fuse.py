@@ -205,6 +205,10 @@ def test_estimate_point_normals_matches_oracle():
         clouds.append(np.stack([xy[:, 0], xy[:, 1], 0.05 * xy[:, 0] + 0.03 * xy[:, 1] + rng.normal(0, 0.003, len(xy))], 1))
         clouds.append(rng.normal(0, 1, (6000, 3)) * [3.0, 1.0, 0.2])                                 # a volumetric blob: uneven density, no surface
         clouds.append(np.concatenate([clouds[0][:300] * 50, rng.uniform(-1, 1, (12, 3)) * 1e-3]))   # far apart sparse points + a tiny cluster
+        # isolated outliers tens to thousands of point spacings away from a dense surface: the fine grid's capped search cannot finish them,
+        # the coarser levels of the grid hierarchy must (exact k-NN, like CGAL's unbounded search)
+        far = np.concatenate([rng.uniform(-1, 1, (30, 3)) * [40, 40, 40], rng.uniform(-1, 1, (10, 3)) * [600, 600, 600]])
+        clouds.append(np.concatenate([clouds[0], far]))
         cams = np.asarray(syn.Cc, np.float64).reshape(-1, 3)
         for ci, pts in enumerate(clouds):
             pts = pts.astype(np.float32)
