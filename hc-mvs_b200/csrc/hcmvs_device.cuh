@@ -21,6 +21,9 @@
 #ifndef HCMVS_FLOOR_FADD
 #define HCMVS_FLOOR_FADD 1
 #endif
+#ifndef HCMVS_HULL_TEST
+#define HCMVS_HULL_TEST 1               // patches whose corners lie inside the neighbour image with slack walk without per-texel border tests
+#endif
 #ifndef HCMVS_EARLY_REJECT
 #define HCMVS_EARLY_REJECT 0
 #endif
