@@ -785,7 +785,7 @@ static int EstimateRows(hcmvs_ctx* ctx, uint32_t ref, int it_external, uint64_t 
 	for (unsigned iter=0; iter<P.nEstimationIters; ++iter) {
 		rc.pass = 1u+iter+(uint32_t)it_external*64u;
 		rc.lastPass = it_external == (int)P.nEstimationIters_external-1 && iter == P.nEstimationIters-1;
-		for (int colour=0; colour<2; ++colour) { CK(hcmvs_launch_sweep(rc, colour, tex, ctx->stream, P.sampler == 2)); ++ctx->nLaunches; }
+		for (int colour=0; colour<2; ++colour) { CK(hcmvs_launch_sweep(rc, colour, tex, ctx->stream, P.sampler == 2 && iter >= 1)); ++ctx->nLaunches; }
 	}
 	hcmvs_time_end(ctx);
 	// PASS C, SceneDensify.cpp:1035-1056

@@ -13,10 +13,13 @@
 #ifndef HCMVS_RB6
 #define HCMVS_RB6 2                     // rows of a 6x6 patch whose texture gathers are in flight together (k_sweep batches)
 #endif
+#ifndef HCMVS_RB6_PLAIN
+#define HCMVS_RB6_PLAIN 3               // ... in the plain sweep (it_external 0, no extra hypotheses): 18 gathers per thread, 168 registers, no spills
+#endif
 // shared-memory windows of the neighbour images (sampler 2): per CTA and matching view a HCMVS_WIN x HCMVS_WIN texel window
 // around the footprint of the tile's current estimates; hypotheses whose whole patch falls inside are sampled with LDS
 #define HCMVS_WIN 40
-#define HCMVS_WINP 41                   // row pitch in floats
+#define HCMVS_WINP 44                   // row pitch in floats (12 mod 32: the 32 pixels of a warp's 8x8 checkerboard block hit 32 distinct banks under an identity-like mapping)
 #define HCMVS_WINV 5                    // views that get a window (the reference's runs match against 5)
 #ifndef HCMVS_FLOOR_FADD
 #define HCMVS_FLOOR_FADD 1
