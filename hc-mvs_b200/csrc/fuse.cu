@@ -41,7 +41,8 @@ struct FuseView {
 	FuseRec* rec; float4* dn; const uint8_t* bgr;
 	uint32_t* alive;   // 1 bit per pixel: depth != 0, not merged into a point, not zeroed (SceneDensify.cpp:3347-3354, :3396-3398). All views
 	                   // together are ~12 MB: L2 resident. It IS the liveness: every transition clears the bit before the phase's barrier.
-	uint32_t* claim;   // per pixel: CLAIM_FREE or the raster index of the seed that reserved it (4 B/px: 8 pixels per sector)
+	uint32_t* claim;   // per pixel: CLAIM_FREE or the raster index of the seed that reserved it (4 B/px: 8 pixels per sector); three planes
+	                   // (FuseJob::claimPlane apart) that rotate through the rounds of a view: read / being written / being cleared
 	int w, h; int hasMaps; int hasBgr;
 	CamConst cam;
 };
@@ -66,15 +67,17 @@ struct FuseSlots {
 };
 
 struct FuseCtl {
-	unsigned wlCount[2]; int overflow; int pad;
+	unsigned wlCount[3]; int overflow;        // worklist counters rotate like the claim planes: read / being filled / being zeroed
+	unsigned stCount[2]; unsigned pad[2];     // deferred staging lists of the two slot sets
 	unsigned long long cumPoints, cumRefs;   // cloud size after the views emitted so far
 	unsigned long long rounds, seeds, probes;
 };
 
 struct FuseJob {
 	FuseView* views; const FusePlanView* plan; int nPlan;
-	FuseSlots sl[2]; size_t probeStride;
+	FuseSlots sl[2]; size_t probeStride; size_t claimPlane;
 	uint32_t* wl[2];                  // undecided slots of the current / next round
+	uint32_t* stl[2];                 // per slot set: seeds that became final in a later round; their points are staged by the next view's count stage
 	unsigned* blkSeeds; unsigned* blkEmit; // per-block counts of the two ordered compactions (blkEmit: points, view references)
 	FuseCtl* ctl;
 	unsigned nMinViewsFuse; float depthTh, normalError;
@@ -134,8 +137,13 @@ __global__ void __launch_bounds__(256) k_fuse_build(const FuseView* __restrict__
 	}
 	const unsigned word = __ballot_sync(0xffffffffu, valid);
 	if ((threadIdx.x&31) == 0 && i < n) V.alive[i>>5] = word;
-	valid = __reduce_add_sync(0xffffffffu, valid);
-	if ((threadIdx.x&31) == 0 && valid) atomicAdd(nValid, (unsigned long long)valid);
+	// one global atomic per block (one per warp = 60 k atomics on one address per C2 view: they, not the 105 MB of traffic, set the kernel's time)
+	__shared__ unsigned sValid;
+	if (threadIdx.x == 0) sValid = 0;
+	__syncthreads();
+	if ((threadIdx.x&31) == 0 && word) atomicAdd(&sValid, (unsigned)__popc(word));
+	__syncthreads();
+	if (threadIdx.x == 0 && sValid) atomicAdd(nValid, (unsigned long long)sValid);
 }
 
 // ------------------------------------------------------------------ block helpers (256 threads)
@@ -177,21 +185,23 @@ __device__ __forceinline__ unsigned long long block_sum(unsigned long long v, un
 #define FUSE_CHK(cond, id) do { } while (0)
 #define FUSE_CHKR(cond, id) do { } while (0)
 #endif
+#ifndef FUSE_CH
 #define FUSE_CH 6      // probes whose bitmap tests / record gathers are in flight together in the probe stage
+#endif
 #define FUSE_RCH 12    // probes per chunk of the reserve / resolve stages (DepthData::neighbors holds <= nMaxViews = 12)
 __device__ __forceinline__ bool bit_alive(const FuseView& B, uint32_t q) { return (__ldcg(B.alive+(q>>5))>>(q&31)) & 1u; }
 __device__ __forceinline__ void bit_clear(const FuseView& B, uint32_t q) { atomicAnd(B.alive+(q>>5), ~(1u<<(q&31))); }
 
 // classify the probes of seed slot s (the f64 geometry, once) and place the first round's reservations. The bitmap answers "already
 // part of a point / no depth" without touching the pixel's record: only probes of live pixels cost a DRAM sector.
-__device__ FUSE_FN void probe_slot(const FuseJob& a, const FusePlanView& pv, const FuseSlots& S, const int s) {
-	const FuseView& R = a.views[pv.view];
+__device__ FUSE_FN void probe_slot(const FuseJob& a, const FusePlanView& pv, const FuseView* sv, const FuseSlots& S, const int s) {
+	const FuseView& R = sv[0];
 	const int p = (int)__ldcg(S.seeds+s);
 	FUSE_CHK(s >= 0 && (size_t)s < a.probeStride, 101); FUSE_CHK(p >= 0 && p < R.w*R.h, 102); FUSE_CHK(pv.nNb >= 0 && pv.nNb <= HCMVS_MAX_FUSE_VIEWS, 103);
 	const uint4 r0 = __ldcg(reinterpret_cast<const uint4*>(R.rec+p));
 	const float nz = __ldcg(&R.rec[p].nz);
 	const float depth = __uint_as_float(r0.x);
-	S.state[s] = 1;
+	S.state[s] = 1; __stcg(S.mask+s, 0u);
 	const int x = p%R.w, y = p/R.w;
 	const float3 point = seed_point(R, x, y, depth);
 	const float3 normal = make_float3(__uint_as_float(r0.z), __uint_as_float(r0.w), nz);
@@ -200,14 +210,14 @@ __device__ FUSE_FN void probe_slot(const FuseJob& a, const FusePlanView& pv, con
 		#pragma unroll
 		for (int j=0; j<FUSE_CH; ++j) {
 			pr[j].q = -1; pr[j].z = 0.f;
-			if (k0+j < pv.nNb) { const FuseView& B = a.views[pv.nb[k0+j]]; if (B.hasMaps) pr[j] = probe_view(B, point); }
+			if (k0+j < pv.nNb) { const FuseView& B = sv[1+(k0+j)]; if (B.hasMaps) pr[j] = probe_view(B, point); }
 		}
 		#pragma unroll
-		for (int j=0; j<FUSE_CH; ++j) { word[j] = 0u; if (pr[j].q >= 0) word[j] = __ldcg(a.views[pv.nb[k0+j]].alive+(pr[j].q>>5)); }
+		for (int j=0; j<FUSE_CH; ++j) { word[j] = 0u; if (pr[j].q >= 0) word[j] = __ldcg(sv[1+(k0+j)].alive+(pr[j].q>>5)); }
 		#pragma unroll
 		for (int j=0; j<FUSE_CH; ++j) {
 			eB[j] = make_uint4(0u, 0u, 0u, 0u); nzB[j] = 0.f;
-			if (pr[j].q >= 0 && ((word[j]>>(pr[j].q&31)) & 1u)) { const FuseRec* rb = a.views[pv.nb[k0+j]].rec+pr[j].q; eB[j] = __ldcg(reinterpret_cast<const uint4*>(rb)); nzB[j] = __ldcg(&rb->nz); }
+			if (pr[j].q >= 0 && ((word[j]>>(pr[j].q&31)) & 1u)) { const FuseRec* rb = sv[1+(k0+j)].rec+pr[j].q; eB[j] = __ldcg(reinterpret_cast<const uint4*>(rb)); nzB[j] = __ldcg(&rb->nz); }
 		}
 		#pragma unroll
 		for (int j=0; j<FUSE_CH; ++j) {
@@ -221,28 +231,11 @@ __device__ FUSE_FN void probe_slot(const FuseJob& a, const FusePlanView& pv, con
 						merge = dot3f(normal, make_float3(__uint_as_float(eB[j].z), __uint_as_float(eB[j].w), nzB[j])) > a.normalError;
 					if (merge) cls = PROBE_MERGE; else if (pr[j].z < depthB) cls = PROBE_INVAL;
 					code = (uint32_t)pr[j].q | (cls<<30);
-					if (cls != PROBE_NONE) atomicMin(a.views[pv.nb[k0+j]].claim+pr[j].q, (uint32_t)p);
+					if (cls != PROBE_NONE) atomicMin(sv[1+(k0+j)].claim+pr[j].q, (uint32_t)p);
 				}
 				__stcg(S.probes+(size_t)(k0+j)*a.probeStride+s, code);
 			}
 		}
-	}
-}
-
-// every unfinished seed reserves each live neighbour pixel it has not dealt with yet (rounds >= 2)
-__device__ FUSE_FN void reserve_slot(const FuseJob& a, const FusePlanView& pv, const FuseSlots& S, const int s) {
-	const uint8_t st = __ldcg(S.state+s);
-	if (st != 1 && st != 3) return;
-	const uint32_t p = __ldcg(S.seeds+s); // the raster index orders the reservations
-	FUSE_CHK(s >= 0 && (size_t)s < a.probeStride, 201);
-	for (int k0=0; k0<pv.nNb; k0+=FUSE_RCH) {
-		uint32_t code[FUSE_RCH]; bool live[FUSE_RCH];
-		#pragma unroll
-		for (int j=0; j<FUSE_RCH; ++j) code[j] = k0+j < pv.nNb ? __ldcg(S.probes+(size_t)(k0+j)*a.probeStride+s) : PROBE_DEAD;
-		#pragma unroll
-		for (int j=0; j<FUSE_RCH; ++j) live[j] = code[j] != PROBE_DEAD && (code[j]>>30) != PROBE_NONE && bit_alive(a.views[pv.nb[k0+j]], code[j]&PROBE_PIX);
-		#pragma unroll
-		for (int j=0; j<FUSE_RCH; ++j) if (live[j]) atomicMin(a.views[pv.nb[k0+j]].claim+(code[j]&PROBE_PIX), p);
 	}
 }
 
@@ -255,16 +248,25 @@ __device__ FUSE_FN void reserve_slot(const FuseJob& a, const FusePlanView& pv, c
 //  * a seed that cannot reach nMinViewsFuse even if every contested agreeing pixel were still alive at its turn will NOT be
 //    emitted: it releases everything;
 //  * otherwise it waits for the lower seeds it conflicts with (the lowest unfinished seed never waits).
-__device__ FUSE_FN int resolve_slot(const FuseJob& a, const FusePlanView& pv, const FuseSlots& S, const int s) {
+// Round k reads the claim plane (k-1)%3 (the reservations of the seeds that were unfinished after round k-1; round 1: those of the probe
+// stage), and every seed that stays unfinished places its reservations for round k+1 in plane k%3 in the SAME phase — one grid-wide
+// phase per round instead of reserve + resolve. Plane (k+1)%3, read a round ago and written again in the next one, is cleared on
+// the way: an entry that still matters there belongs to a live pixel whose holder is unfinished, i.e. in this round's worklist (a
+// holder that finished either killed the pixel or released the entry), so the worklist seeds clearing their own pixels is enough.
+// Readers of the read plane tolerate the releases of this phase (a contested pixel reads as contested either way).
+__device__ FUSE_FN int resolve_slot(const FuseJob& a, const FusePlanView& pv, const FuseView* sv, const FuseSlots& S, const int s, const unsigned round,
+	uint32_t& pOut, uint32_t& mergedOut, uint32_t (&code0)[FUSE_RCH])
+{
+	// one trip for the slot's state, seed and mask (probe_slot initialises the mask)
 	const uint8_t st = __ldcg(S.state+s);
-	if (st != 1 && st != 3) return 0;
-	const FuseView& R = a.views[pv.view];
 	const uint32_t p = __ldcg(S.seeds+s);
+	uint32_t merged = __ldcg(S.mask+s);
+	if (st != 1 && st != 3) return 0;
+	const size_t cR = (size_t)((round-1u)%3u)*a.claimPlane, cW = (size_t)(round%3u)*a.claimPlane, cC = (size_t)((round+1u)%3u)*a.claimPlane;
+	const FuseView& R = sv[0];
 	FUSE_CHKR(s >= 0 && (size_t)s < a.probeStride, 301); FUSE_CHKR((int)p < R.w*R.h, 302);
-	uint32_t merged = st == 3 ? __ldcg(S.mask+s) : 0u;
-	uint32_t heldMerge = 0, heldInval = 0;
+	uint32_t heldMerge = 0, heldInval = 0, want = 0; // want: live probes the seed still depends on (held or contested)
 	unsigned nContested = 0, nContestedMerge = 0;
-	uint32_t code0[FUSE_RCH]; // the first chunk's codes stay in registers for the actions below
 	for (int k0=0; k0<pv.nNb; k0+=FUSE_RCH) {
 		uint32_t code[FUSE_RCH], word[FUSE_RCH], cl[FUSE_RCH];
 		#pragma unroll
@@ -273,10 +275,11 @@ __device__ FUSE_FN int resolve_slot(const FuseJob& a, const FusePlanView& pv, co
 		for (int j=0; j<FUSE_RCH; ++j) {
 			word[j] = 0u; cl[j] = CLAIM_FREE;
 			if (code[j] != PROBE_DEAD && (code[j]>>30) != PROBE_NONE) {
-				const FuseView& B = a.views[pv.nb[k0+j]];
+				const FuseView& B = sv[1+(k0+j)];
 				const uint32_t q = code[j]&PROBE_PIX;
 				FUSE_CHKR((int)q < B.w*B.h && B.claim && B.alive, 303);
-				word[j] = __ldcg(B.alive+(q>>5)); cl[j] = __ldcg(B.claim+q);
+				word[j] = __ldcg(B.alive+(q>>5)); cl[j] = __ldcg(B.claim+cR+q);
+				if (round >= 2u) __stcg(B.claim+cC+q, CLAIM_FREE);
 			}
 		}
 		#pragma unroll
@@ -285,17 +288,20 @@ __device__ FUSE_FN int resolve_slot(const FuseJob& a, const FusePlanView& pv, co
 			if (code[j] == PROBE_DEAD || (code[j]>>30) == PROBE_NONE) continue;
 			const int k = k0+j;
 			if (!((word[j]>>(code[j]&31u)) & 1u)) { __stcg(S.probes+(size_t)k*a.probeStride+s, PROBE_DEAD); continue; }
+			want |= 1u<<k;
 			if (cl[j] == p) { if ((code[j]>>30) == PROBE_MERGE) heldMerge |= 1u<<k; else heldInval |= 1u<<k; }
 			else { ++nContested; nContestedMerge += (code[j]>>30) == PROBE_MERGE; }
 		}
 	}
+	pOut = p;
 	const uint32_t held = heldMerge|heldInval;
 	const unsigned nViews = 1u+__popc(merged)+__popc(heldMerge);
+	int res;
 	if (st == 3 || nViews >= a.nMinViewsFuse) {
 		#pragma unroll
 		for (int k=0; k<FUSE_RCH; ++k) {
 			if (!(held & (1u<<k))) continue;
-			const FuseView& B = a.views[pv.nb[k]];
+			const FuseView& B = sv[1+(k)];
 			uint32_t* pc = S.probes+(size_t)k*a.probeStride+s;
 			const uint32_t q = code0[k] & PROBE_PIX;
 			if (heldMerge & (1u<<k)) __stcg(pc, q | (PROBE_NONE<<30)); // a merged probe is not looked at again; the pixel index stays for the point
@@ -304,7 +310,7 @@ __device__ FUSE_FN int resolve_slot(const FuseJob& a, const FusePlanView& pv, co
 		}
 		for (uint32_t h = held>>FUSE_RCH<<FUSE_RCH; h; h &= h-1) { // neighbours beyond the first chunk (more than 12: not the reference's default)
 			const int k = __ffs(h)-1;
-			const FuseView& B = a.views[pv.nb[k]];
+			const FuseView& B = sv[1+(k)];
 			uint32_t* pc = S.probes+(size_t)k*a.probeStride+s;
 			const uint32_t q = __ldcg(pc) & PROBE_PIX;
 			if (heldMerge & (1u<<k)) __stcg(pc, q | (PROBE_NONE<<30));
@@ -313,48 +319,59 @@ __device__ FUSE_FN int resolve_slot(const FuseJob& a, const FusePlanView& pv, co
 		}
 		merged |= heldMerge;
 		__stcg(S.mask+s, merged);
+		mergedOut = merged;
 		if (nContested == 0) { bit_clear(R, p); S.state[s] = 2; return 2; }
 		S.state[s] = 3;
-		return 1;
-	}
-	if (nViews+nContestedMerge < a.nMinViewsFuse) {
+		want &= ~held; // acted on: those pixels are dead now
+		res = 1;
+	} else if (nViews+nContestedMerge < a.nMinViewsFuse) {
 		#pragma unroll
-		for (int k=0; k<FUSE_RCH; ++k) if (held & (1u<<k)) __stcg(a.views[pv.nb[k]].claim+(code0[k]&PROBE_PIX), CLAIM_FREE);
+		for (int k=0; k<FUSE_RCH; ++k) if (held & (1u<<k)) __stcg(sv[1+(k)].claim+cR+(code0[k]&PROBE_PIX), CLAIM_FREE);
 		for (uint32_t h = held>>FUSE_RCH<<FUSE_RCH; h; h &= h-1) {
 			const int k = __ffs(h)-1;
-			__stcg(a.views[pv.nb[k]].claim+(__ldcg(S.probes+(size_t)k*a.probeStride+s)&PROBE_PIX), CLAIM_FREE);
+			__stcg(sv[1+(k)].claim+cR+(__ldcg(S.probes+(size_t)k*a.probeStride+s)&PROBE_PIX), CLAIM_FREE);
 		}
 		S.state[s] = 0;
 		return 0;
+	} else res = 1;
+	// unfinished: the reservations of the next round (the raster index orders them)
+	#pragma unroll
+	for (int k=0; k<FUSE_RCH; ++k) if (want & (1u<<k)) atomicMin(sv[1+(k)].claim+cW+(code0[k]&PROBE_PIX), p);
+	for (uint32_t h = want>>FUSE_RCH<<FUSE_RCH; h; h &= h-1) {
+		const int k = __ffs(h)-1;
+		atomicMin(sv[1+(k)].claim+cW+(__ldcg(S.probes+(size_t)k*a.probeStride+s)&PROBE_PIX), p);
 	}
-	return 1;
+	return res;
 }
 
-// append the unfinished slots of this thread's warp to the next round's worklist
-__device__ __forceinline__ void worklist_push(uint32_t* wl, unsigned* count, bool keep, int s) {
-	const unsigned m = __ballot_sync(__activemask(), keep);
-	if (!m) return;
-	const int lane = threadIdx.x&31, leader = __ffs(m)-1;
+// append the unfinished slots of this thread's warp to the next round's worklist: the counter's atomic is issued first and its
+// answer used last (wl_commit), so that the staging in between does not wait behind the round trip. Full warps only.
+__device__ __forceinline__ unsigned wl_begin(unsigned* count, bool keep, unsigned& m) {
+	m = __ballot_sync(0xffffffffu, keep);
 	unsigned base = 0;
-	if (lane == leader) base = atomicAdd(count, (unsigned)__popc(m));
-	base = __shfl_sync(__activemask(), base, leader);
-	if (keep) __stcg(wl+base+__popc(m & ((1u<<lane)-1u)), (uint32_t)s);
+	if (m && (int)(threadIdx.x&31) == __ffs(m)-1) base = atomicAdd(count, (unsigned)__popc(m));
+	return base;
+}
+__device__ __forceinline__ void wl_commit(uint32_t* wl, unsigned base, unsigned m, bool keep, int s) {
+	if (!m) return;
+	base = __shfl_sync(0xffffffffu, base, __ffs(m)-1);
+	if (keep) __stcg(wl+base+__popc(m & ((1u<<(threadIdx.x&31))-1u)), (uint32_t)s);
 }
 
 // The fused point of seed slot s (SceneDensify.cpp:3355-3446), computed the moment the seed becomes final — in the same phase that
 // just read the heads of its merged pixels, so their records are still in L2 — and parked in per-slot staging; the ordered
 // compaction of the next stage copies it to its place in the cloud. The sums run over the merged neighbours in the order the seed
 // probed them (the reference's order: rounding is part of the result), four records in flight at a time.
-__device__ FUSE_FN void stage_slot(const FuseJob& a, const FusePlanView& pv, const FuseSlots& S, const int s) {
-	const FuseView& R = a.views[pv.view];
+__device__ FUSE_FN void stage_slot(const FuseJob& a, const FusePlanView& pv, const FuseView* sv, const FuseSlots& S, const int s, const int p, const uint32_t merged,
+	const uint32_t (&code0)[FUSE_RCH])
+{
+	const FuseView& R = sv[0];
 	const FuseOut& out = a.out;
-	const int p = (int)__ldcg(S.seeds+s);
 	const uint4 r0 = __ldcg(reinterpret_cast<const uint4*>(R.rec+p)), r1 = __ldcg(reinterpret_cast<const uint4*>(R.rec+p)+1);
 	const int x = p%R.w, y = p/R.w;
 	const float depth = __uint_as_float(r0.x);
 	const float3 point = seed_point(R, x, y, depth);
 	const float3 normal = make_float3(__uint_as_float(r0.z), __uint_as_float(r0.w), __uint_as_float(r1.x));
-	const uint32_t merged = __ldcg(S.mask+s);
 	// SceneDensify.cpp:3359-3379
 	const float w0 = __uint_as_float(r1.y);
 	__stcg(S.stgW+s, w0);
@@ -368,13 +385,20 @@ __device__ FUSE_FN void stage_slot(const FuseJob& a, const FusePlanView& pv, con
 		#pragma unroll
 		for (int j=0; j<4; ++j) { kk[j] = m ? __ffs(m)-1 : -1; m &= m-1; }
 		#pragma unroll
-		for (int j=0; j<4; ++j) qq[j] = kk[j] >= 0 ? (__ldcg(S.probes+(size_t)kk[j]*a.probeStride+s) & PROBE_PIX) : 0u;
+		for (int j=0; j<4; ++j) { // the pixel of a merged probe: the resolve stage's registers for the first 12 neighbours, the probe cache beyond
+			qq[j] = 0u;
+			if (kk[j] >= FUSE_RCH) qq[j] = __ldcg(S.probes+(size_t)kk[j]*a.probeStride+s) & PROBE_PIX;
+			else {
+				#pragma unroll
+				for (int k=0; k<FUSE_RCH; ++k) if (kk[j] == k) qq[j] = code0[k] & PROBE_PIX;
+			}
+		}
 		#pragma unroll
-		for (int j=0; j<4; ++j) if (kk[j] >= 0) { const FuseRec* rb = a.views[pv.nb[kk[j]]].rec+qq[j]; b0[j] = __ldcg(reinterpret_cast<const uint4*>(rb)); b1[j] = __ldcg(reinterpret_cast<const uint4*>(rb)+1); }
+		for (int j=0; j<4; ++j) if (kk[j] >= 0) { const FuseRec* rb = sv[1+kk[j]].rec+qq[j]; b0[j] = __ldcg(reinterpret_cast<const uint4*>(rb)); b1[j] = __ldcg(reinterpret_cast<const uint4*>(rb)+1); }
 		#pragma unroll
 		for (int j=0; j<4; ++j) {
 			if (kk[j] < 0) continue;
-			const FuseView& B = a.views[pv.nb[kk[j]]];
+			const FuseView& B = sv[1+kk[j]];
 			const int q = (int)qq[j];
 			const int xB = q%B.w, yB = q/B.w;
 			const float depthB = __uint_as_float(b0[j].x);
@@ -402,20 +426,38 @@ __device__ FUSE_FN void stage_slot(const FuseJob& a, const FusePlanView& pv, con
 	}
 }
 
+// staging of a seed that became final in a later round, deferred to the count stage of the next view: those rounds are chains of
+// dependent loads over a few hundred slots (one or two blocks busy, the rest of the grid waiting at the barrier), and the staging
+// — the seed's record, its merged neighbours' records, the f64 sums — was more than half of every such chain
+__device__ FUSE_FN void stage_deferred(const FuseJob& a, const FusePlanView& pv, const FuseView* sv, const FuseSlots& S, const int s) {
+	const uint32_t p = __ldcg(S.seeds+s), merged = __ldcg(S.mask+s);
+	uint32_t code0[FUSE_RCH];
+	#pragma unroll
+	for (int k=0; k<FUSE_RCH; ++k) code0[k] = (k < pv.nNb && (merged & (1u<<k))) ? __ldcg(S.probes+(size_t)k*a.probeStride+s) : PROBE_DEAD;
+	stage_slot(a, pv, sv, S, s, (int)p, merged, code0);
+}
+
 // copy the staged point of final slot s to its place in the cloud; the view list is written sorted by view id (InsertSort,
 // SceneDensify.cpp:3407-3409) through the plan's id order
 __device__ __forceinline__ void emit_slot(const FuseJob& a, const FusePlanView& pv, const FuseSlots& S, const int s, const unsigned long long ip, const unsigned long long iv) {
 	const FuseOut& out = a.out;
 	const float4 P = __ldcg(S.stgPoint+s);
+	const uint32_t merged = __ldcg(S.mask+s);
+	float4 Nn = make_float4(0.f, 0.f, 0.f, 0.f); if (out.estimateNormal) Nn = __ldcg(S.stgNormal+s);
 	out.points[ip*3+0] = P.x; out.points[ip*3+1] = P.y; out.points[ip*3+2] = P.z;
 	if (out.estimateColor) { const uint32_t c = __float_as_uint(P.w); out.colors[ip*3+0] = (uint8_t)(c&255u); out.colors[ip*3+1] = (uint8_t)((c>>8)&255u); out.colors[ip*3+2] = (uint8_t)((c>>16)&255u); }
-	if (out.estimateNormal) { const float4 Nn = __ldcg(S.stgNormal+s); out.normals[ip*3+0] = Nn.x; out.normals[ip*3+1] = Nn.y; out.normals[ip*3+2] = Nn.z; }
+	if (out.estimateNormal) { out.normals[ip*3+0] = Nn.x; out.normals[ip*3+1] = Nn.y; out.normals[ip*3+2] = Nn.z; }
 	out.viewOffsets[ip] = (uint32_t)iv;
-	const uint32_t merged = __ldcg(S.mask+s);
 	unsigned long long o = iv;
-	for (int j=0; j<=pv.nNb; ++j) { // ids ascending: the reference view or neighbour k = order[j]
-		const int k = pv.order[j];
-		if (k < 0 || (merged & (1u<<k))) { out.views[o] = (uint32_t)(k < 0 ? pv.view : pv.nb[k]); out.weights[o] = __ldcg(S.stgW+(size_t)(1+k)*a.probeStride+s); ++o; }
+	for (int j0=0; j0<=pv.nNb; j0+=8) { // ids ascending: the reference view or neighbour k = order[j]; 8 weights in flight, then their stores
+		float wv[8]; int kx[8];
+		#pragma unroll
+		for (int j=0; j<8; ++j) {
+			kx[j] = -2;
+			if (j0+j <= pv.nNb) { const int k = pv.order[j0+j]; if (k < 0 || (merged & (1u<<k))) { kx[j] = k; wv[j] = __ldcg(S.stgW+(size_t)(1+k)*a.probeStride+s); } }
+		}
+		#pragma unroll
+		for (int j=0; j<8; ++j) if (kx[j] != -2) { out.views[o] = (uint32_t)(kx[j] < 0 ? pv.view : pv.nb[kx[j]]); out.weights[o] = wv[j]; ++o; }
 	}
 }
 
@@ -430,12 +472,17 @@ __device__ __forceinline__ void emit_slot(const FuseJob& a, const FusePlanView& 
 // bitmap-word / slot ranges in the two ordered compactions, so the slots and the cloud keep raster order with one block-count
 // prefix (<= gridDim.x words) per compaction.
 #ifndef FUSE_MINB
-#define FUSE_MINB 3
+#define FUSE_MINB 2 // 128 registers: 3 CTAs/SM (80 registers) spill ~800 B per thread into the dependent chains (measured: 4.74 vs 4.24 ms per 16 C2 views)
 #endif
 __global__ void __launch_bounds__(FUSE_NT, FUSE_MINB) k_fuse_scene(const FuseJob a) {
 	cg::grid_group grid = cg::this_grid();
 	__shared__ unsigned long long sw64[FUSE_NT/32];
 	__shared__ unsigned sw[FUSE_NT/32];
+	// the plan entry of the view being fused and the views it touches ([0] the view itself, [1+k] neighbour k), per block in shared
+	// memory; set r&1 belongs to view r, so the other set still describes view r-1 for its emit / deferred staging. Every stage is a
+	// chain of dependent loads: fetching descriptors and cameras through pointers in global memory added two trips to each link.
+	__shared__ FusePlanView sPlan[2];
+	__shared__ FuseView sView[2][HCMVS_MAX_FUSE_VIEWS+1];
 	const int G = (int)gridDim.x, b = (int)blockIdx.x;
 	const int gtid = b*FUSE_NT+threadIdx.x, nThreads = G*FUSE_NT;
 	unsigned nSeedsPrev = 0;
@@ -444,6 +491,18 @@ __global__ void __launch_bounds__(FUSE_NT, FUSE_MINB) k_fuse_scene(const FuseJob
 		const FuseSlots& Sp = a.sl[(r&1)^1];
 		const FusePlanView* pv = r < a.nPlan ? a.plan+r : nullptr;
 		const FusePlanView* pvp = r > 0 ? a.plan+(r-1) : nullptr;
+		if (pv) {
+			static_assert(sizeof(FusePlanView)%4 == 0 && sizeof(FuseView)%8 == 0, "word copies");
+			const uint32_t* src = reinterpret_cast<const uint32_t*>(pv); uint32_t* dst = reinterpret_cast<uint32_t*>(&sPlan[r&1]);
+			for (int i=threadIdx.x; i<(int)(sizeof(FusePlanView)/4); i+=FUSE_NT) dst[i] = src[i];
+			const int nV = 1+pv->nNb, per = (int)(sizeof(FuseView)/8);
+			for (int i=threadIdx.x; i<nV*per; i+=FUSE_NT) {
+				const int v = i/per, o = i-v*per;
+				const int id = v == 0 ? pv->view : pv->nb[v-1];
+				reinterpret_cast<unsigned long long*>(&sView[r&1][v])[o] = reinterpret_cast<const unsigned long long*>(a.views+id)[o];
+			}
+		}
+		__syncthreads();
 		int wLo = 0, wHi = 0; // bitmap words of view r this block compacts
 		const uint32_t* aliveR = nullptr;
 		if (pv) {
@@ -455,12 +514,13 @@ __global__ void __launch_bounds__(FUSE_NT, FUSE_MINB) k_fuse_scene(const FuseJob
 		int sLo = 0, sHi = 0;
 		if (pvp) { const int L = (int)((nSeedsPrev+G-1)/G); sLo = min(b*L, (int)nSeedsPrev); sHi = min(sLo+L, (int)nSeedsPrev); }
 		FUSE_STAMP(0);
-		// ---- [C] counts
+		// ---- [C] counts (+ the deferred staging of view r-1)
 		{
+			if (pvp) { const unsigned nSt = __ldcg(&a.ctl->stCount[(r&1)^1]); for (int i=gtid; i<(int)nSt; i+=nThreads) stage_deferred(a, sPlan[(r&1)^1], sView[(r&1)^1], Sp, (int)__ldcg(a.stl[(r&1)^1]+i)); }
 			unsigned long long nS = 0, nP = 0, nV = 0;
 			for (int i=wLo+threadIdx.x; i<wHi; i+=FUSE_NT) nS += (unsigned)__popc(__ldcg(aliveR+i));
 			for (int s=sLo+threadIdx.x; s<sHi; s+=FUSE_NT)
-				if (__ldcg(Sp.state+s) == 2) { ++nP; nV += 1u+(unsigned)__popc(__ldcg(Sp.mask+s)); }
+				{ const uint8_t st = __ldcg(Sp.state+s); const uint32_t mk = __ldcg(Sp.mask+s); if (st == 2) { ++nP; nV += 1u+(unsigned)__popc(mk); } }
 			nS = block_sum(nS, sw64); nP = block_sum(nP, sw64); nV = block_sum(nV, sw64);
 			if (threadIdx.x == 0) { a.blkSeeds[b] = (unsigned)nS; a.blkEmit[2*b] = (unsigned)nP; a.blkEmit[2*b+1] = (unsigned)nV; }
 		}
@@ -499,15 +559,17 @@ __global__ void __launch_bounds__(FUSE_NT, FUSE_MINB) k_fuse_scene(const FuseJob
 				unsigned long long ip = cumP+preP, iv = cumV+preV;
 				for (int s0=sLo; s0<sHi; s0+=FUSE_NT) {
 					const int s = s0+threadIdx.x;
-					const bool f = s < sHi && __ldcg(Sp.state+s) == 2;
-					const unsigned nv = f ? 1u+(unsigned)__popc(__ldcg(Sp.mask+s)) : 0u;
+					uint8_t st = 0; uint32_t mk = 0;
+					if (s < sHi) { st = __ldcg(Sp.state+s); mk = __ldcg(Sp.mask+s); } // one trip
+					const bool f = st == 2;
+					const unsigned nv = f ? 1u+(unsigned)__popc(mk) : 0u;
 					unsigned tot1;
 					const unsigned ex = block_scan((f ? 1u<<16 : 0u) | nv, sw, tot1); // points in the high half, view references in the low half
-					if (f && fits) emit_slot(a, *pvp, Sp, s, ip+(ex>>16), iv+(ex&0xFFFFu));
+					if (f && fits) emit_slot(a, sPlan[(r&1)^1], Sp, s, ip+(ex>>16), iv+(ex&0xFFFFu));
 					ip += tot1>>16; iv += tot1&0xFFFFu;
 				}
 			}
-			if (gtid == 0) { a.ctl->wlCount[0] = 0; a.ctl->wlCount[1] = 0; if (pv) { a.ctl->seeds += nSeeds; a.ctl->probes += (unsigned long long)nSeeds*(unsigned)pv->nNb; } }
+			if (gtid == 0) { a.ctl->wlCount[0] = 0; a.ctl->wlCount[1] = 0; a.ctl->wlCount[2] = 0; a.ctl->stCount[r&1] = 0; if (pv) { a.ctl->seeds += nSeeds; a.ctl->probes += (unsigned long long)nSeeds*(unsigned)pv->nNb; } }
 		}
 		grid.sync();
 		if (pvp && gtid == 0) { // every block has read the old totals: advance them; the points of view r-1 are final and visible
@@ -522,41 +584,45 @@ __global__ void __launch_bounds__(FUSE_NT, FUSE_MINB) k_fuse_scene(const FuseJob
 		if (!pv) break;
 		FUSE_STAMP(2);
 		// ---- [P] probes + first reservations
-		for (int s=gtid; s<(int)nSeeds; s+=nThreads) probe_slot(a, *pv, S, s);
+		for (int s=gtid; s<(int)nSeeds; s+=nThreads) probe_slot(a, sPlan[r&1], sView[r&1], S, s);
 		grid.sync();
 		FUSE_STAMP(3);
-		// ---- [R] round 1 over every slot; a seed that became final stages its point at once (its merged records were fetched by [P])
+		// ---- [R] round 1 over every slot; a seed that became final stages its point at once (its merged records were fetched by [P]);
+		// round k pushes its unfinished slots to worklist k%2 / counter k%3 and zeroes counter (k+1)%3 for the round after
 		for (int s0=b*FUSE_NT; s0<(int)nSeeds; s0+=nThreads) {
 			const int s = s0+threadIdx.x;
-			const int res = s < (int)nSeeds ? resolve_slot(a, *pv, S, s) : 0;
-			worklist_push(a.wl[0], &a.ctl->wlCount[0], res == 1, s);
-			if (res == 2) stage_slot(a, *pv, S, s);
+			uint32_t p = 0, merged = 0, code0[FUSE_RCH];
+			const int res = s < (int)nSeeds ? resolve_slot(a, sPlan[r&1], sView[r&1], S, s, 1u, p, merged, code0) : 0;
+			unsigned m; const unsigned base = wl_begin(&a.ctl->wlCount[1], res == 1, m);
+			if (res == 2) stage_slot(a, sPlan[r&1], sView[r&1], S, s, (int)p, merged, code0);
+			wl_commit(a.wl[1], base, m, res == 1, s);
 		}
 		grid.sync();
 		FUSE_STAMP(4);
-		// ---- later rounds over the worklist of unfinished slots (finishing short worklists with 1 or 32 blocks and a barrier of their
-		// own was measured: not faster — a round is bound by its chain of dependent loads, not by the barrier; profiles/r02_notes.md)
-		int cur = 0; unsigned rounds = 1; unsigned long long wlSum = 0;
-		for (;;) {
-			unsigned nw = __ldcg(&a.ctl->wlCount[cur]);
+		// ---- later rounds over the worklist of unfinished slots: ONE phase per round (resolve + next reservations, see resolve_slot)
+		unsigned rounds = 1; unsigned long long wlSum = 0, syncNs = 0; // syncNs (debug): what thread 0 waits in the rounds' barriers
+		for (unsigned k=2; ; ++k) {
+			const unsigned nw = __ldcg(&a.ctl->wlCount[(k-1u)%3u]);
 			if (!nw) break;
 			wlSum += nw;
-			const uint32_t* wl = a.wl[cur];
-			for (int i=gtid; i<(int)nw; i+=nThreads) reserve_slot(a, *pv, S, (int)__ldcg(wl+i));
-			if (gtid == 0) a.ctl->wlCount[cur^1] = 0;
-			grid.sync();
+			const uint32_t* wl = a.wl[(k-1u)&1u];
+			if (gtid == 0) a.ctl->wlCount[(k+1u)%3u] = 0;
 			for (int i0=b*FUSE_NT; i0<(int)nw; i0+=nThreads) {
 				const int i = i0+threadIdx.x;
 				const int s = i < (int)nw ? (int)__ldcg(wl+i) : 0;
-				const int res = i < (int)nw ? resolve_slot(a, *pv, S, s) : 0;
-				worklist_push(a.wl[cur^1], &a.ctl->wlCount[cur^1], res == 1, s);
-				if (res == 2) stage_slot(a, *pv, S, s);
+				uint32_t p = 0, merged = 0, code0[FUSE_RCH];
+				const int res = i < (int)nw ? resolve_slot(a, sPlan[r&1], sView[r&1], S, s, k, p, merged, code0) : 0;
+				unsigned m, m2; const unsigned base = wl_begin(&a.ctl->wlCount[k%3u], res == 1, m), base2 = wl_begin(&a.ctl->stCount[r&1], res == 2, m2);
+				wl_commit(a.wl[k&1u], base, m, res == 1, s);
+				wl_commit(a.stl[r&1], base2, m2, res == 2, s);
 			}
+			const unsigned long long t0 = a.trace && gtid == 0 ? gtimer() : 0ull;
 			grid.sync();
-			cur ^= 1; ++rounds;
+			if (a.trace && gtid == 0) syncNs += gtimer()-t0;
+			++rounds;
 		}
 		FUSE_STAMP(5);
-		if (a.trace && gtid == 0) { a.trace[8*r+6] = nSeeds | ((unsigned long long)rounds<<32); a.trace[8*r+7] = wlSum; }
+		if (a.trace && gtid == 0) { a.trace[8*r+6] = nSeeds | ((unsigned long long)rounds<<32); a.trace[8*r+7] = (wlSum & 0xFFFFFFFFull) | (syncNs<<32); }
 		if (gtid == 0) a.ctl->rounds += rounds;
 		nSeedsPrev = nSeeds;
 	}
@@ -625,7 +691,7 @@ struct FuseState {
 	FuseRec* rec_d = nullptr; size_t recCap = 0; std::vector<size_t> recOff; uint32_t* alive_d = nullptr; size_t aliveCap = 0; std::vector<size_t> aliveOff; uint32_t* claim_d = nullptr; size_t claimCap = 0; // per-view records (kept after the fusion: claims, zeroed depths)
 	FusePlanView* plan_d = nullptr; size_t planCap = 0;
 	// per-seed-slot arrays (two sets) + worklists, sized for the largest view
-	uint8_t* state_d[2] = {nullptr, nullptr}; uint32_t* mask_d[2] = {nullptr, nullptr}; uint32_t* seeds_d[2] = {nullptr, nullptr}; uint32_t* wl_d[2] = {nullptr, nullptr}; size_t pixCap = 0;
+	uint8_t* state_d[2] = {nullptr, nullptr}; uint32_t* mask_d[2] = {nullptr, nullptr}; uint32_t* seeds_d[2] = {nullptr, nullptr}; uint32_t* wl_d[2] = {nullptr, nullptr}; uint32_t* stl_d[2] = {nullptr, nullptr}; size_t pixCap = 0;
 	uint32_t* probes_d[2] = {nullptr, nullptr}; float* stgW_d[2] = {nullptr, nullptr}; size_t probeCap = 0;
 	float4* stgPoint_d[2] = {nullptr, nullptr}; float4* stgNormal_d[2] = {nullptr, nullptr};
 	unsigned* blk_d = nullptr; int coopBlocks = 0; size_t smemEmit = 0;
@@ -652,7 +718,7 @@ void hcmvs_fuse_release(hcmvs_ctx* ctx) {
 	if (f->pinned) cudaFreeHost(f->pinned);
 	if (f->progress) cudaFreeHost(f->progress);
 	cudaFree(f->views_d); cudaFree(f->rec_d); cudaFree(f->alive_d); cudaFree(f->claim_d); cudaFree(f->plan_d); cudaFree(f->blk_d); cudaFree(f->ctl_d); cudaFree(f->nValid_d);
-	for (int i=0; i<2; ++i) { cudaFree(f->state_d[i]); cudaFree(f->mask_d[i]); cudaFree(f->seeds_d[i]); cudaFree(f->wl_d[i]); cudaFree(f->probes_d[i]); cudaFree(f->stgW_d[i]); cudaFree(f->stgPoint_d[i]); cudaFree(f->stgNormal_d[i]); }
+	for (int i=0; i<2; ++i) { cudaFree(f->state_d[i]); cudaFree(f->mask_d[i]); cudaFree(f->seeds_d[i]); cudaFree(f->wl_d[i]); cudaFree(f->stl_d[i]); cudaFree(f->probes_d[i]); cudaFree(f->stgW_d[i]); cudaFree(f->stgPoint_d[i]); cudaFree(f->stgNormal_d[i]); }
 	cudaFree(f->points); cudaFree(f->normals); cudaFree(f->colors); cudaFree(f->viewOffsets); cudaFree(f->oviews); cudaFree(f->weights);
 	delete f; ctx->fuse = nullptr;
 }
@@ -715,7 +781,7 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 	if (estimate_color && !anyColor) estimate_color = 0;
 	if (f->recCap < totalPix) { int r = Realloc(ctx, f->rec_d, totalPix); if (r) return r; f->recCap = totalPix; }
 	if (f->aliveCap < totalWords) { int r = Realloc(ctx, f->alive_d, totalWords); if (r) return r; f->aliveCap = totalWords; }
-	if (f->claimCap < totalPix) { int r = Realloc(ctx, f->claim_d, totalPix); if (r) return r; f->claimCap = totalPix; }
+	if (f->claimCap < 3*totalPix) { int r = Realloc(ctx, f->claim_d, 3*totalPix); if (r) return r; f->claimCap = 3*totalPix; }
 	for (size_t i=0; i<V; ++i) if (f->recOff[i] != (size_t)-1) { hv[i].rec = f->rec_d+f->recOff[i]; hv[i].alive = f->alive_d+aliveOff[i]; hv[i].claim = f->claim_d+f->recOff[i]; }
 	if (f->nViews < V) { int r = Realloc(ctx, f->views_d, V); if (r) return r; f->nViews = V; }
 	CK(cudaMemcpyAsync(f->views_d, hv.data(), V*sizeof(FuseView), cudaMemcpyHostToDevice, ctx->stream));
@@ -736,7 +802,7 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 	if (f->pixCap < maxPix) {
 		for (int i=0; i<2; ++i) {
 			int r;
-			if ((r = Realloc(ctx, f->state_d[i], maxPix)) || (r = Realloc(ctx, f->mask_d[i], maxPix)) || (r = Realloc(ctx, f->seeds_d[i], maxPix)) || (r = Realloc(ctx, f->wl_d[i], maxPix)) ||
+			if ((r = Realloc(ctx, f->state_d[i], maxPix)) || (r = Realloc(ctx, f->mask_d[i], maxPix)) || (r = Realloc(ctx, f->seeds_d[i], maxPix)) || (r = Realloc(ctx, f->wl_d[i], maxPix)) || (r = Realloc(ctx, f->stl_d[i], maxPix)) ||
 			    (r = Realloc(ctx, f->stgPoint_d[i], maxPix)) || (r = Realloc(ctx, f->stgNormal_d[i], maxPix))) return r;
 		}
 		f->pixCap = maxPix;
@@ -776,7 +842,7 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 	// ---- records of every view with maps + the number of valid depths (bounds the cloud)
 	CK(cudaMemsetAsync(f->nValid_d, 0, sizeof(unsigned long long), ctx->stream));
 	CK(cudaMemsetAsync(f->ctl_d, 0, sizeof(FuseCtl), ctx->stream));
-	CK(cudaMemsetAsync(f->claim_d, 0xFF, totalPix*sizeof(uint32_t), ctx->stream)); // CLAIM_FREE
+	CK(cudaMemsetAsync(f->claim_d, 0xFF, 3*totalPix*sizeof(uint32_t), ctx->stream)); // CLAIM_FREE, the three rotating planes
 	for (size_t i=0; i<V; ++i) {
 		if (f->recOff[i] == (size_t)-1) continue;
 		const size_t n = (size_t)hv[i].w*hv[i].h;
@@ -805,8 +871,8 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 	memset(f->progress, 0, f->progressCap*sizeof(unsigned long long));
 	FuseJob a; memset(&a, 0, sizeof(a));
 	a.views = f->views_d; a.plan = f->plan_d; a.nPlan = (int)plan.size();
-	for (int i=0; i<2; ++i) { a.sl[i].seeds = f->seeds_d[i]; a.sl[i].state = f->state_d[i]; a.sl[i].mask = f->mask_d[i]; a.sl[i].probes = f->probes_d[i]; a.sl[i].stgPoint = f->stgPoint_d[i]; a.sl[i].stgNormal = f->stgNormal_d[i]; a.sl[i].stgW = f->stgW_d[i]; a.wl[i] = f->wl_d[i]; }
-	a.probeStride = maxPix;
+	for (int i=0; i<2; ++i) { a.sl[i].seeds = f->seeds_d[i]; a.sl[i].state = f->state_d[i]; a.sl[i].mask = f->mask_d[i]; a.sl[i].probes = f->probes_d[i]; a.sl[i].stgPoint = f->stgPoint_d[i]; a.sl[i].stgNormal = f->stgNormal_d[i]; a.sl[i].stgW = f->stgW_d[i]; a.wl[i] = f->wl_d[i]; a.stl[i] = f->stl_d[i]; }
+	a.probeStride = maxPix; a.claimPlane = totalPix;
 	a.blkSeeds = f->blk_d; a.blkEmit = f->blk_d+f->coopBlocks;
 	a.ctl = f->ctl_d;
 	a.nMinViewsFuse = nMinViewsFuse; a.depthTh = P.fDepthDiffThreshold*P.depthweight; a.normalError = normalError;
@@ -860,7 +926,8 @@ extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int esti
 		for (size_t r=0; r<plan.size(); ++r) for (int i=0; i<5; ++i) acc[i] += (double)(tr[8*r+i+1]-tr[8*r+i])*1e-3;
 		for (size_t r=0; r<plan.size(); r += (r < 8 ? 1 : 8))
 			fprintf(stderr, "[fuse] view #%zu (%d): count %.1f scatter+emit %.1f probe %.1f resolve-1 %.1f rounds %.1f us; %llu seeds, %llu rounds, worklist entries summed over the rounds %llu\n", r, plan[r].view,
-				(tr[8*r+1]-tr[8*r])*1e-3, (tr[8*r+2]-tr[8*r+1])*1e-3, (tr[8*r+3]-tr[8*r+2])*1e-3, (tr[8*r+4]-tr[8*r+3])*1e-3, (tr[8*r+5]-tr[8*r+4])*1e-3, tr[8*r+6]&0xFFFFFFFFull, tr[8*r+6]>>32, tr[8*r+7]);
+				(tr[8*r+1]-tr[8*r])*1e-3, (tr[8*r+2]-tr[8*r+1])*1e-3, (tr[8*r+3]-tr[8*r+2])*1e-3, (tr[8*r+4]-tr[8*r+3])*1e-3, (tr[8*r+5]-tr[8*r+4])*1e-3, tr[8*r+6]&0xFFFFFFFFull, tr[8*r+6]>>32, tr[8*r+7]&0xFFFFFFFFull);
+		for (size_t r=0; r<plan.size(); r += (r < 8 ? 1 : 8)) fprintf(stderr, "[fuse] view #%zu: thread 0 spent %.1f us in the barriers of the later rounds\n", r, (double)(tr[8*r+7]>>32)*1e-3);
 		fprintf(stderr, "[fuse] us per scene: count %.0f, scatter+emit %.0f, probe %.0f, resolve-1 %.0f, rounds %.0f; total %.0f\n", acc[0], acc[1], acc[2], acc[3], acc[4], (double)(tr[8*(plan.size()-1)+5]-tr[0])*1e-3);
 	}
 	if (debug) fprintf(stderr, "[fuse] %zu views, %llu seeds, %llu rounds, %zu points, %zu view refs, %d blocks\n", plan.size(), ctl.seeds, ctl.rounds, nPoints, nViewRefs, f->coopBlocks);
