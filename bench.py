@@ -130,7 +130,7 @@ def make_scene(args, only=None):
 
 def ncu_traffic_per_launch():
     """dram__bytes_read.sum + dram__bytes_write.sum of one k_sweep launch from the committed `ncu --set full` summary (profiles/)."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_k_sweep_final.txt")
+    path = os.path.join(ROOT, "profiles", "r02b_ncu_k_sweep_tex.txt")
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     tot, found = 0.0, 0
     try:
@@ -299,7 +299,7 @@ def sweep_roofline(tm, P, sms, peaks, peak_src, n_sweep_launches):
         "hbm": {"achieved": hbm_bytes / sweep_s / 1e9 if sweep_s > 0 else 0.0, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                 "frac": (hbm_bytes / sweep_s / 1e9) / peaks.get("hbm_gbs", 1.0) if sweep_s > 0 else None, "bytes_per_pixel_iter": 64},
         "traffic": ncu_traffic_per_launch(),
-        "traffic_note": "DRAM bytes of one k_sweep launch (ncu --set full, profiles/r01_ncu_k_sweep_final.txt; C2 view) vs 0.96 Mpix x 64 B = 61 MB algorithmic",
+        "traffic_note": "DRAM bytes of one k_sweep launch (ncu --set full, profiles/r02b_ncu_k_sweep_tex.txt; iteration-3 launch of a C2 view) vs 0.96 Mpix x 64 B = 61 MB algorithmic",
         "sweep_mpix_iter_s": tm["n_pixel_iters"] / sweep_s / 1e6 if sweep_s > 0 else None,
         "hyp_per_pixel_iter": tm["n_hypotheses"] / max(tm["n_pixel_iters"], 1),
     }
@@ -308,7 +308,7 @@ def sweep_roofline(tm, P, sms, peaks, peak_src, n_sweep_launches):
     tex_peak = 2.0 * sms * peaks.get("sm_max_mhz", 1965.0) * 1e6
     tex_rate = tm["n_view_scores"] * texels / sweep_s if sweep_s > 0 else 0.0
     roofline["tex_wall"] = {"achieved": tex_rate / 1e9, "peak": tex_peak / 1e9, "unit": "Gsample/s", "frac": tex_rate / tex_peak if tex_peak else None,
-                            "note": "texture write-back 32 B/clk/SM, 16 B per bilinear sample (ncu l1tex__tex_writeback_active 79.4 %, profiles/r01_ncu_k_sweep_final.txt)"}
+                            "note": "texture write-back 32 B/clk/SM, 16 B per bilinear sample (ncu l1tex__tex_writeback_active 80.1 % in an iteration-3 launch, profiles/r02b_ncu_k_sweep_tex.txt)"}
     return roofline
 
 
