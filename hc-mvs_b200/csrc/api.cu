@@ -348,14 +348,34 @@ static int AllocMaps(hcmvs_ctx* ctx, View* v) {
 	return HCMVS_OK;
 }
 
+// Before a view's maps are overwritten on the copy stream: they may still be in use by queued compute work (re-initialisation of an
+// estimated view — every scene after the first when a context is reused). Without further knowledge that is "everything queued so
+// far", which makes the upload of view i+1 wait for the estimation of view i and serialises the host with the GPU (measured: one
+// view enqueued every 20 ms, 44 ms of a 1.02 s C2 scene). After hcmvs_begin_scene the caller has promised that only a view's own
+// init / estimate calls touch its maps until the first multi-view consumer, so the view's own last use is enough.
+static int WaitMapsFree(hcmvs_ctx* ctx, View* v) {
+	if (!v->dn_d) return HCMVS_OK;
+	if (ctx->freshScene) { if (v->lastUse) CK(cudaStreamWaitEvent(ctx->copyStream, v->lastUse, 0)); return HCMVS_OK; }
+	cudaEvent_t done; CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming)); CK(cudaEventRecord(done, ctx->stream)); CK(cudaStreamWaitEvent(ctx->copyStream, done, 0)); CK(cudaEventDestroy(done));
+	return HCMVS_OK;
+}
+
+extern "C" int hcmvs_begin_scene(hcmvs_ctx* ctx) {
+	if (!ctx) { hcmvs_set_error("null argument"); return HCMVS_ERR_ARG; }
+	cudaSetDevice(ctx->device);
+	CK(cudaStreamSynchronize(ctx->stream)); CK(cudaStreamSynchronize(ctx->copyStream));
+	if (ctx->dlStream) CK(cudaStreamSynchronize(ctx->dlStream));
+	ctx->freshScene = true;
+	return HCMVS_OK;
+}
+
 // Upload a view's maps on the COPY stream (H2D + packing kernel), so that it overlaps whatever the compute stream is doing
 // for other views; consumers on the compute stream wait on v->ready. Returns once the host buffers may be reused.
 static int UploadMaps(hcmvs_ctx* ctx, View* v, const float* depth, const float* normal, const float* conf) {
 	const size_t n = (size_t)v->w*v->h;
 	v->depthValid = false;
 	cudaStream_t cs = ctx->copyStream;
-	// the view's buffers may still be in use by earlier compute work (re-initialisation of an estimated view)
-	if (v->dn_d) { cudaEvent_t done; CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming)); CK(cudaEventRecord(done, ctx->stream)); CK(cudaStreamWaitEvent(cs, done, 0)); CK(cudaEventDestroy(done)); }
+	{ int r = WaitMapsFree(ctx, v); if (r) return r; }
 	if (!v->dn_d) CK(cudaMalloc(&v->dn_d, n*sizeof(float4)));
 	if (!v->conf_d) CK(cudaMalloc(&v->conf_d, n*4));
 	if (ctx->uploadBytes < n*16) {
@@ -419,7 +439,7 @@ extern "C" int hcmvs_init_depthmap_triangles(hcmvs_ctx* ctx, uint32_t ref, const
 		for (int y=miny; y<maxy; y+=8) for (int x=minx; x<maxx; x+=32) chunks.push_back(make_int3(t, x, y));
 	}
 	cudaStream_t cs = ctx->copyStream;
-	if (v->dn_d) { cudaEvent_t done; CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming)); CK(cudaEventRecord(done, ctx->stream)); CK(cudaStreamWaitEvent(cs, done, 0)); CK(cudaEventDestroy(done)); }
+	{ int r = WaitMapsFree(ctx, v); if (r) return r; }
 	if (!v->dn_d) CK(cudaMalloc(&v->dn_d, n*sizeof(float4)));
 	if (!v->conf_d) CK(cudaMalloc(&v->conf_d, n*4));
 	const size_t bV = ((size_t)n_vertices*24+255)&~(size_t)255, bT = ((size_t)n_tris*12+255)&~(size_t)255, bC = (chunks.size()*sizeof(int3)+255)&~(size_t)255, need = bV+bT+bC+n*4;
@@ -500,6 +520,7 @@ extern "C" int hcmvs_download_depthmap_begin(hcmvs_ctx* ctx, uint32_t view, int 
 	CK(hcmvs_launch_unpack(v->dn_d, d.dev, d.dev+n, n, ctx->stream)); ++ctx->nLaunches;
 	CK(cudaMemcpyAsync(d.dev+n*4, v->conf_d, n*4, cudaMemcpyDeviceToDevice, ctx->stream));
 	CK(cudaEventRecord(d.unpacked, ctx->stream));
+	{ int r = hcmvs_mark_image_use(ctx, *v); if (r) return r; } // a later re-initialisation of this view waits for the unpack (hcmvs_begin_scene)
 	CK(cudaStreamWaitEvent(ctx->dlStream, d.unpacked, 0));
 	CK(cudaMemcpyAsync(d.host, d.dev, n*20, cudaMemcpyDeviceToHost, ctx->dlStream));
 	CK(cudaEventRecord(d.landed, ctx->dlStream));
@@ -526,6 +547,7 @@ extern "C" int hcmvs_download_depthmap_wait(hcmvs_ctx* ctx, int slot, const floa
 }
 
 extern "C" int hcmvs_get_depthmap_device(hcmvs_ctx* ctx, uint32_t view, void** dn_d, void** conf_d, float* dMin, float* dMax) {
+	if (ctx) ctx->freshScene = false; // a consumer of other views' maps ends the "own maps only" phase of hcmvs_begin_scene
 	View* v = GetView(ctx, view, true); if (!v) return HCMVS_ERR_ARG;
 	if (!v->hasMaps) { hcmvs_set_error("view %u has no depth map", view); return HCMVS_ERR_STATE; }
 	if (dn_d) { *dn_d = v->dn_d; v->depthValid = false; } // the caller may write through the pointer
@@ -535,6 +557,7 @@ extern "C" int hcmvs_get_depthmap_device(hcmvs_ctx* ctx, uint32_t view, void** d
 	return HCMVS_OK;
 }
 extern "C" int hcmvs_export_maps_d(hcmvs_ctx* ctx, uint32_t view, void* dn_d, void* conf_d) {
+	if (ctx) ctx->freshScene = false; // a consumer of other views' maps ends the "own maps only" phase of hcmvs_begin_scene
 	View* v = GetView(ctx, view, true); if (!v) return HCMVS_ERR_ARG;
 	if (!v->hasMaps) { hcmvs_set_error("view %u has no depth map", view); return HCMVS_ERR_STATE; }
 	cudaSetDevice(ctx->device);
@@ -544,6 +567,7 @@ extern "C" int hcmvs_export_maps_d(hcmvs_ctx* ctx, uint32_t view, void* dn_d, vo
 	return HCMVS_OK;
 }
 extern "C" int hcmvs_import_maps_d(hcmvs_ctx* ctx, uint32_t view, const void* dn_d, const void* conf_d, float dMin, float dMax) {
+	if (ctx) ctx->freshScene = false; // a consumer of other views' maps ends the "own maps only" phase of hcmvs_begin_scene
 	View* v = GetView(ctx, view, true); if (!v) return HCMVS_ERR_ARG;
 	cudaSetDevice(ctx->device);
 	int r = AllocMaps(ctx, v); if (r) return r;
@@ -559,6 +583,7 @@ extern "C" int hcmvs_set_depth_range(hcmvs_ctx* ctx, uint32_t view, float dMin, 
 }
 
 extern "C" int hcmvs_set_coarse_estimate(hcmvs_ctx* ctx, uint32_t view, int wc, int hc, const float* depth, const float* normal) {
+	if (ctx) ctx->freshScene = false; // a consumer of other views' maps ends the "own maps only" phase of hcmvs_begin_scene
 	View* v = GetView(ctx, view, true); if (!v) return HCMVS_ERR_ARG;
 	cudaSetDevice(ctx->device);
 	if (!depth) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(v->coarse_d); v->coarse_d = nullptr; return HCMVS_OK; }
@@ -596,6 +621,7 @@ extern "C" int hcmvs_get_coarse_estimate(hcmvs_ctx* ctx, uint32_t view, float* d
 }
 
 extern "C" int hcmvs_snapshot_maps(hcmvs_ctx* ctx) {
+	if (ctx) ctx->freshScene = false; // a consumer of other views' maps ends the "own maps only" phase of hcmvs_begin_scene
 	if (!ctx) { hcmvs_set_error("null context"); return HCMVS_ERR_ARG; }
 	cudaSetDevice(ctx->device);
 	for (View& v: ctx->views) {
@@ -611,6 +637,7 @@ extern "C" int hcmvs_snapshot_maps(hcmvs_ctx* ctx) {
 }
 
 extern "C" int hcmvs_restore_snapshot(hcmvs_ctx* ctx) {
+	if (ctx) ctx->freshScene = false; // a consumer of other views' maps ends the "own maps only" phase of hcmvs_begin_scene
 	if (!ctx) { hcmvs_set_error("null context"); return HCMVS_ERR_ARG; }
 	cudaSetDevice(ctx->device);
 	for (View& v: ctx->views) {
@@ -717,7 +744,7 @@ extern "C" int hcmvs_end_depthmap(hcmvs_ctx* ctx, uint32_t ref) {
 	hcmvs_time_begin(ctx, ST_END);
 	CK(hcmvs_launch_end(v->dn_d, v->conf_d, (size_t)v->w*v->h, ctx->P.fNCCThresholdKeep, ctx->stream)); ++ctx->nLaunches;
 	hcmvs_time_end(ctx);
-	return HCMVS_OK;
+	return hcmvs_mark_image_use(ctx, *v);
 }
 
 static int EstimateRows(hcmvs_ctx* ctx, uint32_t ref, int it_external, uint64_t seed, int rowBegin, int rowEnd);

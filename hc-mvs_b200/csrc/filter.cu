@@ -229,6 +229,7 @@ static int EnsureDepthPlane(hcmvs_ctx* ctx, View& v) {
 }
 
 extern "C" int hcmvs_filter_depthmap(hcmvs_ctx* ctx, uint32_t ref, const uint32_t* nb_idx, int n, int bAdjust, float* out_depth, float* out_conf) {
+	if (ctx) ctx->freshScene = false; // a consumer of other views' maps ends the "own maps only" phase of hcmvs_begin_scene
 	if (!ctx || !nb_idx) { hcmvs_set_error("null argument"); return HCMVS_ERR_ARG; }
 	if (ref >= ctx->views.size() || !ctx->views[ref].set || !ctx->views[ref].hasMaps) { hcmvs_set_error("view %u has no depth map", ref); return HCMVS_ERR_STATE; }
 	View& v = ctx->views[ref];
@@ -283,6 +284,7 @@ extern "C" int hcmvs_filter_depthmap(hcmvs_ctx* ctx, uint32_t ref, const uint32_
 }
 
 extern "C" int hcmvs_commit_filtered(hcmvs_ctx* ctx) {
+	if (ctx) ctx->freshScene = false; // a consumer of other views' maps ends the "own maps only" phase of hcmvs_begin_scene
 	if (!ctx) return HCMVS_ERR_ARG;
 	cudaSetDevice(ctx->device);
 	hcmvs_time_begin(ctx, ST_FILTER);

@@ -747,6 +747,7 @@ extern "C" int hcmvs_set_fuse_priority(hcmvs_ctx* ctx, uint32_t view, float scor
 }
 
 extern "C" int hcmvs_fuse_depthmaps(hcmvs_ctx* ctx, int estimate_color, int estimate_normal, hcmvs_pointcloud* out) {
+	if (ctx) ctx->freshScene = false; // a consumer of other views' maps ends the "own maps only" phase of hcmvs_begin_scene
 	if (!ctx) { hcmvs_set_error("null argument"); return HCMVS_ERR_ARG; }
 	if (out) memset(out, 0, sizeof(*out));
 	cudaSetDevice(ctx->device);
@@ -1009,6 +1010,7 @@ extern "C" int hcmvs_download_fused_pinned(hcmvs_ctx* ctx, hcmvs_pointcloud* out
 }
 
 extern "C" int hcmvs_get_fused_support(hcmvs_ctx* ctx, uint32_t view, float* depth_fuse, float* normal_fuse) {
+	if (ctx) ctx->freshScene = false; // a consumer of other views' maps ends the "own maps only" phase of hcmvs_begin_scene
 	if (!ctx || view >= ctx->views.size() || !ctx->views[view].set) { hcmvs_set_error("view %u not set", view); return HCMVS_ERR_ARG; }
 	View& v = ctx->views[view];
 	FuseState* f = ctx->fuse;

@@ -53,6 +53,7 @@ struct hcmvs_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	cudaStream_t copyStream = nullptr;   // H2D uploads + layout kernels, overlapping the compute stream
+	bool freshScene = false;             // hcmvs_begin_scene: until the first multi-view consumer, a view's maps are only touched by its own init / estimate calls
 	void* upload_d = nullptr; size_t uploadBytes = 0; // staging for uploads (copy stream only)
 	hcmvs_params P;
 	std::vector<View> views;

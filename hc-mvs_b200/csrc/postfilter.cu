@@ -152,6 +152,7 @@ using namespace hcmvs;
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { hcmvs_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return HCMVS_ERR_CUDA; } } while (0)
 
 extern "C" int hcmvs_remove_small_segments(hcmvs_ctx* ctx, uint32_t view, unsigned speckle_size, uint64_t* n_removed) {
+	if (ctx) ctx->freshScene = false; // a consumer of other views' maps ends the "own maps only" phase of hcmvs_begin_scene
 	if (!ctx || view >= ctx->views.size() || !ctx->views[view].set) { hcmvs_set_error("view %u not set", view); return HCMVS_ERR_ARG; }
 	View& v = ctx->views[view];
 	if (!v.hasMaps || !v.dn_d) { hcmvs_set_error("view %u has no depth map", view); return HCMVS_ERR_STATE; }

@@ -30,6 +30,7 @@ def lib():
         L.hcmvs_host_add_image.argtypes = [vp, i32, i32, vp, vp, vp, vp, C.c_char_p]
         L.hcmvs_host_set_sparse.argtypes = [vp, i32, vp, vp, vp]
         L.hcmvs_host_select_views.argtypes = [vp, C.POINTER(api.Params), i32]
+        L.hcmvs_host_select_views_mt.argtypes = [vp, C.POINTER(api.Params), i32, i32]
         L.hcmvs_host_get_neighbors.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, i32]
         L.hcmvs_host_get_gray.argtypes = [vp, i32, vp]
         L.hcmvs_host_scale_image.argtypes = [vp, i32, i32, C.c_float, vp, C.POINTER(i32), C.POINTER(i32), vp, vp]
@@ -116,8 +117,8 @@ class HostScene:
         xyz = np.ascontiguousarray(xyz, np.float32); off = np.ascontiguousarray(off, np.int32); views = np.ascontiguousarray(views, np.uint32)
         self.L.hcmvs_host_set_sparse(self.h, len(xyz), _p(xyz), _p(off), _p(views))
 
-    def select_views(self, params, idx):
-        return self.L.hcmvs_host_select_views(self.h, C.byref(params), idx)
+    def select_views(self, params, idx, threads=1):
+        return self.L.hcmvs_host_select_views_mt(self.h, C.byref(params), idx, threads)
 
     def neighbors(self, idx, which=1, cap=64):
         ids = np.zeros(cap, np.uint32); pts = np.zeros(cap, np.uint32)

@@ -279,70 +279,112 @@ static inline float CosAngle(const float* a, const float* b) { // ComputeAngle<f
 }
 static inline bool Contains(const std::vector<uint32_t>& sortedViews, uint32_t id) { return std::binary_search(sortedViews.begin(), sortedViews.end(), id); }
 
-bool Scene::SelectNeighborViews(uint32_t ID, std::vector<uint32_t>& points, unsigned nMinViews, unsigned nMinPointViews, float fOptimAngle) {
-	// Scene.cpp:545-662, "Multi-View Stereo for Community Photo Collections" style view scoring
+// static chunks of [0, n) on nThreads threads (the caller's included); every item writes only its own output slot, so the result does
+// not depend on the thread count
+template<typename F>
+static void ParallelChunks(size_t n, unsigned nThreads, size_t grain, F&& body) {
+	nThreads = (unsigned)std::max<size_t>(1, std::min<size_t>(nThreads, n/grain+1));
+	if (nThreads == 1) { body((size_t)0, n, 0u); return; }
+	std::vector<std::thread> th;
+	for (unsigned t=1; t<nThreads; ++t) th.emplace_back([&, t]() { body(n*t/nThreads, n*(t+1)/nThreads, t); });
+	body((size_t)0, n/nThreads, 0u);
+	for (std::thread& x: th) x.join();
+}
+
+bool Scene::SelectNeighborViews(uint32_t ID, std::vector<uint32_t>& points, unsigned nMinViews, unsigned nMinPointViews, float fOptimAngle, unsigned nThreads) {
+	// Scene.cpp:545-662, "Multi-View Stereo for Community Photo Collections" style view scoring.
+	// The reference runs one image per OpenMP thread (:3652-3667); the view a GPU is waiting for is on the critical path, so the work
+	// INSIDE one image can be spread over nThreads as well: the expensive per-(point, view) terms (acos, pow, two projections) are
+	// computed in parallel into per-point slots and the f32 sums are then formed serially in the reference's point order — the
+	// result is bit-identical for every thread count (test_host_view_selection_and_image_prep_bit_exact).
 	Image& ref = images[ID];
 	ref.neighbors.clear();
 	struct Acc { float score = 0, scale = 0, angle = 0; uint32_t n = 0; };
 	std::vector<Acc> acc(images.size());
 	nMinPointViews = std::min(nMinPointViews, nCalibratedImages());
-	unsigned nSeen = 0;
 	ref.avgDepth = 0;
-	for (size_t ip=0; ip<pointcloud.size(); ++ip) {
-		const std::vector<uint32_t>& pv = pointcloud.views[ip];
-		if (!Contains(pv, ID)) continue;
-		const float* X = &pointcloud.xyz[ip*3];
-		if (pv.size() >= nMinPointViews) points.push_back((uint32_t)ip);
-		ref.avgDepth += (float)PointDepth(ref.camera, X);
-		++nSeen;
-		const float toRef[3] = {(float)(ref.camera.C[0]-(double)X[0]), (float)(ref.camera.C[1]-(double)X[1]), (float)(ref.camera.C[2]-(double)X[2])};
-		const float fpRef = (float)(ref.camera.K[0]/PointDepth(ref.camera, X)); // Footprint, Scene.cpp:531-539
-		for (uint32_t other: pv) {
-			if (other == ID) continue;
-			const Image& o = images[other];
-			const float toOther[3] = {(float)(o.camera.C[0]-(double)X[0]), (float)(o.camera.C[1]-(double)X[1]), (float)(o.camera.C[2]-(double)X[2])};
-			const float ang = std::acos(CosAngle(toRef, toOther));
-			const float wAngle = std::min(std::pow(ang/fOptimAngle, 1.5f), 1.f);
-			const float fpOther = (float)(o.camera.K[0]/PointDepth(o.camera, X));
-			const float ratio = fpRef/fpOther;
-			float wScale;
-			if (ratio > 1.6f) { const float q = 1.6f/ratio; wScale = q*q; }
-			else if (ratio >= 1.f) wScale = 1.f;
-			else wScale = ratio*ratio;
-			Acc& a = acc[other];
-			a.score += wAngle*wScale; a.scale += ratio; a.angle += ang; ++a.n;
-		}
+	// pass 0: the points this image sees, in cloud order
+	std::vector<uint32_t> seen;
+	{
+		std::vector<std::vector<uint32_t>> part(std::max(1u, nThreads));
+		ParallelChunks(pointcloud.size(), nThreads, 4096, [&](size_t lo, size_t hi, unsigned t) {
+			for (size_t ip=lo; ip<hi; ++ip) if (Contains(pointcloud.views[ip], ID)) part[t].push_back((uint32_t)ip);
+		});
+		for (const auto& v: part) seen.insert(seen.end(), v.begin(), v.end());
 	}
+	// pass 1: per point its depth in the reference view and one term per other view that sees it
+	struct Term { uint32_t other; float w, ratio, ang; };
+	std::vector<size_t> off(seen.size()+1, 0);
+	for (size_t k=0; k<seen.size(); ++k) off[k+1] = off[k]+pointcloud.views[seen[k]].size()-1;
+	std::vector<Term> terms(off.back());
+	std::vector<float> depthRef(seen.size());
+	ParallelChunks(seen.size(), nThreads, 256, [&](size_t lo, size_t hi, unsigned) {
+		for (size_t k=lo; k<hi; ++k) {
+			const size_t ip = seen[k];
+			const std::vector<uint32_t>& pv = pointcloud.views[ip];
+			const float* X = &pointcloud.xyz[ip*3];
+			depthRef[k] = (float)PointDepth(ref.camera, X);
+			const float toRef[3] = {(float)(ref.camera.C[0]-(double)X[0]), (float)(ref.camera.C[1]-(double)X[1]), (float)(ref.camera.C[2]-(double)X[2])};
+			const float fpRef = (float)(ref.camera.K[0]/PointDepth(ref.camera, X)); // Footprint, Scene.cpp:531-539
+			Term* out = terms.data()+off[k];
+			for (uint32_t other: pv) {
+				if (other == ID) continue;
+				const Image& o = images[other];
+				const float toOther[3] = {(float)(o.camera.C[0]-(double)X[0]), (float)(o.camera.C[1]-(double)X[1]), (float)(o.camera.C[2]-(double)X[2])};
+				const float ang = std::acos(CosAngle(toRef, toOther));
+				const float wAngle = std::min(std::pow(ang/fOptimAngle, 1.5f), 1.f);
+				const float fpOther = (float)(o.camera.K[0]/PointDepth(o.camera, X));
+				const float ratio = fpRef/fpOther;
+				float wScale;
+				if (ratio > 1.6f) { const float q = 1.6f/ratio; wScale = q*q; }
+				else if (ratio >= 1.f) wScale = 1.f;
+				else wScale = ratio*ratio;
+				*out++ = Term{other, wAngle*wScale, ratio, ang};
+			}
+		}
+	});
+	// pass 2: the sums, serially in cloud order
+	for (size_t k=0; k<seen.size(); ++k) {
+		if (pointcloud.views[seen[k]].size() >= nMinPointViews) points.push_back(seen[k]);
+		ref.avgDepth += depthRef[k];
+		for (size_t j=off[k]; j<off[k+1]; ++j) { const Term& t = terms[j]; Acc& a = acc[t.other]; a.score += t.w; a.scale += t.ratio; a.angle += t.ang; ++a.n; }
+	}
+	const unsigned nSeen = (unsigned)seen.size();
 	ref.avgDepth /= nSeen;
-	std::vector<float> projA;
-	for (uint32_t IDB=0; IDB<images.size(); ++IDB) {
-		const Acc& a = acc[IDB];
-		if (a.n < 3) continue;
-		const Image& B = images[IDB];
-		const float wA = (float)ref.width, hA = (float)ref.height, wB = (float)B.width, hB = (float)B.height;
-		projA.clear();
-		for (uint32_t ip: points) {
-			if (!Contains(pointcloud.views[ip], IDB)) continue;
-			const float* X = &pointcloud.xyz[(size_t)ip*3];
-			float ua, va, ub, vb;
-			ProjectPointP(ref.camera, X, ua, va);
-			ProjectPointP(B.camera, X, ub, vb);
-			if (ua >= 0 && va >= 0 && ua < wA && va < hA && ub >= 0 && vb >= 0 && ub < wB && vb < hB) { projA.push_back(ua); projA.push_back(va); }
+	// pass 3: the area the common points cover in the reference image, per candidate view
+	std::vector<ViewScore> cand(images.size()); std::vector<char> has(images.size(), 0);
+	ParallelChunks(images.size(), nThreads, 1, [&](size_t lo, size_t hi, unsigned) {
+		std::vector<float> projA;
+		for (size_t IDB=lo; IDB<hi; ++IDB) {
+			const Acc& a = acc[IDB];
+			if (a.n < 3) continue;
+			const Image& B = images[IDB];
+			const float wA = (float)ref.width, hA = (float)ref.height, wB = (float)B.width, hB = (float)B.height;
+			projA.clear();
+			for (uint32_t ip: points) {
+				if (!Contains(pointcloud.views[ip], (uint32_t)IDB)) continue;
+				const float* X = &pointcloud.xyz[(size_t)ip*3];
+				float ua, va, ub, vb;
+				ProjectPointP(ref.camera, X, ua, va);
+				ProjectPointP(B.camera, X, ub, vb);
+				if (ua >= 0 && va >= 0 && ua < wA && va < hA && ub >= 0 && vb >= 0 && ub < wB && vb < hB) { projA.push_back(ua); projA.push_back(va); }
+			}
+			if (projA.empty()) continue;
+			// ComputeCoveredArea<float,2,16,false>, Common/Util.inl:711-730
+			bool cell[16][16] = {};
+			for (size_t k=0; k<projA.size(); k+=2) {
+				const float gx = (projA[k]/wA+0.f)*16.f, gy = (projA[k+1]/hA+0.f)*16.f;
+				cell[(int)std::floor(gx)][(int)std::floor(gy)] = true;
+			}
+			unsigned covered = 0;
+			for (auto& row: cell) for (bool c: row) covered += c ? 1u : 0u;
+			const float area = float(covered)/256;
+			ViewScore vs;
+			vs.ID = (uint32_t)IDB; vs.points = a.n; vs.scale = a.scale/a.n; vs.angle = a.angle/a.n; vs.area = area; vs.score = a.score*area;
+			cand[IDB] = vs; has[IDB] = 1;
 		}
-		if (projA.empty()) continue;
-		// ComputeCoveredArea<float,2,16,false>, Common/Util.inl:711-730
-		bool cell[16][16] = {};
-		for (size_t k=0; k<projA.size(); k+=2) {
-			const float gx = (projA[k]/wA+0.f)*16.f, gy = (projA[k+1]/hA+0.f)*16.f;
-			cell[(int)std::floor(gx)][(int)std::floor(gy)] = true;
-		}
-		unsigned covered = 0;
-		for (auto& row: cell) for (bool c: row) covered += c ? 1u : 0u;
-		const float area = float(covered)/256;
-		ViewScore vs;
-		vs.ID = IDB; vs.points = a.n; vs.scale = a.scale/a.n; vs.angle = a.angle/a.n; vs.area = area; vs.score = a.score*area;
-		ref.neighbors.push_back(vs);
-	}
+	});
+	for (size_t IDB=0; IDB<images.size(); ++IDB) if (has[IDB]) ref.neighbors.push_back(cand[IDB]);
 	std::stable_sort(ref.neighbors.begin(), ref.neighbors.end(), [](const ViewScore& l, const ViewScore& r) { return l.score > r.score; });
 	return points.size() > 3 && ref.neighbors.size() >= std::min(nMinViews, nCalibratedImages()-1);
 }
@@ -368,12 +410,12 @@ bool DepthMapsData::Fail(const char* what) {
 	return false;
 }
 
-bool DepthMapsData::SelectViews(uint32_t idxImage) {
+bool DepthMapsData::SelectViews(uint32_t idxImage, unsigned nThreads) {
 	// SceneDensify.cpp:307-327
 	DepthData& dd = arrDepthData[idxImage];
 	dd.points.clear(); dd.neighbors.clear(); dd.valid = false;
 	if (!scene.images[idxImage].calibrated) return false; // !imageData.IsValid(), SceneDensify.cpp:3655
-	if (!scene.SelectNeighborViews(idxImage, dd.points, P.nMinViews, P.nMinViewsTrustPoint > 1 ? P.nMinViewsTrustPoint : 2, Deg2Rad(VS.fOptimAngle)))
+	if (!scene.SelectNeighborViews(idxImage, dd.points, P.nMinViews, P.nMinViewsTrustPoint > 1 ? P.nMinViewsTrustPoint : 2, Deg2Rad(VS.fOptimAngle), nThreads))
 		return false;
 	dd.neighbors = scene.images[idxImage].neighbors;
 	if (!Scene::FilterNeighborViews(dd.neighbors, VS.fMinArea, 0.2f, 3.2f, Deg2Rad(VS.fMinAngle), Deg2Rad(VS.fMaxAngle), P.nMaxViews))
@@ -712,6 +754,8 @@ bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, co
 	double t0 = Now();
 	const uint32_t nImages = (uint32_t)scene.images.size();
 	for (Image& im: scene.images) im.camera.ComposeP();
+	// a reused context: initial-map uploads of later views only wait for their own view's previous use, not for the running estimation
+	if (hcmvs_begin_scene(ctx) != HCMVS_OK) return fail(std::string("hcmvs_begin_scene: ")+hcmvs_last_error());
 	// Host workers select the neighbour views (the reference does it with `#pragma omp parallel for`, :3652-3667 — each call only
 	// writes image i's state) and splat the sparse points into the initial depth map (:783-808), in image order, while this
 	// thread uploads the images and then feeds the GPU: view i is estimated as soon as ITS selection is done, so the host work
@@ -728,17 +772,23 @@ bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, co
 	const unsigned hc = std::thread::hardware_concurrency();
 	const unsigned nt = std::max(1u, std::min(hc > 1 ? hc-1 : 1u, nImages));
 	std::vector<std::thread> pool;
+	auto prepareOne = [&](uint32_t i, unsigned threads) {
+		const bool ok = data.SelectViews(i, threads);
+		if (ok && triangulate) {
+			prep[i].ok = TriangulateInit(scene, i, data.arrDepthData[i].points, true, prep[i].vertices, prep[i].tris, prep[i].dMin, prep[i].dMax);
+			prep[i].dMin *= 0.9f; prep[i].dMax *= 1.1f;
+		} else if (ok) SparseInitDepth(scene, i, data.arrDepthData[i].points, prep[i].depth, prep[i].dMin, prep[i].dMax);
+		tSelectEnd.store(Now());
+		state[i].store(ok ? 1 : -1, std::memory_order_release);
+	};
+	// the first view is what the GPU waits for: every core works INSIDE its selection (bit-identical to the one-thread form), then the
+	// workers take one view each as the reference does
+	if (nImages > 0) { prepareOne(0, std::max(1u, hc)); next.store(1); }
 	for (unsigned t=0; t<nt; ++t) pool.emplace_back([&]() {
 		uint32_t i;
 		while ((i = next.fetch_add(1)) < nImages) {
 			while (i >= consumed.load(std::memory_order_acquire)+lookahead) std::this_thread::sleep_for(std::chrono::microseconds(200)); // throttled: sleep, do not spin
-			const bool ok = data.SelectViews(i);
-			if (ok && triangulate) {
-				prep[i].ok = TriangulateInit(scene, i, data.arrDepthData[i].points, true, prep[i].vertices, prep[i].tris, prep[i].dMin, prep[i].dMax);
-				prep[i].dMin *= 0.9f; prep[i].dMax *= 1.1f;
-			} else if (ok) SparseInitDepth(scene, i, data.arrDepthData[i].points, prep[i].depth, prep[i].dMin, prep[i].dMax);
-			tSelectEnd.store(Now());
-			state[i].store(ok ? 1 : -1, std::memory_order_release);
+			prepareOne(i, 1);
 		}
 	});
 	struct Joiner { std::vector<std::thread>& p; std::atomic<uint32_t>& c; ~Joiner() { c.store(0x7fffffffu); for (std::thread& th: p) if (th.joinable()) th.join(); } } joiner{pool, consumed};
@@ -748,9 +798,13 @@ bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, co
 	if (!dmapDir.empty()) writer.reset(new DmapWriter(ctx, scene, data.arrDepthData, dmapDir));
 	const bool singleOuter = P.nEstimationIters_external <= 1; // the maps are final (and saved, :3984) after the LAST outer iteration
 	std::vector<uint32_t> valid;
+	const bool hostDebug = getenv("HCMVS_HOST_DEBUG") != nullptr;
+	double waitedSum = 0;
 	for (uint32_t i=0; i<nImages; ++i) {
 		int s;
+		const double tw = Now();
 		while ((s = state[i].load(std::memory_order_acquire)) == 0) std::this_thread::yield();
+		const double waited = Now()-tw; waitedSum += waited;
 		if (s > 0) {
 			valid.push_back(i);
 			DepthData& dd = data.arrDepthData[i];
@@ -767,6 +821,7 @@ bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, co
 					st.h2dBytes += (uint64_t)scene.images[i].width*scene.images[i].height*4;
 				}
 				if (hcmvs_estimate_depthmap(ctx, i, 0, seed) != HCMVS_OK) return fail(std::string("hcmvs_estimate_depthmap: ")+hcmvs_last_error());
+				if (hostDebug && valid.size() <= 3) fprintf(stderr, "[host] view %u enqueued at %.1f ms (waited %.1f ms for its selection)\n", i, (Now()-t0)*1e3, waited*1e3);
 				if (writer && singleOuter && !writer->Submit(i)) return fail(writer->err);
 			}
 		}
@@ -789,8 +844,10 @@ bool DenseReconstruction(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& P, co
 			if (writer && it+1 == P.nEstimationIters_external && !writer->Submit(i)) return fail(writer->err);
 		}
 	}
+	const double tEnq = Now();
 	if (hcmvs_sync(ctx) != HCMVS_OK) return fail(hcmvs_last_error());
 	double t3 = Now(); st.secEstimate = t3-t1;
+	if (hostDebug) fprintf(stderr, "[host] all views enqueued at %.1f ms (waited %.1f ms for selections in total), GPU done at %.1f ms\n", (tEnq-t0)*1e3, waitedSum*1e3, (t3-t0)*1e3);
 	// (the last read-backs / .dmap files finish behind the filter and fusion kernels; the writer is joined before returning)
 	if (runFilter) {
 		// Scene::DenseReconstructionFilter, SceneDensify.cpp:4093-4185: neighbours = those with a depth map, at most 8

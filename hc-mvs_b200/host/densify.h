@@ -95,7 +95,8 @@ struct Scene {
 	long PointCloudFilter(hcmvs_ctx* ctx, int thRemove, std::string* err = nullptr);
 	bool ReloadImages(unsigned nResolutionLevel, unsigned nMinResolution = 640, unsigned nMaxResolution = 3200, std::string* err = nullptr);
 	// Scene::SelectNeighborViews / FilterNeighborViews, libs/MVS/Scene.cpp:545-678
-	bool SelectNeighborViews(uint32_t ID, std::vector<uint32_t>& points, unsigned nMinViews, unsigned nMinPointViews, float fOptimAngle);
+	// nThreads > 1 spreads the work inside ONE image over threads (bit-identical for every thread count): for the view a GPU waits for
+	bool SelectNeighborViews(uint32_t ID, std::vector<uint32_t>& points, unsigned nMinViews, unsigned nMinPointViews, float fOptimAngle, unsigned nThreads = 1);
 	static bool FilterNeighborViews(std::vector<ViewScore>& neighbors, float fMinArea, float fMinScale, float fMaxScale, float fMinAngle, float fMaxAngle, unsigned nMaxViews);
 };
 
@@ -143,7 +144,7 @@ bool TriangulateInit(const Scene& scene, uint32_t idxImage, const std::vector<ui
 class DepthMapsData {
 public:
 	DepthMapsData(Scene& scene, hcmvs_ctx* ctx, const hcmvs_params& params, const ViewSelectionParams& vs = ViewSelectionParams());
-	bool SelectViews(uint32_t idxImage);                                   // SceneDensify.cpp:307-327
+	bool SelectViews(uint32_t idxImage, unsigned nThreads = 1);            // SceneDensify.cpp:307-327
 	bool InitViews(uint32_t idxImage, uint32_t numNeighbors);              // SceneDensify.cpp:336-397
 	// SceneDensify.cpp:772-812: nMinViewsTrustPoint < 2 -> sparse points splatted on the host; else (the reference's default) the
 	// triangulated sparse cloud (InitDepthMap :514-525 -> TriangulatePoints2DepthMap), triangulated here and rasterised on the device

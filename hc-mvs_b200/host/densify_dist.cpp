@@ -88,7 +88,7 @@ struct DistributedReconstruction::Impl {
 	int Owner(uint32_t i) const { return (int)(i%(uint32_t)world); } // uploads the image, selects its neighbours, estimates it (unless row-split), filters it
 	unsigned Threads(size_t work) const { const unsigned hc = std::thread::hardware_concurrency(); return (unsigned)std::max<size_t>(1, std::min<size_t>((hc > 1 ? hc-1 : 1u)/(unsigned)world+1u, work)); }
 	bool Prepare();
-	bool SelectOne(uint32_t i);   // SelectViews + the initial maps of a view this rank estimates (worker threads)
+	bool SelectOne(uint32_t i, unsigned threads = 1);   // SelectViews + the initial maps of a view this rank estimates (worker threads)
 	bool Gather();                // all-gather of the selection results; neighbour lists of every view on this rank
 	bool InitOne(uint32_t i);     // InitViews (neighbour lists to the device)
 	bool UploadOne(uint32_t i);
@@ -96,8 +96,8 @@ struct DistributedReconstruction::Impl {
 	bool Run(uint64_t seed, bool runFilter, bool download);
 };
 
-bool DistributedReconstruction::Impl::SelectOne(uint32_t i) {
-	ok[i] = data.SelectViews(i) ? 1 : 0;
+bool DistributedReconstruction::Impl::SelectOne(uint32_t i, unsigned threads) {
+	ok[i] = data.SelectViews(i, threads) ? 1 : 0;
 	if (!ok[i]) return true;
 	DepthData& dd = data.arrDepthData[i];
 	if (P.nMinViewsTrustPoint >= 2) { // SceneDensify.cpp:781-812
@@ -136,6 +136,7 @@ bool DistributedReconstruction::Impl::Prepare() {
 	const uint32_t nImages = (uint32_t)scene.images.size();
 	const double t0 = NowD();
 	for (Image& im: scene.images) { im.camera.ComposeP(); im.neighbors.clear(); }
+	if (hcmvs_begin_scene(ctx) != HCMVS_OK) return lib("hcmvs_begin_scene"); // initial-map uploads overlap the running estimation (see the header)
 	for (DepthData& dd: data.arrDepthData) dd = DepthData();
 	ok.assign(nImages, 0); inited.assign(nImages, 0); init.assign(nImages, Init()); gathered = false;
 	// The plan needs nothing but the image count: views in INDEX order, view i whole on rank i % world in round i / world, the last
@@ -246,6 +247,8 @@ bool DistributedReconstruction::Impl::Run(uint64_t seed, bool runFilter, bool do
 	if (lazy) {
 		// the other views this rank OWNS but does not estimate whole (none: owners estimate their views) need no work here; the row-split
 		// views are selected by every rank
+		// the first view is what this rank's GPU waits for: all of the rank's share of the cores work inside its selection first
+		if (!est.empty()) { ready[0].store(SelectOne(est[0], Threads(64)+1) ? 1 : -1, std::memory_order_release); nextSel.store(1); }
 		for (unsigned t=0; t<Threads(est.size()); ++t) pool.emplace_back([&]() { size_t k; while ((k = nextSel.fetch_add(1)) < est.size()) ready[k].store(SelectOne(est[k]) ? 1 : -1, std::memory_order_release); });
 	}
 	size_t nextEst = 0; // position in `est`

@@ -48,10 +48,11 @@ int hcmvs_host_set_sparse(hcmvs_host_scene* s, int n, const float* xyz, const in
 	return 0;
 }
 
-int hcmvs_host_select_views(hcmvs_host_scene* s, const hcmvs_params* p, int idx) {
-	if (!s || !p || idx < 0 || idx >= (int)s->scene.images.size()) return -1;
+int hcmvs_host_select_views(hcmvs_host_scene* s, const hcmvs_params* p, int idx) { return hcmvs_host_select_views_mt(s, p, idx, 1); }
+int hcmvs_host_select_views_mt(hcmvs_host_scene* s, const hcmvs_params* p, int idx, int threads) {
+	if (!s || !p || idx < 0 || idx >= (int)s->scene.images.size() || threads < 1) return -1;
 	DepthMapsData data(s->scene, nullptr, *p);
-	if (!data.SelectViews((uint32_t)idx)) return -1;
+	if (!data.SelectViews((uint32_t)idx, (unsigned)threads)) return -1;
 	if (s->dd.size() != s->scene.images.size()) s->dd.resize(s->scene.images.size());
 	s->dd[idx] = data.arrDepthData[idx];
 	return (int)s->dd[idx].neighbors.size();

@@ -92,6 +92,13 @@ int hcmvs_set_view(hcmvs_ctx* ctx, uint32_t view, int W, int H, const double K[9
 /* Result of DepthMapsData::SelectViews (SceneDensify.cpp:307-327): ids[0..n_all) sorted by score; the first
  * n_match are the matching views InitViews keeps (SceneDensify.cpp:361-376); all n_all are probed by fusion. */
 int hcmvs_set_neighbors(hcmvs_ctx* ctx, uint32_t ref, const uint32_t* ids, const float* scores, int n_match, int n_all);
+/* Optional, once per scene on a context that is reused: waits for everything queued on the context, then declares that until the
+ * first hcmvs_filter_depthmap / hcmvs_commit_filtered / hcmvs_fuse_depthmaps / snapshot / export call a view's maps are only touched by
+ * ITS OWN hcmvs_init_depthmap* / hcmvs_estimate_depthmap* / hcmvs_end_depthmap / hcmvs_download_depthmap_begin calls (what
+ * DepthMapsData::EstimateDepthMap does, SceneDensify.cpp:772-1056). The upload of view i+1's initial maps then waits only for that
+ * view's own last use instead of for everything queued so far (the estimation of view i), i.e. it overlaps the kernels. Without
+ * this call every re-initialisation is conservatively ordered after all queued work. */
+int hcmvs_begin_scene(hcmvs_ctx* ctx);
 /* it_external==0 initialisation of EstimateDepthMap (SceneDensify.cpp:772-819): caller-provided rough depth
  * (0 = unknown), optional normals, depth range; builds the gradient map (InitGraMap, :581-595) on device. */
 int hcmvs_init_depthmap(hcmvs_ctx* ctx, uint32_t ref, const float* depth0, const float* normal0, float dMin, float dMax);

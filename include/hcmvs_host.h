@@ -19,6 +19,9 @@ int hcmvs_host_add_image(hcmvs_host_scene* s, int w, int h, const double K[9], c
 int hcmvs_host_set_sparse(hcmvs_host_scene* s, int n, const float* xyz, const int32_t* offsets, const uint32_t* view_ids);
 /* DepthMapsData::SelectViews for one image (host only, needs no device). Returns #filtered neighbours or -1. */
 int hcmvs_host_select_views(hcmvs_host_scene* s, const hcmvs_params* p, int idx);
+/* The same with the work inside the one image spread over `threads` threads (what DenseReconstruction does for the first view, the one
+ * the GPU waits for); bit-identical to the one-thread form. */
+int hcmvs_host_select_views_mt(hcmvs_host_scene* s, const hcmvs_params* p, int idx, int threads);
 /* which: 0 = Image::neighbors (all scored), 1 = DepthData::neighbors (filtered). Returns the list length. */
 int hcmvs_host_get_neighbors(hcmvs_host_scene* s, int idx, int which, uint32_t* ids, uint32_t* points, float* scale, float* angle, float* area, float* score, int cap);
 /* sparse-point initial depth map + depth range of a selected view (SceneDensify.cpp:783-808) */

@@ -74,7 +74,8 @@ def test_host_view_selection_and_image_prep_bit_exact(built):
         hs = host.HostScene.from_synth(syn, imgs)
         P = api.default_params(nMinViewsTrustPoint=1)
         for i in range(syn.n_views):
-            r = hs.select_views(P, i)
+            # every third view with the work inside the image spread over 5 threads (DenseReconstruction's first view): same bits
+            r = hs.select_views(P, i, threads=5 if i % 3 == 0 else 1)
             assert (r > 0) == ok[i]
             for which in (0, 1):
                 a, b = hs.neighbors(i, which), osc.neighbors(i, which)
