@@ -177,7 +177,9 @@ __device__ __forceinline__ unsigned long long block_sum(unsigned long long v, un
 }
 
 // ------------------------------------------------------------------ stages of one view
+#ifndef FUSE_FN
 #define FUSE_FN __forceinline__
+#endif
 #ifdef FUSE_CHECK
 #define FUSE_CHK(cond, id) do { if (!(cond)) { atomicCAS(&a.ctl->overflow, 0, (id)); return; } } while (0)
 #define FUSE_CHKR(cond, id) do { if (!(cond)) { atomicCAS(&a.ctl->overflow, 0, (id)); return 0; } } while (0)
