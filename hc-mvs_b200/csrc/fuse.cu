@@ -12,9 +12,10 @@
 //
 // Round 2 layout (profiles/r02_notes.md): the whole scene is fused by ONE persistent cooperative kernel
 // (k_fuse_scene; grid.sync between the stages of a view, no launch gaps, no host round trip per view), over
-// 32-byte per-pixel RECORDS {depth, claim, world normal, weight, colour} built once per scene, so that every
+// 32-byte per-pixel read-only RECORDS {depth, world normal, weight, colour} built once per scene, so that every
 // probe of a neighbour pixel is ONE aligned DRAM sector (the round-1 kernels gathered float4 + claim word +
-// conf + colour from four arrays: 2 sectors per probe, 3 more per merged view in the emit).
+// conf + colour from four arrays: 2 sectors per probe, 3 more per merged view in the emit); what changes during
+// the fusion — liveness and reservations — lives in a 1-bit-per-pixel bitmap and three rotating planes of claim words.
 #include "hcmvs_internal.h"
 #include "camera.cuh"
 #include <cooperative_groups.h>
@@ -464,15 +465,17 @@ __device__ __forceinline__ void emit_slot(const FuseJob& a, const FusePlanView& 
 }
 
 // ------------------------------------------------------------------ the whole scene: one persistent cooperative kernel
-// Per view r (fusion order): [C] count the seeds of r per block (+ the final slots of r-1) | [D] ordered scatter of the seeds
-// (+ ordered copy of r-1's staged points into the cloud) | then the seed slots in TILES of FUSE_TILE, in raster order:
-// [P] classify the tile's probes + first reservations, re-reserve for the unfinished slots of earlier tiles | [R] resolve both, stage
-// the points of the seeds that became final. A tile's record sectors (one per live probe) are fetched from DRAM once, by [P];
-// [R] and the staging find them in L2 (126 MB) — without tiles the three stages of a 1.9 M-seed view each missed. Tiles are exact:
-// every seed of a later tile follows every seed of an earlier one in raster order, and the unfinished seeds of earlier tiles keep
-// taking part in the reservations. After the last tile the rounds go on over the worklist until it is empty. Blocks own contiguous
-// bitmap-word / slot ranges in the two ordered compactions, so the slots and the cloud keep raster order with one block-count
-// prefix (<= gridDim.x words) per compaction.
+// Per view r (fusion order), separated by grid barriers:
+//  [C] count the seeds of r per block (+ the final slots of r-1, + the deferred staging of r-1's later-round finals)
+//  [D] ordered scatter of the seeds of r into slots (+ ordered copy of r-1's staged points into the cloud, progress to the host)
+//  [P] classify every seed's probes (the f64 geometry, once) and place the first reservations (claim plane 0)
+//  [R] round 1 over every slot: resolve, reserve for round 2 (plane 1), stage the points of the seeds that became final — their
+//      merged records were fetched by [P] and are still in L2
+//  [R'] rounds k >= 2 over the worklist of unfinished slots, ONE phase each: resolve against plane (k-1)%3, reserve in plane k%3,
+//      clear plane (k+1)%3; seeds that become final are listed for the next view's [C]
+// Blocks own contiguous bitmap-word / slot ranges in the two ordered compactions, so the slots and the cloud keep raster order with
+// one block-count prefix (<= gridDim.x words) per compaction. (Processing the slots in L2-sized tiles was measured and rejected: a
+// tile step cannot be shorter than its dependent chain — profiles/r02_notes.md.)
 #ifndef FUSE_MINB
 #define FUSE_MINB 2 // 128 registers: 3 CTAs/SM (80 registers) spill ~800 B per thread into the dependent chains (measured: 4.74 vs 4.24 ms per 16 C2 views)
 #endif
