@@ -82,7 +82,11 @@ struct DistributedReconstruction::Impl {
 	bool gathered = false;
 	DenseReconstructionStats st;
 	std::string err;
+	// lazy jobs: the selection + initial maps of the FIRST view this rank estimates (what its GPU waits for) start with Prepare(), on
+	// their own threads, so that they overlap the image uploads and the NVLink image exchange instead of following them
+	std::thread firstSel; int firstSelRes = 0;
 	Impl(Scene& s, hcmvs_ctx* c, const hcmvs_params& p, const ViewSelectionParams& vs, int r, int w): scene(s), ctx(c), P(p), VS(vs), rank(r), world(w), data(s, c, p, vs) {}
+	~Impl() { if (firstSel.joinable()) firstSel.join(); }
 	bool fail(const std::string& m) { err = "rank "+std::to_string(rank)+": "+m; return false; }
 	bool lib(const char* what) { return fail(std::string(what)+": "+hcmvs_last_error()); }
 	int Owner(uint32_t i) const { return (int)(i%(uint32_t)world); } // uploads the image, selects its neighbours, estimates it (unless row-split), filters it
@@ -149,6 +153,9 @@ bool DistributedReconstruction::Impl::Prepare() {
 	}
 	mineWhole = plan.WholeViewsOf(rank); split = plan.SplitViews(); mine = plan.ViewsOf(rank);
 	est = mineWhole; est.insert(est.end(), split.begin(), split.end());
+	if (firstSel.joinable()) firstSel.join(); // a Prepare() whose Run() never came
+	firstSelRes = 0;
+	if (lazy && !est.empty()) firstSel = std::thread([this]() { firstSelRes = SelectOne(est[0], Threads(64)+1) ? 1 : -1; });
 	// colour travels with the gray image; a rank only knows it for the images it holds, and the scene is homogeneous in that respect
 	uint32_t hasColor = 0;
 	for (uint32_t i=0; i<nImages; ++i) if (Owner(i) == rank && !scene.images[i].bgr.empty()) hasColor = 1;
@@ -248,7 +255,8 @@ bool DistributedReconstruction::Impl::Run(uint64_t seed, bool runFilter, bool do
 		// the other views this rank OWNS but does not estimate whole (none: owners estimate their views) need no work here; the row-split
 		// views are selected by every rank
 		// the first view is what this rank's GPU waits for: all of the rank's share of the cores work inside its selection first
-		if (!est.empty()) { ready[0].store(SelectOne(est[0], Threads(64)+1) ? 1 : -1, std::memory_order_release); nextSel.store(1); }
+		if (firstSel.joinable()) firstSel.join();
+		if (!est.empty()) { ready[0].store(firstSelRes != 0 ? firstSelRes : (SelectOne(est[0], Threads(64)+1) ? 1 : -1), std::memory_order_release); nextSel.store(1); }
 		for (unsigned t=0; t<Threads(est.size()); ++t) pool.emplace_back([&]() { size_t k; while ((k = nextSel.fetch_add(1)) < est.size()) ready[k].store(SelectOne(est[k]) ? 1 : -1, std::memory_order_release); });
 	}
 	size_t nextEst = 0; // position in `est`
