@@ -136,14 +136,26 @@ __global__ void __launch_bounds__(256) k_filter_vote(const __grid_constant__ Fil
 			float avgDepth = __fmul_rn(depth, posConf);
 			unsigned nPos = 0, nNeg = 0;
 			bool discard = false;
+			// the winners of all neighbour z-buffers and their confidences first (independent loads: the kernel was a chain of 2 x N
+			// dependent DRAM trips per pixel — ncu: 23 % issue-active, long_scoreboard 26), then the reference's loop in registers
+			constexpr int VB = 8; // FilterDepthMap is called with at most 8 neighbours (SceneDensify.cpp:4093-4185); more: further batches
+			unsigned long long kk[VB]; float cb[VB];
 			for (int n=N-1; n>=0; --n) {
-				const unsigned long long k = proj[(size_t)n*plane+o];
+				const int jb = (N-1-n)%VB; // position in the batch (j and i are the pixel)
+				if (jb == 0) {
+					#pragma unroll
+					for (int t=0; t<VB; ++t) kk[t] = n-t >= 0 ? proj[(size_t)(n-t)*plane+o] : FILTER_EMPTY;
+					#pragma unroll
+					for (int t=0; t<VB; ++t) cb[t] = kk[t] != FILTER_EMPTY ? fc->conf[n-t][proj_src(kk[t])] : 0.f;
+				}
+				unsigned long long k = kk[0]; float cproj = cb[0];
+				#pragma unroll
+				for (int t=1; t<VB; ++t) if (jb == t) { k = kk[t]; cproj = cb[t]; }
 				const float d = proj_depth(k);
 				if (d == 0.f) {
 					if (nPos+nNeg+(unsigned)n < fc->nMinViews) { discard = true; break; }
 					continue;
 				}
-				const float cproj = fc->conf[n][proj_src(k)];
 				if (depth_similar(depth, d, 0.12f)) { // hard-coded in the fork, :3127
 					avgDepth = __fadd_rn(avgDepth, __fmul_rn(d, cproj));
 					posConf = __fadd_rn(posConf, cproj);
