@@ -89,6 +89,29 @@ def test_host_view_selection_and_image_prep_bit_exact(built):
                 assert np.array_equal(d0, d1) and lo == lo1 and hi == hi1
 
 
+def test_view_selection_is_independent_of_the_thread_count(built):
+    """Scene::SelectNeighborViews with the work inside one image spread over threads (DenseReconstruction's first view, the one the GPU
+    waits for): per-point terms in parallel, f32 sums serially in cloud order -> the same bits for 1, 2, 3, 7 and 16 threads."""
+    from hcmvs_b200 import api, host
+    syn, osc, gt, imgs, ok = common.make_scene(2, 0.125, 0)
+    hs = host.HostScene.from_synth(syn, imgs)
+    P = api.default_params(nMinViewsTrustPoint=1)
+    for i in (0, 7, 24, 48):
+        ref = None
+        for th in (1, 2, 3, 7, 16):
+            r = hs.select_views(P, i, threads=th)
+            cur = (r, {w: {k: v.copy() for k, v in hs.neighbors(i, w).items()} for w in (0, 1)}, hs.init_depth(i) if r > 0 else None)
+            if ref is None:
+                ref = cur
+                continue
+            assert cur[0] == ref[0]
+            for w in (0, 1):
+                for k in ref[1][w]:
+                    assert np.array_equal(cur[1][w][k], ref[1][w][k]), (i, th, w, k)
+            if ref[2] is not None:
+                assert np.array_equal(cur[2][0], ref[2][0]) and cur[2][1:] == ref[2][1:]
+
+
 def test_dmap_roundtrip_and_layout(built, tmp_path):
     """Raw 'DR' depth-data file (Interface.h:634-652, DepthMap.cpp:2781-2925): 28-byte header, name, ids, K R C, maps."""
     from hcmvs_b200 import host
